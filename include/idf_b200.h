@@ -1,0 +1,182 @@
+/* idf_b200 -- C ABI of the B200-native InfoDiffusion denoising hot path.
+ *
+ * The reference (isjakewong/InfoDiffusion) has no FFI: its boundary is the Python nn.Module
+ * call surface.  Every entry point below therefore names the reference
+ * Python construct whose arithmetic it replaces (file:line in the reference checkout).  The
+ * host-side mirror of the reference interface (infodiffusion_b200/{models,modules,sampling,utils}.py)
+ * binds these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless stated.
+ *  - every launcher is asynchronous on `stream`, allocates nothing, keeps no global state
+ *    besides the plan objects the caller owns, and is CUDA-graph capturable.
+ *  - return value: 0 on success, negative idf_status on error; idf_last_error() gives text.
+ *  - activations live in the "pad-flat" NHWC layout: image n, pixel (y,x), channel c of an
+ *    H x W x C map is element ((n*(H+1) + y)*(W+1) + x)*C + c; row y==H and column x==W of every
+ *    image are zero padding shared with the neighbouring row/image, so a 3x3 tap is a constant
+ *    row offset (dy*(W+1)+dx) and the zero border implements `padding=1`.  Kernels never write
+ *    pad rows; buffers must be zero-initialised once by the caller.
+ *  - 16-bit storage type is bfloat16 (IDF_BF16).
+ */
+#ifndef IDF_B200_H_
+#define IDF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* idf_stream_t; /* == cudaStream_t */
+
+typedef enum {
+  IDF_OK = 0,
+  IDF_ERR_ARG = -1,      /* bad argument / unsupported shape           */
+  IDF_ERR_CUDA = -2,     /* CUDA runtime/driver error                  */
+  IDF_ERR_ARCH = -3,     /* device is not sm_100 (no fallback exists)  */
+  IDF_ERR_NOMEM = -4
+} idf_status;
+
+int idf_version(void);
+const char* idf_last_error(void);
+/* Checks that the current device is sm_100 and raises dynamic-smem limits. */
+int idf_init(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ * Replaces nn.Conv2d 3x3/1x1 at modules.py:66,81,133-136,216,222,228,231,267,281,287,291,337,
+ * 343,346 and models.py:246,283,431,467 (cuDNN in the reference), plus -- through the epilogue
+ * modes -- the residual add modules.py:255,322,364, the attention residual modules.py:164 and
+ * the sampler updates sampling.py:35-37,52-59,71-72.
+ *
+ * GEMM view: out[r, n] = sum_kb  A_kb[r + rowoff_kb, c0_kb : c0_kb+64] . Wp[n, 64*kb : 64*kb+64]
+ * where A_kb is one of up to three pad-flat activation matrices (concat-K / fused 1x1 shortcut),
+ * r runs over the pad-flat rows of the OUTPUT geometry and Wp is the packed bf16 weight matrix
+ * [Cout_pad, 64*num_kb] (K contiguous).
+ * ------------------------------------------------------------------------------------------ */
+#define IDF_CONV_MAX_KB 48
+#define IDF_CONV_MAX_SRC 3
+
+typedef enum {
+  IDF_EPI_BF16 = 0,        /* out(bf16 pad-flat)[r, n] = acc + bias[n] (+ residual[r, n])            */
+  IDF_EPI_F32_NCHW = 1,    /* out_f32 (NCHW [B,Cout,H,W]) = acc + bias                                */
+  IDF_EPI_SAMPLER = 2      /* eps = acc + bias;  x = cx*x + ce*eps + cn*noise  (x, noise fp32 NCHW);
+                              (cx,ce,cn) = coef[3*step], step = *step_ptr; eps also stored if out_f32 */
+} idf_conv_epilogue;
+
+typedef struct {
+  /* A sources: pad-flat bf16 matrices [src_rows, src_ld] */
+  int32_t n_src;
+  const void* src[IDF_CONV_MAX_SRC];
+  int64_t src_rows[IDF_CONV_MAX_SRC];
+  int32_t src_ld[IDF_CONV_MAX_SRC];   /* channels per row (multiple of 64)                       */
+  /* K-block table */
+  int32_t num_kb;
+  int32_t kb_src[IDF_CONV_MAX_KB];
+  int32_t kb_c0[IDF_CONV_MAX_KB];     /* first channel of the 64-wide slice                      */
+  int32_t kb_rowoff[IDF_CONV_MAX_KB]; /* signed row offset of the tap                            */
+  /* B: packed weights [cout_pad, 64*num_kb] bf16, row-major */
+  const void* weight;
+  int32_t cout_pad;                   /* multiple of block_n                                     */
+  int32_t block_n;                    /* 16, 64 or 128                                           */
+  int32_t cout;                       /* real output channels                                    */
+  const float* bias;                  /* [cout_pad] fp32                                         */
+  /* output geometry */
+  int32_t batch, H, W;                /* rows = batch*(H+1)*(W+1)                                */
+  int32_t epilogue;                   /* idf_conv_epilogue                                       */
+  void* out;                          /* bf16 pad-flat [rows, out_ld] (IDF_EPI_BF16)             */
+  int32_t out_ld;
+  const void* residual;               /* optional bf16 pad-flat [rows, res_ld]                   */
+  int32_t res_ld;
+  float* out_f32;                     /* NCHW fp32 (modes 1,2; may be NULL in mode 2)            */
+  float* x_io;                        /* NCHW fp32, updated in place (mode 2)                    */
+  const float* noise;                 /* NCHW fp32 (mode 2; may be NULL => cn ignored)           */
+  const float* coef;                  /* [n_steps, 3] fp32 (mode 2)                              */
+  const int32_t* step_ptr;            /* device scalar (mode 2)                                  */
+} idf_conv_desc;
+
+typedef struct idf_conv_plan idf_conv_plan;
+int idf_conv_plan_create(const idf_conv_desc* desc, idf_conv_plan** plan);
+int idf_conv_plan_destroy(idf_conv_plan* plan);
+int idf_conv_run(const idf_conv_plan* plan, idf_stream_t stream);
+/* number of 128-row x block_n tiles a run processes (for roofline accounting) */
+int64_t idf_conv_plan_tiles(const idf_conv_plan* plan);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused AdaGN: GroupNorm(32) statistics + affine + timestep scale/shift + latent-z scale/shift
+ * + SiLU, one HBM read and one HBM write.  Replaces nn.GroupNorm + the modulation chain + nn.SiLU
+ * at modules.py:214-215, 219-221, 225-227, 249-253, 265-266, 278-280, 284-286, 312-319, 335-336,
+ * 340-341, the attention GroupNorm modules.py:132,147 and the torch.cat of models.py:321,505
+ * (two sources are normalised as one concatenated map).
+ *   y = silu?( ((gn(x)*gamma+beta) * (1+s_t) + b_t) * (1+s_z) + b_z )
+ * mod_t / mod_z point at [.., 2*C] rows holding (scale | shift); the row used for sample n is
+ *   mod + (step_ptr ? *step_ptr : 0) * step_stride + n * batch_stride        (either may be NULL)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* src0; int32_t c0;       /* bf16 pad-flat [rows, c0]                                */
+  const void* src1; int32_t c1;       /* optional second source (concat along C), c1 may be 0    */
+  void* out;                          /* bf16 pad-flat [rows, c0+c1]                             */
+  int32_t batch, H, W;
+  const float* gamma; const float* beta;   /* [c0+c1]                                            */
+  float eps;
+  const float* mod_t; int64_t mod_t_step_stride; int64_t mod_t_batch_stride;
+  const float* mod_z; int64_t mod_z_step_stride; int64_t mod_z_batch_stride;
+  const int32_t* step_ptr;
+  int32_t apply_silu;
+} idf_adagn_args;
+int idf_adagn_silu_fwd(const idf_adagn_args* args, idf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused single-head self attention (QK^T -> softmax -> PV on tcgen05), S = H*W tokens, d = 128.
+ * Replaces torch.bmm / F.softmax / permutes at modules.py:152-161.
+ * qkv: bf16 pad-flat [rows, 3*d] (q | k | v), out: bf16 pad-flat [rows, d]; scale = d^-0.5.
+ * ------------------------------------------------------------------------------------------ */
+int idf_attn_fwd(const void* qkv, void* out, int32_t batch, int32_t H, int32_t W, int32_t d, float scale,
+                 idf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small fp32 linear:  y[m, n] = sum_k act(x[m, k]) * w[n, k] + b[n]   (act = SiLU if silu_in)
+ * Replaces nn.Linear at modules.py:24,26,211,271,275 and models.py:244,470-472 (cuBLAS addmm).
+ * ------------------------------------------------------------------------------------------ */
+int idf_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int32_t M,
+                   int32_t N, int32_t K, int32_t silu_in, idf_stream_t stream);
+/* y[m, :] = table[idx[m], :]  (nn.Embedding lookup, modules.py:23,37) */
+int idf_gather_rows_f32(const float* table, const int64_t* idx, float* y, int32_t M, int32_t N, idf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / data-movement kernels
+ * ------------------------------------------------------------------------------------------ */
+/* x NCHW fp32 [B,C,H,W] (C<=7) -> 3x3 im2col patches bf16 pad-flat [rows, 64] (k = tap*C + c,
+ * zero beyond 9*C): turns the head conv (models.py:246,304,431) into a K=64 1x1 GEMM. */
+int idf_im2col_head(const float* x, void* out, int32_t batch, int32_t C, int32_t H, int32_t W, idf_stream_t stream);
+/* nearest x2 upsample (F.interpolate, modules.py:90-91) in pad-flat layout: [B,H,W,C] -> [B,2H,2W,C] */
+int idf_upsample2x(const void* in, void* out, int32_t batch, int32_t H, int32_t W, int32_t C, idf_stream_t stream);
+/* space-to-depth split for the stride-2 conv (modules.py:66): in [B,H,W,C] -> out[4][B,H/2,W/2,C],
+ * out[py*2+px][n,y,x] = in[n,2y+py,2x+px]. */
+int idf_space_to_depth(const void* in, void* out, int32_t batch, int32_t H, int32_t W, int32_t C,
+                       idf_stream_t stream);
+/* pad-flat bf16 [B,H,W,C] <-> NCHW fp32 (debug / block-level tests / training boundary) */
+int idf_nchw_to_padflat(const float* x, void* out, int32_t batch, int32_t C, int32_t H, int32_t W,
+                        idf_stream_t stream);
+int idf_padflat_to_nchw(const void* in, float* y, int32_t batch, int32_t C, int32_t H, int32_t W,
+                        idf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone sampler update (the unfused variant of IDF_EPI_SAMPLER):
+ *   x = cx*x + ce*eps + cn*noise,  (cx,ce,cn) = coef[3*step].  sampling.py:35-37, 52-59, 71-72.
+ * ------------------------------------------------------------------------------------------ */
+int idf_sampler_update(float* x, const float* eps, const float* noise, const float* coef, const int32_t* step_ptr,
+                       int64_t n, idf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MMD prior loss (utils.py:74-90), fused pairwise Gaussian-kernel reduction.
+ *   loss = mean k(x,x) + mean k(y,y) - 2 mean k(x,y),  k(u,v) = exp(-|u-v|^2 / D^2)
+ * x: prior samples [B,D], y: latents [B,D]; grad_y (optional) = d loss / d y.
+ * ------------------------------------------------------------------------------------------ */
+int idf_mmd_fwd_bwd(const float* x, const float* y, float* loss, float* grad_y, int32_t B, int32_t D,
+                    idf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDF_B200_H_ */

@@ -1,0 +1,75 @@
+"""Builds libidf_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+The library is plain C ABI (include/idf_b200.h): no torch headers, so it compiles in seconds and
+the built .so travels with the source tree.  `python -m infodiffusion_b200.build` rebuilds it.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libidf_b200.so"
+STAMP = PKG / "csrc" / ".build_stamp"
+
+SOURCES = ["capi.cu", "conv_igemm.cu", "adagn.cu", "attention.cu", "misc.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "idf_b200.h"]):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_fresh() -> bool:
+    return LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == _digest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and is_fresh():
+        return LIB
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = CSRC / (src[:-3] + ".o")
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(str(obj))
+    failed = False
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0 or verbose:
+            sys.stderr.write(f"--- nvcc {src} (rc={pr.returncode})\n{out}\n")
+        failed |= pr.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed building libidf_b200.so")
+    link = [_nvcc(), "-shared", "-o", str(LIB), *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    subprocess.run(link, check=True)
+    STAMP.write_text(_digest())
+    return LIB
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p)

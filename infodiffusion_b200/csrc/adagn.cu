@@ -1,0 +1,237 @@
+// Fused AdaGN: GroupNorm(32) statistics + affine + timestep / latent-z scale-shift + SiLU.
+//
+// One thread-block CLUSTER per sample (CL = 1..8 CTAs, chosen from the sample's byte size).  Every CTA
+// streams its slice of the sample's pad-flat rows with 16-byte vector loads (8 bf16 channels per
+// thread, fully coalesced: consecutive threads cover consecutive channels of a row), accumulates
+// per-channel sum / sum-of-squares in fp32, the cluster combines the partials through distributed
+// shared memory, each CTA folds mean/rstd, gamma/beta and both modulations into one (A,B) pair per
+// channel, and a second sweep over the same rows (served by L2: the cluster's working set is small)
+// applies y = silu(A*x + B) and writes bf16.  HBM traffic: one read + one write of the tensor.
+//
+// Two sources (c1 > 0) are treated as one map concatenated along C, which is how the reference's
+// torch.cat([h, skip]) followed by GroupNorm behaves (models.py:321 -> modules.py:265).
+#include <cooperative_groups.h>
+
+#include "kernels.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace idf {
+
+constexpr int kAdaThreads = 256;
+constexpr int kMaxC = 256;
+constexpr int kUnroll = 4;
+
+struct AdaGNParams {
+  const bf16* src0;
+  const bf16* src1;
+  bf16* out;
+  int c0, c1, C;
+  int Hp, Wp, H, W;
+  int rows_per_img;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  const float* mod_t;
+  long long mod_t_step_stride, mod_t_batch_stride;
+  const float* mod_z;
+  long long mod_z_step_stride, mod_z_batch_stride;
+  const int* step_ptr;
+  int apply_silu;
+};
+
+__device__ __forceinline__ uint4 ld_row_vec(const AdaGNParams& p, long long row, int vl, int v0) {
+  // vl: index of the 8-channel vector inside the concatenated row; v0 = c0/8
+  const bf16* ptr = (vl < v0) ? (p.src0 + row * p.c0 + vl * 8) : (p.src1 + row * p.c1 + (vl - v0) * 8);
+  return __ldg(reinterpret_cast<const uint4*>(ptr));
+}
+
+__global__ void __launch_bounds__(kAdaThreads) adagn_kernel(const AdaGNParams p) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = static_cast<int>(cluster.num_blocks());
+  const int crank = static_cast<int>(cluster.block_rank());
+  const int n = blockIdx.y;
+
+  __shared__ float s_part[kAdaThreads][17];   // per-thread partials: 8 sums + 8 sums of squares (+1 pad)
+  __shared__ float s_cta[2 * kMaxC];          // this CTA's per-channel (sum | sumsq), read by cluster peers
+  __shared__ float s_tot[2 * kMaxC];
+  __shared__ float s_mean[32], s_rstd[32];
+  __shared__ float2 s_ab[kMaxC];
+
+  const int C = p.C;
+  const int VPR = C >> 3;                       // 16-byte vectors per row
+  const int rpp = kAdaThreads / VPR;            // rows per pass
+  const int t = threadIdx.x;
+  const bool active = t < rpp * VPR;
+  const int vl = t % VPR;
+  const int rsub = t / VPR;
+  const int v0 = p.c0 >> 3;
+
+  // this CTA's slice of the sample's rows
+  const int rows = p.rows_per_img;
+  const int chunk = (rows + CL - 1) / CL;
+  const int r_begin = crank * chunk;
+  const int r_end = min(rows, r_begin + chunk);
+  const long long row_base = static_cast<long long>(n) * rows;
+
+  // ---------------------------------------------------------------- sweep 1: statistics
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+  if (active) {
+    for (int r = r_begin + rsub; r < r_end; r += kUnroll * rpp) {
+      uint4 u[kUnroll];
+      bool ok[kUnroll];
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {       // issue all loads first (memory-level parallelism)
+        const int rr = r + k * rpp;
+        const int y = rr / p.Wp;
+        const int x = rr - y * p.Wp;
+        ok[k] = (rr < r_end) && (x < p.W) && (y < p.H);   // pad rows are zero: skip the load
+        if (ok[k]) u[k] = ld_row_vec(p, row_base + rr, vl, v0);
+      }
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        if (!ok[k]) continue;
+        const float2 a0 = unpack_bf16x2(u[k].x), a1 = unpack_bf16x2(u[k].y), a2 = unpack_bf16x2(u[k].z),
+                     a3 = unpack_bf16x2(u[k].w);
+        const float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s_part[t][j] = s[j]; s_part[t][8 + j] = ss[j]; }
+  __syncthreads();
+  // per-channel totals of this CTA: channel ch = vl*8 + j lives in threads (rs*VPR + vl), rs = 0..rpp-1
+  for (int i = t; i < 2 * C; i += kAdaThreads) {
+    const int which = i / C;                    // 0: sum, 1: sumsq
+    const int ch = i - which * C;
+    const int cvl = ch >> 3, j = ch & 7;
+    float acc = 0.f;
+    for (int rs = 0; rs < rpp; ++rs) acc += s_part[rs * VPR + cvl][which * 8 + j];
+    s_cta[i] = acc;
+  }
+  cluster.sync();
+  // ---------------------------------------------------------------- cluster reduction (DSMEM)
+  for (int i = t; i < 2 * C; i += kAdaThreads) {
+    float acc = 0.f;
+    for (int rk = 0; rk < CL; ++rk) {
+      const float* remote = cluster.map_shared_rank(s_cta, rk);
+      acc += remote[i];
+    }
+    s_tot[i] = acc;
+  }
+  cluster.barrier_arrive();                     // peers may exit once everyone has read; waited at the end
+  __syncthreads();
+  const int cpg = C / 32;
+  if (t < 32) {
+    float gs = 0.f, gq = 0.f;
+    for (int j = 0; j < cpg; ++j) { gs += s_tot[t * cpg + j]; gq += s_tot[C + t * cpg + j]; }
+    const float inv_cnt = 1.0f / (static_cast<float>(cpg) * p.H * p.W);
+    const float mean = gs * inv_cnt;
+    const float var = fmaxf(gq * inv_cnt - mean * mean, 0.f);
+    s_mean[t] = mean;
+    s_rstd[t] = rsqrtf(var + p.eps);
+  }
+  __syncthreads();
+  const int step = p.step_ptr ? *p.step_ptr : 0;
+  for (int ch = t; ch < C; ch += kAdaThreads) {
+    const int g = ch / cpg;
+    const float rstd = s_rstd[g], mean = s_mean[g];
+    float A = rstd * p.gamma[ch];
+    float B = p.beta[ch] - mean * A;
+    if (p.mod_t != nullptr) {
+      const float* m = p.mod_t + step * p.mod_t_step_stride + n * p.mod_t_batch_stride;
+      const float sc = 1.0f + m[ch], sh = m[C + ch];
+      A *= sc;
+      B = B * sc + sh;
+    }
+    if (p.mod_z != nullptr) {
+      const float* m = p.mod_z + step * p.mod_z_step_stride + n * p.mod_z_batch_stride;
+      const float sc = 1.0f + m[ch], sh = m[C + ch];
+      A *= sc;
+      B = B * sc + sh;
+    }
+    s_ab[ch] = make_float2(A, B);
+  }
+  __syncthreads();
+  // ---------------------------------------------------------------- sweep 2: normalise + activate
+  if (active) {
+    float A[8], B[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float2 ab = s_ab[vl * 8 + j]; A[j] = ab.x; B[j] = ab.y; }
+    const bool do_silu = p.apply_silu != 0;
+    for (int r = r_begin + rsub; r < r_end; r += kUnroll * rpp) {
+      uint4 u[kUnroll];
+      bool ok[kUnroll];
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        const int rr = r + k * rpp;
+        const int y = rr / p.Wp;
+        const int x = rr - y * p.Wp;
+        ok[k] = (rr < r_end) && (x < p.W) && (y < p.H);   // never write pad rows
+        if (ok[k]) u[k] = ld_row_vec(p, row_base + rr, vl, v0);
+      }
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        if (!ok[k]) continue;
+        const float2 a0 = unpack_bf16x2(u[k].x), a1 = unpack_bf16x2(u[k].y), a2 = unpack_bf16x2(u[k].z),
+                     a3 = unpack_bf16x2(u[k].w);
+        float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = fmaf(f[j], A[j], B[j]);
+          f[j] = do_silu ? silu_f(v) : v;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]);
+        o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]);
+        o.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(p.out + (row_base + r + k * rpp) * C + vl * 8) = o;
+      }
+    }
+  }
+  cluster.barrier_wait();
+}
+
+cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
+  AdaGNParams p;
+  p.src0 = static_cast<const bf16*>(a.src0);
+  p.src1 = static_cast<const bf16*>(a.src1);
+  p.out = static_cast<bf16*>(a.out);
+  p.c0 = a.c0;
+  p.c1 = a.src1 ? a.c1 : 0;
+  p.C = p.c0 + p.c1;
+  p.H = a.H; p.W = a.W; p.Hp = a.H + 1; p.Wp = a.W + 1;
+  p.rows_per_img = p.Hp * p.Wp;
+  p.gamma = a.gamma; p.beta = a.beta; p.eps = a.eps;
+  p.mod_t = a.mod_t; p.mod_t_step_stride = a.mod_t_step_stride; p.mod_t_batch_stride = a.mod_t_batch_stride;
+  p.mod_z = a.mod_z; p.mod_z_step_stride = a.mod_z_step_stride; p.mod_z_batch_stride = a.mod_z_batch_stride;
+  p.step_ptr = a.step_ptr;
+  p.apply_silu = a.apply_silu;
+  if (p.C > kMaxC || p.C % 32 != 0 || p.c0 % 8 != 0 || p.c1 % 8 != 0 || a.batch <= 0) return cudaErrorInvalidValue;
+
+  // cluster size from the sample's byte size: ~64 KB of rows per CTA, at most 8 CTAs (portable limit)
+  const long long bytes = static_cast<long long>(p.rows_per_img) * p.C * 2;
+  int CL = 1;
+  while (CL < 8 && bytes > static_cast<long long>(CL) * 65536) CL <<= 1;
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CL, a.batch, 1);
+  cfg.blockDim = dim3(kAdaThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, adagn_kernel, p);
+}
+
+}  // namespace idf

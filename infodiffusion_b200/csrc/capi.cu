@@ -1,0 +1,258 @@
+// extern "C" boundary of libidf_b200.so (declared in include/idf_b200.h).
+// Plain pointers and sizes only; TMA tensor maps are built here so callers never see CUtensorMap.
+#include <cudaTypedefs.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "kernels.cuh"
+
+using namespace idf;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(IDF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+int g_num_sms = 0;
+
+int ensure_init() {
+  if (g_encode != nullptr) return IDF_OK;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(IDF_ERR_ARCH, "idf_b200 requires an sm_100 device (found sm_%d%d); there is no fallback path",
+                prop.major, prop.minor);
+  g_num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess)
+    return fail(IDF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return IDF_OK;
+}
+
+// 2-D bf16 row-major matrix [rows, ld] -> box {64 elements, box_rows}, 128B swizzle
+int encode_2d(CUtensorMap* tm, const void* base, int64_t rows, int32_t ld, int32_t box_rows) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(IDF_ERR_ARG, "TMA base not 16-byte aligned");
+  if (ld % 64 != 0 && ld % 8 != 0) return fail(IDF_ERR_ARG, "row pitch must be a multiple of 16 bytes");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(IDF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return IDF_OK;
+}
+
+}  // namespace
+
+struct idf_conv_plan {
+  ConvKernelParams params;
+  int block_n;
+  int grid;
+};
+
+extern "C" {
+
+int idf_version(void) { return 100; }
+const char* idf_last_error(void) { return g_err; }
+int idf_init(void) { return ensure_init(); }
+
+int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
+  if (d == nullptr || out_plan == nullptr) return fail(IDF_ERR_ARG, "null argument");
+  int rc = ensure_init();
+  if (rc != IDF_OK) return rc;
+  if (d->n_src < 1 || d->n_src > IDF_CONV_MAX_SRC) return fail(IDF_ERR_ARG, "n_src out of range");
+  if (d->num_kb < 1 || d->num_kb > IDF_CONV_MAX_KB) return fail(IDF_ERR_ARG, "num_kb out of range (%d)", d->num_kb);
+  if (d->block_n != 16 && d->block_n != 64 && d->block_n != 128) return fail(IDF_ERR_ARG, "block_n must be 16/64/128");
+  if (d->cout_pad % d->block_n != 0) return fail(IDF_ERR_ARG, "cout_pad must be a multiple of block_n");
+  if (d->batch < 1 || d->H < 1 || d->W < 1) return fail(IDF_ERR_ARG, "bad geometry");
+  if (d->epilogue == IDF_EPI_BF16) {
+    if (d->block_n < 64) return fail(IDF_ERR_ARG, "bf16 epilogue needs block_n >= 64");
+    if (d->out == nullptr || d->out_ld % 8 != 0 || d->cout != d->cout_pad)
+      return fail(IDF_ERR_ARG, "bf16 epilogue: out/out_ld/cout invalid");
+    if (d->residual != nullptr && d->res_ld % 8 != 0) return fail(IDF_ERR_ARG, "res_ld must be a multiple of 8");
+  } else if (d->epilogue == IDF_EPI_F32_NCHW || d->epilogue == IDF_EPI_SAMPLER) {
+    if (d->block_n != 16 || d->cout > 16) return fail(IDF_ERR_ARG, "fp32/sampler epilogue needs block_n == 16");
+    if (d->epilogue == IDF_EPI_F32_NCHW && d->out_f32 == nullptr) return fail(IDF_ERR_ARG, "out_f32 is null");
+    if (d->epilogue == IDF_EPI_SAMPLER && (d->x_io == nullptr || d->coef == nullptr))
+      return fail(IDF_ERR_ARG, "sampler epilogue needs x_io and coef");
+  } else {
+    return fail(IDF_ERR_ARG, "unknown epilogue %d", d->epilogue);
+  }
+  idf_conv_plan* pl = new (std::nothrow) idf_conv_plan;
+  if (pl == nullptr) return fail(IDF_ERR_NOMEM, "out of host memory");
+  std::memset(pl, 0, sizeof(*pl));
+  ConvKernelParams& p = pl->params;
+  for (int i = 0; i < d->n_src; ++i) {
+    if (d->src[i] == nullptr || d->src_ld[i] % 64 != 0) {
+      delete pl;
+      return fail(IDF_ERR_ARG, "source %d: null or channel count not a multiple of 64", i);
+    }
+    rc = encode_2d(&p.tmA[i], d->src[i], d->src_rows[i], d->src_ld[i], kBM);
+    if (rc != IDF_OK) { delete pl; return rc; }
+  }
+  rc = encode_2d(&p.tmB, d->weight, d->cout_pad, d->num_kb * kBK, d->block_n);
+  if (rc != IDF_OK) { delete pl; return rc; }
+  p.n_src = d->n_src;
+  p.num_kb = d->num_kb;
+  for (int k = 0; k < d->num_kb; ++k) {
+    if (d->kb_src[k] < 0 || d->kb_src[k] >= d->n_src || d->kb_c0[k] < 0 ||
+        d->kb_c0[k] + kBK > d->src_ld[d->kb_src[k]]) {
+      delete pl;
+      return fail(IDF_ERR_ARG, "k-block %d out of range", k);
+    }
+    p.kb_src[k] = d->kb_src[k];
+    p.kb_c0[k] = d->kb_c0[k];
+    p.kb_rowoff[k] = d->kb_rowoff[k];
+  }
+  p.Hp = d->H + 1;
+  p.Wp = d->W + 1;
+  p.H = d->H;
+  p.W = d->W;
+  p.rows = static_cast<int64_t>(d->batch) * p.Hp * p.Wp;
+  p.m_tiles = static_cast<int32_t>((p.rows + kBM - 1) / kBM);
+  p.n_tiles = d->cout_pad / d->block_n;
+  p.cout = d->cout;
+  p.epilogue = d->epilogue;
+  p.bias = d->bias;
+  p.out = static_cast<bf16*>(d->out);
+  p.out_ld = d->out_ld;
+  p.residual = static_cast<const bf16*>(d->residual);
+  p.res_ld = d->res_ld;
+  p.out_f32 = d->out_f32;
+  p.x_io = d->x_io;
+  p.noise = d->noise;
+  p.coef = d->coef;
+  p.step_ptr = d->step_ptr;
+  if (p.bias == nullptr) { delete pl; return fail(IDF_ERR_ARG, "bias is null"); }
+  pl->block_n = d->block_n;
+  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  pl->grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+  *out_plan = pl;
+  return IDF_OK;
+}
+
+int idf_conv_plan_destroy(idf_conv_plan* plan) {
+  delete plan;
+  return IDF_OK;
+}
+
+int64_t idf_conv_plan_tiles(const idf_conv_plan* plan) {
+  return plan ? static_cast<int64_t>(plan->params.m_tiles) * plan->params.n_tiles : 0;
+}
+
+int idf_conv_run(const idf_conv_plan* plan, idf_stream_t stream) {
+  if (plan == nullptr) return fail(IDF_ERR_ARG, "null plan");
+  cudaError_t e = launch_conv_igemm(plan->params, plan->block_n, plan->grid, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "conv_igemm launch");
+  return IDF_OK;
+}
+
+int idf_adagn_silu_fwd(const idf_adagn_args* a, idf_stream_t stream) {
+  if (a == nullptr || a->src0 == nullptr || a->out == nullptr) return fail(IDF_ERR_ARG, "null argument");
+  cudaError_t e = launch_adagn(*a, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "adagn launch");
+  return IDF_OK;
+}
+
+int idf_attn_fwd(const void* qkv, void* out, int32_t batch, int32_t H, int32_t W, int32_t d, float scale,
+                 idf_stream_t stream) {
+  if (qkv == nullptr || out == nullptr) return fail(IDF_ERR_ARG, "null argument");
+  cudaError_t e = launch_attn(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), batch, H, W, d, scale,
+                              reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "attention launch (supported: d=128, H*W in {64,256})");
+  return IDF_OK;
+}
+
+int idf_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int32_t M,
+                   int32_t N, int32_t K, int32_t silu_in, idf_stream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return fail(IDF_ERR_ARG, "bad linear shape");
+  cudaError_t e = launch_linear_f32(x, ldx, w, b, y, ldy, M, N, K, silu_in, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "linear launch");
+  return IDF_OK;
+}
+
+int idf_gather_rows_f32(const float* table, const int64_t* idx, float* y, int32_t M, int32_t N, idf_stream_t stream) {
+  cudaError_t e = launch_gather_rows(table, idx, y, M, N, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "gather launch");
+  return IDF_OK;
+}
+
+int idf_im2col_head(const float* x, void* out, int32_t batch, int32_t C, int32_t H, int32_t W, idf_stream_t stream) {
+  cudaError_t e = launch_im2col_head(x, static_cast<bf16*>(out), batch, C, H, W, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "im2col_head launch (needs 9*C <= 64)");
+  return IDF_OK;
+}
+
+int idf_upsample2x(const void* in, void* out, int32_t batch, int32_t H, int32_t W, int32_t C, idf_stream_t stream) {
+  cudaError_t e = launch_upsample2x(static_cast<const bf16*>(in), static_cast<bf16*>(out), batch, H, W, C,
+                                    reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "upsample2x launch");
+  return IDF_OK;
+}
+
+int idf_space_to_depth(const void* in, void* out, int32_t batch, int32_t H, int32_t W, int32_t C,
+                       idf_stream_t stream) {
+  cudaError_t e = launch_space_to_depth(static_cast<const bf16*>(in), static_cast<bf16*>(out), batch, H, W, C,
+                                        reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "space_to_depth launch");
+  return IDF_OK;
+}
+
+int idf_nchw_to_padflat(const float* x, void* out, int32_t batch, int32_t C, int32_t H, int32_t W,
+                        idf_stream_t stream) {
+  cudaError_t e = launch_nchw_to_padflat(x, static_cast<bf16*>(out), batch, C, H, W, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "nchw_to_padflat launch");
+  return IDF_OK;
+}
+
+int idf_padflat_to_nchw(const void* in, float* y, int32_t batch, int32_t C, int32_t H, int32_t W,
+                        idf_stream_t stream) {
+  cudaError_t e = launch_padflat_to_nchw(static_cast<const bf16*>(in), y, batch, C, H, W, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "padflat_to_nchw launch");
+  return IDF_OK;
+}
+
+int idf_sampler_update(float* x, const float* eps, const float* noise, const float* coef, const int32_t* step_ptr,
+                       int64_t n, idf_stream_t stream) {
+  if (x == nullptr || eps == nullptr || coef == nullptr) return fail(IDF_ERR_ARG, "null argument");
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(eps) | reinterpret_cast<uintptr_t>(noise)) & 15)
+    return fail(IDF_ERR_ARG, "sampler_update needs 16-byte aligned tensors");
+  cudaError_t e = launch_sampler_update(x, eps, noise, coef, step_ptr, n, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "sampler_update launch");
+  return IDF_OK;
+}
+
+int idf_mmd_fwd_bwd(const float* x, const float* y, float* loss, float* grad_y, int32_t B, int32_t D,
+                    idf_stream_t stream) {
+  if (x == nullptr || y == nullptr || loss == nullptr || B <= 0 || D <= 0 || D > 4096)
+    return fail(IDF_ERR_ARG, "bad mmd arguments");
+  cudaError_t e = launch_mmd(x, y, loss, grad_y, B, D, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "mmd launch");
+  return IDF_OK;
+}
+
+}  // extern "C"

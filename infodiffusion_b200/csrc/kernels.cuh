@@ -1,0 +1,53 @@
+// Internal declarations shared by the kernel translation units and the C-ABI shim (capi.cu).
+#pragma once
+#include "../../include/idf_b200.h"
+#include "ptx.cuh"
+
+namespace idf {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int kBM = 128;  // output rows (pixels) per tile == UMMA M
+constexpr int kBK = 64;   // K elements per k-block == one 128-byte swizzle row
+
+struct alignas(64) ConvKernelParams {
+  CUtensorMap tmA[IDF_CONV_MAX_SRC];
+  CUtensorMap tmB;
+  int32_t n_src;
+  int32_t num_kb;
+  int32_t kb_src[IDF_CONV_MAX_KB];
+  int32_t kb_c0[IDF_CONV_MAX_KB];
+  int32_t kb_rowoff[IDF_CONV_MAX_KB];
+  int32_t m_tiles, n_tiles;
+  int64_t rows;
+  int32_t Hp, Wp, H, W;
+  int32_t cout;
+  int32_t epilogue;
+  const float* bias;
+  bf16* out;
+  int32_t out_ld;
+  const bf16* residual;
+  int32_t res_ld;
+  float* out_f32;
+  float* x_io;
+  const float* noise;
+  const float* coef;
+  const int32_t* step_ptr;
+};
+
+cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int grid, cudaStream_t stream);
+cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream);
+cudaError_t launch_attn(const bf16* qkv, bf16* out, int batch, int H, int W, int d, float scale, cudaStream_t stream);
+cudaError_t launch_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy,
+                              int M, int N, int K, int silu_in, cudaStream_t stream);
+cudaError_t launch_gather_rows(const float* table, const int64_t* idx, float* y, int M, int N, cudaStream_t stream);
+cudaError_t launch_im2col_head(const float* x, bf16* out, int batch, int C, int H, int W, cudaStream_t stream);
+cudaError_t launch_upsample2x(const bf16* in, bf16* out, int batch, int H, int W, int C, cudaStream_t stream);
+cudaError_t launch_space_to_depth(const bf16* in, bf16* out, int batch, int H, int W, int C, cudaStream_t stream);
+cudaError_t launch_nchw_to_padflat(const float* x, bf16* out, int batch, int C, int H, int W, cudaStream_t stream);
+cudaError_t launch_padflat_to_nchw(const bf16* in, float* y, int batch, int C, int H, int W, cudaStream_t stream);
+cudaError_t launch_sampler_update(float* x, const float* eps, const float* noise, const float* coef,
+                                  const int32_t* step_ptr, int64_t n, cudaStream_t stream);
+cudaError_t launch_mmd(const float* x, const float* y, float* loss, float* grad_y, int B, int D, cudaStream_t stream);
+
+}  // namespace idf

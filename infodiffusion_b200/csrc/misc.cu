@@ -1,0 +1,338 @@
+// HBM-bound helper kernels: layout conversion, head im2col, nearest upsample, space-to-depth,
+// stand-alone sampler update, small fp32 linears and the fused MMD loss.
+#include "kernels.cuh"
+
+namespace idf {
+
+// ----------------------------------------------------------------------------------------------
+// head im2col: x NCHW fp32 [B,C,H,W] -> bf16 pad-flat [rows, 64], k = tap*C + c for 3x3/pad 1
+// one thread = one interior pixel x one 16-byte granule (8 k's)
+// ----------------------------------------------------------------------------------------------
+__global__ void im2col_head_kernel(const float* __restrict__ x, bf16* __restrict__ out, int batch, int C, int H,
+                                   int W) {
+  const long long total = static_cast<long long>(batch) * H * W * 8;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int g = static_cast<int>(i & 7);
+  const long long pix = i >> 3;
+  const int px = static_cast<int>(pix % W);
+  const int py = static_cast<int>((pix / W) % H);
+  const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = g * 8 + j;
+    float v = 0.f;
+    if (k < 9 * C) {
+      const int tap = k / C, c = k - tap * C;
+      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(x + ((static_cast<long long>(n) * C + c) * H + yy) * W + xx);
+    }
+    f[j] = v;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  const long long row = (static_cast<long long>(n) * (H + 1) + py) * (W + 1) + px;
+  *reinterpret_cast<uint4*>(out + row * 64 + g * 8) = o;
+}
+
+cudaError_t launch_im2col_head(const float* x, bf16* out, int batch, int C, int H, int W, cudaStream_t stream) {
+  if (9 * C > 64) return cudaErrorInvalidValue;
+  const long long total = static_cast<long long>(batch) * H * W * 8;
+  im2col_head_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, out, batch, C, H, W);
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------
+// nearest x2 upsample, pad-flat bf16: one thread = one OUTPUT pixel x one 16-byte granule
+// ----------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int batch, int H, int W,
+                                  int C) {
+  const int V = C >> 3;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total = static_cast<long long>(batch) * Ho * Wo * V;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % V);
+  const long long pix = i / V;
+  const int ox = static_cast<int>(pix % Wo);
+  const int oy = static_cast<int>((pix / Wo) % Ho);
+  const int n = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+  const long long rin = (static_cast<long long>(n) * (H + 1) + (oy >> 1)) * (W + 1) + (ox >> 1);
+  const long long rout = (static_cast<long long>(n) * (Ho + 1) + oy) * (Wo + 1) + ox;
+  *reinterpret_cast<uint4*>(out + rout * C + v * 8) = __ldg(reinterpret_cast<const uint4*>(in + rin * C + v * 8));
+}
+
+cudaError_t launch_upsample2x(const bf16* in, bf16* out, int batch, int H, int W, int C, cudaStream_t stream) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const long long total = static_cast<long long>(batch) * 4 * H * W * (C >> 3);
+  upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, out, batch, H, W, C);
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------
+// space-to-depth: in [B,H,W,C] -> out[phase=py*2+px][B,H/2,W/2,C] (each phase pad-flat)
+// ----------------------------------------------------------------------------------------------
+__global__ void space_to_depth_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int batch, int H, int W,
+                                      int C) {
+  const int V = C >> 3;
+  const long long total = static_cast<long long>(batch) * H * W * V;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % V);
+  const long long pix = i / V;
+  const int x = static_cast<int>(pix % W);
+  const int y = static_cast<int>((pix / W) % H);
+  const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long rows_o = static_cast<long long>(batch) * (Ho + 1) * (Wo + 1);
+  const int phase = (y & 1) * 2 + (x & 1);
+  const long long rin = (static_cast<long long>(n) * (H + 1) + y) * (W + 1) + x;
+  const long long rout = phase * rows_o + (static_cast<long long>(n) * (Ho + 1) + (y >> 1)) * (Wo + 1) + (x >> 1);
+  *reinterpret_cast<uint4*>(out + rout * C + v * 8) = __ldg(reinterpret_cast<const uint4*>(in + rin * C + v * 8));
+}
+
+cudaError_t launch_space_to_depth(const bf16* in, bf16* out, int batch, int H, int W, int C, cudaStream_t stream) {
+  if ((C % 8) || (H & 1) || (W & 1)) return cudaErrorInvalidValue;
+  const long long total = static_cast<long long>(batch) * H * W * (C >> 3);
+  space_to_depth_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, out, batch, H, W, C);
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------
+// NCHW fp32 <-> pad-flat bf16 (boundary / test helpers).  Tiled through shared memory so that both
+// sides are coalesced: a tile is 32 pixels (along W) x 32 channels.
+// ----------------------------------------------------------------------------------------------
+__global__ void nchw_to_padflat_kernel(const float* __restrict__ x, bf16* __restrict__ out, int C, int H, int W) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32;
+  const long long p0 = static_cast<long long>(blockIdx.x) * 32;   // pixel index y*W+x
+  const long long HW = static_cast<long long>(H) * W;
+  const int tx = threadIdx.x, ty = threadIdx.y;                  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const long long p = p0 + tx;
+    tile[j][tx] = (c < C && p < HW) ? x[(static_cast<long long>(n) * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const long long p = p0 + j;
+    const int c = c0 + tx;
+    if (p < HW && c < C) {
+      const int yy = static_cast<int>(p / W), xx = static_cast<int>(p % W);
+      const long long row = (static_cast<long long>(n) * (H + 1) + yy) * (W + 1) + xx;
+      out[row * C + c] = __float2bfloat16(tile[tx][j]);
+    }
+  }
+}
+__global__ void padflat_to_nchw_kernel(const bf16* __restrict__ in, float* __restrict__ y, int C, int H, int W) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32;
+  const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+  const long long HW = static_cast<long long>(H) * W;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int j = ty; j < 32; j += 8) {
+    const long long p = p0 + j;
+    const int c = c0 + tx;
+    float v = 0.f;
+    if (p < HW && c < C) {
+      const int yy = static_cast<int>(p / W), xx = static_cast<int>(p % W);
+      const long long row = (static_cast<long long>(n) * (H + 1) + yy) * (W + 1) + xx;
+      v = __bfloat162float(in[row * C + c]);
+    }
+    tile[j][tx] = v;   // [pixel][channel]
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const long long p = p0 + tx;
+    if (c < C && p < HW) y[(static_cast<long long>(n) * C + c) * HW + p] = tile[tx][j];
+  }
+}
+
+cudaError_t launch_nchw_to_padflat(const float* x, bf16* out, int batch, int C, int H, int W, cudaStream_t stream) {
+  dim3 grid(static_cast<unsigned>((static_cast<long long>(H) * W + 31) / 32), (C + 31) / 32, batch);
+  nchw_to_padflat_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, out, C, H, W);
+  return cudaGetLastError();
+}
+cudaError_t launch_padflat_to_nchw(const bf16* in, float* y, int batch, int C, int H, int W, cudaStream_t stream) {
+  dim3 grid(static_cast<unsigned>((static_cast<long long>(H) * W + 31) / 32), (C + 31) / 32, batch);
+  padflat_to_nchw_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, y, C, H, W);
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------
+// stand-alone sampler update: x = cx*x + ce*eps + cn*noise (float4 vectorised)
+// ----------------------------------------------------------------------------------------------
+__global__ void sampler_update_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                                      const float* __restrict__ noise, const float* __restrict__ coef,
+                                      const int32_t* __restrict__ step_ptr, long long n4, long long n) {
+  const int step = step_ptr ? *step_ptr : 0;
+  const float cx = coef[3 * step], ce = coef[3 * step + 1], cn = coef[3 * step + 2];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    float4 xv = reinterpret_cast<float4*>(x)[i];
+    const float4 ev = __ldg(reinterpret_cast<const float4*>(eps) + i);
+    float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (noise) nv = __ldg(reinterpret_cast<const float4*>(noise) + i);
+    xv.x = cx * xv.x + ce * ev.x + cn * nv.x;
+    xv.y = cx * xv.y + ce * ev.y + cn * nv.y;
+    xv.z = cx * xv.z + ce * ev.z + cn * nv.z;
+    xv.w = cx * xv.w + ce * ev.w + cn * nv.w;
+    reinterpret_cast<float4*>(x)[i] = xv;
+  }
+  // tail (n not a multiple of 4)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (long long i = n4 * 4; i < n; ++i) x[i] = cx * x[i] + ce * eps[i] + cn * (noise ? noise[i] : 0.f);
+  }
+}
+
+cudaError_t launch_sampler_update(float* x, const float* eps, const float* noise, const float* coef,
+                                  const int32_t* step_ptr, int64_t n, cudaStream_t stream) {
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  sampler_update_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, eps, noise, coef, step_ptr, n4, n);
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------
+// small fp32 linear: y[m,n] = sum_k act(x[m,k]) w[n,k] + b[n]; 16x64 output tile, K in chunks of 32
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict__ x, long long ldx,
+                                                         const float* __restrict__ w, const float* __restrict__ b,
+                                                         float* __restrict__ y, long long ldy, int M, int N, int K,
+                                                         int silu_in) {
+  __shared__ float xs[16][33];
+  __shared__ float ws[64][33];
+  const int m0 = blockIdx.y * 16, n0 = blockIdx.x * 64;
+  const int t = threadIdx.x;
+  const int tm = t >> 4;          // 0..15
+  const int tn = (t & 15) * 4;    // 0..60
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int i = t; i < 16 * 32; i += 256) {
+      const int r = i >> 5, c = i & 31;
+      float v = 0.f;
+      if (m0 + r < M && k0 + c < K) {
+        v = x[(m0 + r) * ldx + k0 + c];
+        if (silu_in) v = v / (1.0f + expf(-v));
+      }
+      xs[r][c] = v;
+    }
+    for (int i = t; i < 64 * 32; i += 256) {
+      const int r = i >> 5, c = i & 31;
+      ws[r][c] = (n0 + r < N && k0 + c < K) ? w[static_cast<long long>(n0 + r) * K + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const float xv = xs[tm][c];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(xv, ws[tn + j][c], acc[j]);
+    }
+    __syncthreads();
+  }
+  if (m0 + tm < M) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tn + j;
+      if (n < N) y[(m0 + tm) * ldy + n] = acc[j] + (b ? b[n] : 0.f);
+    }
+  }
+}
+
+cudaError_t launch_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy,
+                              int M, int N, int K, int silu_in, cudaStream_t stream) {
+  dim3 grid((N + 63) / 64, (M + 15) / 16, 1);
+  linear_f32_kernel<<<grid, 256, 0, stream>>>(x, ldx, w, b, y, ldy, M, N, K, silu_in);
+  return cudaGetLastError();
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx,
+                                   float* __restrict__ y, int N) {
+  const int m = blockIdx.x;
+  const long long row = idx[m];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) y[static_cast<long long>(m) * N + i] = table[row * N + i];
+}
+cudaError_t launch_gather_rows(const float* table, const int64_t* idx, float* y, int M, int N, cudaStream_t stream) {
+  gather_rows_kernel<<<M, 128, 0, stream>>>(table, idx, y, N);
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------
+// MMD (utils.py:74-90): loss = mean k(x,x) + mean k(y,y) - 2 mean k(x,y), k(u,v)=exp(-|u-v|^2/D^2)
+// One block per column index j: accumulates sum_i [k(x_i,x_j) + k(y_i,y_j) - 2 k(x_i,y_j)] and
+// d loss / d y_j.  The per-block partial is added to *loss with one atomicAdd (loss must be zeroed).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mmd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                  float* __restrict__ loss, float* __restrict__ grad_y, int B,
+                                                  int D) {
+  extern __shared__ float sm[];
+  float* xj = sm;            // [D]
+  float* yj = sm + D;        // [D]
+  float* gacc = sm + 2 * D;  // [D]
+  __shared__ float red[4];
+  const int j = blockIdx.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  for (int d = t; d < D; d += 128) {
+    xj[d] = x[static_cast<long long>(j) * D + d];
+    yj[d] = y[static_cast<long long>(j) * D + d];
+    gacc[d] = 0.f;
+  }
+  __syncthreads();
+  const float inv_d2 = 1.0f / (static_cast<float>(D) * static_cast<float>(D));
+  const float inv_b2 = 1.0f / (static_cast<float>(B) * static_cast<float>(B));
+  float part = 0.f;
+  // one warp per i; lanes stride over D
+  for (int i = warp; i < B; i += 4) {
+    const float* xi = x + static_cast<long long>(i) * D;
+    const float* yi = y + static_cast<long long>(i) * D;
+    float dxx = 0.f, dyy = 0.f, dxy = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float a = xi[d], bb = yi[d];
+      const float e0 = a - xj[d], e1 = bb - yj[d], e2 = a - yj[d];
+      dxx = fmaf(e0, e0, dxx);
+      dyy = fmaf(e1, e1, dyy);
+      dxy = fmaf(e2, e2, dxy);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dxx += __shfl_xor_sync(0xffffffffu, dxx, o);
+      dyy += __shfl_xor_sync(0xffffffffu, dyy, o);
+      dxy += __shfl_xor_sync(0xffffffffu, dxy, o);
+    }
+    const float kxx = expf(-dxx * inv_d2), kyy = expf(-dyy * inv_d2), kxy = expf(-dxy * inv_d2);
+    if (lane == 0) part += kxx + kyy - 2.0f * kxy;
+    if (grad_y != nullptr) {
+      // d/dy_j: 2 * k(y_i,y_j) * (-2 (y_j - y_i)/D^2)  -  2 * k(x_i,y_j) * (-2 (y_j - x_i)/D^2), all / B^2
+      const float cy = -4.0f * kyy * inv_d2 * inv_b2;
+      const float cxy = 4.0f * kxy * inv_d2 * inv_b2;
+      for (int d = lane; d < D; d += 32) {
+        const float g = cy * (yj[d] - yi[d]) + cxy * (yj[d] - xi[d]);
+        atomicAdd(&gacc[d], g);
+      }
+    }
+  }
+  if (lane == 0) red[warp] = part;
+  __syncthreads();
+  if (t == 0) atomicAdd(loss, (red[0] + red[1] + red[2] + red[3]) * inv_b2);
+  if (grad_y != nullptr)
+    for (int d = t; d < D; d += 128) grad_y[static_cast<long long>(j) * D + d] = gacc[d];
+}
+
+cudaError_t launch_mmd(const float* x, const float* y, float* loss, float* grad_y, int B, int D,
+                       cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), stream);
+  if (e != cudaSuccess) return e;
+  mmd_kernel<<<B, 128, 3 * D * sizeof(float), stream>>>(x, y, loss, grad_y, B, D);
+  return cudaGetLastError();
+}
+
+}  // namespace idf

@@ -1,0 +1,589 @@
+"""Network-level execution engine: lowers AuxiliaryUNet / Encoder onto the libidf_b200 kernels.
+
+A *plan* is a static list of kernel launches over a preallocated workspace, built once per
+(network, batch).  It is CUDA-graph capturable: no allocation, no host sync, every per-step value
+(timestep row of the modulation table, sampler coefficients) is read from device memory through a
+device-resident step counter.
+
+Data layout in HBM (see include/idf_b200.h): activations are bf16 "pad-flat" NHWC -- image n,
+pixel (y, x) lives at row (n*(H+1) + y)*(W+1) + x of a [rows, C] matrix; the extra row / column
+per image is a shared zero border, which turns every 3x3 tap into a constant row offset and makes
+`padding=1` free.  Weights are packed once to bf16 [Cout, K] with K = (tap, cin) order.
+
+Fusions relative to the reference's one-op-per-kernel execution (modules.py / models.py):
+  * GroupNorm + (1+s_t),b_t + (1+s_z),b_z + SiLU + torch.cat        -> one AdaGN kernel
+  * conv + bias + residual add (+ 1x1 shortcut conv as extra K-blocks) -> one implicit-GEMM kernel
+  * q,k,v 1x1 convs -> one N=384 GEMM; QK^T, softmax, PV -> one attention kernel
+  * proj 1x1 conv + attention residual                               -> GEMM epilogue
+  * tail conv + DDPM/DDIM/reverse-DDIM update of x                   -> GEMM epilogue (sampler mode)
+  * every temb_proj / aemb_proj Linear of all 22 blocks              -> two batched GEMMs, hoisted out
+    of the step loop (the timestep side becomes a [T, 4992] table, the z side is step-invariant)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import EPI_BF16, EPI_F32_NCHW, EPI_SAMPLER, AdaGNArgs, ConvDesc
+from .layout import pack_conv1x1, pack_conv3x3, pad_cols as _pad_cols, pad_rows as _pad_rows, taps1x1, taps3x3, taps_stride2
+from .modules import AttnBlock, AuxResBlock, DownSample, ResBlock, ResBlock_encoder, UpSample
+
+BF16 = torch.bfloat16
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must live on a CUDA (sm_100) device: infodiffusion_b200 has no CPU path")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# workspace
+# ------------------------------------------------------------------------------------------------
+class Act:
+    """A pad-flat bf16 activation buffer [phases * B*(H+1)*(W+1), C]."""
+    __slots__ = ("t", "H", "C", "phases", "rows")
+
+    def __init__(self, t, H, C, phases, rows):
+        self.t, self.H, self.C, self.phases, self.rows = t, H, C, phases, rows
+
+
+class Workspace:
+    """Pool of zero-initialised pad-flat buffers.  Buffers are only ever recycled for the same
+    (H, C, phases) geometry, so the zero border written at allocation time is never disturbed
+    (kernels write interior rows only)."""
+
+    def __init__(self, batch: int, device):
+        self.batch, self.device = batch, device
+        self.free_lists: Dict[Tuple[int, int, int], List[Act]] = {}
+        self.bytes = 0
+
+    def alloc(self, H: int, C_: int, phases: int = 1) -> Act:
+        key = (H, C_, phases)
+        fl = self.free_lists.get(key)
+        if fl:
+            return fl.pop()
+        rows = self.batch * (H + 1) * (H + 1)
+        t = torch.zeros(phases * rows, C_, dtype=BF16, device=self.device)
+        self.bytes += t.numel() * 2
+        return Act(t, H, C_, phases, rows)
+
+    def free(self, a: Act) -> None:
+        self.free_lists.setdefault((a.H, a.C, a.phases), []).append(a)
+
+
+# ------------------------------------------------------------------------------------------------
+# plan builder
+# ------------------------------------------------------------------------------------------------
+class Plan:
+    """Ordered list of kernel launches + everything they reference."""
+
+    def __init__(self, batch: int, device, ws: Optional[Workspace] = None):
+        self.lib = _lib.load()
+        _lib.check(self.lib.idf_init())
+        self.B = batch
+        self.device = device
+        self.ws = ws if ws is not None else Workspace(batch, device)
+        self.ops: List = []          # (callable, args tuple); last arg slot is the stream
+        self.keep: List = []         # tensors / ctypes structs that must outlive the plan
+        self.conv_plans: List[int] = []
+        self.flops = 0               # algorithmic conv/attention FLOPs of one run
+        self.conv_tiles = 0
+        self.adagn_bytes = 0         # algorithmic AdaGN bytes (1 read + 1 write) of one run
+
+    def __del__(self):
+        try:
+            for h in self.conv_plans:
+                self.lib.idf_conv_plan_destroy(h)
+        except Exception:
+            pass
+
+    # ---- execution -----------------------------------------------------------------------------
+    def run(self, stream: Optional[int] = None) -> None:
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        check = _lib.check
+        for fn, args in self.ops:
+            check(fn(*args, stream))
+        _lib.count_launch(len(self.ops))
+
+    # ---- op emitters ---------------------------------------------------------------------------
+    def weight(self, m: torch.Tensor) -> torch.Tensor:
+        t = m.to(device=self.device, dtype=BF16).contiguous()
+        self.keep.append(t)
+        return t
+
+    def f32(self, m: torch.Tensor) -> torch.Tensor:
+        t = m.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self.keep.append(t)
+        return t
+
+    def conv(self, srcs: Sequence[Act], kblocks: Sequence[Tuple[int, int, int]], wp: torch.Tensor,
+             bias: torch.Tensor, H: int, cout: int, block_n: int, out: Optional[Act] = None,
+             residual: Optional[Act] = None, epilogue: int = EPI_BF16, out_f32=None, x_io=None, noise=None,
+             coef=None, step=None, real_macs_per_row: Optional[int] = None) -> None:
+        d = ConvDesc()
+        d.n_src = len(srcs)
+        for i, s in enumerate(srcs):
+            d.src[i] = s.t.data_ptr()
+            d.src_rows[i] = s.t.shape[0]
+            d.src_ld[i] = s.C
+        d.num_kb = len(kblocks)
+        for k, (si, c0, off) in enumerate(kblocks):
+            d.kb_src[k], d.kb_c0[k], d.kb_rowoff[k] = si, c0, off
+        assert wp.dtype == BF16 and wp.shape[1] == 64 * len(kblocks), (wp.shape, len(kblocks))
+        assert wp.shape[0] % block_n == 0 and bias.numel() == wp.shape[0]
+        d.weight = wp.data_ptr()
+        d.cout_pad = wp.shape[0]
+        d.block_n = block_n
+        d.cout = cout
+        d.bias = bias.data_ptr()
+        d.batch, d.H, d.W = self.B, H, H
+        d.epilogue = epilogue
+        if out is not None:
+            assert out.H == H and out.C == cout
+            d.out, d.out_ld = out.t.data_ptr(), out.C
+        if residual is not None:
+            assert residual.H == H and residual.C == cout
+            d.residual, d.res_ld = residual.t.data_ptr(), residual.C
+        d.out_f32, d.x_io, d.noise, d.coef, d.step_ptr = _ptr(out_f32), _ptr(x_io), _ptr(noise), _ptr(coef), _ptr(step)
+        h = C.c_void_p()
+        _lib.check(self.lib.idf_conv_plan_create(C.byref(d), C.byref(h)))
+        self.conv_plans.append(h)
+        self.keep.append(d)
+        self.ops.append((self.lib.idf_conv_run, (h,)))
+        self.conv_tiles += int(self.lib.idf_conv_plan_tiles(h))
+        macs = real_macs_per_row if real_macs_per_row is not None else 64 * len(kblocks) * cout
+        self.flops += 2 * self.B * H * H * macs
+
+    def adagn(self, src0: Act, src1: Optional[Act], out: Act, gn: nn.GroupNorm, silu: bool, mod_t=None, mod_z=None,
+              step=None) -> None:
+        a = AdaGNArgs()
+        a.src0, a.c0 = src0.t.data_ptr(), src0.C
+        if src1 is not None:
+            a.src1, a.c1 = src1.t.data_ptr(), src1.C
+        a.out = out.t.data_ptr()
+        a.batch, a.H, a.W = self.B, src0.H, src0.H
+        a.gamma, a.beta = self.f32(gn.weight).data_ptr(), self.f32(gn.bias).data_ptr()
+        a.eps = float(gn.eps)
+        if mod_t is not None:
+            a.mod_t, a.mod_t_step_stride, a.mod_t_batch_stride = mod_t
+        if mod_z is not None:
+            a.mod_z, a.mod_z_step_stride, a.mod_z_batch_stride = mod_z
+        a.step_ptr = _ptr(step)
+        a.apply_silu = 1 if silu else 0
+        self.keep.append(a)
+        self.ops.append((self.lib.idf_adagn_silu_fwd, (C.byref(a),)))
+        self.adagn_bytes += 2 * 2 * self.B * src0.H * src0.H * out.C
+
+    def attention(self, qkv: Act, out: Act, d: int) -> None:
+        self.ops.append((self.lib.idf_attn_fwd, (qkv.t.data_ptr(), out.t.data_ptr(), self.B, qkv.H, qkv.H, d,
+                                                 float(d) ** -0.5)))
+        S = qkv.H * qkv.H
+        self.flops += self.B * 4 * S * S * d
+
+    def linear(self, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], y: torch.Tensor, silu_in: bool) -> None:
+        M, K = x.shape
+        N = w.shape[0]
+        assert w.shape[1] == K and y.shape == (M, N) and x.stride(1) == 1 and y.stride(1) == 1
+        self.ops.append((self.lib.idf_linear_f32, (x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), y.data_ptr(),
+                                                   y.stride(0), M, N, K, 1 if silu_in else 0)))
+
+    # ---- composite emitters ----------------------------------------------------------------------
+    @staticmethod
+    def taps3x3(cin: int, H: int, src: int = 0):
+        return taps3x3(cin, H, H, src)
+
+    def conv3x3(self, src: Act, conv: nn.Conv2d, residual: Optional[Act] = None,
+                shortcut: Optional[Tuple[nn.Conv2d, Sequence[Act]]] = None) -> Act:
+        """3x3 / stride 1 / pad 1 conv (+ residual, or + 1x1 shortcut conv over raw sources as extra K-blocks)."""
+        cin, cout, H = src.C, conv.out_channels, src.H
+        assert conv.in_channels == cin and cout % 64 == 0
+        kb = self.taps3x3(cin, H)
+        wp = pack_conv3x3(conv.weight)
+        bias = conv.bias.detach().float()
+        srcs = [src]
+        if shortcut is not None:
+            sc_conv, raws = shortcut
+            wp = torch.cat([wp, pack_conv1x1(sc_conv.weight)], dim=1)
+            bias = bias + sc_conv.bias.detach().float()
+            for r in raws:
+                srcs.append(r)
+                kb += [(len(srcs) - 1, c0, 0) for c0 in range(0, r.C, 64)]
+        out = self.ws.alloc(H, cout)
+        self.conv(srcs, kb, self.weight(wp), self.f32(bias), H, cout, 128 if cout % 128 == 0 else 64, out=out,
+                  residual=residual)
+        return out
+
+    def conv1x1(self, src: Act, w: torch.Tensor, b: torch.Tensor, residual: Optional[Act] = None) -> Act:
+        cout = w.shape[0]
+        kb = taps1x1(src.C)
+        out = self.ws.alloc(src.H, cout)
+        self.conv([src], kb, self.weight(_pad_cols(w, 64 * len(kb))), self.f32(b), src.H, cout,
+                  128 if cout % 128 == 0 else 64, out=out, residual=residual)
+        return out
+
+    def downsample(self, src: Act, conv: nn.Conv2d) -> Act:
+        """3x3 stride-2 conv: space-to-depth split into 4 phase maps, then 9 taps over the phases."""
+        H, Ho, Cc = src.H, src.H // 2, src.C
+        ph = self.ws.alloc(Ho, Cc, phases=4)
+        self.ops.append((self.lib.idf_space_to_depth, (src.t.data_ptr(), ph.t.data_ptr(), self.B, H, H, Cc)))
+        kb = taps_stride2(Cc, Ho, Ho, ph.rows)
+        out = self.ws.alloc(Ho, conv.out_channels)
+        self.conv([ph], kb, self.weight(pack_conv3x3(conv.weight)), self.f32(conv.bias), Ho, conv.out_channels,
+                  128 if conv.out_channels % 128 == 0 else 64, out=out)
+        self.ws.free(ph)
+        return out
+
+    def upsample(self, src: Act, conv: nn.Conv2d) -> Act:
+        up = self.ws.alloc(src.H * 2, src.C)
+        self.ops.append((self.lib.idf_upsample2x, (src.t.data_ptr(), up.t.data_ptr(), self.B, src.H, src.H, src.C)))
+        out = self.conv3x3(up, conv)
+        self.ws.free(up)
+        return out
+
+    def attn_block(self, x: Act, blk: AttnBlock) -> Act:
+        """GroupNorm -> fused qkv GEMM -> attention -> proj GEMM + residual (reference modules.py:145-164)."""
+        Cc = x.C
+        an = self.ws.alloc(x.H, Cc)
+        self.adagn(x, None, an, blk.group_norm, silu=False)
+        wqkv = torch.cat([pack_conv1x1(m.weight) for m in (blk.proj_q, blk.proj_k, blk.proj_v)], dim=0)
+        bqkv = torch.cat([m.bias.detach() for m in (blk.proj_q, blk.proj_k, blk.proj_v)], dim=0)
+        qkv = self.conv1x1(an, wqkv, bqkv)
+        self.ws.free(an)
+        ao = self.ws.alloc(x.H, Cc)
+        self.attention(qkv, ao, Cc)
+        self.ws.free(qkv)
+        out = self.conv1x1(ao, pack_conv1x1(blk.proj.weight), blk.proj.bias.detach(), residual=x)
+        self.ws.free(ao)
+        self.ws.free(x)
+        return out
+
+    def res_block(self, xs: Sequence[Act], blk, mod_t=None, mod_z=None, step=None, free_inputs=True) -> Act:
+        """AuxResBlock / ResBlock / ResBlock_encoder over one or two (concatenated) inputs."""
+        H = xs[0].H
+        cin = sum(x.C for x in xs)
+        assert cin == blk.in_ch
+        cout = blk.out_ch
+        x1 = xs[1] if len(xs) > 1 else None
+        a1 = self.ws.alloc(H, cin)
+        self.adagn(xs[0], x1, a1, blk.block1[0], silu=True)
+        h = self.conv3x3(a1, blk.block1[-1])
+        self.ws.free(a1)
+        a2 = self.ws.alloc(H, cout)
+        self.adagn(h, None, a2, blk.block2[0], silu=True, mod_t=mod_t, mod_z=mod_z, step=step)
+        self.ws.free(h)
+        last_in = a2
+        has_block3 = hasattr(blk, "block3")
+        if has_block3:
+            h = self.conv3x3(a2, blk.block2[-1])
+            self.ws.free(a2)
+            a3 = self.ws.alloc(H, cout)
+            self.adagn(h, None, a3, blk.block3[0], silu=True)
+            self.ws.free(h)
+            last_in = a3
+        last_conv = blk.block3[-1] if has_block3 else blk.block2[-1]
+        if isinstance(blk.shortcut, nn.Conv2d):
+            out = self.conv3x3(last_in, last_conv, shortcut=(blk.shortcut, list(xs)))
+        else:
+            assert len(xs) == 1
+            out = self.conv3x3(last_in, last_conv, residual=xs[0])
+        self.ws.free(last_in)
+        if free_inputs:
+            for x in xs:
+                self.ws.free(x)
+        if isinstance(blk.attn, AttnBlock):
+            out = self.attn_block(out, blk.attn)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# modulation (temb_proj / aemb_proj of every block, batched)
+# ------------------------------------------------------------------------------------------------
+class ModulationPack:
+    """Column layout of the concatenated per-block (scale | shift) projections."""
+
+    def __init__(self, blocks: Sequence[nn.Module], device):
+        self.offsets: Dict[int, int] = {}
+        wt, bt, wz, bz = [], [], [], []
+        off = 0
+        self.has_z = False
+        for blk in blocks:
+            self.offsets[id(blk)] = off
+            lin_t = blk.temb_proj[1]
+            wt.append(lin_t.weight.detach())
+            bt.append(lin_t.bias.detach())
+            if hasattr(blk, "aemb_proj"):
+                self.has_z = True
+                wz.append(blk.aemb_proj[1].weight.detach())
+                bz.append(blk.aemb_proj[1].bias.detach())
+            else:
+                wz.append(torch.zeros_like(lin_t.weight))
+                bz.append(torch.zeros_like(lin_t.bias))
+            off += lin_t.out_features
+        self.ncol = off
+        f = lambda xs: torch.cat(xs, 0).to(device=device, dtype=torch.float32).contiguous()
+        self.w_t, self.b_t, self.w_z, self.b_z = f(wt), f(bt), f(wz), f(bz)
+
+
+def conditioned_blocks(net) -> List[nn.Module]:
+    return [b for b in list(net.downblocks) + list(net.middleblocks) + list(net.upblocks)
+            if isinstance(b, (AuxResBlock, ResBlock))]
+
+
+# ------------------------------------------------------------------------------------------------
+# backbone plan (AuxiliaryUNet)
+# ------------------------------------------------------------------------------------------------
+class BackbonePlan(Plan):
+    """eps = backbone(x, t, a) for a fixed batch, optionally with the sampler update fused into the tail.
+
+    mode 'eps'     : x_in, t_idx, a_in -> eps_out; the modulation rows are computed per call.
+    mode 'sampler' : x_io is updated in place, x <- cx*x + ce*eps + cn*noise with (cx,ce,cn) = coef[*step];
+                     the timestep modulation is a precomputed [T, ncol] table indexed by *step, the z
+                     modulation [B, ncol] is computed once per sampling call by `set_latent`.
+    """
+
+    def __init__(self, net, batch: int, device, mode: str = "eps", ws: Optional[Workspace] = None,
+                 x_io: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                 coef: Optional[torch.Tensor] = None, step: Optional[torch.Tensor] = None,
+                 mod_t_table: Optional[torch.Tensor] = None, mod_z: Optional[torch.Tensor] = None,
+                 eps_out: Optional[torch.Tensor] = None, pack: Optional[ModulationPack] = None):
+        super().__init__(batch, device, ws)
+        assert mode in ("eps", "sampler")
+        self.mode = mode
+        Cimg, H, W = net.shape
+        assert H == W, "square images only"
+        assert H in (32, 64), "the sm_100a plan supports 32x32 / 64x64 inputs (attention at 16x16 / 8x8)"
+        self.net = net
+        B = batch
+        f32 = dict(dtype=torch.float32, device=device)
+        self.pack = pack if pack is not None else ModulationPack(conditioned_blocks(net), device)
+        ncol = self.pack.ncol
+        self.step = step
+        if mode == "eps":
+            self.x_in = torch.zeros(B, Cimg, H, W, **f32)
+            self.t_idx = torch.zeros(B, dtype=torch.long, device=device)
+            self.a_in = torch.zeros(B, net.a_dim, **f32)
+            self.eps_out = torch.zeros(B, Cimg, H, W, **f32)
+            self.mod_t = torch.zeros(B, ncol, **f32)
+            self.mod_z = torch.zeros(B, ncol, **f32)
+            self._emit_time_mlp(self.t_idx, self.mod_t)
+            self._emit_latent_mlp(self.a_in, self.mod_z)
+            mod_t_arg = (self.mod_t.data_ptr(), 0, ncol)
+            x_src = self.x_in
+        else:
+            assert x_io is not None and coef is not None and step is not None and mod_t_table is not None
+            self.x_in = x_io
+            self.eps_out = eps_out
+            self.mod_z = mod_z if mod_z is not None else torch.zeros(B, ncol, **f32)
+            mod_t_arg = (mod_t_table.data_ptr(), ncol, 0)
+            x_src = x_io
+        mod_z_arg = (self.mod_z.data_ptr(), 0, ncol)
+
+        def mods(blk):
+            off = self.pack.offsets[id(blk)] * 4
+            mt = (mod_t_arg[0] + off, mod_t_arg[1], mod_t_arg[2])
+            mz = (mod_z_arg[0] + off, mod_z_arg[1], mod_z_arg[2]) if hasattr(blk, "aemb_proj") else None
+            return mt, mz
+
+        # ---- head: im2col + K=64 GEMM
+        ws = self.ws
+        patches = ws.alloc(H, 64)
+        self.ops.append((self.lib.idf_im2col_head, (x_src.data_ptr(), patches.t.data_ptr(), B, Cimg, H, W)))
+        hw = _pad_cols(pack_conv3x3(net.head.weight), 64)
+        h = ws.alloc(H, net.head.out_channels)
+        self.conv([patches], [(0, 0, 0)], self.weight(hw), self.f32(net.head.bias), H, net.head.out_channels,
+                  128 if net.head.out_channels % 128 == 0 else 64, out=h,
+                  real_macs_per_row=9 * Cimg * net.head.out_channels)
+        ws.free(patches)
+
+        skips = [h]
+        for layer in net.downblocks:
+            if isinstance(layer, DownSample):
+                h = self.downsample(h, layer.main)
+            else:
+                mt, mz = mods(layer)
+                h = self.res_block([h], layer, mod_t=mt, mod_z=mz, step=self.step, free_inputs=False)
+            skips.append(h)
+        first = True
+        for layer in net.middleblocks:
+            mt, mz = mods(layer)
+            # the first middle block reads the last skip tensor, which must stay alive for the up path
+            h = self.res_block([h], layer, mod_t=mt, mod_z=mz, step=self.step, free_inputs=not first)
+            first = False
+        for layer in net.upblocks:
+            if isinstance(layer, UpSample):
+                h2 = self.upsample(h, layer.main)
+                ws.free(h)
+                h = h2
+            else:
+                mt, mz = mods(layer)
+                h = self.res_block([h, skips.pop()], layer, mod_t=mt, mod_z=mz, step=self.step, free_inputs=True)
+        assert not skips
+        # ---- tail: AdaGN + 3x3 conv to Cimg channels, fp32 NCHW out or fused sampler update
+        ta = ws.alloc(H, h.C)
+        self.adagn(h, None, ta, net.tail[0], silu=True)
+        ws.free(h)
+        tconv = net.tail[-1]
+        wp = _pad_rows(pack_conv3x3(tconv.weight), 16)
+        bias = _pad_rows(tconv.bias.detach().float(), 16)
+        kb = self.taps3x3(ta.C, H)
+        if mode == "eps":
+            self.conv([ta], kb, self.weight(wp), self.f32(bias), H, Cimg, 16, epilogue=EPI_F32_NCHW,
+                      out_f32=self.eps_out)
+        else:
+            self.conv([ta], kb, self.weight(wp), self.f32(bias), H, Cimg, 16, epilogue=EPI_SAMPLER,
+                      out_f32=self.eps_out, x_io=x_io, noise=noise, coef=coef, step=step)
+        ws.free(ta)
+
+    # modulation MLPs ------------------------------------------------------------------------------
+    def _emit_time_mlp(self, t_idx: torch.Tensor, out: torch.Tensor) -> None:
+        """out[m] = concat_blocks temb_proj(SiLU(time_embedding(t_idx[m])))  (modules.py:36-38, 249, 312)."""
+        te = self.net.time_embedding.timembedding
+        M = t_idx.shape[0]
+        f32 = dict(dtype=torch.float32, device=self.device)
+        e0 = torch.zeros(M, te[0].weight.shape[1], **f32)
+        e1 = torch.zeros(M, te[1].out_features, **f32)
+        e2 = torch.zeros(M, te[3].out_features, **f32)
+        self.keep += [e0, e1, e2]
+        table = self.f32(te[0].weight)
+        self.ops.append((self.lib.idf_gather_rows_f32, (table.data_ptr(), t_idx.data_ptr(), e0.data_ptr(), M,
+                                                        e0.shape[1])))
+        self.linear(e0, self.f32(te[1].weight), self.f32(te[1].bias), e1, silu_in=False)
+        self.linear(e1, self.f32(te[3].weight), self.f32(te[3].bias), e2, silu_in=True)
+        self.linear(e2, self.pack.w_t, self.pack.b_t, out, silu_in=True)
+
+    def _emit_latent_mlp(self, a_in: torch.Tensor, out: torch.Tensor) -> None:
+        """out[n] = concat_blocks aemb_proj(SiLU(fc_a(a[n])))  (models.py:298; modules.py:316)."""
+        fc = self.net.fc_a
+        aemb = torch.zeros(a_in.shape[0], fc.out_features, dtype=torch.float32, device=self.device)
+        self.keep.append(aemb)
+        self.linear(a_in, self.f32(fc.weight), self.f32(fc.bias), aemb, silu_in=False)
+        self.linear(aemb, self.pack.w_z, self.pack.b_z, out, silu_in=True)
+
+
+class ModulationTables(Plan):
+    """One-off plans that fill the [T, ncol] timestep table and the [B, ncol] latent rows."""
+
+    def __init__(self, net, device, pack: ModulationPack, T: int):
+        super().__init__(1, device)
+        self.net, self.pack = net, pack
+        self.t_all = torch.arange(T, dtype=torch.long, device=device)
+        self.table = torch.zeros(T, pack.ncol, dtype=torch.float32, device=device)
+        BackbonePlan._emit_time_mlp(self, self.t_all, self.table)
+
+    def latent_rows(self, a: torch.Tensor, out: torch.Tensor) -> None:
+        p = Plan(1, self.device)
+        p.net, p.pack = self.net, self.pack
+        BackbonePlan._emit_latent_mlp(p, a, out)
+        p.run()
+        torch.cuda.current_stream(self.device).synchronize()  # p's temporaries die with it
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder plan
+# ------------------------------------------------------------------------------------------------
+class EncoderPlan(Plan):
+    """(a, mu, log_var) = Encoder(x) for a fixed batch (reference models.py:488-518)."""
+
+    def __init__(self, net, batch: int, device, ws: Optional[Workspace] = None, x_in: Optional[torch.Tensor] = None):
+        super().__init__(batch, device, ws)
+        Cimg, H, W = net.shape
+        assert H == W and H in (32, 64)
+        B = batch
+        f32 = dict(dtype=torch.float32, device=device)
+        self.x_in = x_in if x_in is not None else torch.zeros(B, Cimg, H, W, **f32)
+        self.map_out = torch.zeros(B, 1, H, W, **f32)
+        self.a = torch.zeros(B, net.a_dim, **f32)
+        self.mu = torch.zeros(B, net.a_dim, **f32)
+        self.log_var = torch.zeros(B, net.a_dim, **f32)
+        ws = self.ws
+        patches = ws.alloc(H, 64)
+        self.ops.append((self.lib.idf_im2col_head, (self.x_in.data_ptr(), patches.t.data_ptr(), B, Cimg, H, W)))
+        h = ws.alloc(H, net.head.out_channels)
+        self.conv([patches], [(0, 0, 0)], self.weight(_pad_cols(pack_conv3x3(net.head.weight), 64)),
+                  self.f32(net.head.bias), H, net.head.out_channels, 128 if net.head.out_channels % 128 == 0 else 64,
+                  out=h, real_macs_per_row=9 * Cimg * net.head.out_channels)
+        ws.free(patches)
+        skips = [h]
+        for layer in net.downblocks:
+            if isinstance(layer, DownSample):
+                h = self.downsample(h, layer.main)
+            else:
+                h = self.res_block([h], layer, free_inputs=False)
+            skips.append(h)
+        first = True
+        for layer in net.middleblocks:
+            h = self.res_block([h], layer, free_inputs=not first)
+            first = False
+        for layer in net.upblocks:
+            if isinstance(layer, UpSample):
+                h2 = self.upsample(h, layer.main)
+                ws.free(h)
+                h = h2
+            else:
+                h = self.res_block([h, skips.pop()], layer, free_inputs=True)
+        assert not skips
+        ta = ws.alloc(H, h.C)
+        self.adagn(h, None, ta, net.tail[0], silu=True)
+        ws.free(h)
+        tconv = net.tail[-1]
+        self.conv([ta], self.taps3x3(ta.C, H), self.weight(_pad_rows(pack_conv3x3(tconv.weight), 16)),
+                  self.f32(_pad_rows(tconv.bias.detach().float(), 16)), H, 1, 16, epilogue=EPI_F32_NCHW,
+                  out_f32=self.map_out)
+        ws.free(ta)
+        flat = self.map_out.view(B, H * W)
+        self.linear(flat, self.f32(net.fc_a.weight), self.f32(net.fc_a.bias), self.a, silu_in=False)
+        self.linear(self.a, self.f32(net.fc_mu.weight), self.f32(net.fc_mu.bias), self.mu, silu_in=False)
+        self.linear(self.a, self.f32(net.fc_var.weight), self.f32(net.fc_var.bias), self.log_var, silu_in=False)
+
+
+# ------------------------------------------------------------------------------------------------
+# nn.Module entry points
+# ------------------------------------------------------------------------------------------------
+def _check_eval(net) -> None:
+    if net.training:
+        raise RuntimeError(
+            "the sm_100a path implements the inference forward (Dropout = identity); call .eval() first. "
+            "Training through these kernels (dropout masks + backward) is a later SURVEY section-8 row.")
+
+
+@torch.no_grad()
+def backbone_forward(net, x: torch.Tensor, t: torch.Tensor, a: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x, "x")
+    _check_eval(net)
+    B = x.shape[0]
+    key = ("eps", B, x.device.index)
+    plans = net._plans()
+    if key not in plans:
+        plans[key] = BackbonePlan(net, B, x.device, mode="eps")
+    p: BackbonePlan = plans[key]
+    p.x_in.copy_(x)
+    p.t_idx.copy_(t.to(torch.long))
+    p.a_in.copy_(a)
+    p.run()
+    return p.eps_out.clone()
+
+
+@torch.no_grad()
+def encoder_forward(net, x: torch.Tensor):
+    _require_cuda(x, "x")
+    _check_eval(net)
+    B = x.shape[0]
+    key = ("enc", B, x.device.index)
+    plans = net._plans()
+    if key not in plans:
+        plans[key] = EncoderPlan(net, B, x.device)
+    p: EncoderPlan = plans[key]
+    p.x_in.copy_(x)
+    p.run()
+    a, mu, log_var = p.a.clone(), p.mu.clone(), p.log_var.clone()
+    a_q = mu + torch.randn_like(mu) * torch.exp(0.5 * log_var)      # reference models.py:515
+    return a, a_q, mu, log_var

@@ -1,0 +1,81 @@
+"""Pure host-side layout logic (no CUDA): pad-flat geometry, K-block tables, weight packing.
+
+Pad-flat NHWC: image n, pixel (y, x) of an H x W x C map is row (n*(H+1) + y)*(W+1) + x of a
+[rows, C] matrix; row y == H and column x == W of every image are zero and double as the
+top / left border of the next row / image, so a 3x3 tap (dy, dx) is the constant row offset
+dy*(W+1) + dx and TMA's out-of-bounds zero fill covers the very first / last image.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+
+KBlock = Tuple[int, int, int]   # (source index, first channel of the 64-wide slice, signed row offset)
+
+
+def padflat_rows(batch: int, H: int, W: int) -> int:
+    return batch * (H + 1) * (W + 1)
+
+
+def taps3x3(cin: int, H: int, W: int, src: int = 0) -> List[KBlock]:
+    """K-blocks of a 3x3 / stride 1 / pad 1 conv: tap-major, then 64-channel slices."""
+    kb: List[KBlock] = []
+    for tap in range(9):
+        ky, kx = divmod(tap, 3)
+        off = (ky - 1) * (W + 1) + (kx - 1)
+        kb += [(src, c0, off) for c0 in range(0, cin, 64)]
+    return kb
+
+
+def taps_stride2(cin: int, Ho: int, Wo: int, phase_rows: int, src: int = 0) -> List[KBlock]:
+    """K-blocks of a 3x3 / stride 2 / pad 1 conv over a space-to-depth source holding the four phase
+    maps phase[py*2+px][n, y, x] = in[n, 2y+py, 2x+px] stacked along rows (each pad-flat Ho x Wo).
+    Input row 2*oy + ky - 1:  ky=0 -> odd phase, previous half-res row;  ky=1 -> even phase, same row;
+    ky=2 -> odd phase, same row (likewise for columns)."""
+    sel = {0: (1, -1), 1: (0, 0), 2: (1, 0)}
+    kb: List[KBlock] = []
+    for tap in range(9):
+        ky, kx = divmod(tap, 3)
+        (py, dy), (px, dx) = sel[ky], sel[kx]
+        off = (py * 2 + px) * phase_rows + dy * (Wo + 1) + dx
+        kb += [(src, c0, off) for c0 in range(0, cin, 64)]
+    return kb
+
+
+def taps1x1(cin: int, src: int = 0) -> List[KBlock]:
+    return [(src, c0, 0) for c0 in range(0, cin, 64)]
+
+
+def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> [Cout, 9*Cin] with k = (ky*3+kx)*Cin + c."""
+    co, ci = w.shape[0], w.shape[1]
+    return w.detach().permute(0, 2, 3, 1).reshape(co, 9 * ci)
+
+
+def pack_conv1x1(w: torch.Tensor) -> torch.Tensor:
+    return w.detach().reshape(w.shape[0], w.shape[1])
+
+
+def pad_rows(m: torch.Tensor, rows: int) -> torch.Tensor:
+    if m.shape[0] == rows:
+        return m
+    out = torch.zeros(rows, *m.shape[1:], dtype=m.dtype, device=m.device)
+    out[: m.shape[0]] = m
+    return out
+
+
+def pad_cols(m: torch.Tensor, cols: int) -> torch.Tensor:
+    if m.shape[1] == cols:
+        return m
+    out = torch.zeros(m.shape[0], cols, dtype=m.dtype, device=m.device)
+    out[:, : m.shape[1]] = m
+    return out
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous batch shard of `total` independent samples for `rank` (sampling / encoding are
+    per-sample independent: GroupNorm and attention never mix samples)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

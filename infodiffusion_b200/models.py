@@ -1,0 +1,193 @@
+"""InfoDiffusion networks and model wrappers -- host-side mirror of the reference's ``models.py``.
+
+Same class names, constructor arguments, ``forward`` signatures, attributes and ``state_dict`` keys
+as the reference (models.py:7-779), so ``run.py``-style callers and checkpoints switch over
+unchanged.  All tensor arithmetic is executed by the sm_100a kernels of libidf_b200.so through
+``infodiffusion_b200.engine``; nothing here falls back to PyTorch ops or to the CPU.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+from torch.nn import init
+
+from .modules import (AuxResBlock, DownSample, ResBlock, ResBlock_encoder, TimeEmbedding, UpSample,
+                      timestep_embedding)
+from .utils import compute_mmd
+
+
+def _unet_stacks(make_block, ch, ch_mult, attn, num_res_blocks, mid_factory):
+    """Shared down / middle / up topology of every UNet-shaped network in the reference
+    (models.py:16-46, 248-278, 342-372, 432-462)."""
+    down, up = nn.ModuleList(), nn.ModuleList()
+    widths = [ch]
+    cur = ch
+    for level, mult in enumerate(ch_mult):
+        out = ch * mult
+        for _ in range(num_res_blocks):
+            down.append(make_block(cur, out, level in attn))
+            cur = out
+            widths.append(cur)
+        if level != len(ch_mult) - 1:
+            down.append(DownSample(cur))
+            widths.append(cur)
+    mid = mid_factory(cur)
+    for level, mult in reversed(list(enumerate(ch_mult))):
+        out = ch * mult
+        for _ in range(num_res_blocks + 1):
+            up.append(make_block(widths.pop() + cur, out, level in attn))
+            cur = out
+        if level != 0:
+            up.append(UpSample(cur))
+    assert not widths
+    return down, mid, up, cur
+
+
+def _tail(cur, out_ch):
+    return nn.Sequential(nn.GroupNorm(32, cur), nn.SiLU(), nn.Conv2d(cur, out_ch, 3, stride=1, padding=1))
+
+
+class _EngineNet(nn.Module):
+    """Common plumbing: lazily builds (and caches per batch size) the kernel plan for this network."""
+
+    def _plans(self):
+        if "_idf_plans" not in self.__dict__:
+            self.__dict__["_idf_plans"] = {}
+        return self.__dict__["_idf_plans"]
+
+    def invalidate_plans(self):
+        """Drop packed bf16 weights / workspaces (call after the fp32 parameters change)."""
+        self._plans().clear()
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self.invalidate_plans()
+        return out
+
+
+class AuxiliaryUNet(_EngineNet):
+    """eps-network conditioned on timestep t and auxiliary latent a (reference models.py:237-326)."""
+
+    def __init__(self, T, ch=64, ch_mult=[1, 2, 4, 8], attn=[2], num_res_blocks=2, dropout=0.1, a_dim=32, shape=None):
+        super().__init__()
+        assert all(i < len(ch_mult) for i in attn), 'attn index out of bound'
+        tdim = ch * 4
+        self.a_dim = a_dim
+        self.T, self.ch, self.ch_mult, self.shape = T, ch, list(ch_mult), tuple(shape)
+        self.time_embedding = TimeEmbedding(T, ch, tdim)
+        self.fc_a = nn.Linear(a_dim, tdim)
+        self.head = nn.Conv2d(shape[0], ch, kernel_size=3, stride=1, padding=1)
+        self.downblocks, self.middleblocks, self.upblocks, cur = _unet_stacks(
+            lambda i, o, at: AuxResBlock(in_ch=i, out_ch=o, tdim=tdim, dropout=dropout, attn=at),
+            ch, ch_mult, attn, num_res_blocks,
+            lambda c: nn.ModuleList([AuxResBlock(c, c, tdim, dropout, attn=True, crossattn=False),
+                                     AuxResBlock(c, c, tdim, dropout, attn=False, crossattn=False)]))
+        self.tail = _tail(cur, shape[0])
+        init.xavier_uniform_(self.head.weight)
+        init.zeros_(self.head.bias)
+        init.xavier_uniform_(self.fc_a.weight)
+        init.zeros_(self.fc_a.bias)
+        init.xavier_uniform_(self.tail[-1].weight, gain=1e-5)
+        init.zeros_(self.tail[-1].bias)
+
+    def forward(self, x, t, a):
+        """x [B,C,H,W] fp32, t int64 [B], a [B,a_dim] -> eps [B,C,H,W] fp32 (reference models.py:296)."""
+        from .engine import backbone_forward
+        return backbone_forward(self, x, t, a)
+
+
+class Encoder(_EngineNet):
+    """UNet-shaped encoder x -> (a, a_q, mu, log_var) (reference models.py:424-518)."""
+
+    def __init__(self, ch=64, ch_mult=[1, 2, 4, 8, 8], attn=[2], num_res_blocks=2, dropout=0.1, a_dim=32, shape=None):
+        super().__init__()
+        assert all(i < len(ch_mult) for i in attn), 'attn index out of bound'
+        self.shape = shape
+        self.a_dim = a_dim
+        self.ch, self.ch_mult = ch, list(ch_mult)
+        self.head = nn.Conv2d(shape[0], ch, kernel_size=3, stride=1, padding=1)
+        self.downblocks, self.middleblocks, self.upblocks, cur = _unet_stacks(
+            lambda i, o, at: ResBlock_encoder(in_ch=i, out_ch=o, dropout=dropout, attn=at),
+            ch, ch_mult, attn, num_res_blocks,
+            lambda c: nn.ModuleList([ResBlock_encoder(c, c, dropout, attn=True),
+                                     ResBlock_encoder(c, c, dropout, attn=False)]))
+        self.tail = _tail(cur, 1)
+        self.fc_a = nn.Linear(self.shape[1] * self.shape[2], self.a_dim)
+        self.fc_mu = nn.Linear(self.a_dim, self.a_dim)
+        self.fc_var = nn.Linear(self.a_dim, self.a_dim)
+        for m in (self.head, self.fc_a, self.fc_mu, self.fc_var):
+            init.xavier_uniform_(m.weight)
+            init.zeros_(m.bias)
+        init.xavier_uniform_(self.tail[-1].weight, gain=1e-5)
+        init.zeros_(self.tail[-1].bias)
+
+    def forward(self, x):
+        from .engine import encoder_forward
+        return encoder_forward(self, x)
+
+
+class InfoDiff(nn.Module):
+    """Model wrapper: noise schedule, q(x_t|x_0), z routing and losses (reference models.py:605-723)."""
+
+    def __init__(self, args, device, shape):
+        super().__init__()
+        self.device = device
+        lin = lambda: torch.linspace(start=args.beta1, end=args.betaT, steps=args.diffusion_steps)
+        self.alpha_bars = torch.cumprod(1 - lin(), dim=0).to(device=device)
+        self.betas = lin().to(device=device)
+        self.alphas = 1 - self.betas
+        self.alpha_prev_bars = torch.cat([torch.Tensor([1]).to(device=device), self.alpha_bars[:-1]])
+        ch_mult = [1, 2, 4] if args.input_size == 28 else [1, 2, 2, 2]
+        if getattr(args, "is_bottleneck", False):
+            raise NotImplementedError("BottleneckAuxUNet is a later SURVEY section-8f row; not built yet")
+        self.backbone = AuxiliaryUNet(ch_mult=ch_mult, T=args.diffusion_steps, ch=args.unets_channels,
+                                      a_dim=args.a_dim, shape=shape)
+        self.encoder = Encoder(ch_mult=ch_mult, ch=args.encoder_channels, a_dim=args.a_dim, shape=shape)
+        self.mmd_weight: float = args.mmd_weight
+        self.kld_weight: float = args.kld_weight
+        self.to(device)
+
+    def _uses_sampled_latent(self) -> bool:
+        # reference models.py:714-721: a_q whenever the KLD term is on, the deterministic a otherwise
+        return self.kld_weight != 0
+
+    def forward(self, x, idx=None, a=None, get_target=False):
+        epsilon = mu = log_var = None
+        if idx is None:
+            idx = torch.randint(0, len(self.alpha_bars), (x.size(0),)).to(device=self.device)
+            used = self.alpha_bars[idx][:, None, None, None]
+            epsilon = torch.randn_like(x)
+            x_tilde = torch.sqrt(used) * x + torch.sqrt(1 - used) * epsilon
+        else:
+            if not torch.is_tensor(idx):
+                idx = torch.full((x.size(0),), int(idx), dtype=torch.long, device=self.device)
+            x_tilde = x
+        if a is None:
+            a, a_q, mu, log_var = self.encoder(x)
+        else:
+            a_q = a
+        output = self.backbone(x_tilde, idx, a_q if self._uses_sampled_latent() else a)
+        return (output, epsilon, a, mu, log_var) if get_target else output
+
+    def loss_fn(self, args, x, idx=None, curr_epoch=0):
+        """Forward value of the training objective (reference models.py:632-696), prior='regular'.
+        The backward pass through the sm_100a kernels is a later row of SURVEY section 8 and is not
+        built yet; the returned tensor carries no autograd graph."""
+        output, epsilon, a, mu, log_var = self.forward(x, idx=idx, get_target=True)
+        loss = (output - epsilon).square().mean()
+        x_0 = torch.sqrt(1 / self.alphas[0]) * (x - self.betas[0] / torch.sqrt(1 - self.alpha_bars[0]) * output)
+        loss = loss + (x_0 - x).square().mean() / args.diffusion_steps
+        if args.mmd_weight != 0:
+            if args.prior != 'regular':
+                raise NotImplementedError("only --prior regular is in scope (SURVEY section 2)")
+            true_samples = torch.randn_like(a, device=self.device)
+            loss = loss + args.mmd_weight * compute_mmd(true_samples, mu if args.kld_weight != 0 else a)
+        if args.kld_weight != 0:
+            kld = torch.sum(-0.5 * torch.sum(1 + log_var - mu ** 2 - log_var.exp(), dim=1), dim=0)
+            if getattr(args, "use_C", False):
+                c_max = torch.tensor([args.C_max], dtype=torch.float32, device=self.device)
+                cc = torch.clamp(c_max / args.epochs * curr_epoch, torch.zeros_like(c_max), c_max)
+                loss = loss + args.kld_weight * (kld - cc.squeeze(dim=0)).abs()
+            else:
+                loss = loss + args.kld_weight * kld
+        return loss

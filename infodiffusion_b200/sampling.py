@@ -1,0 +1,222 @@
+"""DDPM / DDIM / reverse-DDIM step loops -- mirror of the reference's ``sampling.py``.
+
+Same class and method names as the reference (sampling.py:3-101): ``DiffusionProcess(args,
+diffusion_fn, device, shape)`` with ``.sampling(sampling_number, xT, a)`` and
+``.reverse_sampling(x0, a)``.  The loop body is different: one step is a single CUDA-graph replay of
+the whole UNet with the x_{t-1} update fused into the output convolution's epilogue; per-step values
+come from device tables indexed by a device-resident step counter, so the host does nothing per
+step except (for stochastic steps) drawing that step's noise with torch's generator, in the
+reference's order, so identical seeds give identical noise.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .engine import (BackbonePlan, EncoderPlan, ModulationPack, ModulationTables, Plan, Workspace,
+                     conditioned_blocks)
+
+
+def make_schedule(beta1: float, betaT: float, T: int):
+    """fp32 schedule exactly as the reference builds it (sampling.py:12-15)."""
+    betas = torch.linspace(start=beta1, end=betaT, steps=T)
+    alphas = 1 - betas
+    alpha_bars = torch.cumprod(1 - torch.linspace(start=beta1, end=betaT, steps=T), dim=0)
+    alpha_prev_bars = torch.cat([torch.Tensor([1]), alpha_bars[:-1]])
+    return betas, alphas, alpha_bars, alpha_prev_bars
+
+
+def step_coefficients(kind: str, betas, alphas, alpha_bars, alpha_prev_bars) -> torch.Tensor:
+    """[T, 3] table (cx, ce, cn) with  x_next = cx*x + ce*eps + cn*noise  for step index idx.
+
+    Derived from the reference's update formulas (DDPM sampling.py:30-37, DDIM 52-59 with eta = 0.01
+    and alpha_prev_bars[idx] as the current abar, reverse DDIM 71-72); evaluated in float64 from the
+    fp32 schedule so the collapsed form carries no extra cancellation error.
+    """
+    b, al, ab, apb = (t.double() for t in (betas, alphas, alpha_bars, alpha_prev_bars))
+    T = len(ab)
+    out = torch.zeros(T, 3, dtype=torch.float64)
+    for i in range(T):
+        if kind == "ddpm":
+            cx = torch.sqrt(1 / al[i])
+            ce = -cx * b[i] / torch.sqrt(1 - ab[i])
+            cn = torch.sqrt((1 - apb[i]) / (1 - ab[i]) * b[i]) if i > 0 else torch.zeros(())
+        elif kind == "ddim":
+            inv = 1 / torch.sqrt(apb[i])
+            if i == 0:
+                cx, ce, cn = inv, -torch.sqrt(1 - apb[0]) * inv, torch.zeros(())
+            else:
+                sigma = 0.01 * torch.sqrt((1 - apb[i - 1]) / (1 - ab[i - 1])) * torch.sqrt(b[i - 1])
+                cx = torch.sqrt(apb[i - 1]) * inv
+                ce = torch.sqrt(1 - apb[i - 1] - sigma ** 2) - torch.sqrt(apb[i - 1]) * torch.sqrt(1 - apb[i]) * inv
+                cn = sigma
+        elif kind == "reverse":
+            if i == 0 or i + 1 >= T:
+                cx, ce, cn = torch.ones(()), torch.zeros(()), torch.zeros(())   # idx 0 yields x unchanged
+            else:
+                inv = 1 / torch.sqrt(apb[i])
+                cx = torch.sqrt(apb[i + 1]) * inv
+                ce = torch.sqrt(1 - apb[i + 1]) - torch.sqrt(apb[i + 1]) * torch.sqrt(1 - apb[i]) * inv
+                cn = torch.zeros(())
+        else:
+            raise ValueError(kind)
+        out[i, 0], out[i, 1], out[i, 2] = cx, ce, cn
+    return out.float()
+
+
+class _FusedSampler:
+    """Graph-captured step for an InfoDiff model: UNet forward + fused x update, for a fixed batch."""
+
+    def __init__(self, proc: "DiffusionProcess", kind: str, batch: int, chunk: Optional[int] = None,
+                 record_eps: bool = False, with_encoder: bool = False):
+        model = proc.diffusion_fn
+        net = model.backbone
+        dev = proc.device
+        self.kind, self.B = kind, batch
+        T = len(proc.alpha_bars)
+        self.T = T
+        Cimg, H, W = net.shape
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.x = torch.zeros(batch, Cimg, H, W, **f32)
+        self.noise = torch.zeros(batch, Cimg, H, W, **f32) if kind != "reverse" else None
+        self.eps = torch.zeros(batch, Cimg, H, W, **f32) if record_eps else None
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.coef = step_coefficients(kind, proc.betas.cpu(), proc.alphas.cpu(), proc.alpha_bars.cpu(),
+                                      proc.alpha_prev_bars.cpu()).to(dev).contiguous()
+        self.pack = ModulationPack(conditioned_blocks(net), dev)
+        self.tables = ModulationTables(net, dev, self.pack, T)
+        self.tables.run()
+        self.mod_z = torch.zeros(batch, self.pack.ncol, **f32)
+        chunk = batch if chunk is None else min(chunk, batch)
+        assert batch % chunk == 0, "chunk must divide the batch"
+        self.ws = Workspace(chunk, dev)
+        self.plans: List[Plan] = []
+        for c0 in range(0, batch, chunk):
+            sl = slice(c0, c0 + chunk)
+            if with_encoder:
+                # bug-compatible reverse DDIM: re-encode the current x_t every step (sampling.py:84,
+                # models.py:709-710) and derive this chunk's z-modulation rows from the fresh latent
+                if model.kld_weight != 0:
+                    raise NotImplementedError("re-encoding reverse DDIM with a sampled latent (kld_weight != 0)")
+                ep = EncoderPlan(model.encoder, chunk, dev, ws=self.ws, x_in=self.x[sl])
+                zp = Plan(chunk, dev, ws=self.ws)
+                zp.net, zp.pack = net, self.pack
+                BackbonePlan._emit_latent_mlp(zp, ep.a, self.mod_z[sl])
+                self.plans += [ep, zp]
+            bp = BackbonePlan(net, chunk, dev, mode="sampler", ws=self.ws, x_io=self.x[sl],
+                              noise=None if self.noise is None else self.noise[sl], coef=self.coef, step=self.step,
+                              mod_t_table=self.tables.table, mod_z=self.mod_z[sl],
+                              eps_out=None if self.eps is None else self.eps[sl], pack=self.pack)
+            self.plans.append(bp)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.n_launch = sum(len(p.ops) for p in self.plans)
+
+    def set_latent(self, a: torch.Tensor) -> None:
+        self.tables.latent_rows(a.contiguous().float(), self.mod_z)
+
+    def _enqueue(self) -> None:
+        for p in self.plans:
+            p.run()
+
+    def capture(self) -> None:
+        torch.cuda.synchronize(self.x.device)
+        s = torch.cuda.Stream(self.x.device)
+        s.wait_stream(torch.cuda.current_stream(self.x.device))
+        with torch.cuda.stream(s):
+            self._enqueue()          # warm-up (also sets func attributes outside capture)
+        torch.cuda.current_stream(self.x.device).wait_stream(s)
+        torch.cuda.synchronize(self.x.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue()
+        self.graph = g
+
+    def run_step(self, idx: int, use_graph: bool = True) -> None:
+        self.step.fill_(idx)
+        if use_graph:
+            if self.graph is None:
+                x_save = self.x.clone()
+                self.capture()
+                self.x.copy_(x_save)
+                self.step.fill_(idx)
+            self.graph.replay()
+            _lib.count_launch(self.n_launch)
+        else:
+            self._enqueue()
+
+
+class DiffusionProcess():
+    """Drop-in for the reference's DiffusionProcess (sampling.py:3-101)."""
+
+    def __init__(self, args, diffusion_fn, device, shape):
+        self.betas, self.alphas, ab, apb = make_schedule(args.beta1, args.betaT, args.diffusion_steps)
+        self.alpha_bars = ab.to(device=device)
+        self.alpha_prev_bars = apb.to(device=device)
+        self.shape = shape
+        self.deterministic = args.deterministic
+        self.a_dim = args.a_dim
+        self.model = args.model
+        self.diffusion_fn = diffusion_fn.to(device=device)
+        self.device = device
+        self.chunk = getattr(args, "sample_chunk", None)      # micro-batch per graph segment (None = whole batch)
+        self.use_graph = getattr(args, "cuda_graph", True)
+        self.honor_latent_in_reverse = getattr(args, "reverse_uses_given_latent", False)
+        self._samplers = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _sampler(self, kind: str, batch: int, record_eps: bool = False, with_encoder: bool = False) -> _FusedSampler:
+        if self.model == 'vanilla' or not hasattr(self.diffusion_fn, "backbone"):
+            raise NotImplementedError("only the InfoDiff (--model diff) sampler path is built so far")
+        if self.diffusion_fn.backbone.training:
+            raise RuntimeError("sampling runs the inference forward; call model.eval() first")
+        key = (kind, batch, record_eps, with_encoder)
+        if key not in self._samplers:
+            self._samplers[key] = _FusedSampler(self, kind, batch, self.chunk, record_eps, with_encoder)
+        return self._samplers[key]
+
+    def _run(self, kind: str, x: torch.Tensor, a: Optional[torch.Tensor], trace=None) -> torch.Tensor:
+        B = x.shape[0]
+        T = len(self.alpha_bars)
+        with_encoder = (kind == "reverse") and (a is None)
+        s = self._sampler(kind, B, record_eps=trace is not None, with_encoder=with_encoder)
+        s.x.copy_(x)
+        if a is not None:
+            s.set_latent(a)
+        if kind == "reverse":
+            order = range(1, T - 1)                     # idx 0 yields x unchanged (sampling.py:64-65)
+        else:
+            order = reversed(range(T))
+        for idx in order:
+            if kind == "ddpm":
+                if idx > 0:
+                    s.noise.normal_()                   # drawn BEFORE the model call (sampling.py:29)
+            elif kind == "ddim":
+                if idx > 0:
+                    s.noise.normal_()                   # reference draws it after the model call (sampling.py:56);
+                                                        # the model call consumes no random numbers, so the
+                                                        # generator stream is identical
+            s.run_step(idx, use_graph=self.use_graph)
+            if trace is not None:
+                trace.append((idx, s.eps.clone(), s.x.clone()))
+        return s.x.clone()
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def reverse_sampling(self, x0, a=None, trace=None):
+        """x0 -> xT by deterministic reverse DDIM (reference sampling.py:81-87).  The reference drops
+        ``a`` and re-encodes x_t at every step; that is the default here too.  Set
+        ``args.reverse_uses_given_latent = True`` to honour the caller's ``a`` instead."""
+        if not self.honor_latent_in_reverse:
+            a = None
+        return self._run("reverse", x0, a, trace)
+
+    @torch.no_grad()
+    def sampling(self, sampling_number=16, xT=None, a=None, trace=None):
+        """reference sampling.py:89-101: draws xT then a (in that order) when they are not given."""
+        if xT is None:
+            xT = torch.randn([sampling_number, *self.shape]).to(device=self.device)
+        if a is None:
+            a = torch.randn([sampling_number, self.a_dim]).to(device=self.device)
+        return self._run("ddim" if self.deterministic else "ddpm", xT, a, trace)

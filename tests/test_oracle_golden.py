@@ -1,0 +1,100 @@
+"""The CPU oracle reproduces the golden vectors minted from the unmodified reference
+(oracle/make_golden.py).  This is what pins the oracle; no GPU needed."""
+import numpy as np
+import torch
+
+from oracle import infodiff_oracle as orc
+from oracle.golden_util import SEED, make_args, perturb_state_dict, rand_inputs, rel_l2, step_noise
+
+_cache = {}
+
+
+def model_sd(a_dim, T):
+    """Weights are regenerated from the seed through our reference-identical constructors."""
+    key = (a_dim, T)
+    if key not in _cache:
+        from infodiffusion_b200.models import InfoDiff
+        torch.manual_seed(SEED)
+        m = InfoDiff(make_args(a_dim=a_dim, diffusion_steps=T), "cpu", (3, 64, 64))
+        _cache[key] = perturb_state_dict(m.state_dict())
+    return _cache[key]
+
+
+def test_backbone_eps(golden_dir):
+    g = np.load(golden_dir / "backbone_a32_T1000.npz")
+    sd = model_sd(32, 1000)
+    x, t, a = rand_inputs(2, 32, 1000)
+    with torch.no_grad():
+        eps = orc.aux_unet_forward(sd, x, t, a)
+    assert rel_l2(eps, torch.from_numpy(g["eps"])) < 1e-6
+    assert float(eps.std()) > 0.1       # not the vacuous 1e-5-gain output
+
+
+def test_encoder(golden_dir):
+    g = np.load(golden_dir / "encoder_a32.npz")
+    sd = model_sd(32, 1000)
+    x, _, _ = rand_inputs(2, 32, 1000)
+    noise = torch.randn(2, 32, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        a, a_q, mu, lv = orc.encoder_forward(sd, x, noise=noise)
+    for name, v in (("a", a), ("a_q", a_q), ("mu", mu), ("log_var", lv)):
+        assert rel_l2(v, torch.from_numpy(g[name])) < 1e-6, name
+
+
+def test_mmd(golden_dir):
+    g = np.load(golden_dir / "mmd.npz")
+    for D in (32, 256):
+        gen = torch.Generator().manual_seed(11 + D)
+        xs = torch.randn(32, D, generator=gen)
+        ys = (torch.randn(32, D, generator=gen) * 0.7 + 0.2).requires_grad_(True)
+        v = orc.compute_mmd(xs, ys)
+        (gr,) = torch.autograd.grad(v, ys)
+        assert rel_l2(v.detach(), torch.from_numpy(g[f"v{D}"])) < 1e-6
+        assert rel_l2(gr, torch.from_numpy(g[f"g{D}"])) < 1e-5
+
+
+def test_loss_value(golden_dir):
+    g = np.load(golden_dir / "loss_a32.npz")
+    sd = model_sd(32, 1000)
+    gl = torch.Generator().manual_seed(21)
+    xb = torch.rand(4, 3, 64, 64, generator=gl) * 2 - 1
+    idx = torch.randint(0, 1000, (4,), generator=gl)
+    eps = torch.randn(4, 3, 64, 64, generator=gl)
+    encn = torch.randn(4, 32, generator=gl)
+    prior = torch.randn(4, 32, generator=gl)
+    sch = orc.Schedule.make(1e-5, 1e-2, 1000)
+    with torch.no_grad():
+        terms = orc.infodiff_loss(sd, sch, xb, idx, eps, encn, prior, 0.1, 0.0, 1000)
+    assert rel_l2(terms["loss"], torch.from_numpy(g["loss"])) < 1e-6
+
+
+def test_sampler_trajectories(golden_dir):
+    T = 10
+    sd = model_sd(32, T)
+    sch = orc.Schedule.make(1e-5, 1e-2, T)
+    _, _, a = rand_inputs(2, 32, T, seed=8)
+    xT = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(3))
+    shape = tuple(xT.shape)
+    for kind, det in (("ddim", True), ("ddpm", False)):
+        g = np.load(golden_dir / f"{kind}10_a32.npz")
+        rec = []
+        orc.sample(sd, sch, xT, a, det, noise_fn=lambda i, like: step_noise(i, shape), record=rec)
+        for idx, eps, x in rec:
+            if f"x_{idx}" in g:
+                assert rel_l2(x, torch.from_numpy(g[f"x_{idx}"])) < 2e-6, (kind, idx)
+        rms = np.array([float(x.pow(2).mean().sqrt()) for _, _, x in rec])
+        assert np.allclose(rms, g["x_rms"], rtol=1e-5)
+
+
+def test_reverse_ddim(golden_dir):
+    T = 10
+    g = np.load(golden_dir / "reverse10_a32.npz")
+    sd = model_sd(32, T)
+    sch = orc.Schedule.make(1e-5, 1e-2, T)
+    _, _, a = rand_inputs(2, 32, T, seed=8)
+    x0 = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(4)) * 2 - 1
+    xT = orc.reverse_sample(sd, sch, x0, a=None, enc_noise_fn=lambda xx: torch.zeros(2, 32))
+    assert rel_l2(xT, torch.from_numpy(g["xT_reencode"])) < 2e-6
+    xTa = orc.reverse_sample(sd, sch, x0, a=a)
+    assert rel_l2(xTa, torch.from_numpy(g["xT_given_a"])) < 2e-6
+    assert rel_l2(xTa, xT) > 1e-4      # the two variants really differ
