@@ -163,6 +163,9 @@ class DiffusionProcess():
         self.chunk = getattr(args, "sample_chunk", None)      # micro-batch per graph segment (None = whole batch)
         self.use_graph = getattr(args, "cuda_graph", True)
         self.honor_latent_in_reverse = getattr(args, "reverse_uses_given_latent", False)
+        # noise_fn(idx, out) fills `out` with the step's N(0,1) noise; the default draws from torch's CUDA
+        # generator exactly where the reference calls torch.randn_like (parity tests inject fixed tensors)
+        self.noise_fn = lambda idx, out: out.normal_()
         self._samplers = {}
 
     # ------------------------------------------------------------------------------------------
@@ -191,10 +194,10 @@ class DiffusionProcess():
         for idx in order:
             if kind == "ddpm":
                 if idx > 0:
-                    s.noise.normal_()                   # drawn BEFORE the model call (sampling.py:29)
+                    self.noise_fn(idx, s.noise)         # drawn BEFORE the model call (sampling.py:29)
             elif kind == "ddim":
                 if idx > 0:
-                    s.noise.normal_()                   # reference draws it after the model call (sampling.py:56);
+                    self.noise_fn(idx, s.noise)         # reference draws it after the model call (sampling.py:56);
                                                         # the model call consumes no random numbers, so the
                                                         # generator stream is identical
             s.run_step(idx, use_graph=self.use_graph)

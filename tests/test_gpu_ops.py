@@ -1,0 +1,334 @@
+"""Per-kernel parity tests on the B200, every call going through the C ABI (ctypes).
+
+Inputs are rounded to bf16 first, the comparator is plain fp32/fp64 torch arithmetic on those same
+values (the op-level slice of the oracle), so the only admissible differences are fp32 accumulation
+order and the final bf16 rounding of the output (2^-9 relative).  Tolerances are written per test.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from infodiffusion_b200 import _lib
+    l = _lib.load()
+    _lib.check(l.idf_init())
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return l
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(rc):
+    from infodiffusion_b200 import _lib
+    _lib.check(rc)
+
+
+def rbf(x):
+    """round to bf16 and back (values exactly representable in the kernels' storage type)"""
+    return x.to(BF).float()
+
+
+def pf(x):
+    """NCHW fp32 (cuda) -> pad-flat bf16 via plain torch ops"""
+    B, Cc, H, W = x.shape
+    buf = torch.zeros(B, H + 1, W + 1, Cc, device=x.device, dtype=torch.float32)
+    buf[:, :H, :W, :] = x.permute(0, 2, 3, 1)
+    return buf.reshape(-1, Cc).to(BF).contiguous()
+
+
+def unpf(m, B, H, W):
+    return m.float().reshape(B, H + 1, W + 1, -1)[:, :H, :W, :].permute(0, 3, 1, 2).contiguous()
+
+
+def pad_is_zero(m, B, H, W):
+    v = m.float().reshape(B, H + 1, W + 1, -1)
+    return bool((v[:, H, :, :] == 0).all() and (v[:, :, W, :] == 0).all())
+
+
+def assert_close(got, ref, rel_l2=3e-3, max_rel=1.6e-2, what=""):
+    got, ref = got.double(), ref.double()
+    err = (got - ref).norm() / ref.norm().clamp_min(1e-30)
+    mx = (got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    assert err < rel_l2 and mx < max_rel, f"{what}: rel-L2 {err:.3e} (tol {rel_l2}), max-rel {mx:.3e} (tol {max_rel})"
+
+
+def run_conv(lib, srcs, kblocks, wp, bias, B, H, cout, block_n, residual=None, epilogue=0, **extra):
+    from infodiffusion_b200._lib import ConvDesc
+    d = ConvDesc()
+    d.n_src = len(srcs)
+    for i, s in enumerate(srcs):
+        d.src[i], d.src_rows[i], d.src_ld[i] = s.data_ptr(), s.shape[0], s.shape[1]
+    d.num_kb = len(kblocks)
+    for k, (si, c0, off) in enumerate(kblocks):
+        d.kb_src[k], d.kb_c0[k], d.kb_rowoff[k] = si, c0, off
+    d.weight, d.cout_pad, d.block_n, d.cout = wp.data_ptr(), wp.shape[0], block_n, cout
+    d.bias = bias.data_ptr()
+    d.batch, d.H, d.W, d.epilogue = B, H, H, epilogue
+    out = None
+    if epilogue == 0:
+        out = torch.zeros(B * (H + 1) * (H + 1), cout, device=DEV, dtype=BF)
+        d.out, d.out_ld = out.data_ptr(), cout
+        if residual is not None:
+            d.residual, d.res_ld = residual.data_ptr(), residual.shape[1]
+    for k, v in extra.items():
+        setattr(d, k, v.data_ptr() if torch.is_tensor(v) else v)
+    h = C.c_void_p()
+    check(lib.idf_conv_plan_create(C.byref(d), C.byref(h)))
+    check(lib.idf_conv_run(h, stream()))
+    torch.cuda.synchronize()
+    lib.idf_conv_plan_destroy(h)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def test_layout_kernels(lib):
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for (B, Cc, H) in [(2, 64, 8), (3, 128, 16), (1, 192, 32)]:
+        x = torch.randn(B, Cc, H, H, device=DEV, generator=g)
+        out = torch.zeros(B * (H + 1) * (H + 1), Cc, device=DEV, dtype=BF)
+        check(lib.idf_nchw_to_padflat(x.data_ptr(), out.data_ptr(), B, Cc, H, H, stream()))
+        assert torch.equal(out, pf(x))
+        back = torch.zeros_like(x)
+        check(lib.idf_padflat_to_nchw(out.data_ptr(), back.data_ptr(), B, Cc, H, H, stream()))
+        assert torch.equal(back, rbf(x))
+
+
+@pytest.mark.parametrize("cin,cout,H,B,res", [
+    (64, 64, 16, 2, False), (64, 64, 16, 2, True), (128, 128, 8, 3, True), (256, 128, 16, 2, False),
+    (192, 64, 8, 2, False), (64, 128, 32, 1, False), (128, 128, 64, 1, True), (128, 128, 8, 37, False)])
+def test_conv3x3(lib, cin, cout, H, B, res):
+    from infodiffusion_b200 import layout
+    g = torch.Generator(device=DEV).manual_seed(cin + cout + H)
+    x = rbf(torch.randn(B, cin, H, H, device=DEV, generator=g))
+    w = rbf(torch.randn(cout, cin, 3, 3, device=DEV, generator=g) * (2.0 / (9 * cin)) ** 0.5)
+    b = torch.randn(cout, device=DEV, generator=g)
+    r = rbf(torch.randn(B, cout, H, H, device=DEV, generator=g)) if res else None
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    if res:
+        ref = ref + r.double()
+    out = run_conv(lib, [pf(x)], layout.taps3x3(cin, H, H), layout.pack_conv3x3(w).to(BF).contiguous(), b, B, H, cout,
+                   128 if cout % 128 == 0 else 64, residual=pf(r) if res else None)
+    assert pad_is_zero(out, B, H, H), "kernel wrote a pad row"
+    assert_close(unpf(out, B, H, H), ref, what=f"conv3x3 {cin}->{cout}@{H} B={B} res={res}")
+
+
+def test_conv1x1_qkv(lib):
+    from infodiffusion_b200 import layout
+    g = torch.Generator(device=DEV).manual_seed(5)
+    B, H, cin, cout = 3, 16, 128, 384
+    x = rbf(torch.randn(B, cin, H, H, device=DEV, generator=g))
+    w = rbf(torch.randn(cout, cin, 1, 1, device=DEV, generator=g) * cin ** -0.5)
+    b = torch.randn(cout, device=DEV, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double())
+    out = run_conv(lib, [pf(x)], layout.taps1x1(cin), layout.pack_conv1x1(w).to(BF).contiguous(), b, B, H, cout, 128)
+    assert_close(unpf(out, B, H, H), ref, what="conv1x1 qkv")
+
+
+def test_conv3x3_fused_shortcut(lib):
+    """conv3(act) + shortcut1x1(cat(h, skip)): three A sources in one K loop."""
+    from infodiffusion_b200 import layout
+    g = torch.Generator(device=DEV).manual_seed(6)
+    B, H, ch, cs, cout = 2, 16, 128, 64, 128
+    act = rbf(torch.randn(B, cout, H, H, device=DEV, generator=g))
+    h = rbf(torch.randn(B, ch, H, H, device=DEV, generator=g))
+    s = rbf(torch.randn(B, cs, H, H, device=DEV, generator=g))
+    w3 = rbf(torch.randn(cout, cout, 3, 3, device=DEV, generator=g) * 0.03)
+    wsc = rbf(torch.randn(cout, ch + cs, 1, 1, device=DEV, generator=g) * 0.07)
+    b = torch.randn(cout, device=DEV, generator=g)
+    ref = F.conv2d(act.double(), w3.double(), b.double(), padding=1) + F.conv2d(torch.cat([h, s], 1).double(), wsc.double())
+    kb = layout.taps3x3(cout, H, H, 0) + layout.taps1x1(ch, 1) + layout.taps1x1(cs, 2)
+    wp = torch.cat([layout.pack_conv3x3(w3), layout.pack_conv1x1(wsc)], 1).to(BF).contiguous()
+    out = run_conv(lib, [pf(act), pf(h), pf(s)], kb, wp, b, B, H, cout, 128)
+    assert_close(unpf(out, B, H, H), ref, what="conv3 + fused shortcut")
+
+
+@pytest.mark.parametrize("Cc,H,B", [(64, 16, 2), (128, 32, 3)])
+def test_downsample_stride2(lib, Cc, H, B):
+    from infodiffusion_b200 import layout
+    g = torch.Generator(device=DEV).manual_seed(7)
+    x = rbf(torch.randn(B, Cc, H, H, device=DEV, generator=g))
+    w = rbf(torch.randn(Cc, Cc, 3, 3, device=DEV, generator=g) * (2.0 / (9 * Cc)) ** 0.5)
+    b = torch.randn(Cc, device=DEV, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=2, padding=1)
+    Ho = H // 2
+    rows_o = B * (Ho + 1) * (Ho + 1)
+    ph = torch.zeros(4 * rows_o, Cc, device=DEV, dtype=BF)
+    check(lib.idf_space_to_depth(pf(x).data_ptr(), ph.data_ptr(), B, H, H, Cc, stream()))
+    out = run_conv(lib, [ph], layout.taps_stride2(Cc, Ho, Ho, rows_o), layout.pack_conv3x3(w).to(BF).contiguous(), b, B,
+                   Ho, Cc, 128 if Cc % 128 == 0 else 64)
+    assert_close(unpf(out, B, Ho, Ho), ref, what="stride-2 conv")
+
+
+def test_upsample2x(lib):
+    g = torch.Generator(device=DEV).manual_seed(8)
+    B, Cc, H = 3, 128, 8
+    x = rbf(torch.randn(B, Cc, H, H, device=DEV, generator=g))
+    out = torch.zeros(B * (2 * H + 1) * (2 * H + 1), Cc, device=DEV, dtype=BF)
+    check(lib.idf_upsample2x(pf(x).data_ptr(), out.data_ptr(), B, H, H, Cc, stream()))
+    assert torch.equal(unpf(out, B, 2 * H, 2 * H), F.interpolate(x, scale_factor=2.0, mode="nearest"))
+    assert pad_is_zero(out, B, 2 * H, 2 * H)
+
+
+def test_im2col_head_and_gemm(lib):
+    from infodiffusion_b200 import layout
+    g = torch.Generator(device=DEV).manual_seed(9)
+    B, H = 3, 64
+    x = torch.rand(B, 3, H, H, device=DEV, generator=g) * 2 - 1
+    w = rbf(torch.randn(64, 3, 3, 3, device=DEV, generator=g) * 0.2)
+    b = torch.randn(64, device=DEV, generator=g)
+    patches = torch.zeros(B * (H + 1) * (H + 1), 64, device=DEV, dtype=BF)
+    check(lib.idf_im2col_head(x.data_ptr(), patches.data_ptr(), B, 3, H, H, stream()))
+    ref = F.conv2d(rbf(x).double(), w.double(), b.double(), padding=1)
+    wp = layout.pad_cols(layout.pack_conv3x3(w), 64).to(BF).contiguous()
+    out = run_conv(lib, [patches], [(0, 0, 0)], wp, b, B, H, 64, 64)
+    assert_close(unpf(out, B, H, H), ref, what="head conv (im2col + K=64 GEMM)")
+
+
+def test_tail_fp32_and_sampler_epilogue(lib):
+    from infodiffusion_b200 import layout
+    g = torch.Generator(device=DEV).manual_seed(10)
+    B, H, cin = 3, 16, 64
+    a = rbf(torch.randn(B, cin, H, H, device=DEV, generator=g))
+    w = rbf(torch.randn(3, cin, 3, 3, device=DEV, generator=g) * 0.05)
+    b = torch.randn(3, device=DEV, generator=g)
+    eps_ref = F.conv2d(a.double(), w.double(), b.double(), padding=1)
+    wp = layout.pad_rows(layout.pack_conv3x3(w), 16).to(BF).contiguous()
+    bias = layout.pad_rows(b, 16).contiguous()
+    kb = layout.taps3x3(cin, H, H)
+    eps = torch.zeros(B, 3, H, H, device=DEV)
+    run_conv(lib, [pf(a)], kb, wp, bias, B, H, 3, 16, epilogue=1, out_f32=eps)
+    assert_close(eps, eps_ref, rel_l2=1e-5, max_rel=1e-5, what="tail fp32 NCHW")   # fp32 out: accumulation order only
+    # fused sampler update, step-indexed coefficients
+    coef = torch.tensor([[9., 9., 9.], [0.7, -0.3, 0.05], [1., 1., 1.]], device=DEV)
+    step = torch.tensor([1], dtype=torch.int32, device=DEV)
+    x = torch.randn(B, 3, H, H, device=DEV, generator=g)
+    nz = torch.randn(B, 3, H, H, device=DEV, generator=g)
+    x_ref = 0.7 * x.double() - 0.3 * eps_ref + 0.05 * nz.double()
+    x_io, eps2 = x.clone(), torch.zeros_like(eps)
+    run_conv(lib, [pf(a)], kb, wp, bias, B, H, 3, 16, epilogue=2, out_f32=eps2, x_io=x_io, noise=nz, coef=coef,
+             step_ptr=step)
+    assert torch.equal(eps2, eps)
+    assert_close(x_io, x_ref, rel_l2=1e-5, max_rel=1e-5, what="fused sampler update")
+
+
+@pytest.mark.parametrize("c0,c1,H,B,mod,silu", [
+    (64, 0, 64, 2, False, True), (128, 0, 32, 3, True, True), (128, 64, 32, 2, False, True),
+    (128, 128, 16, 3, True, True), (128, 0, 8, 5, False, False), (64, 64, 64, 1, True, True)])
+def test_adagn(lib, c0, c1, H, B, mod, silu):
+    from infodiffusion_b200._lib import AdaGNArgs
+    g = torch.Generator(device=DEV).manual_seed(c0 + c1 + H)
+    Cc = c0 + c1
+    x0 = rbf(torch.randn(B, c0, H, H, device=DEV, generator=g) * 1.5 + 0.3)
+    x1 = rbf(torch.randn(B, c1, H, H, device=DEV, generator=g) * 0.7 - 0.2) if c1 else None
+    gamma = 1 + 0.1 * torch.randn(Cc, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(Cc, device=DEV, generator=g)
+    xin = torch.cat([x0, x1], 1) if c1 else x0
+    ref = F.group_norm(xin.double(), 32, gamma.double(), beta.double(), 1e-5)
+    a = AdaGNArgs()
+    s0 = pf(x0)
+    a.src0, a.c0 = s0.data_ptr(), c0
+    if c1:
+        s1 = pf(x1)
+        a.src1, a.c1 = s1.data_ptr(), c1
+    out = torch.zeros(B * (H + 1) * (H + 1), Cc, device=DEV, dtype=BF)
+    a.out, a.batch, a.H, a.W = out.data_ptr(), B, H, H
+    a.gamma, a.beta, a.eps = gamma.data_ptr(), beta.data_ptr(), 1e-5
+    if mod:
+        nsteps, ncol, off = 4, 3 * 2 * Cc, 2 * Cc          # a wider table: this block's columns start at `off`
+        tt = 0.3 * torch.randn(nsteps, ncol, device=DEV, generator=g)   # step-indexed, shared by the batch
+        zz = 0.3 * torch.randn(B, ncol, device=DEV, generator=g)        # per-sample
+        step = torch.tensor([2], dtype=torch.int32, device=DEV)
+        a.mod_t, a.mod_t_step_stride, a.mod_t_batch_stride = tt.data_ptr() + off * 4, ncol, 0
+        a.mod_z, a.mod_z_step_stride, a.mod_z_batch_stride = zz.data_ptr() + off * 4, 0, ncol
+        a.step_ptr = step.data_ptr()
+        st, bt = tt[2, off:off + Cc].double(), tt[2, off + Cc:off + 2 * Cc].double()
+        sz, bz = zz[:, off:off + Cc].double(), zz[:, off + Cc:off + 2 * Cc].double()
+        ref = ref * (1 + st)[None, :, None, None] + bt[None, :, None, None]
+        ref = ref * (1 + sz)[:, :, None, None] + bz[:, :, None, None]
+    a.apply_silu = 1 if silu else 0
+    if silu:
+        ref = F.silu(ref)
+    check(lib.idf_adagn_silu_fwd(C.byref(a), stream()))
+    torch.cuda.synchronize()
+    assert pad_is_zero(out, B, H, H)
+    assert_close(unpf(out, B, H, H), ref, rel_l2=3e-3, max_rel=8e-3, what=f"adagn C={c0}+{c1}@{H}")
+
+
+@pytest.mark.parametrize("H,B", [(16, 3), (8, 5)])
+def test_attention(lib, H, B):
+    g = torch.Generator(device=DEV).manual_seed(11 + H)
+    d, S = 128, H * H
+    q, k, v = (rbf(torch.randn(B, d, H, H, device=DEV, generator=g) * s) for s in (1.2, 1.2, 1.0))
+    qkv = pf(torch.cat([q, k, v], 1))
+    out = torch.zeros(B * (H + 1) * (H + 1), d, device=DEV, dtype=BF)
+    check(lib.idf_attn_fwd(qkv.data_ptr(), out.data_ptr(), B, H, H, d, d ** -0.5, stream()))
+    torch.cuda.synchronize()
+    qq = q.double().permute(0, 2, 3, 1).reshape(B, S, d)
+    kk = k.double().reshape(B, d, S)
+    vv = v.double().permute(0, 2, 3, 1).reshape(B, S, d)
+    w = torch.softmax(torch.bmm(qq, kk) * d ** -0.5, dim=-1)
+    ref = torch.bmm(w, vv).reshape(B, H, H, d).permute(0, 3, 1, 2)
+    assert pad_is_zero(out, B, H, H)
+    # P is rounded to bf16 before the PV product: 2^-9 per probability, averaged over S keys
+    assert_close(unpf(out, B, H, H), ref, rel_l2=6e-3, max_rel=2e-2, what=f"attention S={S}")
+
+
+def test_linear_and_gather(lib):
+    g = torch.Generator(device=DEV).manual_seed(12)
+    for (M, N, K, silu) in [(100, 4992, 256, True), (37, 256, 64, False), (2, 32, 4096, False)]:
+        x = torch.randn(M, K, device=DEV, generator=g)
+        w = torch.randn(N, K, device=DEV, generator=g) * K ** -0.5
+        b = torch.randn(N, device=DEV, generator=g)
+        y = torch.zeros(M, N, device=DEV)
+        check(lib.idf_linear_f32(x.data_ptr(), K, w.data_ptr(), b.data_ptr(), y.data_ptr(), N, M, N, K, int(silu), stream()))
+        xin = F.silu(x.double()) if silu else x.double()
+        assert_close(y, xin @ w.double().t() + b.double(), rel_l2=2e-6, max_rel=2e-5, what=f"linear {M}x{N}x{K}")
+    table = torch.randn(50, 64, device=DEV, generator=g)
+    idx = torch.randint(0, 50, (17,), device=DEV, generator=g)
+    y = torch.zeros(17, 64, device=DEV)
+    check(lib.idf_gather_rows_f32(table.data_ptr(), idx.data_ptr(), y.data_ptr(), 17, 64, stream()))
+    assert torch.equal(y, table[idx])
+
+
+def test_sampler_update(lib):
+    g = torch.Generator(device=DEV).manual_seed(13)
+    n = 2 * 3 * 64 * 64 + 4
+    x, e, z = (torch.randn(n, device=DEV, generator=g) for _ in range(3))
+    coef = torch.tensor([[1., 2., 3.], [0.9, -0.2, 0.01]], device=DEV)
+    step = torch.tensor([1], dtype=torch.int32, device=DEV)
+    ref = 0.9 * x.double() - 0.2 * e.double() + 0.01 * z.double()
+    check(lib.idf_sampler_update(x.data_ptr(), e.data_ptr(), z.data_ptr(), coef.data_ptr(), step.data_ptr(), n, stream()))
+    assert_close(x, ref, rel_l2=1e-6, max_rel=1e-6, what="sampler update")
+
+
+def test_mmd_against_oracle_and_golden(lib, golden_dir):
+    from infodiffusion_b200.utils import compute_mmd
+    from oracle import infodiff_oracle as orc
+    gold = np.load(golden_dir / "mmd.npz")
+    for D in (32, 256):
+        gen = torch.Generator().manual_seed(11 + D)
+        xs = torch.randn(32, D, generator=gen)
+        ys = torch.randn(32, D, generator=gen) * 0.7 + 0.2
+        yo = ys.clone().requires_grad_(True)
+        vo = orc.compute_mmd(xs, yo)
+        (go,) = torch.autograd.grad(vo, yo)
+        yg = ys.to(DEV).requires_grad_(True)
+        vg = compute_mmd(xs.to(DEV), yg)
+        (gg,) = torch.autograd.grad(vg, yg)
+        assert_close(vg.cpu(), vo.detach(), rel_l2=1e-5, max_rel=1e-5, what=f"mmd value D={D}")
+        assert_close(gg.cpu(), go, rel_l2=1e-5, max_rel=1e-4, what=f"mmd grad D={D}")
+        assert_close(vg.cpu(), torch.from_numpy(gold[f"v{D}"]), rel_l2=1e-5, max_rel=1e-5, what="mmd vs golden")
