@@ -92,6 +92,7 @@ class Plan:
         self.device = device
         self.ws = ws if ws is not None else Workspace(batch, device)
         self.ops: List = []          # (callable, args tuple); last arg slot is the stream
+        self.meta: List[dict] = []   # per op: kernel class, algorithmic flops / bytes
         self.keep: List = []         # tensors / ctypes structs that must outlive the plan
         self.conv_plans: List[int] = []
         self.flops = 0               # algorithmic conv/attention FLOPs of one run
@@ -105,7 +106,26 @@ class Plan:
         except Exception:
             pass
 
+    def _emit(self, tag: str, fn, args: tuple, flops: int = 0, nbytes: int = 0) -> None:
+        self.ops.append((fn, args))
+        self.meta.append(dict(tag=tag, flops=flops, bytes=nbytes))
+        self.flops += flops
+        self.adagn_bytes += nbytes if tag == "adagn" else 0
+
     # ---- execution -----------------------------------------------------------------------------
+    def run_timed(self) -> List[Tuple[str, float, int, int]]:
+        """Eager run with a CUDA-event pair around every launch (on the launching stream).
+        Returns [(kernel class, milliseconds, algorithmic flops, algorithmic bytes)]."""
+        st = torch.cuda.current_stream(self.device)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.ops) + 1)]
+        evs[0].record(st)
+        for i, (fn, args) in enumerate(self.ops):
+            _lib.check(fn(*args, st.cuda_stream))
+            evs[i + 1].record(st)
+        st.synchronize()
+        _lib.count_launch(len(self.ops))
+        return [(m["tag"], evs[i].elapsed_time(evs[i + 1]), m["flops"], m["bytes"]) for i, m in enumerate(self.meta)]
+
     def run(self, stream: Optional[int] = None) -> None:
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -158,10 +178,9 @@ class Plan:
         _lib.check(self.lib.idf_conv_plan_create(C.byref(d), C.byref(h)))
         self.conv_plans.append(h)
         self.keep.append(d)
-        self.ops.append((self.lib.idf_conv_run, (h,)))
         self.conv_tiles += int(self.lib.idf_conv_plan_tiles(h))
         macs = real_macs_per_row if real_macs_per_row is not None else 64 * len(kblocks) * cout
-        self.flops += 2 * self.B * H * H * macs
+        self._emit("conv_igemm", self.lib.idf_conv_run, (h,), flops=2 * self.B * H * H * macs)
 
     def adagn(self, src0: Act, src1: Optional[Act], out: Act, gn: nn.GroupNorm, silu: bool, mod_t=None, mod_z=None,
               step=None) -> None:
@@ -180,21 +199,19 @@ class Plan:
         a.step_ptr = _ptr(step)
         a.apply_silu = 1 if silu else 0
         self.keep.append(a)
-        self.ops.append((self.lib.idf_adagn_silu_fwd, (C.byref(a),)))
-        self.adagn_bytes += 2 * 2 * self.B * src0.H * src0.H * out.C
+        self._emit("adagn", self.lib.idf_adagn_silu_fwd, (C.byref(a),), nbytes=2 * 2 * self.B * src0.H * src0.H * out.C)
 
     def attention(self, qkv: Act, out: Act, d: int) -> None:
-        self.ops.append((self.lib.idf_attn_fwd, (qkv.t.data_ptr(), out.t.data_ptr(), self.B, qkv.H, qkv.H, d,
-                                                 float(d) ** -0.5)))
         S = qkv.H * qkv.H
-        self.flops += self.B * 4 * S * S * d
+        self._emit("attention", self.lib.idf_attn_fwd, (qkv.t.data_ptr(), out.t.data_ptr(), self.B, qkv.H, qkv.H, d,
+                                                        float(d) ** -0.5), flops=self.B * 4 * S * S * d)
 
     def linear(self, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], y: torch.Tensor, silu_in: bool) -> None:
         M, K = x.shape
         N = w.shape[0]
         assert w.shape[1] == K and y.shape == (M, N) and x.stride(1) == 1 and y.stride(1) == 1
-        self.ops.append((self.lib.idf_linear_f32, (x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), y.data_ptr(),
-                                                   y.stride(0), M, N, K, 1 if silu_in else 0)))
+        self._emit("linear", self.lib.idf_linear_f32, (x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), y.data_ptr(),
+                                                       y.stride(0), M, N, K, 1 if silu_in else 0))
 
     # ---- composite emitters ----------------------------------------------------------------------
     @staticmethod
@@ -234,7 +251,7 @@ class Plan:
         """3x3 stride-2 conv: space-to-depth split into 4 phase maps, then 9 taps over the phases."""
         H, Ho, Cc = src.H, src.H // 2, src.C
         ph = self.ws.alloc(Ho, Cc, phases=4)
-        self.ops.append((self.lib.idf_space_to_depth, (src.t.data_ptr(), ph.t.data_ptr(), self.B, H, H, Cc)))
+        self._emit("space_to_depth", self.lib.idf_space_to_depth, (src.t.data_ptr(), ph.t.data_ptr(), self.B, H, H, Cc))
         kb = taps_stride2(Cc, Ho, Ho, ph.rows)
         out = self.ws.alloc(Ho, conv.out_channels)
         self.conv([ph], kb, self.weight(pack_conv3x3(conv.weight)), self.f32(conv.bias), Ho, conv.out_channels,
@@ -244,7 +261,7 @@ class Plan:
 
     def upsample(self, src: Act, conv: nn.Conv2d) -> Act:
         up = self.ws.alloc(src.H * 2, src.C)
-        self.ops.append((self.lib.idf_upsample2x, (src.t.data_ptr(), up.t.data_ptr(), self.B, src.H, src.H, src.C)))
+        self._emit("upsample2x", self.lib.idf_upsample2x, (src.t.data_ptr(), up.t.data_ptr(), self.B, src.H, src.H, src.C))
         out = self.conv3x3(up, conv)
         self.ws.free(up)
         return out
@@ -396,7 +413,7 @@ class BackbonePlan(Plan):
         # ---- head: im2col + K=64 GEMM
         ws = self.ws
         patches = ws.alloc(H, 64)
-        self.ops.append((self.lib.idf_im2col_head, (x_src.data_ptr(), patches.t.data_ptr(), B, Cimg, H, W)))
+        self._emit("im2col_head", self.lib.idf_im2col_head, (x_src.data_ptr(), patches.t.data_ptr(), B, Cimg, H, W))
         hw = _pad_cols(pack_conv3x3(net.head.weight), 64)
         h = ws.alloc(H, net.head.out_channels)
         self.conv([patches], [(0, 0, 0)], self.weight(hw), self.f32(net.head.bias), H, net.head.out_channels,
@@ -454,8 +471,8 @@ class BackbonePlan(Plan):
         e2 = torch.zeros(M, te[3].out_features, **f32)
         self.keep += [e0, e1, e2]
         table = self.f32(te[0].weight)
-        self.ops.append((self.lib.idf_gather_rows_f32, (table.data_ptr(), t_idx.data_ptr(), e0.data_ptr(), M,
-                                                        e0.shape[1])))
+        self._emit("gather_rows", self.lib.idf_gather_rows_f32, (table.data_ptr(), t_idx.data_ptr(), e0.data_ptr(), M,
+                                                                 e0.shape[1]))
         self.linear(e0, self.f32(te[1].weight), self.f32(te[1].bias), e1, silu_in=False)
         self.linear(e1, self.f32(te[3].weight), self.f32(te[3].bias), e2, silu_in=True)
         self.linear(e2, self.pack.w_t, self.pack.b_t, out, silu_in=True)
@@ -506,7 +523,7 @@ class EncoderPlan(Plan):
         self.log_var = torch.zeros(B, net.a_dim, **f32)
         ws = self.ws
         patches = ws.alloc(H, 64)
-        self.ops.append((self.lib.idf_im2col_head, (self.x_in.data_ptr(), patches.t.data_ptr(), B, Cimg, H, W)))
+        self._emit("im2col_head", self.lib.idf_im2col_head, (self.x_in.data_ptr(), patches.t.data_ptr(), B, Cimg, H, W))
         h = ws.alloc(H, net.head.out_channels)
         self.conv([patches], [(0, 0, 0)], self.weight(_pad_cols(pack_conv3x3(net.head.weight), 64)),
                   self.f32(net.head.bias), H, net.head.out_channels, 128 if net.head.out_channels % 128 == 0 else 64,
