@@ -41,6 +41,10 @@ int idf_version(void);
 const char* idf_last_error(void);
 /* Checks that the current device is sm_100 and raises dynamic-smem limits. */
 int idf_init(void);
+/* Implementation switches kept for A/B measurement and tests:
+ *   "attn_impl"     = 1 (thread-gathered operands) | 2 (TMA-fed, default)
+ *   "conv_force_mt" = 0 (auto) | 1 | 2 | 4   128-row tiles per CTA work unit of the conv kernel */
+int idf_set_option(const char* key, int32_t value);
 
 /* ------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (TMA-fed, TMEM accumulators).

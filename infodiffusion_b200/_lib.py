@@ -65,6 +65,7 @@ SIGNATURES = {
     "idf_version": (C.c_int, []),
     "idf_last_error": (C.c_char_p, []),
     "idf_init": (C.c_int, []),
+    "idf_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
     "idf_conv_plan_create": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_void_p)]),
     "idf_conv_plan_destroy": (C.c_int, [C.c_void_p]),
     "idf_conv_run": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -1,12 +1,16 @@
-// Fused AdaGN: GroupNorm(32) statistics + affine + timestep / latent-z scale-shift + SiLU.
+// Fused AdaGN: GroupNorm(32) statistics + affine + timestep / latent-z scale-shift + SiLU (+ concat).
 //
-// One thread-block CLUSTER per sample (CL = 1..8 CTAs, chosen from the sample's byte size).  Every CTA
-// streams its slice of the sample's pad-flat rows with 16-byte vector loads (8 bf16 channels per
-// thread, fully coalesced: consecutive threads cover consecutive channels of a row), accumulates
-// per-channel sum / sum-of-squares in fp32, the cluster combines the partials through distributed
-// shared memory, each CTA folds mean/rstd, gamma/beta and both modulations into one (A,B) pair per
-// channel, and a second sweep over the same rows (served by L2: the cluster's working set is small)
-// applies y = silu(A*x + B) and writes bf16.  HBM traffic: one read + one write of the tensor.
+// v2 (smem-resident): one thread-block CLUSTER per sample (1..8 CTAs).  Each CTA pulls its contiguous
+// slice of the sample's pad-flat rows into shared memory with ONE bulk-async copy per source
+// (cp.async.bulk, completion on an mbarrier: no load instructions, the whole slice is in flight
+// immediately), accumulates per-channel sum / sum-of-squares from shared memory, the cluster combines
+// the partials through distributed shared memory (fixed order: deterministic), every CTA folds
+// mean/rstd, gamma/beta and both modulations into one (A, B) pair per channel, and a second sweep over
+// the slice -- still in shared memory -- applies y = silu(A*x + B) and streams bf16 to HBM with 16-byte
+// coalesced stores.  HBM traffic is exactly one read + one write of the tensor.
+//
+// v1 re-read the slice from L2 for the second sweep and spent ~50 instructions + two integer divisions
+// per 16 bytes; ncu showed it issue-bound (sm throughput 55 %, 28 % of HBM peak).
 //
 // Two sources (c1 > 0) are treated as one map concatenated along C, which is how the reference's
 // torch.cat([h, skip]) followed by GroupNorm behaves (models.py:321 -> modules.py:265).
@@ -29,6 +33,7 @@ struct AdaGNParams {
   int c0, c1, C;
   int Hp, Wp, H, W;
   int rows_per_img;
+  int chunk_rows;      // rows per CTA (last CTA of the cluster may have fewer)
   const float* gamma;
   const float* beta;
   float eps;
@@ -40,10 +45,12 @@ struct AdaGNParams {
   int apply_silu;
 };
 
-__device__ __forceinline__ uint4 ld_row_vec(const AdaGNParams& p, long long row, int vl, int v0) {
-  // vl: index of the 8-channel vector inside the concatenated row; v0 = c0/8
-  const bf16* ptr = (vl < v0) ? (p.src0 + row * p.c0 + vl * 8) : (p.src1 + row * p.c1 + (vl - v0) * 8);
-  return __ldg(reinterpret_cast<const uint4*>(ptr));
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 __global__ void __launch_bounds__(kAdaThreads) adagn_kernel(const AdaGNParams p) {
@@ -52,14 +59,16 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_kernel(const AdaGNParams p)
   const int crank = static_cast<int>(cluster.block_rank());
   const int n = blockIdx.y;
 
+  extern __shared__ __align__(128) uint8_t slice_raw[];
   __shared__ float s_part[kAdaThreads][17];   // per-thread partials: 8 sums + 8 sums of squares (+1 pad)
   __shared__ float s_cta[2 * kMaxC];          // this CTA's per-channel (sum | sumsq), read by cluster peers
   __shared__ float s_tot[2 * kMaxC];
   __shared__ float s_mean[32], s_rstd[32];
   __shared__ float2 s_ab[kMaxC];
+  __shared__ __align__(8) uint64_t s_bar;
 
   const int C = p.C;
-  const int VPR = C >> 3;                       // 16-byte vectors per row
+  const int VPR = C >> 3;                       // 16-byte vectors per (concatenated) row
   const int rpp = kAdaThreads / VPR;            // rows per pass
   const int t = threadIdx.x;
   const bool active = t < rpp * VPR;
@@ -67,44 +76,60 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_kernel(const AdaGNParams p)
   const int rsub = t / VPR;
   const int v0 = p.c0 >> 3;
 
-  // this CTA's slice of the sample's rows
   const int rows = p.rows_per_img;
-  const int chunk = (rows + CL - 1) / CL;
-  const int r_begin = crank * chunk;
-  const int r_end = min(rows, r_begin + chunk);
-  const long long row_base = static_cast<long long>(n) * rows;
+  const int r_begin = min(rows, crank * p.chunk_rows);
+  const int r_end = min(rows, r_begin + p.chunk_rows);
+  const int nrows = r_end - r_begin;
+  const long long row_base = static_cast<long long>(n) * rows + r_begin;
 
-  // ---------------------------------------------------------------- sweep 1: statistics
+  uint8_t* slice0 = slice_raw;
+  uint8_t* slice1 = slice_raw + static_cast<size_t>(p.chunk_rows) * p.c0 * 2;
+
+  // ---------------------------------------------------------------- bulk load of the slice
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (t == 0) {
+    const uint32_t b0 = static_cast<uint32_t>(nrows) * p.c0 * 2;
+    const uint32_t b1 = static_cast<uint32_t>(nrows) * p.c1 * 2;
+    mbar_arrive_expect_tx(&s_bar, b0 + b1);
+    if (b0) bulk_load(slice0, p.src0 + row_base * p.c0, b0, &s_bar);
+    if (b1) bulk_load(slice1, p.src1 + row_base * p.c1, b1, &s_bar);
+  }
+  // this thread's 16-byte column of the concatenated row, inside the smem slice
+  const uint8_t* my_base = (vl < v0) ? (slice0 + vl * 16) : (slice1 + (vl - v0) * 16);
+  const int my_pitch = (vl < v0) ? p.c0 * 2 : p.c1 * 2;
+  mbar_wait(&s_bar, 0);
+
+  // ---------------------------------------------------------------- sweep 1: statistics (pad rows are zeros)
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
   if (active) {
-    for (int r = r_begin + rsub; r < r_end; r += kUnroll * rpp) {
+    for (int r = rsub; r < nrows; r += kUnroll * rpp) {
       uint4 u[kUnroll];
-      bool ok[kUnroll];
 #pragma unroll
-      for (int k = 0; k < kUnroll; ++k) {       // issue all loads first (memory-level parallelism)
+      for (int k = 0; k < kUnroll; ++k) {
         const int rr = r + k * rpp;
-        const int y = rr / p.Wp;
-        const int x = rr - y * p.Wp;
-        ok[k] = (rr < r_end) && (x < p.W) && (y < p.H);   // pad rows are zero: skip the load
-        if (ok[k]) u[k] = ld_row_vec(p, row_base + rr, vl, v0);
+        u[k] = (rr < nrows) ? *reinterpret_cast<const uint4*>(my_base + static_cast<size_t>(rr) * my_pitch)
+                            : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int k = 0; k < kUnroll; ++k) {
-        if (!ok[k]) continue;
         const float2 a0 = unpack_bf16x2(u[k].x), a1 = unpack_bf16x2(u[k].y), a2 = unpack_bf16x2(u[k].z),
                      a3 = unpack_bf16x2(u[k].w);
         const float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+        for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
       }
     }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s_part[t][j] = s[j]; s_part[t][8 + j] = ss[j]; }
   __syncthreads();
-  // per-channel totals of this CTA: channel ch = vl*8 + j lives in threads (rs*VPR + vl), rs = 0..rpp-1
+  // per-channel totals of this CTA: channel ch = cvl*8 + j lives in threads (rs*VPR + cvl), rs = 0..rpp-1
   for (int i = t; i < 2 * C; i += kAdaThreads) {
     const int which = i / C;                    // 0: sum, 1: sumsq
     const int ch = i - which * C;
@@ -114,7 +139,7 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_kernel(const AdaGNParams p)
     s_cta[i] = acc;
   }
   cluster.sync();
-  // ---------------------------------------------------------------- cluster reduction (DSMEM)
+  // ---------------------------------------------------------------- cluster reduction (DSMEM, fixed order)
   for (int i = t; i < 2 * C; i += kAdaThreads) {
     float acc = 0.f;
     for (int rk = 0; rk < CL; ++rk) {
@@ -157,41 +182,36 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_kernel(const AdaGNParams p)
     s_ab[ch] = make_float2(A, B);
   }
   __syncthreads();
-  // ---------------------------------------------------------------- sweep 2: normalise + activate
+  // ---------------------------------------------------------------- sweep 2: normalise + activate + store
   if (active) {
     float A[8], B[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { const float2 ab = s_ab[vl * 8 + j]; A[j] = ab.x; B[j] = ab.y; }
     const bool do_silu = p.apply_silu != 0;
-    for (int r = r_begin + rsub; r < r_end; r += kUnroll * rpp) {
-      uint4 u[kUnroll];
-      bool ok[kUnroll];
-#pragma unroll
-      for (int k = 0; k < kUnroll; ++k) {
-        const int rr = r + k * rpp;
-        const int y = rr / p.Wp;
-        const int x = rr - y * p.Wp;
-        ok[k] = (rr < r_end) && (x < p.W) && (y < p.H);   // never write pad rows
-        if (ok[k]) u[k] = ld_row_vec(p, row_base + rr, vl, v0);
-      }
-#pragma unroll
-      for (int k = 0; k < kUnroll; ++k) {
-        if (!ok[k]) continue;
-        const float2 a0 = unpack_bf16x2(u[k].x), a1 = unpack_bf16x2(u[k].y), a2 = unpack_bf16x2(u[k].z),
-                     a3 = unpack_bf16x2(u[k].w);
+    // (y, x) of this thread's first row, advanced incrementally (no per-row division)
+    int gy = (r_begin + rsub) / p.Wp;
+    int gx = (r_begin + rsub) - gy * p.Wp;
+    bf16* out_col = p.out + row_base * C + vl * 8;
+    for (int r = rsub; r < nrows; r += rpp) {
+      const bool interior = (gx < p.W) && (gy < p.H);       // never write pad rows
+      if (interior) {
+        const uint4 u = *reinterpret_cast<const uint4*>(my_base + static_cast<size_t>(r) * my_pitch);
+        const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
         float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float v = fmaf(f[j], A[j], B[j]);
-          f[j] = do_silu ? silu_f(v) : v;
+          f[j] = do_silu ? __fdividef(v, 1.0f + __expf(-v)) : v;
         }
         uint4 o;
         o.x = pack_bf16x2(f[0], f[1]);
         o.y = pack_bf16x2(f[2], f[3]);
         o.z = pack_bf16x2(f[4], f[5]);
         o.w = pack_bf16x2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(p.out + (row_base + r + k * rpp) * C + vl * 8) = o;
+        *reinterpret_cast<uint4*>(out_col + static_cast<size_t>(r) * C) = o;
       }
+      gx += rpp;
+      while (gx >= p.Wp) { gx -= p.Wp; ++gy; }
     }
   }
   cluster.barrier_wait();
@@ -214,15 +234,24 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
   p.apply_silu = a.apply_silu;
   if (p.C > kMaxC || p.C % 32 != 0 || p.c0 % 8 != 0 || p.c1 % 8 != 0 || a.batch <= 0) return cudaErrorInvalidValue;
 
-  // cluster size from the sample's byte size: ~64 KB of rows per CTA, at most 8 CTAs (portable limit)
+  // cluster size: slices of <= ~72 KB (3 CTAs per SM) when possible, at most 8 CTAs (portable limit)
   const long long bytes = static_cast<long long>(p.rows_per_img) * p.C * 2;
   int CL = 1;
-  while (CL < 8 && bytes > static_cast<long long>(CL) * 65536) CL <<= 1;
+  while (CL < 8 && bytes > static_cast<long long>(CL) * 72 * 1024) CL <<= 1;
+  p.chunk_rows = (p.rows_per_img + CL - 1) / CL;
+  const size_t smem = static_cast<size_t>(p.chunk_rows) * p.C * 2;
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(adagn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL, a.batch, 1);
   cfg.blockDim = dim3(kAdaThreads, 1, 1);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -22,7 +22,7 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int g) {
 
 template <int S>
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int Hp, int Wp, int W, float scale_log2e) {
+attn_gather_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int Hp, int Wp, int W, float scale_log2e) {
   // shared-memory map (all tiles are [rows x 64 elem] SW128 blocks, 1024-aligned):
   //   Q  : 2 d-chunks   x [128 x 128B]          = 32 KB
   //   K  : 2 d-chunks   x [S   x 128B]          = S/4 KB   (re-used for P: S/64 key-chunks x [128 x 128B])
@@ -195,29 +195,243 @@ attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int Hp, int Wp
 }
 
 template <int S>
-static cudaError_t launch_attn_s(const bf16* qkv, bf16* out, int batch, int H, int W, float scale,
+static cudaError_t launch_attn_gather(const bf16* qkv, bf16* out, int batch, int H, int W, float scale,
                                  cudaStream_t stream) {
   constexpr int KCH = S / 64;
   constexpr uint32_t K_BYTES = (2 * S * 128 > KCH * 128 * 128) ? 2 * S * 128 : KCH * 128 * 128;
   constexpr uint32_t SMEM = 2 * 128 * 128 + K_BYTES + KCH * 128 * 128 + 64 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_gather_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(SMEM));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid((S + 127) / 128, batch, 1);
-  attn_kernel<S><<<grid, kAttnThreads, SMEM, stream>>>(qkv, out, H + 1, W + 1, W, scale * 1.4426950408889634f);
+  attn_gather_kernel<S><<<grid, kAttnThreads, SMEM, stream>>>(qkv, out, H + 1, W + 1, W, scale * 1.4426950408889634f);
   return cudaGetLastError();
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// v2: TMA-fed.  Tokens of one image row are W consecutive pad-flat rows, so Q, K and V arrive as
+// [W x 64] TMA boxes (one per image row and 64-wide d-chunk) straight into the swizzled K-major
+// layout -- no gather instructions.  V is NOT transposed: it is used as an MN-major B operand
+// (N = d contiguous), described by LBO = distance between the two 64-wide d-chunks and
+// SBO = 1024 B (8 keys); the K loop of O = P V advances 16 keys = 2048 B per MMA.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fffu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int S>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_tma_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ out, int Hp, int Wp, int W,
+                float scale_log2e) {
+  constexpr int KCH = S / 64;
+  constexpr uint32_t Q_BYTES = 2 * 128 * 128;
+  constexpr uint32_t KV_CHUNK = S * 128;                    // one 64-wide d-chunk of K or V: [S x 128 B]
+  constexpr uint32_t K_BYTES = (2 * KV_CHUNK > KCH * 128 * 128) ? 2 * KV_CHUNK : KCH * 128 * 128;
+  constexpr uint32_t V_BYTES = 2 * KV_CHUNK;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smQ = smem;
+  uint8_t* smK = smQ + Q_BYTES;                    // later: P
+  uint8_t* smV = smK + K_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smV + V_BYTES);   // 0: Q,K landed  1: V landed  2: S ready  3: O ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const int n = blockIdx.y;
+  const int q0 = blockIdx.x * 128;
+  const int img_row0 = n * Hp * Wp;
+  const int H = S / W;
+  const int q_rows = (S - q0 < 128) ? (S - q0) : 128;        // valid query tokens in this tile
+  const int qy0 = q0 / W, q_imgrows = q_rows / W;
+
+  if (t == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  // query rows beyond S (S = 64 case) are never loaded: zero them so the MMA reads defined data
+  if (q_rows < 128) {
+    for (int i = t; i < (128 - q_rows) * 16; i += kAttnThreads) {
+      const int r = q_rows + (i >> 4), g = i & 15;
+      *reinterpret_cast<uint4*>(smQ + (g >> 3) * (128 * 128) + sw128_off(r, g & 7)) = make_uint4(0, 0, 0, 0);
+    }
+    fence_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 256;
+
+  if (t == 0) {
+    const uint32_t box = static_cast<uint32_t>(W) * 128u;   // bytes per TMA box
+    mbar_arrive_expect_tx(bars + 0, box * 2u * static_cast<uint32_t>(q_imgrows + H));
+    for (int c = 0; c < 2; ++c)
+      for (int y = 0; y < q_imgrows; ++y)
+        tma_load_2d(smQ + c * (128 * 128) + y * box, &tm, bars + 0, c * 64, img_row0 + (qy0 + y) * Wp);
+    for (int c = 0; c < 2; ++c)
+      for (int y = 0; y < H; ++y)
+        tma_load_2d(smK + c * KV_CHUNK + y * box, &tm, bars + 0, kD + c * 64, img_row0 + y * Wp);
+    mbar_arrive_expect_tx(bars + 1, box * 2u * static_cast<uint32_t>(H));
+    for (int c = 0; c < 2; ++c)
+      for (int y = 0; y < H; ++y)
+        tma_load_2d(smV + c * KV_CHUNK + y * box, &tm, bars + 1, 2 * kD + c * 64, img_row0 + y * Wp);
+    // ---- S = Q K^T
+    mbar_wait(bars + 0, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_f16(128, S, kFmtBF16);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint64_t da = umma_desc_k_sw128(smem_u32(smQ + c * (128 * 128)));
+      const uint64_t db = umma_desc_k_sw128(smem_u32(smK + c * KV_CHUNK));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_f16(tmem_S, da + 2 * k, db + 2 * k, idesc, (c | k) != 0 ? 1u : 0u);
+    }
+    umma_commit(bars + 2);
+  }
+  mbar_wait(bars + 2, 0);
+  tc_fence_after();
+
+  // ---- softmax: thread owns query row (warp*32 + lane) == TMEM lane
+  const int row = warp * 32 + lane;
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < S / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+  }
+  float sum = 0.f;
+  const float mxs = mx * scale_log2e;
+#pragma unroll 1
+  for (int c = 0; c < S / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
+    tmem_ld_wait();
+    uint8_t* chunk = smK + (c >> 1) * (128 * 128);         // P tile for keys [64*(c/2), +64)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float e[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        e[j] = exp2f(fmaf(__uint_as_float(v[g * 8 + j]), scale_log2e, -mxs));
+        sum += e[j];
+      }
+      uint4 o;
+      o.x = pack_bf16x2(e[0], e[1]);
+      o.y = pack_bf16x2(e[2], e[3]);
+      o.z = pack_bf16x2(e[4], e[5]);
+      o.w = pack_bf16x2(e[6], e[7]);
+      *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + g)) = o;
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // ---- O = P V   (A = P K-major; B = V MN-major: N = d contiguous, K = keys)
+  if (t == 0) {
+    mbar_wait(bars + 1, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_f16(128, kD, kFmtBF16) | (1u << 16);   // bit 16: B is MN-major
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      const uint64_t da = umma_desc_k_sw128(smem_u32(smK + c * (128 * 128)));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int key0 = c * 64 + k * 16;
+        const uint64_t db = umma_desc_mn_sw128(smem_u32(smV + key0 * 128), KV_CHUNK, 1024);
+        umma_f16(tmem_O, da + 2 * k, db, idesc, (c | k) != 0 ? 1u : 0u);
+      }
+    }
+    umma_commit(bars + 3);
+  }
+  mbar_wait(bars + 3, 0);
+  tc_fence_after();
+
+  const float inv = 1.0f / sum;
+  const int tok = q0 + row;
+  const bool valid = tok < S;
+  bf16* orow = out + (valid ? (static_cast<long long>(img_row0) + (tok / W) * Wp + (tok % W)) : 0) * kD;
+#pragma unroll 1
+  for (int c = 0; c < kD / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
+    tmem_ld_wait();
+    if (valid) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int S>
+static cudaError_t launch_attn_tma(const CUtensorMap& tm, bf16* out, int batch, int H, int W, float scale,
+                                   cudaStream_t stream) {
+  constexpr int KCH = S / 64;
+  constexpr uint32_t KV_CHUNK = S * 128;
+  constexpr uint32_t K_BYTES = (2 * KV_CHUNK > KCH * 128 * 128) ? 2 * KV_CHUNK : KCH * 128 * 128;
+  constexpr uint32_t SMEM = 2 * 128 * 128 + K_BYTES + 2 * KV_CHUNK + 64 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(SMEM));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((S + 127) / 128, batch, 1);
+  attn_tma_kernel<S><<<grid, kAttnThreads, SMEM, stream>>>(tm, out, H + 1, W + 1, W, scale * 1.4426950408889634f);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attn_v2(const CUtensorMap& tm, bf16* out, int batch, int H, int W, int d, float scale,
+                           cudaStream_t stream) {
+  if (d != kD) return cudaErrorInvalidValue;
+  const int S = H * W;
+  if (S == 256) return launch_attn_tma<256>(tm, out, batch, H, W, scale, stream);
+  if (S == 64) return launch_attn_tma<64>(tm, out, batch, H, W, scale, stream);
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_attn(const bf16* qkv, bf16* out, int batch, int H, int W, int d, float scale,
                         cudaStream_t stream) {
   if (d != kD) return cudaErrorInvalidValue;
   const int S = H * W;
-  if (S == 256) return launch_attn_s<256>(qkv, out, batch, H, W, scale, stream);
-  if (S == 64) return launch_attn_s<64>(qkv, out, batch, H, W, scale, stream);
+  if (S == 256) return launch_attn_gather<256>(qkv, out, batch, H, W, scale, stream);
+  if (S == 64) return launch_attn_gather<64>(qkv, out, batch, H, W, scale, stream);
   return cudaErrorInvalidValue;
 }
 

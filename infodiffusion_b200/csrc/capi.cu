@@ -5,7 +5,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <new>
+#include <vector>
 
 #include "kernels.cuh"
 
@@ -29,6 +31,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int g_num_sms = 0;
+int g_attn_impl = 2;
+int g_force_mt = 0;   // 0 = choose automatically
 
 int ensure_init() {
   if (g_encode != nullptr) return IDF_OK;
@@ -71,7 +75,9 @@ int encode_2d(CUtensorMap* tm, const void* base, int64_t rows, int32_t ld, int32
 struct idf_conv_plan {
   ConvKernelParams params;
   int block_n;
+  int mt;      // 128-row tiles per CTA work unit
   int grid;
+  int64_t tiles;
 };
 
 extern "C" {
@@ -79,6 +85,18 @@ extern "C" {
 int idf_version(void) { return 100; }
 const char* idf_last_error(void) { return g_err; }
 int idf_init(void) { return ensure_init(); }
+
+int idf_set_option(const char* key, int32_t value) {
+  if (key != nullptr && std::strcmp(key, "attn_impl") == 0 && (value == 1 || value == 2)) {
+    g_attn_impl = value;
+    return IDF_OK;
+  }
+  if (key != nullptr && std::strcmp(key, "conv_force_mt") == 0 && (value == 0 || value == 1 || value == 2 || value == 4)) {
+    g_force_mt = value;
+    return IDF_OK;
+  }
+  return fail(IDF_ERR_ARG, "unknown option or value");
+}
 
 int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   if (d == nullptr || out_plan == nullptr) return fail(IDF_ERR_ARG, "null argument");
@@ -111,30 +129,92 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
       delete pl;
       return fail(IDF_ERR_ARG, "source %d: null or channel count not a multiple of 64", i);
     }
-    rc = encode_2d(&p.tmA[i], d->src[i], d->src_rows[i], d->src_ld[i], kBM);
-    if (rc != IDF_OK) { delete pl; return rc; }
   }
-  rc = encode_2d(&p.tmB, d->weight, d->cout_pad, d->num_kb * kBK, d->block_n);
-  if (rc != IDF_OK) { delete pl; return rc; }
-  p.n_src = d->n_src;
-  p.num_kb = d->num_kb;
+  // ---- K-block table -> groups: per (source, 64-channel slice), taps whose row offsets lie within a
+  //      few hundred rows of each other share one halo load (3x3 taps; the phases of a stride-2 conv
+  //      are far apart and form separate groups).
+  struct Tap { int src, c0, off, kb; };
+  std::vector<Tap> taps;
   for (int k = 0; k < d->num_kb; ++k) {
-    if (d->kb_src[k] < 0 || d->kb_src[k] >= d->n_src || d->kb_c0[k] < 0 ||
+    if (d->kb_src[k] < 0 || d->kb_src[k] >= d->n_src || d->kb_c0[k] < 0 || d->kb_c0[k] % 64 != 0 ||
         d->kb_c0[k] + kBK > d->src_ld[d->kb_src[k]]) {
       delete pl;
       return fail(IDF_ERR_ARG, "k-block %d out of range", k);
     }
-    p.kb_src[k] = d->kb_src[k];
-    p.kb_c0[k] = d->kb_c0[k];
-    p.kb_rowoff[k] = d->kb_rowoff[k];
+    taps.push_back({d->kb_src[k], d->kb_c0[k], d->kb_rowoff[k], k});
   }
+  std::stable_sort(taps.begin(), taps.end(), [](const Tap& a, const Tap& b) {
+    if (a.src != b.src) return a.src < b.src;
+    if (a.c0 != b.c0) return a.c0 < b.c0;
+    return a.off < b.off;
+  });
+  p.n_src = d->n_src;
+  p.n_groups = 0;
+  p.n_taps = 0;
+  int group_hi[kMaxGroups] = {0};
+  for (size_t i = 0; i < taps.size(); ++i) {
+    const Tap& t = taps[i];
+    int g = p.n_groups - 1;
+    const bool same = g >= 0 && p.g_src[g] == t.src && p.g_c0[g] == t.c0 && (t.off - p.g_lo[g]) <= 248;
+    if (!same) {
+      if (p.n_groups == kMaxGroups) { delete pl; return fail(IDF_ERR_ARG, "too many halo groups"); }
+      g = p.n_groups++;
+      p.g_src[g] = t.src; p.g_c0[g] = t.c0; p.g_lo[g] = t.off; p.g_ntaps[g] = 0;
+    }
+    p.t_rel[p.n_taps] = t.off - p.g_lo[g];
+    p.t_kb[p.n_taps] = t.kb;
+    p.n_taps++;
+    p.g_ntaps[g]++;
+    group_hi[g] = t.off;
+  }
+  int extra_max = 0;
+  for (int i = 0; i < d->n_src; ++i) p.extra_rows[i] = 0;
+  for (int g = 0; g < p.n_groups; ++g) {
+    const int ex = (group_hi[g] - p.g_lo[g] + 7) / 8 * 8;
+    if (ex > p.extra_rows[p.g_src[g]]) p.extra_rows[p.g_src[g]] = ex;
+    if (ex > extra_max) extra_max = ex;
+  }
+  // ---- geometry and tile shape
   p.Hp = d->H + 1;
   p.Wp = d->W + 1;
   p.H = d->H;
   p.W = d->W;
   p.rows = static_cast<int64_t>(d->batch) * p.Hp * p.Wp;
-  p.m_tiles = static_cast<int32_t>((p.rows + kBM - 1) / kBM);
+  const int64_t m_tiles = (p.rows + kBM - 1) / kBM;
   p.n_tiles = d->cout_pad / d->block_n;
+  // MT 128-row tiles per CTA: as many as TMEM/smem allow while keeping >= 2 waves of work units
+  const int mt_max = (d->block_n == 128) ? 2 : 4;
+  int mt = 1;
+  for (int cand = mt_max; cand > 1; cand >>= 1) {
+    if (d->block_n == 16 && cand == 2) continue;   // instantiated: 16x{1,4}
+    const int64_t units = (m_tiles + cand - 1) / cand * p.n_tiles;
+    const int stage = ((cand * kBM + extra_max) * 128 + 1023) / 1024 * 1024;
+    if (units >= 2 * static_cast<int64_t>(g_num_sms) && conv_config_smem(d->block_n, stage) <= 227 * 1024) {
+      mt = cand;
+      break;
+    }
+  }
+  if (g_force_mt != 0) {
+    mt = g_force_mt;
+    if (mt > mt_max || (d->block_n == 16 && mt == 2)) { delete pl; return fail(IDF_ERR_ARG, "forced MT not available"); }
+  }
+  p.a_stage_bytes = ((mt * kBM + extra_max) * 128 + 1023) / 1024 * 1024;
+  if (conv_config_smem(d->block_n, p.a_stage_bytes) > 227 * 1024) {
+    delete pl;
+    return fail(IDF_ERR_ARG, "halo does not fit in shared memory (extra rows %d)", extra_max);
+  }
+  p.m_super = static_cast<int32_t>((m_tiles + mt - 1) / mt);
+  for (int i = 0; i < d->n_src; ++i) {
+    rc = encode_2d(&p.tmA[i], d->src[i], d->src_rows[i], d->src_ld[i], kBM);
+    if (rc != IDF_OK) { delete pl; return rc; }
+    if (p.extra_rows[i] > 0) {
+      if (p.extra_rows[i] > 256) { delete pl; return fail(IDF_ERR_ARG, "tap spread too large for one TMA box"); }
+      rc = encode_2d(&p.tmAx[i], d->src[i], d->src_rows[i], d->src_ld[i], p.extra_rows[i]);
+      if (rc != IDF_OK) { delete pl; return rc; }
+    }
+  }
+  rc = encode_2d(&p.tmB, d->weight, d->cout_pad, d->num_kb * kBK, d->block_n);
+  if (rc != IDF_OK) { delete pl; return rc; }
   p.cout = d->cout;
   p.epilogue = d->epilogue;
   p.bias = d->bias;
@@ -149,8 +229,10 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   p.step_ptr = d->step_ptr;
   if (p.bias == nullptr) { delete pl; return fail(IDF_ERR_ARG, "bias is null"); }
   pl->block_n = d->block_n;
-  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
-  pl->grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+  pl->mt = mt;
+  pl->tiles = m_tiles * p.n_tiles;
+  const long long units = static_cast<long long>(p.m_super) * p.n_tiles;
+  pl->grid = static_cast<int>(units < g_num_sms ? units : g_num_sms);
   *out_plan = pl;
   return IDF_OK;
 }
@@ -161,12 +243,12 @@ int idf_conv_plan_destroy(idf_conv_plan* plan) {
 }
 
 int64_t idf_conv_plan_tiles(const idf_conv_plan* plan) {
-  return plan ? static_cast<int64_t>(plan->params.m_tiles) * plan->params.n_tiles : 0;
+  return plan ? plan->tiles : 0;
 }
 
 int idf_conv_run(const idf_conv_plan* plan, idf_stream_t stream) {
   if (plan == nullptr) return fail(IDF_ERR_ARG, "null plan");
-  cudaError_t e = launch_conv_igemm(plan->params, plan->block_n, plan->grid, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_conv_igemm(plan->params, plan->block_n, plan->mt, plan->grid, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "conv_igemm launch");
   return IDF_OK;
 }
@@ -181,8 +263,18 @@ int idf_adagn_silu_fwd(const idf_adagn_args* a, idf_stream_t stream) {
 int idf_attn_fwd(const void* qkv, void* out, int32_t batch, int32_t H, int32_t W, int32_t d, float scale,
                  idf_stream_t stream) {
   if (qkv == nullptr || out == nullptr) return fail(IDF_ERR_ARG, "null argument");
-  cudaError_t e = launch_attn(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), batch, H, W, d, scale,
-                              reinterpret_cast<cudaStream_t>(stream));
+  int rc = ensure_init();
+  if (rc != IDF_OK) return rc;
+  cudaError_t e;
+  if (g_attn_impl == 1) {   // v1: thread-gathered operands, V transposed in shared memory
+    e = launch_attn(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), batch, H, W, d, scale,
+                    reinterpret_cast<cudaStream_t>(stream));
+  } else {                  // v2: TMA boxes per image row, V as MN-major operand
+    CUtensorMap tm;
+    rc = encode_2d(&tm, qkv, static_cast<int64_t>(batch) * (H + 1) * (W + 1), 3 * d, W);
+    if (rc != IDF_OK) return rc;
+    e = launch_attn_v2(tm, static_cast<bf16*>(out), batch, H, W, d, scale, reinterpret_cast<cudaStream_t>(stream));
+  }
   if (e != cudaSuccess) return cuda_fail(e, "attention launch (supported: d=128, H*W in {64,256})");
   return IDF_OK;
 }

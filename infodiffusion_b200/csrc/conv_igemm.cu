@@ -1,58 +1,131 @@
-// Implicit-GEMM convolution for sm_100a: TMA-fed, tcgen05.mma with TMEM accumulators,
-// warp-specialised persistent kernel.  See include/idf_b200.h for the contract.
+// Implicit-GEMM convolution for sm_100a, v2: halo-resident A operand, tcgen05.mma, TMEM accumulators.
+// See include/idf_b200.h for the contract.
 //
-// Roles (256 threads):  warp 0 = TMA producer (1 thread)   warp 1 = UMMA issuer (1 thread)
-//                       warp 2 = TMEM allocator            warps 4..7 = epilogue (TMEM -> regs -> HBM)
-// Pipelines: smem ring full/empty (TMA <-> UMMA), TMEM accumulator full/empty x2 (UMMA <-> epilogue).
+// Why v2: the v1 kernel loaded one [128 x 64] A tile per (tap, channel-chunk) and was bound by
+// L2->SM operand traffic (ncu: 12 TB/s from L2, tensor pipe 41-44 %).  In the pad-flat layout the nine
+// taps of a 3x3 conv are the SAME rows shifted by a constant, and a K-major SWIZZLE_128B UMMA
+// descriptor may start at any 128-byte row (the swizzle is a function of the absolute shared-memory
+// address; verified with tools/probe_shift.py).  So per 64-channel chunk the CTA loads ONE halo
+//   rows [row0 + lo, row0 + 128*MT + hi)        (lo/hi = min/max tap offset, +-(W+2) for 3x3)
+// and every (tap, m) operand is a descriptor into it.  One CTA owns MT consecutive 128-row tiles
+// (MT accumulators in TMEM), so each streamed weight tile B[BN x 64] feeds MT MMAs as well.
+// Operand bytes per MMA drop 3-7x (e.g. 64->64 @64^2: 221 KB -> 33 KB + weights per 128 rows).
 //
-// One tile = 128 pad-flat output rows x BN output channels.  For k-block kb the A operand is the
-// [128 x 64] slice  src[kb_src][row0 + kb_rowoff : +128, kb_c0 : +64]  (TMA zero-fills rows outside
-// the tensor) and the B operand is Wp[n0 : n0+BN, 64*kb : 64*kb+64]; both land in shared memory in
-// the K-major 128B-swizzled layout that the UMMA descriptors of ptx.cuh describe.
+// Roles (384 threads): warp 0 = A (halo) TMA producer     warp 3 = B (weights) TMA producer
+//                      warp 1 = UMMA issuer (1 thread)    warp 2 = TMEM allocator
+//                      warps 4..11 = epilogue (two warps per TMEM lane quarter)
+// Pipelines: A halo stages x2, B ring x6-8 (full/empty mbarriers), TMEM accumulator sets x2.
 #include "kernels.cuh"
 
 namespace idf {
 
-template <int BN>
-struct ConvCfg {
-  static constexpr int STAGES = (BN == 128) ? 6 : 8;
-  static constexpr uint32_t A_BYTES = kBM * kBK * 2;
+__host__ __device__ constexpr int conv_b_stages(int bn) { return bn == 16 ? 8 : 6; }
+
+template <int BN, int MT>
+struct HaloCfg {
+  static constexpr int A_STAGES = 2;
+  static constexpr int B_STAGES = conv_b_stages(BN);
   static constexpr uint32_t B_BYTES = BN * kBK * 2;
-  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr uint32_t ACC_COLS = MT * BN;                       // one accumulator set
+  static constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64
+                                        : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
+  static_assert(2 * ACC_COLS <= 512, "accumulators do not fit in TMEM");
+  static constexpr int NBARS = 2 * A_STAGES + 2 * B_STAGES + 4;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = ConvCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+__host__ __device__ inline uint32_t conv_smem_bytes(int a_stage_bytes, int a_stages, int b_stages, int b_bytes) {
+  return static_cast<uint32_t>(a_stages * a_stage_bytes + b_stages * b_bytes + 512 /*barriers*/ + 1024 /*align*/);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// epilogue for one (accumulator m, 32-column chunk) work item held in registers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, const uint32_t (&v)[32], int64_t r,
+                                                    int col0) {
+  const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = __ldg(bp + j);
+    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+  }
+  if (p.residual != nullptr) {
+    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + r * p.res_ld + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 u = __ldg(rp + j);
+      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+      f[8 * j + 0] += a0.x; f[8 * j + 1] += a0.y; f[8 * j + 2] += a1.x; f[8 * j + 3] += a1.y;
+      f[8 * j + 4] += a2.x; f[8 * j + 5] += a2.y; f[8 * j + 6] += a3.x; f[8 * j + 7] += a3.y;
+    }
+  }
+  uint4* op = reinterpret_cast<uint4*>(p.out + r * p.out_ld + col0);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+    u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+    u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+    u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+    op[j] = u;
+  }
+}
+
+__device__ __forceinline__ void epilogue_narrow(const ConvKernelParams& p, const uint32_t (&v)[16], int img, int y,
+                                                int x, float cx, float ce, float cn) {
+  const int64_t plane = static_cast<int64_t>(p.H) * p.W;
+  const int64_t base = static_cast<int64_t>(img) * p.cout * plane + static_cast<int64_t>(y) * p.W + x;
+#pragma unroll
+  for (int ch = 0; ch < 16; ++ch) {
+    if (ch < p.cout) {
+      const float e = __uint_as_float(v[ch]) + __ldg(p.bias + ch);
+      const int64_t o = base + ch * plane;
+      if (p.epilogue == IDF_EPI_SAMPLER) {
+        const float xv = p.x_io[o];
+        const float nz = (p.noise != nullptr) ? __ldg(p.noise + o) : 0.f;
+        p.x_io[o] = cx * xv + ce * e + cn * nz;
+        if (p.out_f32 != nullptr) p.out_f32[o] = e;
+      } else {
+        p.out_f32[o] = e;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int MT>
+__global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant__ ConvKernelParams p) {
+  using Cfg = HaloCfg<BN, MT>;
+  constexpr int AS = Cfg::A_STAGES, BS = Cfg::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smA = smem;
-  uint8_t* smB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* smA = smem;                                            // AS halo stages
+  uint8_t* smB = smem + AS * p.a_stage_bytes;                     // BS weight tiles
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smB + BS * Cfg::B_BYTES);
+  uint64_t* a_empty = a_full + AS;
+  uint64_t* b_full = a_empty + AS;
+  uint64_t* b_empty = b_full + BS;
+  uint64_t* tfull = b_empty + BS;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < p.n_src; ++i) tma_prefetch_desc(&p.tmA[i]);
+    for (int i = 0; i < p.n_src; ++i) {
+      tma_prefetch_desc(&p.tmA[i]);
+      if (p.extra_rows[i] > 0) tma_prefetch_desc(&p.tmAx[i]);
+    }
     tma_prefetch_desc(&p.tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar + s, 1);
-      mbar_init(empty_bar + s, 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar + a, 1);
-      mbar_init(tempty_bar + a, 128);
-    }
+    for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < BS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 256); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -64,24 +137,43 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total = p.m_super * p.n_tiles;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ A producer: one halo per group
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles;
-        const int nt = tile - mt * p.n_tiles;
-        const int row0 = mt * kBM;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(empty_bar + stage, phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar + stage, Cfg::STAGE_BYTES);
-          tma_load_2d(smA + stage * Cfg::A_BYTES, &p.tmA[p.kb_src[kb]], full_bar + stage, p.kb_c0[kb],
-                      row0 + p.kb_rowoff[kb]);
-          tma_load_2d(smB + stage * Cfg::B_BYTES, &p.tmB, full_bar + stage, kb * kBK, nt * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int st = blockIdx.x; st < total; st += gridDim.x) {
+        const int ms = st / p.n_tiles;
+        const int row0 = ms * (MT * kBM);
+        for (int g = 0; g < p.n_groups; ++g) {
+          const int src = p.g_src[g];
+          const int ex = p.extra_rows[src];
+          mbar_wait(a_empty + sa, pa ^ 1u);
+          mbar_arrive_expect_tx(a_full + sa, static_cast<uint32_t>((MT * kBM + ex) * 128));
+          uint8_t* dst = smA + sa * p.a_stage_bytes;
+          const int r = row0 + p.g_lo[g];
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+            tma_load_2d(dst + m * (kBM * 128), &p.tmA[src], a_full + sa, p.g_c0[g], r + m * kBM);
+          if (ex > 0) tma_load_2d(dst + MT * (kBM * 128), &p.tmAx[src], a_full + sa, p.g_c0[g], r + MT * kBM);
+          if (++sa == AS) { sa = 0; pa ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ B producer: one weight tile per tap
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t pb = 0;
+      for (int st = blockIdx.x; st < total; st += gridDim.x) {
+        const int nt = st % p.n_tiles;
+        for (int t = 0; t < p.n_taps; ++t) {
+          mbar_wait(b_empty + sb, pb ^ 1u);
+          mbar_arrive_expect_tx(b_full + sb, Cfg::B_BYTES);
+          tma_load_2d(smB + sb * Cfg::B_BYTES, &p.tmB, b_full + sb, p.t_kb[t] * kBK, nt * BN);
+          if (++sb == BS) { sb = 0; pb ^= 1u; }
         }
       }
     }
@@ -89,35 +181,45 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
     // ------------------------------------------------------------------ UMMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(kBM, BN, kFmtBF16);
-      int stage = 0;
-      uint32_t phase = 0;
-      int iter = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      int sa = 0, sb = 0, iter = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
         const int as = iter & 1;
-        const uint32_t aphase = (iter >> 1) & 1u;
-        mbar_wait(tempty_bar + as, aphase ^ 1u);  // epilogue has drained this accumulator
+        mbar_wait(tempty + as, ((iter >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(full_bar + stage, phase);
-          tc_fence_after();
-          const uint64_t da = umma_desc_k_sw128(smem_u32(smA + stage * Cfg::A_BYTES));
-          const uint64_t db = umma_desc_k_sw128(smem_u32(smB + stage * Cfg::B_BYTES));
+        const uint32_t d0 = tmem_base + static_cast<uint32_t>(as * Cfg::ACC_COLS);
+        int t = 0;
+        for (int g = 0; g < p.n_groups; ++g) {
+          mbar_wait(a_full + sa, pa);
+          const uint32_t a_base = smem_u32(smA + sa * p.a_stage_bytes);
+          const int t_end = t + p.g_ntaps[g];
+          for (; t < t_end; ++t) {
+            mbar_wait(b_full + sb, pb);
+            tc_fence_after();
+            const uint64_t db = umma_desc_k_sw128(smem_u32(smB + sb * Cfg::B_BYTES));
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // +32 bytes (16 bf16) along K inside the 128B swizzle atom == +2 in the (addr>>4) field
-            umma_f16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                     (kb | k) != 0 ? 1u : 0u);
+            for (int m = 0; m < MT; ++m) {
+              // tap view: rows [t_rel + 128 m, +128) of the halo; any 128-byte row start is legal
+              const uint64_t da = umma_desc_k_sw128(a_base + static_cast<uint32_t>((p.t_rel[t] + m * kBM) * 128));
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k)
+                umma_f16(d0 + static_cast<uint32_t>(m * BN), da + static_cast<uint64_t>(2 * k),
+                         db + static_cast<uint64_t>(2 * k), idesc, (t | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(b_empty + sb);
+            if (++sb == BS) { sb = 0; pb ^= 1u; }
           }
-          umma_commit(empty_bar + stage);                          // smem slot free once these MMAs retire
-          if (kb == p.num_kb - 1) umma_commit(tfull_bar + as);     // accumulator complete
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          umma_commit(a_empty + sa);
+          if (++sa == AS) { sa = 0; pa ^= 1u; }
         }
+        umma_commit(tfull + as);
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int e = warp - 4;
+    const int q = e & 3;      // TMEM lane quarter (== warp % 4)
+    const int half = e >> 2;  // which half of the (m, chunk) work items
     float cx = 0.f, ce = 0.f, cn = 0.f;
     if (p.epilogue == IDF_EPI_SAMPLER) {
       const int step = p.step_ptr ? *p.step_ptr : 0;
@@ -125,95 +227,43 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       ce = p.coef[3 * step + 1];
       cn = p.coef[3 * step + 2];
     }
+    constexpr int CHUNKS = (BN >= 32) ? BN / 32 : 1;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      const int mt = tile / p.n_tiles;
-      const int nt = tile - mt * p.n_tiles;
+    for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
+      const int ms = st / p.n_tiles;
+      const int nt = st - ms * p.n_tiles;
       const int as = iter & 1;
-      const uint32_t aphase = (iter >> 1) & 1u;
-      mbar_wait(tfull_bar + as, aphase);
+      mbar_wait(tfull + as, (iter >> 1) & 1u);
       tc_fence_after();
-
-      const int64_t r = static_cast<int64_t>(mt) * kBM + q * 32 + lane;
-      bool valid = r < p.rows;
-      int img = 0, y = 0, x = 0;
-      if (valid) {
-        const int rq = static_cast<int>(r / p.Wp);
-        x = static_cast<int>(r - static_cast<int64_t>(rq) * p.Wp);
-        img = rq / p.Hp;
-        y = rq - img * p.Hp;
-        valid = (x < p.W) && (y < p.H);
-      }
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
-
-      if constexpr (BN >= 32) {
+      const uint32_t t0 = tmem_base + static_cast<uint32_t>(as * Cfg::ACC_COLS) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
-          tmem_ld_wait();
-          if (valid) {
-            const int col0 = nt * BN + c * 32;
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(bp + j);
-              f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
-            }
-            if (p.residual != nullptr) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + r * p.res_ld + col0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 u = __ldg(rp + j);
-                const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z),
-                             a3 = unpack_bf16x2(u.w);
-                f[8 * j + 0] += a0.x; f[8 * j + 1] += a0.y; f[8 * j + 2] += a1.x; f[8 * j + 3] += a1.y;
-                f[8 * j + 4] += a2.x; f[8 * j + 5] += a2.y; f[8 * j + 6] += a3.x; f[8 * j + 7] += a3.y;
-              }
-            }
-            uint4* op = reinterpret_cast<uint4*>(p.out + r * p.out_ld + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-              u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              op[j] = u;
-            }
-          }
-        }
-      } else {
-        // BN == 16: narrow outputs (eps / encoder map), fp32 NCHW store or fused sampler update
-        uint32_t v[16];
-        tmem_ld_32x16(taddr, v);
-        tmem_ld_wait();
+      for (int item = half; item < MT * CHUNKS; item += 2) {
+        const int m = item / CHUNKS;
+        const int c = item - m * CHUNKS;
+        const int64_t r = (static_cast<int64_t>(ms) * MT + m) * kBM + q * 32 + lane;
+        bool valid = r < p.rows;
+        int img = 0, y = 0, x = 0;
         if (valid) {
-          const int64_t plane = static_cast<int64_t>(p.H) * p.W;
-          const int64_t base = static_cast<int64_t>(img) * p.cout * plane + static_cast<int64_t>(y) * p.W + x;
-#pragma unroll
-          for (int ch = 0; ch < 16; ++ch) {
-            if (ch < p.cout) {
-              const float e = __uint_as_float(v[ch]) + __ldg(p.bias + ch);
-              const int64_t o = base + ch * plane;
-              if (p.epilogue == IDF_EPI_SAMPLER) {
-                const float xv = p.x_io[o];
-                const float nz = (p.noise != nullptr) ? __ldg(p.noise + o) : 0.f;
-                p.x_io[o] = cx * xv + ce * e + cn * nz;
-                if (p.out_f32 != nullptr) p.out_f32[o] = e;
-              } else {
-                p.out_f32[o] = e;
-              }
-            }
-          }
+          const int rq = static_cast<int>(r / p.Wp);
+          x = static_cast<int>(r - static_cast<int64_t>(rq) * p.Wp);
+          img = rq / p.Hp;
+          y = rq - img * p.Hp;
+          valid = (x < p.W) && (y < p.H);
+        }
+        if constexpr (BN >= 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t0 + static_cast<uint32_t>(m * BN + c * 32), v);
+          tmem_ld_wait();
+          if (valid) epilogue_bf16_chunk(p, v, r, nt * BN + c * 32);
+        } else {
+          uint32_t v[16];
+          tmem_ld_32x16(t0 + static_cast<uint32_t>(m * BN), v);
+          tmem_ld_wait();
+          if (valid) epilogue_narrow(p, v, img, y, x, cx, ce, cn);
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar + as);
+      mbar_arrive(tempty + as);
     }
   }
 
@@ -225,27 +275,38 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
   }
 }
 
-template <int BN>
-static cudaError_t launch_bn(const ConvKernelParams& p, int grid, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(Cfg::SMEM_BYTES));
+template <int BN, int MT>
+static cudaError_t launch_cfg(const ConvKernelParams& p, int grid, cudaStream_t stream) {
+  using Cfg = HaloCfg<BN, MT>;
+  const uint32_t smem = conv_smem_bytes(p.a_stage_bytes, Cfg::A_STAGES, Cfg::B_STAGES, Cfg::B_BYTES);
+  static uint32_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_smem = smem;
   }
-  conv_igemm_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+  conv_halo_kernel<BN, MT><<<grid, 384, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int grid, cudaStream_t stream) {
-  switch (block_n) {
-    case 128: return launch_bn<128>(p, grid, stream);
-    case 64: return launch_bn<64>(p, grid, stream);
-    case 16: return launch_bn<16>(p, grid, stream);
+cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, int grid, cudaStream_t stream) {
+  const int key = block_n * 10 + mt;
+  switch (key) {
+    case 1281: return launch_cfg<128, 1>(p, grid, stream);
+    case 1282: return launch_cfg<128, 2>(p, grid, stream);
+    case 641: return launch_cfg<64, 1>(p, grid, stream);
+    case 642: return launch_cfg<64, 2>(p, grid, stream);
+    case 644: return launch_cfg<64, 4>(p, grid, stream);
+    case 161: return launch_cfg<16, 1>(p, grid, stream);
+    case 164: return launch_cfg<16, 4>(p, grid, stream);
     default: return cudaErrorInvalidValue;
   }
+}
+
+// shared-memory need of a configuration (host side, for plan validation)
+uint32_t conv_config_smem(int block_n, int a_stage_bytes) {
+  return conv_smem_bytes(a_stage_bytes, 2, conv_b_stages(block_n), block_n * kBK * 2);
 }
 
 }  // namespace idf

@@ -10,15 +10,25 @@ typedef __nv_bfloat16 bf16;
 constexpr int kBM = 128;  // output rows (pixels) per tile == UMMA M
 constexpr int kBK = 64;   // K elements per k-block == one 128-byte swizzle row
 
+constexpr int kMaxGroups = 16;
+
 struct alignas(64) ConvKernelParams {
-  CUtensorMap tmA[IDF_CONV_MAX_SRC];
-  CUtensorMap tmB;
+  CUtensorMap tmA[IDF_CONV_MAX_SRC];    // box {64, 128 rows}
+  CUtensorMap tmAx[IDF_CONV_MAX_SRC];   // box {64, extra_rows[src]} -- tail of the halo
+  CUtensorMap tmB;                      // box {64, BN}
   int32_t n_src;
-  int32_t num_kb;
-  int32_t kb_src[IDF_CONV_MAX_KB];
-  int32_t kb_c0[IDF_CONV_MAX_KB];
-  int32_t kb_rowoff[IDF_CONV_MAX_KB];
-  int32_t m_tiles, n_tiles;
+  int32_t extra_rows[IDF_CONV_MAX_SRC]; // halo rows beyond 128*MT (multiple of 8, 0 for 1x1 sources)
+  // K loop = groups (one halo load each: source, 64-channel slice, cluster of taps) x taps
+  int32_t n_groups;
+  int32_t g_src[kMaxGroups];
+  int32_t g_c0[kMaxGroups];
+  int32_t g_lo[kMaxGroups];             // row offset of the halo start relative to the tile's first row
+  int32_t g_ntaps[kMaxGroups];
+  int32_t n_taps;                       // total taps == number of 64-wide k-blocks
+  int32_t t_rel[IDF_CONV_MAX_KB];       // tap row offset relative to its group's halo start (>= 0)
+  int32_t t_kb[IDF_CONV_MAX_KB];        // k-block index of the tap in the packed weight matrix
+  int32_t a_stage_bytes;                // bytes of one halo stage (multiple of 1024)
+  int32_t m_super, n_tiles;             // super tiles of MT*128 rows; N tiles
   int64_t rows;
   int32_t Hp, Wp, H, W;
   int32_t cout;
@@ -35,9 +45,12 @@ struct alignas(64) ConvKernelParams {
   const int32_t* step_ptr;
 };
 
-cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int grid, cudaStream_t stream);
+cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, int grid, cudaStream_t stream);
+uint32_t conv_config_smem(int block_n, int a_stage_bytes);
 cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream);
 cudaError_t launch_attn(const bf16* qkv, bf16* out, int batch, int H, int W, int d, float scale, cudaStream_t stream);
+cudaError_t launch_attn_v2(const CUtensorMap& tm, bf16* out, int batch, int H, int W, int d, float scale,
+                           cudaStream_t stream);
 cudaError_t launch_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy,
                               int M, int N, int K, int silu_in, cudaStream_t stream);
 cudaError_t launch_gather_rows(const float* table, const int64_t* idx, float* y, int M, int N, cudaStream_t stream);

@@ -8,41 +8,48 @@ namespace idf {
 // head im2col: x NCHW fp32 [B,C,H,W] -> bf16 pad-flat [rows, 64], k = tap*C + c for 3x3/pad 1
 // one thread = one interior pixel x one 16-byte granule (8 k's)
 // ----------------------------------------------------------------------------------------------
-__global__ void im2col_head_kernel(const float* __restrict__ x, bf16* __restrict__ out, int batch, int C, int H,
-                                   int W) {
-  const long long total = static_cast<long long>(batch) * H * W * 8;
-  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i >= total) return;
-  const int g = static_cast<int>(i & 7);
-  const long long pix = i >> 3;
+template <int C>
+__global__ void __launch_bounds__(256) im2col_head_kernel(const float* __restrict__ x, bf16* __restrict__ out,
+                                                          int batch, int H, int W) {
+  // one thread = one pixel: 9*C neighbour loads (coalesced along x across the warp), one 128-byte row out
+  const long long total = static_cast<long long>(batch) * H * W;
+  const long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (pix >= total) return;
   const int px = static_cast<int>(pix % W);
   const int py = static_cast<int>((pix / W) % H);
   const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-  float f[8];
+  const float* xn = x + static_cast<long long>(n) * C * H * W;
+  uint32_t packed[32];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = g * 8 + j;
-    float v = 0.f;
-    if (k < 9 * C) {
-      const int tap = k / C, c = k - tap * C;
-      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(x + ((static_cast<long long>(n) * C + c) * H + yy) * W + xx);
-    }
-    f[j] = v;
+  for (int i = 0; i < 32; ++i) packed[i] = 0u;
+  float vals[9 * C + 1];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+    const bool in = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      vals[tap * C + c] = in ? __ldg(xn + (static_cast<long long>(c) * H + yy) * W + xx) : 0.f;
   }
-  uint4 o;
-  o.x = pack_bf16x2(f[0], f[1]);
-  o.y = pack_bf16x2(f[2], f[3]);
-  o.z = pack_bf16x2(f[4], f[5]);
-  o.w = pack_bf16x2(f[6], f[7]);
+  vals[9 * C] = 0.f;
+#pragma unroll
+  for (int k = 0; k < (9 * C + 1) / 2; ++k) packed[k] = pack_bf16x2(vals[2 * k], vals[2 * k + 1]);
   const long long row = (static_cast<long long>(n) * (H + 1) + py) * (W + 1) + px;
-  *reinterpret_cast<uint4*>(out + row * 64 + g * 8) = o;
+  uint4* o = reinterpret_cast<uint4*>(out + row * 64);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) o[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
 }
 
 cudaError_t launch_im2col_head(const float* x, bf16* out, int batch, int C, int H, int W, cudaStream_t stream) {
-  if (9 * C > 64) return cudaErrorInvalidValue;
-  const long long total = static_cast<long long>(batch) * H * W * 8;
-  im2col_head_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, out, batch, C, H, W);
+  const long long total = static_cast<long long>(batch) * H * W;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  switch (C) {
+    case 1: im2col_head_kernel<1><<<grid, 256, 0, stream>>>(x, out, batch, H, W); break;
+    case 2: im2col_head_kernel<2><<<grid, 256, 0, stream>>>(x, out, batch, H, W); break;
+    case 3: im2col_head_kernel<3><<<grid, 256, 0, stream>>>(x, out, batch, H, W); break;
+    case 4: im2col_head_kernel<4><<<grid, 256, 0, stream>>>(x, out, batch, H, W); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 

@@ -126,6 +126,40 @@ def test_conv3x3(lib, cin, cout, H, B, res):
     assert_close(unpf(out, B, H, H), ref, what=f"conv3x3 {cin}->{cout}@{H} B={B} res={res}")
 
 
+@pytest.mark.parametrize("cin,cout,H,B,mt", [(64, 64, 16, 3, 2), (64, 64, 16, 3, 4), (128, 128, 16, 3, 2),
+                                              (128, 64, 8, 5, 4), (256, 128, 8, 4, 2)])
+def test_conv3x3_forced_tiles_per_cta(lib, cin, cout, H, B, mt):
+    """Every (BN, MT) instantiation of the halo kernel, including partially filled work units."""
+    from infodiffusion_b200 import layout
+    g = torch.Generator(device=DEV).manual_seed(100 + cin + cout + H + mt)
+    x = rbf(torch.randn(B, cin, H, H, device=DEV, generator=g))
+    w = rbf(torch.randn(cout, cin, 3, 3, device=DEV, generator=g) * (2.0 / (9 * cin)) ** 0.5)
+    b = torch.randn(cout, device=DEV, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    check(lib.idf_set_option(b"conv_force_mt", mt))
+    try:
+        out = run_conv(lib, [pf(x)], layout.taps3x3(cin, H, H), layout.pack_conv3x3(w).to(BF).contiguous(), b, B, H,
+                       cout, 128 if cout % 128 == 0 else 64)
+    finally:
+        check(lib.idf_set_option(b"conv_force_mt", 0))
+    assert pad_is_zero(out, B, H, H)
+    assert_close(unpf(out, B, H, H), ref, what=f"conv3x3 {cin}->{cout}@{H} MT={mt}")
+
+
+def test_conv3x3_large_auto_tiles(lib):
+    """Sizes at which the planner itself picks MT = 4 (BN = 64) and MT = 2 (BN = 128)."""
+    from infodiffusion_b200 import layout
+    for (cin, cout, H, B) in [(64, 64, 64, 40), (128, 128, 32, 80)]:
+        g = torch.Generator(device=DEV).manual_seed(7 + cin)
+        x = rbf(torch.randn(B, cin, H, H, device=DEV, generator=g))
+        w = rbf(torch.randn(cout, cin, 3, 3, device=DEV, generator=g) * (2.0 / (9 * cin)) ** 0.5)
+        b = torch.randn(cout, device=DEV, generator=g)
+        ref = F.conv2d(x, w, b, padding=1)          # fp32 (TF32 disabled by the fixture)
+        out = run_conv(lib, [pf(x)], layout.taps3x3(cin, H, H), layout.pack_conv3x3(w).to(BF).contiguous(), b, B, H,
+                       cout, 128 if cout % 128 == 0 else 64)
+        assert_close(unpf(out, B, H, H), ref, what=f"conv3x3 {cin}->{cout}@{H} B={B}")
+
+
 def test_conv1x1_qkv(lib):
     from infodiffusion_b200 import layout
     g = torch.Generator(device=DEV).manual_seed(5)
@@ -285,6 +319,16 @@ def test_attention(lib, H, B):
     assert pad_is_zero(out, B, H, H)
     # P is rounded to bf16 before the PV product: 2^-9 per probability, averaged over S keys
     assert_close(unpf(out, B, H, H), ref, rel_l2=6e-3, max_rel=2e-2, what=f"attention S={S}")
+    # the thread-gathered v1 kernel must agree with the TMA-fed default bit for bit (same MMAs, same order)
+    out1 = torch.zeros_like(out)
+    check(lib.idf_set_option(b"attn_impl", 1))
+    try:
+        check(lib.idf_attn_fwd(qkv.data_ptr(), out1.data_ptr(), B, H, H, d, d ** -0.5, stream()))
+        torch.cuda.synchronize()
+    finally:
+        check(lib.idf_set_option(b"attn_impl", 2))
+    assert_close(unpf(out1, B, H, H), ref, rel_l2=6e-3, max_rel=2e-2, what=f"attention v1 S={S}")
+    assert torch.equal(out1, out)
 
 
 def test_linear_and_gather(lib):
