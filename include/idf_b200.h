@@ -97,6 +97,10 @@ typedef struct {
   const float* noise;                 /* NCHW fp32 (mode 2; may be NULL => cn ignored)           */
   const float* coef;                  /* [n_steps, 3] fp32 (mode 2)                              */
   const int32_t* step_ptr;            /* device scalar (mode 2)                                  */
+  /* optional (IDF_EPI_BF16): per-tile GroupNorm partial sums of the stored (bf16-rounded) output,
+   * fp32 [ceil(rows/128)][3][cout][2] = (sum, sumsq) over the rows of 128-row tile t that belong to
+   * image (t*128 / ((H+1)*(W+1)) + slot); consumed by idf_adagn_silu_fwd (stats0/stats1).       */
+  float* stats_out;
 } idf_conv_desc;
 
 typedef struct idf_conv_plan idf_conv_plan;
@@ -127,6 +131,9 @@ typedef struct {
   const float* mod_z; int64_t mod_z_step_stride; int64_t mod_z_batch_stride;
   const int32_t* step_ptr;
   int32_t apply_silu;
+  /* optional: per-tile partial sums written by the producing convolution (idf_conv_desc.stats_out).
+   * When given for every source the kernel is a single streaming sweep (no statistics pass).     */
+  const float* stats0; const float* stats1;
 } idf_adagn_args;
 int idf_adagn_silu_fwd(const idf_adagn_args* args, idf_stream_t stream);
 

@@ -42,6 +42,7 @@ class ConvDesc(C.Structure):
         ("noise", C.c_void_p),
         ("coef", C.c_void_p),
         ("step_ptr", C.c_void_p),
+        ("stats_out", C.c_void_p),
     ]
 
 
@@ -57,6 +58,7 @@ class AdaGNArgs(C.Structure):
         ("mod_z", C.c_void_p), ("mod_z_step_stride", C.c_int64), ("mod_z_batch_stride", C.c_int64),
         ("step_ptr", C.c_void_p),
         ("apply_silu", C.c_int32),
+        ("stats0", C.c_void_p), ("stats1", C.c_void_p),
     ]
 
 

@@ -43,6 +43,9 @@ struct AdaGNParams {
   long long mod_z_step_stride, mod_z_batch_stride;
   const int* step_ptr;
   int apply_silu;
+  const float* stats0;   // per-tile partial sums from the producing conv (streaming variant)
+  const float* stats1;
+  int slice_rows;        // rows per CTA of the streaming variant
 };
 
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier
@@ -217,6 +220,121 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_kernel(const AdaGNParams p)
   cluster.barrier_wait();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Streaming variant: the GroupNorm statistics arrive as per-tile partial sums written by the epilogue
+// of the convolution that produced the tensor (conv_igemm.cu), so this kernel is a single sweep:
+// fold partials -> (A, B) per channel, then y = silu(A*x + B) with 16-byte loads / stores, 4 in flight.
+// No clusters, no barriers in the hot loop, one HBM read + one HBM write.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNParams p) {
+  __shared__ float s_tot[2 * kMaxC];
+  __shared__ float s_mean[32], s_rstd[32];
+  __shared__ float2 s_ab[kMaxC];
+  const int n = blockIdx.y;
+  const int t = threadIdx.x;
+  const int C = p.C;
+  const int R = p.rows_per_img;
+
+  // per-channel totals over the 128-row tiles that intersect image n (fixed order: deterministic)
+  const int t_first = (n * R) / kBM;
+  const int t_last = ((n + 1) * R - 1) / kBM;
+  for (int ch = t; ch < C; ch += kAdaThreads) {
+    const bool first = ch < p.c0;
+    const float2* st = reinterpret_cast<const float2*>(first ? p.stats0 : p.stats1);
+    const int cs = first ? p.c0 : p.c1;
+    const int cc = first ? ch : ch - p.c0;
+    float sx = 0.f, sq = 0.f;
+    for (int tile = t_first; tile <= t_last; ++tile) {
+      const int slot = n - (tile * kBM) / R;
+      const float2 v = __ldg(st + (static_cast<long long>(tile) * 3 + slot) * cs + cc);
+      sx += v.x;
+      sq += v.y;
+    }
+    s_tot[ch] = sx;
+    s_tot[C + ch] = sq;
+  }
+  __syncthreads();
+  const int cpg = C / 32;
+  if (t < 32) {
+    float gs = 0.f, gq = 0.f;
+    for (int j = 0; j < cpg; ++j) { gs += s_tot[t * cpg + j]; gq += s_tot[C + t * cpg + j]; }
+    const float inv_cnt = 1.0f / (static_cast<float>(cpg) * p.H * p.W);
+    const float mean = gs * inv_cnt;
+    const float var = fmaxf(gq * inv_cnt - mean * mean, 0.f);
+    s_mean[t] = mean;
+    s_rstd[t] = rsqrtf(var + p.eps);
+  }
+  __syncthreads();
+  const int step = p.step_ptr ? *p.step_ptr : 0;
+  for (int ch = t; ch < C; ch += kAdaThreads) {
+    const int g = ch / cpg;
+    float A = s_rstd[g] * p.gamma[ch];
+    float B = p.beta[ch] - s_mean[g] * A;
+    if (p.mod_t != nullptr) {
+      const float* m = p.mod_t + step * p.mod_t_step_stride + n * p.mod_t_batch_stride;
+      const float sc = 1.0f + m[ch], sh = m[C + ch];
+      A *= sc;
+      B = B * sc + sh;
+    }
+    if (p.mod_z != nullptr) {
+      const float* m = p.mod_z + step * p.mod_z_step_stride + n * p.mod_z_batch_stride;
+      const float sc = 1.0f + m[ch], sh = m[C + ch];
+      A *= sc;
+      B = B * sc + sh;
+    }
+    s_ab[ch] = make_float2(A, B);
+  }
+  __syncthreads();
+
+  const int VPR = C >> 3;
+  const int rpp = kAdaThreads / VPR;
+  if (t >= rpp * VPR) return;
+  const int vl = t % VPR;
+  const int rsub = t / VPR;
+  const int v0 = p.c0 >> 3;
+  float A[8], B[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float2 ab = s_ab[vl * 8 + j]; A[j] = ab.x; B[j] = ab.y; }
+  const bool do_silu = p.apply_silu != 0;
+  const bool from0 = vl < v0;
+  const bf16* src = from0 ? (p.src0 + vl * 8) : (p.src1 + (vl - v0) * 8);
+  const int pitch = from0 ? p.c0 : p.c1;
+  const long long row_base = static_cast<long long>(n) * R;
+  const int r_begin = blockIdx.x * p.slice_rows;
+  const int r_end = min(R, r_begin + p.slice_rows);
+  const float inv_wp = 1.0f / static_cast<float>(p.Wp);
+  for (int r = r_begin + rsub; r < r_end; r += kUnroll * rpp) {
+    uint4 u[kUnroll];
+    bool ok[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {          // all loads first (memory-level parallelism)
+      const int rr = r + k * rpp;
+      const int y = __float2int_rd((static_cast<float>(rr) + 0.5f) * inv_wp);
+      const int x = rr - y * p.Wp;
+      ok[k] = (rr < r_end) && (x < p.W) && (y < p.H);      // pad rows: neither read nor written
+      if (ok[k]) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (row_base + rr) * pitch));
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      if (!ok[k]) continue;
+      const float2 a0 = unpack_bf16x2(u[k].x), a1 = unpack_bf16x2(u[k].y), a2 = unpack_bf16x2(u[k].z),
+                   a3 = unpack_bf16x2(u[k].w);
+      float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = fmaf(f[j], A[j], B[j]);
+        f[j] = do_silu ? __fdividef(v, 1.0f + __expf(-v)) : v;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(f[0], f[1]);
+      o.y = pack_bf16x2(f[2], f[3]);
+      o.z = pack_bf16x2(f[4], f[5]);
+      o.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(p.out + (row_base + r + k * rpp) * C + vl * 8) = o;
+    }
+  }
+}
+
 cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
   AdaGNParams p;
   p.src0 = static_cast<const bf16*>(a.src0);
@@ -233,6 +351,19 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
   p.step_ptr = a.step_ptr;
   p.apply_silu = a.apply_silu;
   if (p.C > kMaxC || p.C % 32 != 0 || p.c0 % 8 != 0 || p.c1 % 8 != 0 || a.batch <= 0) return cudaErrorInvalidValue;
+  p.stats0 = a.stats0;
+  p.stats1 = a.stats1;
+  p.slice_rows = 0;
+  if (p.stats0 != nullptr && (p.c1 == 0 || p.stats1 != nullptr)) {
+    // streaming variant: ~32 KB of rows per CTA
+    const long long bytes_s = static_cast<long long>(p.rows_per_img) * p.C * 2;
+    int slices = static_cast<int>((bytes_s + 32767) / 32768);
+    if (slices < 1) slices = 1;
+    p.slice_rows = (p.rows_per_img + slices - 1) / slices;
+    slices = (p.rows_per_img + p.slice_rows - 1) / p.slice_rows;
+    adagn_apply_kernel<<<dim3(slices, a.batch, 1), kAdaThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
 
   // cluster size: slices of <= ~72 KB (3 CTAs per SM) when possible, at most 8 CTAs (portable limit)
   const long long bytes = static_cast<long long>(p.rows_per_img) * p.C * 2;

@@ -204,6 +204,9 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
     return fail(IDF_ERR_ARG, "halo does not fit in shared memory (extra rows %d)", extra_max);
   }
   p.m_super = static_cast<int32_t>((m_tiles + mt - 1) / mt);
+  p.m_tiles = static_cast<int32_t>(m_tiles);
+  p.stats = (d->epilogue == IDF_EPI_BF16) ? d->stats_out : nullptr;
+  if (p.stats != nullptr && d->out_ld != d->cout) { delete pl; return fail(IDF_ERR_ARG, "stats_out needs out_ld == cout"); }
   for (int i = 0; i < d->n_src; ++i) {
     rc = encode_2d(&p.tmA[i], d->src[i], d->src_rows[i], d->src_ld[i], kBM);
     if (rc != IDF_OK) { delete pl; return rc; }

@@ -20,6 +20,28 @@
 namespace idf {
 
 __host__ __device__ constexpr int conv_b_stages(int bn) { return bn == 16 ? 8 : 6; }
+// GroupNorm partial-statistics exchange between the 4 epilogue warps of one work item:
+// [2 halves][4 lane quarters][3 image slots][32 columns] float2 (sum, sumsq)
+constexpr uint32_t kStatScratchBytes = 2 * 4 * 3 * 32 * 8;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Sum over the 32 lanes of a warp of 32 per-lane values: on return lane L holds the total of v[L] in v[0]
+// (butterfly transpose-reduce, 31 shuffles).
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = up ? v[j] : v[j + s];
+      const float keep = up ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
 
 template <int BN, int MT>
 struct HaloCfg {
@@ -34,14 +56,20 @@ struct HaloCfg {
 };
 
 __host__ __device__ inline uint32_t conv_smem_bytes(int a_stage_bytes, int a_stages, int b_stages, int b_bytes) {
-  return static_cast<uint32_t>(a_stages * a_stage_bytes + b_stages * b_bytes + 512 /*barriers*/ + 1024 /*align*/);
+  return static_cast<uint32_t>(a_stages * a_stage_bytes + b_stages * b_bytes + 512 /*barriers*/ +
+                               kStatScratchBytes + 1024 /*align*/);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // epilogue for one (accumulator m, 32-column chunk) work item held in registers
 // ---------------------------------------------------------------------------------------------------
+// Executed by all 32 lanes of an epilogue warp (invalid rows contribute zeros and store nothing).
+//   out = bf16(acc + bias (+ residual));  optional per-tile GroupNorm partials of the ROUNDED output:
+//   stats[tile][slot][col][2] = (sum, sumsq) over the tile's rows belonging to image (first image of the
+//   tile + slot), combined across the 4 lane-quarter warps in a fixed order (deterministic, no atomics).
 __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, const uint32_t (&v)[32], int64_t r,
-                                                    int col0) {
+                                                    bool valid, int col0, int slot, int tile, int q, int half,
+                                                    int lane, float2* scratch) {
   const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
   float f[32];
 #pragma unroll
@@ -52,7 +80,7 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
     f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
     f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
   }
-  if (p.residual != nullptr) {
+  if (p.residual != nullptr && valid) {
     const uint4* rp = reinterpret_cast<const uint4*>(p.residual + r * p.res_ld + col0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -62,15 +90,46 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
       f[8 * j + 4] += a2.x; f[8 * j + 5] += a2.y; f[8 * j + 6] += a3.x; f[8 * j + 7] += a3.y;
     }
   }
-  uint4* op = reinterpret_cast<uint4*>(p.out + r * p.out_ld + col0);
+  uint32_t pk[16];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 u;
-    u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-    u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-    u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-    u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-    op[j] = u;
+  for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+  if (valid) {
+    uint4* op = reinterpret_cast<uint4*>(p.out + r * p.out_ld + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) op[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  }
+  if (p.stats != nullptr) {
+    float2* my = scratch + ((half * 4 + q) * 3) * 32 + lane;
+#pragma unroll 1
+    for (int s = 0; s < 3; ++s) {
+      const bool mine = valid && (slot == s);
+      float2 res = make_float2(0.f, 0.f);
+      if (__any_sync(0xffffffffu, mine)) {       // warp-uniform
+        float a[32], b[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 w = unpack_bf16x2(pk[j]);
+          a[2 * j] = mine ? w.x : 0.f;
+          a[2 * j + 1] = mine ? w.y : 0.f;
+          b[2 * j] = a[2 * j] * a[2 * j];
+          b[2 * j + 1] = a[2 * j + 1] * a[2 * j + 1];
+        }
+        warp_transpose_reduce(a, lane);
+        warp_transpose_reduce(b, lane);
+        res = make_float2(a[0], b[0]);
+      }
+      my[s * 32] = res;
+    }
+    named_bar_sync(1 + half, 128);
+    if (q < 3 && tile < p.m_tiles) {               // warp q combines image slot q over the four quarters
+      const float2* sc = scratch + (half * 4 * 3 + q) * 32 + lane;
+      const float2 x0 = sc[0 * 96], x1 = sc[1 * 96], x2 = sc[2 * 96], x3 = sc[3 * 96];
+      float2 tot;
+      tot.x = (x0.x + x1.x) + (x2.x + x3.x);
+      tot.y = (x0.y + x1.y) + (x2.y + x3.y);
+      reinterpret_cast<float2*>(p.stats)[(static_cast<int64_t>(tile) * 3 + q) * p.out_ld + col0 + lane] = tot;
+    }
+    named_bar_sync(1 + half, 128);
   }
 }
 
@@ -111,6 +170,7 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
   uint64_t* tfull = b_empty + BS;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float2* stat_scratch = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(a_full) + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -240,7 +300,8 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
       for (int item = half; item < MT * CHUNKS; item += 2) {
         const int m = item / CHUNKS;
         const int c = item - m * CHUNKS;
-        const int64_t r = (static_cast<int64_t>(ms) * MT + m) * kBM + q * 32 + lane;
+        const int tile = ms * MT + m;
+        const int64_t r = static_cast<int64_t>(tile) * kBM + q * 32 + lane;
         bool valid = r < p.rows;
         int img = 0, y = 0, x = 0;
         if (valid) {
@@ -254,7 +315,8 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
           uint32_t v[32];
           tmem_ld_32x32(t0 + static_cast<uint32_t>(m * BN + c * 32), v);
           tmem_ld_wait();
-          if (valid) epilogue_bf16_chunk(p, v, r, nt * BN + c * 32);
+          const int slot = img - static_cast<int>((static_cast<int64_t>(tile) * kBM) / (p.Hp * p.Wp));
+          epilogue_bf16_chunk(p, v, r, valid, nt * BN + c * 32, slot, tile, q, half, lane, stat_scratch);
         } else {
           uint32_t v[16];
           tmem_ld_32x16(t0 + static_cast<uint32_t>(m * BN), v);

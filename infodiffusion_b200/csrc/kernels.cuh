@@ -29,6 +29,8 @@ struct alignas(64) ConvKernelParams {
   int32_t t_kb[IDF_CONV_MAX_KB];        // k-block index of the tap in the packed weight matrix
   int32_t a_stage_bytes;                // bytes of one halo stage (multiple of 1024)
   int32_t m_super, n_tiles;             // super tiles of MT*128 rows; N tiles
+  int32_t m_tiles;                      // 128-row tiles
+  float* stats;                         // optional [m_tiles][3][out_ld][2] GroupNorm partial sums of the output
   int64_t rows;
   int32_t Hp, Wp, H, W;
   int32_t cout;

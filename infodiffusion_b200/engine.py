@@ -49,10 +49,18 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 # ------------------------------------------------------------------------------------------------
 class Act:
     """A pad-flat bf16 activation buffer [phases * B*(H+1)*(W+1), C]."""
-    __slots__ = ("t", "H", "C", "phases", "rows")
+    __slots__ = ("t", "H", "C", "phases", "rows", "stats", "has_stats")
 
     def __init__(self, t, H, C, phases, rows):
         self.t, self.H, self.C, self.phases, self.rows = t, H, C, phases, rows
+        self.stats = None          # fp32 [ceil(rows/128), 3, C, 2] GroupNorm partial sums (written by conv epilogues)
+        self.has_stats = False     # True while `stats` describes the current contents of `t`
+
+    def stats_buffer(self) -> torch.Tensor:
+        if self.stats is None:
+            tiles = (self.rows + 127) // 128
+            self.stats = torch.zeros(tiles * 3 * self.C * 2, dtype=torch.float32, device=self.t.device)
+        return self.stats
 
 
 class Workspace:
@@ -69,7 +77,9 @@ class Workspace:
         key = (H, C_, phases)
         fl = self.free_lists.get(key)
         if fl:
-            return fl.pop()
+            a = fl.pop()
+            a.has_stats = False
+            return a
         rows = self.batch * (H + 1) * (H + 1)
         t = torch.zeros(phases * rows, C_, dtype=BF16, device=self.device)
         self.bytes += t.numel() * 2
@@ -148,7 +158,7 @@ class Plan:
     def conv(self, srcs: Sequence[Act], kblocks: Sequence[Tuple[int, int, int]], wp: torch.Tensor,
              bias: torch.Tensor, H: int, cout: int, block_n: int, out: Optional[Act] = None,
              residual: Optional[Act] = None, epilogue: int = EPI_BF16, out_f32=None, x_io=None, noise=None,
-             coef=None, step=None, real_macs_per_row: Optional[int] = None) -> None:
+             coef=None, step=None, real_macs_per_row: Optional[int] = None, want_stats: bool = True) -> None:
         d = ConvDesc()
         d.n_src = len(srcs)
         for i, s in enumerate(srcs):
@@ -170,6 +180,9 @@ class Plan:
         if out is not None:
             assert out.H == H and out.C == cout
             d.out, d.out_ld = out.t.data_ptr(), out.C
+            if want_stats:
+                d.stats_out = out.stats_buffer().data_ptr()
+                out.has_stats = True
         if residual is not None:
             assert residual.H == H and residual.C == cout
             d.residual, d.res_ld = residual.t.data_ptr(), residual.C
@@ -198,6 +211,11 @@ class Plan:
             a.mod_z, a.mod_z_step_stride, a.mod_z_batch_stride = mod_z
         a.step_ptr = _ptr(step)
         a.apply_silu = 1 if silu else 0
+        if src0.has_stats and (src1 is None or src1.has_stats):
+            a.stats0 = src0.stats.data_ptr()
+            if src1 is not None:
+                a.stats1 = src1.stats.data_ptr()
+        out.has_stats = False
         self.keep.append(a)
         self._emit("adagn", self.lib.idf_adagn_silu_fwd, (C.byref(a),), nbytes=2 * 2 * self.B * src0.H * src0.H * out.C)
 
@@ -239,12 +257,13 @@ class Plan:
                   residual=residual)
         return out
 
-    def conv1x1(self, src: Act, w: torch.Tensor, b: torch.Tensor, residual: Optional[Act] = None) -> Act:
+    def conv1x1(self, src: Act, w: torch.Tensor, b: torch.Tensor, residual: Optional[Act] = None,
+                want_stats: bool = True) -> Act:
         cout = w.shape[0]
         kb = taps1x1(src.C)
         out = self.ws.alloc(src.H, cout)
         self.conv([src], kb, self.weight(_pad_cols(w, 64 * len(kb))), self.f32(b), src.H, cout,
-                  128 if cout % 128 == 0 else 64, out=out, residual=residual)
+                  128 if cout % 128 == 0 else 64, out=out, residual=residual, want_stats=want_stats)
         return out
 
     def downsample(self, src: Act, conv: nn.Conv2d) -> Act:
@@ -273,7 +292,7 @@ class Plan:
         self.adagn(x, None, an, blk.group_norm, silu=False)
         wqkv = torch.cat([pack_conv1x1(m.weight) for m in (blk.proj_q, blk.proj_k, blk.proj_v)], dim=0)
         bqkv = torch.cat([m.bias.detach() for m in (blk.proj_q, blk.proj_k, blk.proj_v)], dim=0)
-        qkv = self.conv1x1(an, wqkv, bqkv)
+        qkv = self.conv1x1(an, wqkv, bqkv, want_stats=False)
         self.ws.free(an)
         ao = self.ws.alloc(x.H, Cc)
         self.attention(qkv, ao, Cc)

@@ -66,6 +66,23 @@ def assert_close(got, ref, rel_l2=3e-3, max_rel=1.6e-2, what=""):
     assert err < rel_l2 and mx < max_rel, f"{what}: rel-L2 {err:.3e} (tol {rel_l2}), max-rel {mx:.3e} (tol {max_rel})"
 
 
+def tile_partials(m, B, H, W):
+    """GroupNorm partial sums of a pad-flat bf16 matrix, laid out as the conv epilogue writes them:
+    fp32 [ceil(rows/128), 3, C, 2], slot = image - first image of the 128-row tile (plain torch)."""
+    rows, Cc = m.shape
+    R = (H + 1) * (W + 1)
+    r = torch.arange(rows, device=m.device)
+    tile = r // 128
+    slot = r // R - (tile * 128) // R
+    idx = tile * 3 + slot
+    ntile = (rows + 127) // 128
+    v = m.float()
+    out = torch.zeros(ntile * 3, Cc, 2, device=m.device)
+    out[:, :, 0].index_add_(0, idx, v)
+    out[:, :, 1].index_add_(0, idx, v * v)
+    return out.reshape(ntile, 3, Cc, 2).contiguous()
+
+
 def run_conv(lib, srcs, kblocks, wp, bias, B, H, cout, block_n, residual=None, epilogue=0, **extra):
     from infodiffusion_b200._lib import ConvDesc
     d = ConvDesc()
@@ -158,6 +175,27 @@ def test_conv3x3_large_auto_tiles(lib):
         out = run_conv(lib, [pf(x)], layout.taps3x3(cin, H, H), layout.pack_conv3x3(w).to(BF).contiguous(), b, B, H,
                        cout, 128 if cout % 128 == 0 else 64)
         assert_close(unpf(out, B, H, H), ref, what=f"conv3x3 {cin}->{cout}@{H} B={B}")
+
+
+@pytest.mark.parametrize("cin,cout,H,B,mt", [(64, 64, 16, 3, 0), (128, 128, 8, 7, 0), (64, 128, 8, 5, 2), (64, 64, 32, 2, 4)])
+def test_conv_epilogue_groupnorm_partials(lib, cin, cout, H, B, mt):
+    """stats_out of the conv epilogue == per-tile (sum, sumsq) of the bf16 output it stored."""
+    from infodiffusion_b200 import layout
+    g = torch.Generator(device=DEV).manual_seed(300 + cin + cout + H)
+    x = rbf(torch.randn(B, cin, H, H, device=DEV, generator=g))
+    w = rbf(torch.randn(cout, cin, 3, 3, device=DEV, generator=g) * (2.0 / (9 * cin)) ** 0.5)
+    b = torch.randn(cout, device=DEV, generator=g)
+    rows = B * (H + 1) * (H + 1)
+    stats = torch.full(((rows + 127) // 128, 3, cout, 2), float("nan"), device=DEV)
+    check(lib.idf_set_option(b"conv_force_mt", mt))
+    try:
+        out = run_conv(lib, [pf(x)], layout.taps3x3(cin, H, H), layout.pack_conv3x3(w).to(BF).contiguous(), b, B, H,
+                       cout, 128 if cout % 128 == 0 else 64, stats_out=stats)
+    finally:
+        check(lib.idf_set_option(b"conv_force_mt", 0))
+    ref = tile_partials(out, B, H, H)
+    assert torch.isfinite(stats).all(), "a partial-sum slot was not written"
+    assert_close(stats, ref, rel_l2=1e-5, max_rel=1e-5, what="conv epilogue GroupNorm partials")
 
 
 def test_conv1x1_qkv(lib):
@@ -300,6 +338,17 @@ def test_adagn(lib, c0, c1, H, B, mod, silu):
     torch.cuda.synchronize()
     assert pad_is_zero(out, B, H, H)
     assert_close(unpf(out, B, H, H), ref, rel_l2=3e-3, max_rel=8e-3, what=f"adagn C={c0}+{c1}@{H}")
+    # streaming variant: statistics supplied as per-tile partial sums (what the conv epilogue writes)
+    out2 = torch.zeros_like(out)
+    st0 = tile_partials(s0, B, H, H)
+    a.stats0, a.out = st0.data_ptr(), out2.data_ptr()
+    if c1:
+        st1 = tile_partials(s1, B, H, H)
+        a.stats1 = st1.data_ptr()
+    check(lib.idf_adagn_silu_fwd(C.byref(a), stream()))
+    torch.cuda.synchronize()
+    assert pad_is_zero(out2, B, H, H)
+    assert_close(unpf(out2, B, H, H), ref, rel_l2=3e-3, max_rel=8e-3, what=f"adagn (streaming) C={c0}+{c1}@{H}")
 
 
 @pytest.mark.parametrize("H,B", [(16, 3), (8, 5)])
@@ -373,6 +422,7 @@ def test_mmd_against_oracle_and_golden(lib, golden_dir):
         yg = ys.to(DEV).requires_grad_(True)
         vg = compute_mmd(xs.to(DEV), yg)
         (gg,) = torch.autograd.grad(vg, yg)
-        assert_close(vg.cpu(), vo.detach(), rel_l2=1e-4, max_rel=1e-4, what=f"mmd value D={D}")  # fp32 sum order
+        # the loss is a small difference of O(1) means: compare on the scale of the terms (fp32 sum order)
+        assert abs(float(vg) - float(vo)) < 5e-6, f"mmd value D={D}: {float(vg)} vs {float(vo)}"
         assert_close(gg.cpu(), go, rel_l2=1e-4, max_rel=1e-3, what=f"mmd grad D={D}")
-        assert_close(vg.cpu(), torch.from_numpy(gold[f"v{D}"]), rel_l2=1e-4, max_rel=1e-4, what="mmd vs golden")
+        assert abs(float(vg) - float(gold[f"v{D}"])) < 5e-6, "mmd vs golden"
