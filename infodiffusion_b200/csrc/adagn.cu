@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_kernel(const AdaGNParams p)
 // No clusters, no barriers in the hot loop, one HBM read + one HBM write.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNParams p) {
+  __shared__ float2 s_sub[4][kMaxC];
   __shared__ float s_tot[2 * kMaxC];
   __shared__ float s_mean[32], s_rstd[32];
   __shared__ float2 s_ab[kMaxC];
@@ -235,21 +236,39 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
   const int C = p.C;
   const int R = p.rows_per_img;
 
-  // per-channel totals over the 128-row tiles that intersect image n (fixed order: deterministic)
+  // per-channel totals over the 128-row tiles that intersect image n.  All 256 threads take part:
+  // thread -> (channel, sub-sequence of tiles), loads issued four at a time; the order of every
+  // addition is a function of (n, geometry) only, so the result is deterministic.
   const int t_first = (n * R) / kBM;
   const int t_last = ((n + 1) * R - 1) / kBM;
-  for (int ch = t; ch < C; ch += kAdaThreads) {
+  const int nsub = (kAdaThreads / C) > 0 ? (kAdaThreads / C) : 1;     // 4, 2, 1, 1 for C = 64, 128, 192, 256
+  for (int idx = t; idx < C * nsub; idx += kAdaThreads) {
+    const int ch = idx % C, sub = idx / C;
     const bool first = ch < p.c0;
-    const float2* st = reinterpret_cast<const float2*>(first ? p.stats0 : p.stats1);
     const int cs = first ? p.c0 : p.c1;
-    const int cc = first ? ch : ch - p.c0;
-    float sx = 0.f, sq = 0.f;
-    for (int tile = t_first; tile <= t_last; ++tile) {
+    const float2* st = reinterpret_cast<const float2*>(first ? p.stats0 : p.stats1) + (first ? ch : ch - p.c0);
+    auto part = [&](int tile) -> float2 {
       const int slot = n - (tile * kBM) / R;
-      const float2 v = __ldg(st + (static_cast<long long>(tile) * 3 + slot) * cs + cc);
+      return __ldg(st + (static_cast<long long>(tile) * 3 + slot) * cs);
+    };
+    float sx = 0.f, sq = 0.f;
+    int tile = t_first + sub;
+    for (; tile + 3 * nsub <= t_last; tile += 4 * nsub) {
+      const float2 v0 = part(tile), v1 = part(tile + nsub), v2 = part(tile + 2 * nsub), v3 = part(tile + 3 * nsub);
+      sx += (v0.x + v1.x) + (v2.x + v3.x);
+      sq += (v0.y + v1.y) + (v2.y + v3.y);
+    }
+    for (; tile <= t_last; tile += nsub) {
+      const float2 v = part(tile);
       sx += v.x;
       sq += v.y;
     }
+    s_sub[sub][ch] = make_float2(sx, sq);
+  }
+  __syncthreads();
+  for (int ch = t; ch < C; ch += kAdaThreads) {
+    float sx = 0.f, sq = 0.f;
+    for (int sub = 0; sub < nsub; ++sub) { sx += s_sub[sub][ch].x; sq += s_sub[sub][ch].y; }
     s_tot[ch] = sx;
     s_tot[C + ch] = sq;
   }
@@ -355,9 +374,9 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
   p.stats1 = a.stats1;
   p.slice_rows = 0;
   if (p.stats0 != nullptr && (p.c1 == 0 || p.stats1 != nullptr)) {
-    // streaming variant: ~32 KB of rows per CTA
+    // streaming variant: ~64 KB of rows per CTA
     const long long bytes_s = static_cast<long long>(p.rows_per_img) * p.C * 2;
-    int slices = static_cast<int>((bytes_s + 32767) / 32768);
+    int slices = static_cast<int>((bytes_s + 65535) / 65536);
     if (slices < 1) slices = 1;
     p.slice_rows = (p.rows_per_img + slices - 1) / slices;
     slices = (p.rows_per_img + p.slice_rows - 1) / p.slice_rows;

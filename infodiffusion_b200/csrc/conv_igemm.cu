@@ -19,10 +19,14 @@
 
 namespace idf {
 
-__host__ __device__ constexpr int conv_b_stages(int bn) { return bn == 16 ? 8 : 6; }
+__host__ __device__ constexpr int conv_b_stages(int bn) { return bn == 16 ? 8 : (bn == 64 ? 4 : 6); }
 // GroupNorm partial-statistics exchange between the 4 epilogue warps of one work item:
 // [2 halves][4 lane quarters][3 image slots][32 columns] float2 (sum, sumsq)
 constexpr uint32_t kStatScratchBytes = 2 * 4 * 3 * 32 * 8;
+// per-epilogue-warp staging tile: 32 rows x 64 B (+16 B pad per row: conflict-free for both the row-per-lane
+// and the 4-lanes-per-row access patterns)
+constexpr uint32_t kStageRowBytes = 80;
+constexpr uint32_t kStageBytes = 8 * 32 * kStageRowBytes;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -53,23 +57,42 @@ struct HaloCfg {
                                         : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
   static_assert(2 * ACC_COLS <= 512, "accumulators do not fit in TMEM");
   static constexpr int NBARS = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int NI = (MT >= 2) ? 2 : 1;                        // UMMA issuing threads (accumulators split)
 };
 
 __host__ __device__ inline uint32_t conv_smem_bytes(int a_stage_bytes, int a_stages, int b_stages, int b_bytes) {
   return static_cast<uint32_t>(a_stages * a_stage_bytes + b_stages * b_bytes + 512 /*barriers*/ +
-                               kStatScratchBytes + 1024 /*align*/);
+                               kStatScratchBytes + 256 /*tap table*/ + kStageBytes + 1024 /*align*/);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // epilogue for one (accumulator m, 32-column chunk) work item held in registers
 // ---------------------------------------------------------------------------------------------------
-// Executed by all 32 lanes of an epilogue warp (invalid rows contribute zeros and store nothing).
-//   out = bf16(acc + bias (+ residual));  optional per-tile GroupNorm partials of the ROUNDED output:
-//   stats[tile][slot][col][2] = (sum, sumsq) over the tile's rows belonging to image (first image of the
-//   tile + slot), combined across the 4 lane-quarter warps in a fixed order (deterministic, no atomics).
-__device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, const uint32_t (&v)[32], int64_t r,
-                                                    bool valid, int col0, int slot, int tile, int q, int half,
-                                                    int lane, float2* scratch) {
+// One (accumulator, 32-column) work item of an epilogue warp; executed by all 32 lanes.
+//   out = bf16(acc + bias (+ residual)), pad rows forced to zero.
+// The warp's 32 rows x 64 B pass through a private shared-memory staging tile so that global traffic is
+// coalesced: 4 lanes cover one row's 64 B, 8 rows per instruction (8 LSU wavefronts instead of the 32 a
+// row-per-lane 16-byte store at 128-byte stride costs) -- for the residual read and for the output write.
+// Optional GroupNorm partials: column sums of the STAGED (bf16-rounded) tile, split at the image
+// boundary inside the warp, combined across the 4 lane-quarter warps in a fixed order and written as
+//   stats[tile][slot][col][2] = (sum, sumsq) over the rows of `tile` in image (first image of tile + slot).
+__device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, const uint32_t (&v)[32],
+                                                    int64_t warp_row0, bool valid, int col0, int slot_a, int n_a,
+                                                    int tile, int q, int half, int lane, uint8_t* stage,
+                                                    float2* scratch) {
+  const int sub_row = lane >> 2, sub_chunk = lane & 3;     // coalesced distribution: row = 8 i + sub_row
+  // ---- residual: coalesced global read -> staging
+  if (p.residual != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = i * 8 + sub_row;
+      const int64_t rr = warp_row0 + row;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (rr < p.rows) u = __ldg(reinterpret_cast<const uint4*>(p.residual + rr * p.res_ld + col0) + sub_chunk);
+      *reinterpret_cast<uint4*>(stage + row * kStageRowBytes + sub_chunk * 16) = u;
+    }
+    __syncwarp();
+  }
   const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
   float f[32];
 #pragma unroll
@@ -80,45 +103,64 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
     f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
     f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
   }
-  if (p.residual != nullptr && valid) {
-    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + r * p.res_ld + col0);
+  uint8_t* my_row = stage + lane * kStageRowBytes;
+  if (p.residual != nullptr) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint4 u = __ldg(rp + j);
+      const uint4 u = *reinterpret_cast<const uint4*>(my_row + j * 16);
       const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
       f[8 * j + 0] += a0.x; f[8 * j + 1] += a0.y; f[8 * j + 2] += a1.x; f[8 * j + 3] += a1.y;
       f[8 * j + 4] += a2.x; f[8 * j + 5] += a2.y; f[8 * j + 6] += a3.x; f[8 * j + 7] += a3.y;
     }
+    __syncwarp();
   }
-  uint32_t pk[16];
+  // ---- own row -> staging (zeros for pad / out-of-range rows)
 #pragma unroll
-  for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-  if (valid) {
-    uint4* op = reinterpret_cast<uint4*>(p.out + r * p.out_ld + col0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) op[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    u.x = valid ? pack_bf16x2(f[8 * j + 0], f[8 * j + 1]) : 0u;
+    u.y = valid ? pack_bf16x2(f[8 * j + 2], f[8 * j + 3]) : 0u;
+    u.z = valid ? pack_bf16x2(f[8 * j + 4], f[8 * j + 5]) : 0u;
+    u.w = valid ? pack_bf16x2(f[8 * j + 6], f[8 * j + 7]) : 0u;
+    *reinterpret_cast<uint4*>(my_row + j * 16) = u;
   }
+  __syncwarp();
+  // ---- coalesced global write (pad rows receive zeros, which is what they already hold)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + sub_row;
+    const int64_t rr = warp_row0 + row;
+    if (rr < p.rows)
+      *(reinterpret_cast<uint4*>(p.out + rr * p.out_ld + col0) + sub_chunk) =
+          *reinterpret_cast<const uint4*>(stage + row * kStageRowBytes + sub_chunk * 16);
+  }
+  // ---- GroupNorm partial sums of the staged tile
   if (p.stats != nullptr) {
-    float2* my = scratch + ((half * 4 + q) * 3) * 32 + lane;
-#pragma unroll 1
-    for (int s = 0; s < 3; ++s) {
-      const bool mine = valid && (slot == s);
-      float2 res = make_float2(0.f, 0.f);
-      if (__any_sync(0xffffffffu, mine)) {       // warp-uniform
-        float a[32], b[32];
+    // lane -> column pair (2 cp, 2 cp + 1), rows [16 h, 16 h + 16); rows < n_a belong to slot_a, the rest to slot_a + 1
+    const int cp = lane & 15, hh = lane >> 4;
+    float sa0 = 0.f, sa1 = 0.f, qa0 = 0.f, qa1 = 0.f, sb0 = 0.f, sb1 = 0.f, qb0 = 0.f, qb1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float2 w = unpack_bf16x2(pk[j]);
-          a[2 * j] = mine ? w.x : 0.f;
-          a[2 * j + 1] = mine ? w.y : 0.f;
-          b[2 * j] = a[2 * j] * a[2 * j];
-          b[2 * j + 1] = a[2 * j + 1] * a[2 * j + 1];
-        }
-        warp_transpose_reduce(a, lane);
-        warp_transpose_reduce(b, lane);
-        res = make_float2(a[0], b[0]);
+    for (int i = 0; i < 16; ++i) {
+      const int row = hh * 16 + i;
+      const float2 w = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(stage + row * kStageRowBytes + cp * 4));
+      if (row < n_a) { sa0 += w.x; sa1 += w.y; qa0 = fmaf(w.x, w.x, qa0); qa1 = fmaf(w.y, w.y, qa1); }
+      else           { sb0 += w.x; sb1 += w.y; qb0 = fmaf(w.x, w.x, qb0); qb1 = fmaf(w.y, w.y, qb1); }
+    }
+    // combine the two row halves (fixed order: lower half + upper half)
+    const float oa0 = __shfl_xor_sync(0xffffffffu, sa0, 16), oa1 = __shfl_xor_sync(0xffffffffu, sa1, 16);
+    const float pa0 = __shfl_xor_sync(0xffffffffu, qa0, 16), pa1 = __shfl_xor_sync(0xffffffffu, qa1, 16);
+    const float ob0 = __shfl_xor_sync(0xffffffffu, sb0, 16), ob1 = __shfl_xor_sync(0xffffffffu, sb1, 16);
+    const float pb0 = __shfl_xor_sync(0xffffffffu, qb0, 16), pb1 = __shfl_xor_sync(0xffffffffu, qb1, 16);
+    if (hh == 0) {
+      float2* my = scratch + ((half * 4 + q) * 3) * 32 + 2 * cp;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        float2 e0 = make_float2(0.f, 0.f), e1 = make_float2(0.f, 0.f);
+        if (s == slot_a) { e0 = make_float2(sa0 + oa0, qa0 + pa0); e1 = make_float2(sa1 + oa1, qa1 + pa1); }
+        else if (s == slot_a + 1) { e0 = make_float2(sb0 + ob0, qb0 + pb0); e1 = make_float2(sb1 + ob1, qb1 + pb1); }
+        my[s * 32] = e0;
+        my[s * 32 + 1] = e1;
       }
-      my[s * 32] = res;
     }
     named_bar_sync(1 + half, 128);
     if (q < 3 && tile < p.m_tiles) {               // warp q combines image slot q over the four quarters
@@ -131,6 +173,7 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
     }
     named_bar_sync(1 + half, 128);
   }
+  __syncwarp();   // staging is reused by the next item
 }
 
 __device__ __forceinline__ void epilogue_narrow(const ConvKernelParams& p, const uint32_t (&v)[16], int img, int y,
@@ -171,6 +214,8 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float2* stat_scratch = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(a_full) + 512);
+  uint32_t* s_tap = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(stat_scratch) + kStatScratchBytes);
+  uint8_t* stage_all = reinterpret_cast<uint8_t*>(s_tap) + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -183,14 +228,18 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
     tma_prefetch_desc(&p.tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
-    for (int s = 0; s < BS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 256); }
+    for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, Cfg::NI); }
+    for (int s = 0; s < BS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, Cfg::NI); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, Cfg::NI); mbar_init(tempty + a, 256); }
     fence_mbar_init();
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
+  }
+  if (warp == 3) {   // per-tap descriptor offsets (16-byte units) for the issuing threads
+    for (int i = lane; i <= IDF_CONV_MAX_KB; i += 32)
+      s_tap[i] = (i < p.n_taps) ? static_cast<uint32_t>(p.t_rel[i]) * 8u : 0u;
   }
   tc_fence_before();
   __syncthreads();
@@ -237,35 +286,40 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ UMMA issuer
+  } else if (warp == 1 || (warp == 2 && Cfg::NI == 2)) {
+    // ------------------------------------------------------------------ UMMA issuers
+    // One thread per issuer; with MT >= 2 the accumulators are split between two issuing threads so
+    // that neither has to sustain more than one MMA per 64 cycles.  Both wait on the same full
+    // barriers; every empty / accumulator-full barrier counts one tcgen05.commit per issuer.
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(kBM, BN, kFmtBF16);
+      constexpr int M_PER = MT / Cfg::NI;
+      const int m_begin = (warp == 1) ? 0 : M_PER;
       int sa = 0, sb = 0, iter = 0;
       uint32_t pa = 0, pb = 0;
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(smB));
       for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
         const int as = iter & 1;
         mbar_wait(tempty + as, ((iter >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + static_cast<uint32_t>(as * Cfg::ACC_COLS);
+        const uint32_t d0 = tmem_base + static_cast<uint32_t>(as * Cfg::ACC_COLS + m_begin * BN);
         int t = 0;
+        uint32_t rel = s_tap[0];
         for (int g = 0; g < p.n_groups; ++g) {
           mbar_wait(a_full + sa, pa);
-          const uint32_t a_base = smem_u32(smA + sa * p.a_stage_bytes);
+          const uint32_t a_lo0 = umma_desc_lo(smem_u32(smA + sa * p.a_stage_bytes)) +
+                                 static_cast<uint32_t>(m_begin * (kBM * 128 / 16));
           const int t_end = t + p.g_ntaps[g];
           for (; t < t_end; ++t) {
             mbar_wait(b_full + sb, pb);
             tc_fence_after();
-            const uint64_t db = umma_desc_k_sw128(smem_u32(smB + sb * Cfg::B_BYTES));
+            const uint32_t a_lo = a_lo0 + rel;           // tap view: any 128-byte row start is legal
+            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(sb) * (Cfg::B_BYTES / 16);
+            rel = s_tap[t + 1];                          // prefetch next tap's offset
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-              // tap view: rows [t_rel + 128 m, +128) of the halo; any 128-byte row start is legal
-              const uint64_t da = umma_desc_k_sw128(a_base + static_cast<uint32_t>((p.t_rel[t] + m * kBM) * 128));
-#pragma unroll
-              for (int k = 0; k < kBK / 16; ++k)
-                umma_f16(d0 + static_cast<uint32_t>(m * BN), da + static_cast<uint64_t>(2 * k),
-                         db + static_cast<uint64_t>(2 * k), idesc, (t | k) != 0 ? 1u : 0u);
-            }
+            for (int m = 0; m < M_PER; ++m)
+              umma_f16_x4(d0 + static_cast<uint32_t>(m * BN), a_lo + static_cast<uint32_t>(m * (kBM * 128 / 16)), b_lo,
+                          idesc, t != 0 ? 1u : 0u);
             umma_commit(b_empty + sb);
             if (++sb == BS) { sb = 0; pb ^= 1u; }
           }
@@ -315,8 +369,15 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
           uint32_t v[32];
           tmem_ld_32x32(t0 + static_cast<uint32_t>(m * BN + c * 32), v);
           tmem_ld_wait();
-          const int slot = img - static_cast<int>((static_cast<int64_t>(tile) * kBM) / (p.Hp * p.Wp));
-          epilogue_bf16_chunk(p, v, r, valid, nt * BN + c * 32, slot, tile, q, half, lane, stat_scratch);
+          // image bookkeeping for the statistics: rows of this warp in the image of its first row
+          const int R = p.Hp * p.Wp;
+          const int64_t wr0 = static_cast<int64_t>(tile) * kBM + q * 32;
+          const int img_w = static_cast<int>(wr0 / R);
+          const int slot_a = img_w - static_cast<int>((static_cast<int64_t>(tile) * kBM) / R);
+          const int64_t next_img_row = static_cast<int64_t>(img_w + 1) * R;
+          const int n_a = static_cast<int>((next_img_row - wr0 < 32) ? (next_img_row - wr0) : 32);
+          epilogue_bf16_chunk(p, v, wr0, valid, nt * BN + c * 32, slot_a, n_a, tile, q, half, lane,
+                              stage_all + e * (32 * kStageRowBytes), stat_scratch);
         } else {
           uint32_t v[16];
           tmem_ld_32x16(t0 + static_cast<uint32_t>(m * BN), v);

@@ -115,6 +115,44 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Four back-to-back K=16 MMAs over one 64-element k-block of K-major SWIZZLE_128B operands: both
+// descriptors advance by 32 bytes (+2 in the address field) per MMA.  The descriptors are passed as
+// their low words (start address | LBO) plus the shared high word, so the issuing thread spends ~4
+// instructions per MMA instead of ~12 (the single issuing thread is the bottleneck for N <= 128).
+// accumulate_first == 0 makes the first MMA overwrite the accumulator.
+constexpr uint32_t kDescHiKSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3fffu) | (1u << 16); }
+__device__ __forceinline__ void umma_f16_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                            uint32_t accumulate_first) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 da, db;\n"
+      ".reg .b32 al, bl;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 q, %4, %4;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+      "add.u32 al, %1, 2;\n"
+      "add.u32 bl, %2, 2;\n"
+      "mov.b64 da, {al, %5};\n"
+      "mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n"
+      "add.u32 al, %1, 4;\n"
+      "add.u32 bl, %2, 4;\n"
+      "mov.b64 da, {al, %5};\n"
+      "mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n"
+      "add.u32 al, %1, 6;\n"
+      "add.u32 bl, %2, 6;\n"
+      "mov.b64 da, {al, %5};\n"
+      "mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "r"(kDescHiKSw128)
+      : "memory");
+}
 // Arrive on an mbarrier when all previously issued UMMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
