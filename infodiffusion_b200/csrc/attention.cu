@@ -268,14 +268,14 @@ attn_tma_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ out, 
   if (q_rows < 128) {
     for (int i = t; i < (128 - q_rows) * 16; i += kAttnThreads) {
       const int r = q_rows + (i >> 4), g = i & 15;
-      *reinterpret_cast<uint4*>(smQ + (g >> 3) * (128 * 128) + sw128_off(r, g & 7)) = make_uint4(0, 0, 0, 0);
+      sts128(smem_u32(smQ) + (g >> 3) * (128 * 128) + sw128_off(r, g & 7), make_uint4(0, 0, 0, 0));
     }
     fence_async_smem();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = lds32(smem_u32(tmem_slot));
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 256;
 
@@ -327,7 +327,7 @@ attn_tma_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ out, 
     uint32_t v[32];
     tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
     tmem_ld_wait();
-    uint8_t* chunk = smK + (c >> 1) * (128 * 128);         // P tile for keys [64*(c/2), +64)
+    const uint32_t chunk = smem_u32(smK) + (c >> 1) * (128 * 128);   // P tile for keys [64*(c/2), +64)
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float e[8];
@@ -341,7 +341,7 @@ attn_tma_kernel(const __grid_constant__ CUtensorMap tm, bf16* __restrict__ out, 
       o.y = pack_bf16x2(e[2], e[3]);
       o.z = pack_bf16x2(e[4], e[5]);
       o.w = pack_bf16x2(e[6], e[7]);
-      *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + g)) = o;
+      sts128(chunk + sw128_off(row, (c & 1) * 4 + g), o);
     }
   }
   fence_async_smem();

@@ -78,8 +78,8 @@ __host__ __device__ inline uint32_t conv_smem_bytes(int a_stage_bytes, int a_sta
 //   stats[tile][slot][col][2] = (sum, sumsq) over the rows of `tile` in image (first image of tile + slot).
 __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, const uint32_t (&v)[32],
                                                     int64_t warp_row0, bool valid, int col0, int slot_a, int n_a,
-                                                    int tile, int q, int half, int lane, uint8_t* stage,
-                                                    float2* scratch) {
+                                                    int tile, int q, int half, int lane, uint32_t stage,
+                                                    uint32_t scratch) {
   const int sub_row = lane >> 2, sub_chunk = lane & 3;     // coalesced distribution: row = 8 i + sub_row
   // ---- residual: coalesced global read -> staging
   if (p.residual != nullptr) {
@@ -89,7 +89,7 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
       const int64_t rr = warp_row0 + row;
       uint4 u = make_uint4(0, 0, 0, 0);
       if (rr < p.rows) u = __ldg(reinterpret_cast<const uint4*>(p.residual + rr * p.res_ld + col0) + sub_chunk);
-      *reinterpret_cast<uint4*>(stage + row * kStageRowBytes + sub_chunk * 16) = u;
+      sts128(stage + row * kStageRowBytes + sub_chunk * 16, u);
     }
     __syncwarp();
   }
@@ -103,11 +103,11 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
     f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
     f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
   }
-  uint8_t* my_row = stage + lane * kStageRowBytes;
+  const uint32_t my_row = stage + lane * kStageRowBytes;
   if (p.residual != nullptr) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint4 u = *reinterpret_cast<const uint4*>(my_row + j * 16);
+      const uint4 u = lds128(my_row + j * 16);
       const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
       f[8 * j + 0] += a0.x; f[8 * j + 1] += a0.y; f[8 * j + 2] += a1.x; f[8 * j + 3] += a1.y;
       f[8 * j + 4] += a2.x; f[8 * j + 5] += a2.y; f[8 * j + 6] += a3.x; f[8 * j + 7] += a3.y;
@@ -122,7 +122,7 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
     u.y = valid ? pack_bf16x2(f[8 * j + 2], f[8 * j + 3]) : 0u;
     u.z = valid ? pack_bf16x2(f[8 * j + 4], f[8 * j + 5]) : 0u;
     u.w = valid ? pack_bf16x2(f[8 * j + 6], f[8 * j + 7]) : 0u;
-    *reinterpret_cast<uint4*>(my_row + j * 16) = u;
+    sts128(my_row + j * 16, u);
   }
   __syncwarp();
   // ---- coalesced global write (pad rows receive zeros, which is what they already hold)
@@ -132,7 +132,7 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
     const int64_t rr = warp_row0 + row;
     if (rr < p.rows)
       *(reinterpret_cast<uint4*>(p.out + rr * p.out_ld + col0) + sub_chunk) =
-          *reinterpret_cast<const uint4*>(stage + row * kStageRowBytes + sub_chunk * 16);
+          lds128(stage + row * kStageRowBytes + sub_chunk * 16);
   }
   // ---- GroupNorm partial sums of the staged tile
   if (p.stats != nullptr) {
@@ -142,7 +142,7 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int row = hh * 16 + i;
-      const float2 w = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(stage + row * kStageRowBytes + cp * 4));
+      const float2 w = unpack_bf16x2(lds32(stage + row * kStageRowBytes + cp * 4));
       if (row < n_a) { sa0 += w.x; sa1 += w.y; qa0 = fmaf(w.x, w.x, qa0); qa1 = fmaf(w.y, w.y, qa1); }
       else           { sb0 += w.x; sb1 += w.y; qb0 = fmaf(w.x, w.x, qb0); qb1 = fmaf(w.y, w.y, qb1); }
     }
@@ -152,20 +152,20 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
     const float ob0 = __shfl_xor_sync(0xffffffffu, sb0, 16), ob1 = __shfl_xor_sync(0xffffffffu, sb1, 16);
     const float pb0 = __shfl_xor_sync(0xffffffffu, qb0, 16), pb1 = __shfl_xor_sync(0xffffffffu, qb1, 16);
     if (hh == 0) {
-      float2* my = scratch + ((half * 4 + q) * 3) * 32 + 2 * cp;
+      const uint32_t my = scratch + (((half * 4 + q) * 3) * 32 + 2 * cp) * 8;
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         float2 e0 = make_float2(0.f, 0.f), e1 = make_float2(0.f, 0.f);
         if (s == slot_a) { e0 = make_float2(sa0 + oa0, qa0 + pa0); e1 = make_float2(sa1 + oa1, qa1 + pa1); }
         else if (s == slot_a + 1) { e0 = make_float2(sb0 + ob0, qb0 + pb0); e1 = make_float2(sb1 + ob1, qb1 + pb1); }
-        my[s * 32] = e0;
-        my[s * 32 + 1] = e1;
+        sts_f2(my + s * 32 * 8, e0);
+        sts_f2(my + s * 32 * 8 + 8, e1);
       }
     }
     named_bar_sync(1 + half, 128);
     if (q < 3 && tile < p.m_tiles) {               // warp q combines image slot q over the four quarters
-      const float2* sc = scratch + (half * 4 * 3 + q) * 32 + lane;
-      const float2 x0 = sc[0 * 96], x1 = sc[1 * 96], x2 = sc[2 * 96], x3 = sc[3 * 96];
+      const uint32_t sc = scratch + ((half * 4 * 3 + q) * 32 + lane) * 8;
+      const float2 x0 = lds_f2(sc), x1 = lds_f2(sc + 96 * 8), x2 = lds_f2(sc + 2 * 96 * 8), x3 = lds_f2(sc + 3 * 96 * 8);
       float2 tot;
       tot.x = (x0.x + x1.x) + (x2.x + x3.x);
       tot.y = (x0.y + x1.y) + (x2.y + x3.y);
@@ -214,8 +214,9 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float2* stat_scratch = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(a_full) + 512);
-  uint32_t* s_tap = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(stat_scratch) + kStatScratchBytes);
-  uint8_t* stage_all = reinterpret_cast<uint8_t*>(s_tap) + 256;
+  const uint32_t scratch_sa = smem_u32(stat_scratch);
+  const uint32_t tap_sa = scratch_sa + kStatScratchBytes;       // per-tap descriptor offsets
+  const uint32_t stage_sa = tap_sa + 256;                       // epilogue staging tiles
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -239,12 +240,12 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
   }
   if (warp == 3) {   // per-tap descriptor offsets (16-byte units) for the issuing threads
     for (int i = lane; i <= IDF_CONV_MAX_KB; i += 32)
-      s_tap[i] = (i < p.n_taps) ? static_cast<uint32_t>(p.t_rel[i]) * 8u : 0u;
+      sts32(tap_sa + 4 * i, (i < p.n_taps) ? static_cast<uint32_t>(p.t_rel[i]) * 8u : 0u);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = lds32(smem_u32(tmem_slot));
 
   const int total = p.m_super * p.n_tiles;
 
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
         tc_fence_after();
         const uint32_t d0 = tmem_base + static_cast<uint32_t>(as * Cfg::ACC_COLS + m_begin * BN);
         int t = 0;
-        uint32_t rel = s_tap[0];
+        uint32_t rel = lds32(tap_sa);
         for (int g = 0; g < p.n_groups; ++g) {
           mbar_wait(a_full + sa, pa);
           const uint32_t a_lo0 = umma_desc_lo(smem_u32(smA + sa * p.a_stage_bytes)) +
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + rel;           // tap view: any 128-byte row start is legal
             const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(sb) * (Cfg::B_BYTES / 16);
-            rel = s_tap[t + 1];                          // prefetch next tap's offset
+            rel = lds32(tap_sa + 4 * (t + 1));           // prefetch next tap's offset
 #pragma unroll
             for (int m = 0; m < M_PER; ++m)
               umma_f16_x4(d0 + static_cast<uint32_t>(m * BN), a_lo + static_cast<uint32_t>(m * (kBM * 128 / 16)), b_lo,
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
           const int64_t next_img_row = static_cast<int64_t>(img_w + 1) * R;
           const int n_a = static_cast<int>((next_img_row - wr0 < 32) ? (next_img_row - wr0) : 32);
           epilogue_bf16_chunk(p, v, wr0, valid, nt * BN + c * 32, slot_a, n_a, tile, q, half, lane,
-                              stage_all + e * (32 * kStageRowBytes), stat_scratch);
+                              stage_sa + e * (32 * kStageRowBytes), scratch_sa);
         } else {
           uint32_t v[16];
           tmem_ld_32x16(t0 + static_cast<uint32_t>(m * BN), v);
