@@ -242,13 +242,15 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
   const int t_first = (n * R) / kBM;
   const int t_last = ((n + 1) * R - 1) / kBM;
   const int nsub = (kAdaThreads / C) > 0 ? (kAdaThreads / C) : 1;     // 4, 2, 1, 1 for C = 64, 128, 192, 256
+  const float inv_R = 1.0f / static_cast<float>(R);
   for (int idx = t; idx < C * nsub; idx += kAdaThreads) {
     const int ch = idx % C, sub = idx / C;
     const bool first = ch < p.c0;
     const int cs = first ? p.c0 : p.c1;
     const float2* st = reinterpret_cast<const float2*>(first ? p.stats0 : p.stats1) + (first ? ch : ch - p.c0);
     auto part = [&](int tile) -> float2 {
-      const int slot = n - (tile * kBM) / R;
+      // first image of the tile = floor(tile*128 / R); exact in fp32 for < 2^23 rows
+      const int slot = n - __float2int_rd((static_cast<float>(tile * kBM) + 0.5f) * inv_R);
       return __ldg(st + (static_cast<long long>(tile) * 3 + slot) * cs);
     };
     float sx = 0.f, sq = 0.f;
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float v = fmaf(f[j], A[j], B[j]);
-        f[j] = do_silu ? __fdividef(v, 1.0f + __expf(-v)) : v;
+        f[j] = do_silu ? silu_fast(v) : v;
       }
       uint4 o;
       o.x = pack_bf16x2(f[0], f[1]);
@@ -374,10 +376,13 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
   p.stats1 = a.stats1;
   p.slice_rows = 0;
   if (p.stats0 != nullptr && (p.c1 == 0 || p.stats1 != nullptr)) {
-    // streaming variant: ~64 KB of rows per CTA
+    // streaming variant: large slices amortise the per-CTA coefficient prologue (~192 KB of rows per CTA),
+    // but keep at least ~600 CTAs in the grid when the tensor allows 32 KB slices
     const long long bytes_s = static_cast<long long>(p.rows_per_img) * p.C * 2;
-    int slices = static_cast<int>((bytes_s + 65535) / 65536);
+    int slices = static_cast<int>((bytes_s + 196607) / 196608);
     if (slices < 1) slices = 1;
+    const int max_slices = static_cast<int>((bytes_s + 32767) / 32768);
+    while (static_cast<long long>(slices) * a.batch < 600 && slices < max_slices) ++slices;
     p.slice_rows = (p.rows_per_img + slices - 1) / slices;
     slices = (p.rows_per_img + p.slice_rows - 1) / p.slice_rows;
     adagn_apply_kernel<<<dim3(slices, a.batch, 1), kAdaThreads, 0, stream>>>(p);

@@ -107,6 +107,9 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   if (d->block_n != 16 && d->block_n != 64 && d->block_n != 128) return fail(IDF_ERR_ARG, "block_n must be 16/64/128");
   if (d->cout_pad % d->block_n != 0) return fail(IDF_ERR_ARG, "cout_pad must be a multiple of block_n");
   if (d->batch < 1 || d->H < 1 || d->W < 1) return fail(IDF_ERR_ARG, "bad geometry");
+  if (d->cout_pad > 512) return fail(IDF_ERR_ARG, "cout_pad > 512 not supported (bias staging)");
+  if (static_cast<int64_t>(d->batch) * (d->H + 1) * (d->W + 1) >= (1 << 22))
+    return fail(IDF_ERR_ARG, "more than 2^22 pad-flat rows per launch: split the batch");
   if (d->epilogue == IDF_EPI_BF16) {
     if (d->block_n < 64) return fail(IDF_ERR_ARG, "bf16 epilogue needs block_n >= 64");
     if (d->out == nullptr || d->out_ld % 8 != 0 || d->cout != d->cout_pad)

@@ -27,6 +27,7 @@ constexpr uint32_t kStatScratchBytes = 2 * 4 * 3 * 32 * 8;
 // and the 4-lanes-per-row access patterns)
 constexpr uint32_t kStageRowBytes = 80;
 constexpr uint32_t kStageBytes = 8 * 32 * kStageRowBytes;
+constexpr uint32_t kBiasBytes = 512 * 4;   // bias vector of the whole conv (cout_pad <= 512), staged once per CTA
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -62,7 +63,7 @@ struct HaloCfg {
 
 __host__ __device__ inline uint32_t conv_smem_bytes(int a_stage_bytes, int a_stages, int b_stages, int b_bytes) {
   return static_cast<uint32_t>(a_stages * a_stage_bytes + b_stages * b_bytes + 512 /*barriers*/ +
-                               kStatScratchBytes + 256 /*tap table*/ + kStageBytes + 1024 /*align*/);
+                               kStatScratchBytes + 256 /*tap table*/ + kStageBytes + kBiasBytes + 1024 /*align*/);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -79,7 +80,7 @@ __host__ __device__ inline uint32_t conv_smem_bytes(int a_stage_bytes, int a_sta
 __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, const uint32_t (&v)[32],
                                                     int64_t warp_row0, bool valid, int col0, int slot_a, int n_a,
                                                     int tile, int q, int half, int lane, uint32_t stage,
-                                                    uint32_t scratch) {
+                                                    uint32_t scratch, uint32_t bias_sa) {
   const int sub_row = lane >> 2, sub_chunk = lane & 3;     // coalesced distribution: row = 8 i + sub_row
   // ---- residual: coalesced global read -> staging
   if (p.residual != nullptr) {
@@ -93,15 +94,14 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
     }
     __syncwarp();
   }
-  const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
   float f[32];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 b = __ldg(bp + j);
-    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+  for (int j = 0; j < 8; ++j) {            // bias staged in shared memory once per CTA (warp-uniform address: broadcast)
+    const uint4 b = lds128(bias_sa + (col0 + 4 * j) * 4);
+    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + __uint_as_float(b.x);
+    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + __uint_as_float(b.y);
+    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + __uint_as_float(b.z);
+    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + __uint_as_float(b.w);
   }
   const uint32_t my_row = stage + lane * kStageRowBytes;
   if (p.residual != nullptr) {
@@ -126,23 +126,27 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
   }
   __syncwarp();
   // ---- coalesced global write (pad rows receive zeros, which is what they already hold)
+  {
+    uint4 o[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = i * 8 + sub_row;
-    const int64_t rr = warp_row0 + row;
-    if (rr < p.rows)
-      *(reinterpret_cast<uint4*>(p.out + rr * p.out_ld + col0) + sub_chunk) =
-          lds128(stage + row * kStageRowBytes + sub_chunk * 16);
+    for (int i = 0; i < 4; ++i) o[i] = lds128(stage + (i * 8 + sub_row) * kStageRowBytes + sub_chunk * 16);
+    bf16* obase = p.out + (warp_row0 + sub_row) * p.out_ld + col0 + sub_chunk * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (warp_row0 + i * 8 + sub_row < p.rows) *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(i) * 8 * p.out_ld) = o[i];
   }
   // ---- GroupNorm partial sums of the staged tile
   if (p.stats != nullptr) {
     // lane -> column pair (2 cp, 2 cp + 1), rows [16 h, 16 h + 16); rows < n_a belong to slot_a, the rest to slot_a + 1
     const int cp = lane & 15, hh = lane >> 4;
     float sa0 = 0.f, sa1 = 0.f, qa0 = 0.f, qa1 = 0.f, sb0 = 0.f, sb1 = 0.f, qb0 = 0.f, qb1 = 0.f;
+    uint32_t raw[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) raw[i] = lds32(stage + (hh * 16 + i) * kStageRowBytes + cp * 4);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int row = hh * 16 + i;
-      const float2 w = unpack_bf16x2(lds32(stage + row * kStageRowBytes + cp * 4));
+      const float2 w = unpack_bf16x2(raw[i]);
       if (row < n_a) { sa0 += w.x; sa1 += w.y; qa0 = fmaf(w.x, w.x, qa0); qa1 = fmaf(w.y, w.y, qa1); }
       else           { sb0 += w.x; sb1 += w.y; qb0 = fmaf(w.x, w.x, qb0); qb1 = fmaf(w.y, w.y, qb1); }
     }
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
   const uint32_t scratch_sa = smem_u32(stat_scratch);
   const uint32_t tap_sa = scratch_sa + kStatScratchBytes;       // per-tap descriptor offsets
   const uint32_t stage_sa = tap_sa + 256;                       // epilogue staging tiles
+  const uint32_t bias_sa = stage_sa + kStageBytes;              // bias vector
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -237,6 +242,10 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
   if (warp == 2) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
+  }
+  if (warp >= 4) {   // bias -> shared memory
+    const int nb = p.n_tiles * BN;
+    for (int i = threadIdx.x - 128; i < nb; i += 256) sts32(bias_sa + 4 * i, __float_as_uint(__ldg(p.bias + i)));
   }
   if (warp == 3) {   // per-tap descriptor offsets (16-byte units) for the issuing threads
     for (int i = lane; i <= IDF_CONV_MAX_KB; i += 32)
@@ -351,43 +360,50 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
       mbar_wait(tfull + as, (iter >> 1) & 1u);
       tc_fence_after();
       const uint32_t t0 = tmem_base + static_cast<uint32_t>(as * Cfg::ACC_COLS) + (static_cast<uint32_t>(q * 32) << 16);
+      const int R = p.Hp * p.Wp;
+      const float inv_wp = 1.0f / static_cast<float>(p.Wp), inv_hp = 1.0f / static_cast<float>(p.Hp),
+                  inv_R = 1.0f / static_cast<float>(R);
 #pragma unroll 1
-      for (int item = half; item < MT * CHUNKS; item += 2) {
-        const int m = item / CHUNKS;
-        const int c = item - m * CHUNKS;
+      for (int m = 0; m < MT; ++m) {
+        // row bookkeeping once per 128-row tile (exact float reciprocals: all quotients < 2^23)
         const int tile = ms * MT + m;
-        const int64_t r = static_cast<int64_t>(tile) * kBM + q * 32 + lane;
-        bool valid = r < p.rows;
-        int img = 0, y = 0, x = 0;
-        if (valid) {
-          const int rq = static_cast<int>(r / p.Wp);
-          x = static_cast<int>(r - static_cast<int64_t>(rq) * p.Wp);
-          img = rq / p.Hp;
-          y = rq - img * p.Hp;
-          valid = (x < p.W) && (y < p.H);
-        }
+        const int64_t wr0 = static_cast<int64_t>(tile) * kBM + q * 32;
+        const int64_t r = wr0 + lane;
+        const int rq = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_wp);
+        const int x = static_cast<int>(r) - rq * p.Wp;
+        const int img = __float2int_rd((static_cast<float>(rq) + 0.5f) * inv_hp);
+        const int y = rq - img * p.Hp;
+        const bool valid = (r < p.rows) && (x < p.W) && (y < p.H);
+        const int img_w = __float2int_rd((static_cast<float>(wr0) + 0.5f) * inv_R);
+        const int slot_a = img_w - __float2int_rd((static_cast<float>(tile * kBM) + 0.5f) * inv_R);
+        const int64_t next_img_row = static_cast<int64_t>(img_w + 1) * R;
+        const int n_a = static_cast<int>((next_img_row - wr0 < 32) ? (next_img_row - wr0) : 32);
         if constexpr (BN >= 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(t0 + static_cast<uint32_t>(m * BN + c * 32), v);
-          tmem_ld_wait();
-          // image bookkeeping for the statistics: rows of this warp in the image of its first row
-          const int R = p.Hp * p.Wp;
-          const int64_t wr0 = static_cast<int64_t>(tile) * kBM + q * 32;
-          const int img_w = static_cast<int>(wr0 / R);
-          const int slot_a = img_w - static_cast<int>((static_cast<int64_t>(tile) * kBM) / R);
-          const int64_t next_img_row = static_cast<int64_t>(img_w + 1) * R;
-          const int n_a = static_cast<int>((next_img_row - wr0 < 32) ? (next_img_row - wr0) : 32);
-          epilogue_bf16_chunk(p, v, wr0, valid, nt * BN + c * 32, slot_a, n_a, tile, q, half, lane,
-                              stage_sa + e * (32 * kStageRowBytes), scratch_sa);
+#pragma unroll 1
+          for (int c = ((m * CHUNKS) & 1) ^ half; c < CHUNKS; c += 2) {   // items (m, c) alternate between the halves
+            uint32_t v[32];
+            tmem_ld_32x32(t0 + static_cast<uint32_t>(m * BN + c * 32), v);
+            tmem_ld_wait();
+            if (m == MT - 1 && c + 2 >= CHUNKS) {       // last TMEM read of this warp: release the accumulators early
+              tc_fence_before();
+              mbar_arrive(tempty + as);
+            }
+            epilogue_bf16_chunk(p, v, wr0, valid, nt * BN + c * 32, slot_a, n_a, tile, q, half, lane,
+                                stage_sa + e * (32 * kStageRowBytes), scratch_sa, bias_sa);
+          }
         } else {
-          uint32_t v[16];
-          tmem_ld_32x16(t0 + static_cast<uint32_t>(m * BN), v);
-          tmem_ld_wait();
-          if (valid) epilogue_narrow(p, v, img, y, x, cx, ce, cn);
+          if ((m & 1) == half) {
+            uint32_t v[16];
+            tmem_ld_32x16(t0 + static_cast<uint32_t>(m * BN), v);
+            tmem_ld_wait();
+            if (valid) epilogue_narrow(p, v, img, y, x, cx, ce, cn);
+          }
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty + as);
+      if constexpr (BN < 32) {
+        tc_fence_before();
+        mbar_arrive(tempty + as);
+      }
     }
   }
 

@@ -256,5 +256,13 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// SiLU through the hardware tanh: x*sigmoid(x) = h + h*tanh(h), h = x/2 -- 3 instructions, 1 MUFU.
+// tanh.approx.f32 has ~2^-11 absolute error, i.e. |error| <= |x| * 2.5e-4: below bf16 output rounding (2^-9).
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 }  // namespace idf
