@@ -33,6 +33,7 @@ PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int g_num_sms = 0;
 int g_attn_impl = 2;
 int g_force_mt = 0;   // 0 = choose automatically
+int g_skip_epilogue = 0;
 
 int ensure_init() {
   if (g_encode != nullptr) return IDF_OK;
@@ -93,6 +94,10 @@ int idf_set_option(const char* key, int32_t value) {
   }
   if (key != nullptr && std::strcmp(key, "conv_force_mt") == 0 && (value == 0 || value == 1 || value == 2 || value == 4)) {
     g_force_mt = value;
+    return IDF_OK;
+  }
+  if (key != nullptr && std::strcmp(key, "conv_debug_skip_epilogue") == 0) {
+    g_skip_epilogue = value ? 1 : 0;
     return IDF_OK;
   }
   return fail(IDF_ERR_ARG, "unknown option or value");
@@ -208,6 +213,7 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   }
   p.m_super = static_cast<int32_t>((m_tiles + mt - 1) / mt);
   p.m_tiles = static_cast<int32_t>(m_tiles);
+  p.debug_skip_epilogue = g_skip_epilogue;
   p.stats = (d->epilogue == IDF_EPI_BF16) ? d->stats_out : nullptr;
   if (p.stats != nullptr && d->out_ld != d->cout) { delete pl; return fail(IDF_ERR_ARG, "stats_out needs out_ld == cout"); }
   for (int i = 0; i < d->n_src; ++i) {

@@ -360,6 +360,11 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
       mbar_wait(tfull + as, (iter >> 1) & 1u);
       tc_fence_after();
       const uint32_t t0 = tmem_base + static_cast<uint32_t>(as * Cfg::ACC_COLS) + (static_cast<uint32_t>(q * 32) << 16);
+      if (p.debug_skip_epilogue) {     // measurement only
+        tc_fence_before();
+        mbar_arrive(tempty + as);
+        continue;
+      }
       const int R = p.Hp * p.Wp;
       const float inv_wp = 1.0f / static_cast<float>(p.Wp), inv_hp = 1.0f / static_cast<float>(p.Hp),
                   inv_R = 1.0f / static_cast<float>(R);

@@ -31,6 +31,7 @@ struct alignas(64) ConvKernelParams {
   int32_t m_super, n_tiles;             // super tiles of MT*128 rows; N tiles
   int32_t m_tiles;                      // 128-row tiles
   float* stats;                         // optional [m_tiles][3][out_ld][2] GroupNorm partial sums of the output
+  int32_t debug_skip_epilogue;          // measurement only: epilogue warps drain nothing (main-loop ceiling)
   int64_t rows;
   int32_t Hp, Wp, H, W;
   int32_t cout;
