@@ -98,9 +98,11 @@ typedef struct {
   const float* noise;                 /* NCHW fp32 (mode 2; may be NULL => cn ignored)           */
   const float* coef;                  /* [n_steps, 3] fp32 (mode 2)                              */
   const int32_t* step_ptr;            /* device scalar (mode 2)                                  */
-  /* optional (IDF_EPI_BF16): per-tile GroupNorm partial sums of the stored (bf16-rounded) output,
-   * fp32 [ceil(rows/128)][3][cout][2] = (sum, sumsq) over the rows of 128-row tile t that belong to
-   * image (t*128 / ((H+1)*(W+1)) + slot); consumed by idf_adagn_silu_fwd (stats0/stats1).       */
+  /* optional (IDF_EPI_BF16): GroupNorm partial sums of the stored (bf16-rounded) output, one record per
+   * 32-row window k = row/32 (windows never span 128-row tiles): fp32 [2][ceil(rows/128)*4][cout][2].
+   *   A[k][c] = (sum, sumsq) over the window's rows in the image of its first row,
+   *   B[k][c] = the same over its rows in the following image (only written if the window straddles).
+   * Consumed by idf_adagn_silu_fwd (stats0 / stats1).                                             */
   float* stats_out;
 } idf_conv_desc;
 

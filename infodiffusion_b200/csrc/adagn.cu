@@ -46,6 +46,7 @@ struct AdaGNParams {
   const float* stats0;   // per-tile partial sums from the producing conv (streaming variant)
   const float* stats1;
   int slice_rows;        // rows per CTA of the streaming variant
+  long long stats_b_windows;   // number of 32-row window records (offset of the B records, in records)
 };
 
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier
@@ -236,32 +237,32 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
   const int C = p.C;
   const int R = p.rows_per_img;
 
-  // per-channel totals over the 128-row tiles that intersect image n.  All 256 threads take part:
-  // thread -> (channel, sub-sequence of tiles), loads issued four at a time; the order of every
+  // per-channel totals over the 32-row window records that intersect image n.  All 256 threads take
+  // part: thread -> (channel, sub-sequence of windows), loads issued four at a time; the order of every
   // addition is a function of (n, geometry) only, so the result is deterministic.
-  const int t_first = (n * R) / kBM;
-  const int t_last = ((n + 1) * R - 1) / kBM;
+  const int w_first = (n * R) / 32;
+  const int w_last = ((n + 1) * R - 1) / 32;
+  const bool first_straddles = (w_first * 32) < n * R;     // window starts in image n-1: take its B record
   const int nsub = (kAdaThreads / C) > 0 ? (kAdaThreads / C) : 1;     // 4, 2, 1, 1 for C = 64, 128, 192, 256
-  const float inv_R = 1.0f / static_cast<float>(R);
   for (int idx = t; idx < C * nsub; idx += kAdaThreads) {
     const int ch = idx % C, sub = idx / C;
     const bool first = ch < p.c0;
     const int cs = first ? p.c0 : p.c1;
-    const float2* st = reinterpret_cast<const float2*>(first ? p.stats0 : p.stats1) + (first ? ch : ch - p.c0);
-    auto part = [&](int tile) -> float2 {
-      // first image of the tile = floor(tile*128 / R); exact in fp32 for < 2^23 rows
-      const int slot = n - __float2int_rd((static_cast<float>(tile * kBM) + 0.5f) * inv_R);
-      return __ldg(st + (static_cast<long long>(tile) * 3 + slot) * cs);
+    const float2* stA = reinterpret_cast<const float2*>(first ? p.stats0 : p.stats1) + (first ? ch : ch - p.c0);
+    const float2* stB = stA + p.stats_b_windows * cs;
+    auto part = [&](int w) -> float2 {
+      const float2* st = (w == w_first && first_straddles) ? stB : stA;
+      return __ldg(st + static_cast<long long>(w) * cs);
     };
     float sx = 0.f, sq = 0.f;
-    int tile = t_first + sub;
-    for (; tile + 3 * nsub <= t_last; tile += 4 * nsub) {
-      const float2 v0 = part(tile), v1 = part(tile + nsub), v2 = part(tile + 2 * nsub), v3 = part(tile + 3 * nsub);
+    int w = w_first + sub;
+    for (; w + 3 * nsub <= w_last; w += 4 * nsub) {
+      const float2 v0 = part(w), v1 = part(w + nsub), v2 = part(w + 2 * nsub), v3 = part(w + 3 * nsub);
       sx += (v0.x + v1.x) + (v2.x + v3.x);
       sq += (v0.y + v1.y) + (v2.y + v3.y);
     }
-    for (; tile <= t_last; tile += nsub) {
-      const float2 v = part(tile);
+    for (; w <= w_last; w += nsub) {
+      const float2 v = part(w);
       sx += v.x;
       sq += v.y;
     }
@@ -375,6 +376,7 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
   p.stats0 = a.stats0;
   p.stats1 = a.stats1;
   p.slice_rows = 0;
+  p.stats_b_windows = (static_cast<long long>(a.batch) * p.rows_per_img + kBM - 1) / kBM * 4;
   if (p.stats0 != nullptr && (p.c1 == 0 || p.stats1 != nullptr)) {
     // streaming variant: large slices amortise the per-CTA coefficient prologue (~192 KB of rows per CTA),
     // but keep at least ~600 CTAs in the grid when the tensor allows 32 KB slices

@@ -190,14 +190,18 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   p.rows = static_cast<int64_t>(d->batch) * p.Hp * p.Wp;
   const int64_t m_tiles = (p.rows + kBM - 1) / kBM;
   p.n_tiles = d->cout_pad / d->block_n;
-  // MT 128-row tiles per CTA: as many as TMEM/smem allow while keeping >= 2 waves of work units
+  // MT 128-row tiles per CTA work unit: the largest (best weight-tile reuse: MT = 1 streams 16 KB of
+  // weights per 256 MMA cycles and is L2-bound) that still fills the machine with <= 15 % quantisation
+  // loss in the number of rounds over the SMs.
   const int mt_max = (d->block_n == 128) ? 2 : 4;
   int mt = 1;
   for (int cand = mt_max; cand > 1; cand >>= 1) {
     if (d->block_n == 16 && cand == 2) continue;   // instantiated: 16x{1,4}
     const int64_t units = (m_tiles + cand - 1) / cand * p.n_tiles;
+    const int64_t rounds = (units + g_num_sms - 1) / g_num_sms;
     const int stage = ((cand * kBM + extra_max) * 128 + 1023) / 1024 * 1024;
-    if (units >= 2 * static_cast<int64_t>(g_num_sms) && conv_config_smem(d->block_n, stage) <= 227 * 1024) {
+    if (units >= g_num_sms && rounds * g_num_sms * 100 <= units * 115 &&
+        conv_config_smem(d->block_n, stage) <= 227 * 1024) {
       mt = cand;
       break;
     }
@@ -215,6 +219,7 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   p.m_tiles = static_cast<int32_t>(m_tiles);
   p.debug_skip_epilogue = g_skip_epilogue;
   p.stats = (d->epilogue == IDF_EPI_BF16) ? d->stats_out : nullptr;
+  p.stats_b_off = static_cast<int64_t>(m_tiles) * 4 * d->cout * 2;
   if (p.stats != nullptr && d->out_ld != d->cout) { delete pl; return fail(IDF_ERR_ARG, "stats_out needs out_ld == cout"); }
   for (int i = 0; i < d->n_src; ++i) {
     rc = encode_2d(&p.tmA[i], d->src[i], d->src_rows[i], d->src_ld[i], kBM);

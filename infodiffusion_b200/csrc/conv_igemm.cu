@@ -63,35 +63,43 @@ struct HaloCfg {
 
 __host__ __device__ inline uint32_t conv_smem_bytes(int a_stage_bytes, int a_stages, int b_stages, int b_bytes) {
   return static_cast<uint32_t>(a_stages * a_stage_bytes + b_stages * b_bytes + 512 /*barriers*/ +
-                               kStatScratchBytes + 256 /*tap table*/ + kStageBytes + kBiasBytes + 1024 /*align*/);
+                               256 /*tap table*/ + kStageBytes + kBiasBytes + 1024 /*align*/);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // epilogue for one (accumulator m, 32-column chunk) work item held in registers
 // ---------------------------------------------------------------------------------------------------
+// Coalesced residual fetch for one work item: 4 lanes cover one row's 64 bytes, 8 rows per instruction.
+// Issued one item ahead of its use so that the DRAM latency hides behind the previous item.
+__device__ __forceinline__ void residual_fetch(const ConvKernelParams& p, int64_t warp_row0, int col0, int lane,
+                                               uint4 (&res)[4]) {
+  const int sub_row = lane >> 2, sub_chunk = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t rr = warp_row0 + i * 8 + sub_row;
+    res[i] = make_uint4(0, 0, 0, 0);
+    if (rr < p.rows) res[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + rr * p.res_ld + col0) + sub_chunk);
+  }
+}
+
 // One (accumulator, 32-column) work item of an epilogue warp; executed by all 32 lanes.
 //   out = bf16(acc + bias (+ residual)), pad rows forced to zero.
 // The warp's 32 rows x 64 B pass through a private shared-memory staging tile so that global traffic is
 // coalesced: 4 lanes cover one row's 64 B, 8 rows per instruction (8 LSU wavefronts instead of the 32 a
 // row-per-lane 16-byte store at 128-byte stride costs) -- for the residual read and for the output write.
-// Optional GroupNorm partials: column sums of the STAGED (bf16-rounded) tile, split at the image
-// boundary inside the warp, combined across the 4 lane-quarter warps in a fixed order and written as
-//   stats[tile][slot][col][2] = (sum, sumsq) over the rows of `tile` in image (first image of tile + slot).
+// Optional GroupNorm partials: column sums of the STAGED (bf16-rounded) tile, written per WARP (no
+// cross-warp exchange, no barriers, fixed summation order => deterministic):
+//   statsA[(tile*4 + q)][col] = (sum, sumsq) over the warp's rows in the image of its first row,
+//   statsB[(tile*4 + q)][col] = the same over the rows that already belong to the next image
+//                               (written only when the 32-row window straddles an image boundary).
 __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, const uint32_t (&v)[32],
-                                                    int64_t warp_row0, bool valid, int col0, int slot_a, int n_a,
-                                                    int tile, int q, int half, int lane, uint32_t stage,
-                                                    uint32_t scratch, uint32_t bias_sa) {
+                                                    int64_t warp_row0, bool valid, int col0, int n_a, int tile, int q,
+                                                    int lane, uint32_t stage, uint32_t bias_sa,
+                                                    const uint4 (&res)[4]) {
   const int sub_row = lane >> 2, sub_chunk = lane & 3;     // coalesced distribution: row = 8 i + sub_row
-  // ---- residual: coalesced global read -> staging
   if (p.residual != nullptr) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = i * 8 + sub_row;
-      const int64_t rr = warp_row0 + row;
-      uint4 u = make_uint4(0, 0, 0, 0);
-      if (rr < p.rows) u = __ldg(reinterpret_cast<const uint4*>(p.residual + rr * p.res_ld + col0) + sub_chunk);
-      sts128(stage + row * kStageRowBytes + sub_chunk * 16, u);
-    }
+    for (int i = 0; i < 4; ++i) sts128(stage + (i * 8 + sub_row) * kStageRowBytes + sub_chunk * 16, res[i]);
     __syncwarp();
   }
   float f[32];
@@ -136,13 +144,13 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
       if (warp_row0 + i * 8 + sub_row < p.rows) *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(i) * 8 * p.out_ld) = o[i];
   }
   // ---- GroupNorm partial sums of the staged tile
-  if (p.stats != nullptr) {
-    // lane -> column pair (2 cp, 2 cp + 1), rows [16 h, 16 h + 16); rows < n_a belong to slot_a, the rest to slot_a + 1
+  if (p.stats != nullptr && tile < p.m_tiles) {
+    // lane -> column pair (2 cp, 2 cp + 1), rows [16 hh, 16 hh + 16); rows < n_a belong to record A, the rest to B
     const int cp = lane & 15, hh = lane >> 4;
-    float sa0 = 0.f, sa1 = 0.f, qa0 = 0.f, qa1 = 0.f, sb0 = 0.f, sb1 = 0.f, qb0 = 0.f, qb1 = 0.f;
     uint32_t raw[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) raw[i] = lds32(stage + (hh * 16 + i) * kStageRowBytes + cp * 4);
+    float sa0 = 0.f, sa1 = 0.f, qa0 = 0.f, qa1 = 0.f, sb0 = 0.f, sb1 = 0.f, qb0 = 0.f, qb1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int row = hh * 16 + i;
@@ -150,32 +158,16 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
       if (row < n_a) { sa0 += w.x; sa1 += w.y; qa0 = fmaf(w.x, w.x, qa0); qa1 = fmaf(w.y, w.y, qa1); }
       else           { sb0 += w.x; sb1 += w.y; qb0 = fmaf(w.x, w.x, qb0); qb1 = fmaf(w.y, w.y, qb1); }
     }
-    // combine the two row halves (fixed order: lower half + upper half)
-    const float oa0 = __shfl_xor_sync(0xffffffffu, sa0, 16), oa1 = __shfl_xor_sync(0xffffffffu, sa1, 16);
-    const float pa0 = __shfl_xor_sync(0xffffffffu, qa0, 16), pa1 = __shfl_xor_sync(0xffffffffu, qa1, 16);
-    const float ob0 = __shfl_xor_sync(0xffffffffu, sb0, 16), ob1 = __shfl_xor_sync(0xffffffffu, sb1, 16);
-    const float pb0 = __shfl_xor_sync(0xffffffffu, qb0, 16), pb1 = __shfl_xor_sync(0xffffffffu, qb1, 16);
-    if (hh == 0) {
-      const uint32_t my = scratch + (((half * 4 + q) * 3) * 32 + 2 * cp) * 8;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        float2 e0 = make_float2(0.f, 0.f), e1 = make_float2(0.f, 0.f);
-        if (s == slot_a) { e0 = make_float2(sa0 + oa0, qa0 + pa0); e1 = make_float2(sa1 + oa1, qa1 + pa1); }
-        else if (s == slot_a + 1) { e0 = make_float2(sb0 + ob0, qb0 + pb0); e1 = make_float2(sb1 + ob1, qb1 + pb1); }
-        sts_f2(my + s * 32 * 8, e0);
-        sts_f2(my + s * 32 * 8 + 8, e1);
-      }
+    // combine the two row halves (fixed order: lower half + upper half); lanes 0..15 write 16 B each = 256 B row
+    sa0 += __shfl_xor_sync(0xffffffffu, sa0, 16); sa1 += __shfl_xor_sync(0xffffffffu, sa1, 16);
+    qa0 += __shfl_xor_sync(0xffffffffu, qa0, 16); qa1 += __shfl_xor_sync(0xffffffffu, qa1, 16);
+    const int64_t rec = (static_cast<int64_t>(tile) * 4 + q) * p.out_ld + col0 + 2 * cp;
+    if (hh == 0) *reinterpret_cast<float4*>(p.stats + 2 * rec) = make_float4(sa0, qa0, sa1, qa1);
+    if (n_a < 32) {                                  // warp-uniform: the window straddles an image boundary
+      sb0 += __shfl_xor_sync(0xffffffffu, sb0, 16); sb1 += __shfl_xor_sync(0xffffffffu, sb1, 16);
+      qb0 += __shfl_xor_sync(0xffffffffu, qb0, 16); qb1 += __shfl_xor_sync(0xffffffffu, qb1, 16);
+      if (hh == 0) *reinterpret_cast<float4*>(p.stats + p.stats_b_off + 2 * rec) = make_float4(sb0, qb0, sb1, qb1);
     }
-    named_bar_sync(1 + half, 128);
-    if (q < 3 && tile < p.m_tiles) {               // warp q combines image slot q over the four quarters
-      const uint32_t sc = scratch + ((half * 4 * 3 + q) * 32 + lane) * 8;
-      const float2 x0 = lds_f2(sc), x1 = lds_f2(sc + 96 * 8), x2 = lds_f2(sc + 2 * 96 * 8), x3 = lds_f2(sc + 3 * 96 * 8);
-      float2 tot;
-      tot.x = (x0.x + x1.x) + (x2.x + x3.x);
-      tot.y = (x0.y + x1.y) + (x2.y + x3.y);
-      reinterpret_cast<float2*>(p.stats)[(static_cast<int64_t>(tile) * 3 + q) * p.out_ld + col0 + lane] = tot;
-    }
-    named_bar_sync(1 + half, 128);
   }
   __syncwarp();   // staging is reused by the next item
 }
@@ -217,9 +209,7 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
   uint64_t* tfull = b_empty + BS;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float2* stat_scratch = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(a_full) + 512);
-  const uint32_t scratch_sa = smem_u32(stat_scratch);
-  const uint32_t tap_sa = scratch_sa + kStatScratchBytes;       // per-tap descriptor offsets
+  const uint32_t tap_sa = smem_u32(a_full) + 512;               // per-tap descriptor offsets
   const uint32_t stage_sa = tap_sa + 256;                       // epilogue staging tiles
   const uint32_t bias_sa = stage_sa + kStageBytes;              // bias vector
 
@@ -352,6 +342,11 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
       cn = p.coef[3 * step + 2];
     }
     constexpr int CHUNKS = (BN >= 32) ? BN / 32 : 1;
+    uint4 res_next[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (BN >= 32 && p.residual != nullptr && static_cast<int>(blockIdx.x) < total) {   // first item of the first super tile
+      const int ms0 = blockIdx.x / p.n_tiles, nt0 = blockIdx.x - ms0 * p.n_tiles;
+      residual_fetch(p, static_cast<int64_t>(ms0) * MT * kBM + q * 32, nt0 * BN + half * 32, lane, res_next);
+    }
     int iter = 0;
     for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
       const int ms = st / p.n_tiles;
@@ -380,7 +375,6 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
         const int y = rq - img * p.Hp;
         const bool valid = (r < p.rows) && (x < p.W) && (y < p.H);
         const int img_w = __float2int_rd((static_cast<float>(wr0) + 0.5f) * inv_R);
-        const int slot_a = img_w - __float2int_rd((static_cast<float>(tile * kBM) + 0.5f) * inv_R);
         const int64_t next_img_row = static_cast<int64_t>(img_w + 1) * R;
         const int n_a = static_cast<int>((next_img_row - wr0 < 32) ? (next_img_row - wr0) : 32);
         if constexpr (BN >= 32) {
@@ -388,13 +382,25 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
           for (int c = ((m * CHUNKS) & 1) ^ half; c < CHUNKS; c += 2) {   // items (m, c) alternate between the halves
             uint32_t v[32];
             tmem_ld_32x32(t0 + static_cast<uint32_t>(m * BN + c * 32), v);
+            uint4 res_cur[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) res_cur[i] = res_next[i];
+            if (p.residual != nullptr) {             // prefetch the NEXT item's residual (this or the next super tile)
+              int nm = m, nc = c + 2, nms = ms, nnt = nt;
+              if (nc >= CHUNKS) { nm = m + 1; nc = (((m + 1) * CHUNKS) & 1) ^ half; }
+              if (nm >= MT) {
+                const int nst = st + static_cast<int>(gridDim.x);
+                nms = nst / p.n_tiles; nnt = nst - nms * p.n_tiles; nm = 0; nc = half;
+              }
+              residual_fetch(p, (static_cast<int64_t>(nms) * MT + nm) * kBM + q * 32, nnt * BN + nc * 32, lane, res_next);
+            }
             tmem_ld_wait();
             if (m == MT - 1 && c + 2 >= CHUNKS) {       // last TMEM read of this warp: release the accumulators early
               tc_fence_before();
               mbar_arrive(tempty + as);
             }
-            epilogue_bf16_chunk(p, v, wr0, valid, nt * BN + c * 32, slot_a, n_a, tile, q, half, lane,
-                                stage_sa + e * (32 * kStageRowBytes), scratch_sa, bias_sa);
+            epilogue_bf16_chunk(p, v, wr0, valid, nt * BN + c * 32, n_a, tile, q, lane,
+                                stage_sa + e * (32 * kStageRowBytes), bias_sa, res_cur);
           }
         } else {
           if ((m & 1) == half) {

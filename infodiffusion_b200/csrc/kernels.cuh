@@ -30,7 +30,9 @@ struct alignas(64) ConvKernelParams {
   int32_t a_stage_bytes;                // bytes of one halo stage (multiple of 1024)
   int32_t m_super, n_tiles;             // super tiles of MT*128 rows; N tiles
   int32_t m_tiles;                      // 128-row tiles
-  float* stats;                         // optional [m_tiles][3][out_ld][2] GroupNorm partial sums of the output
+  float* stats;                         // optional GroupNorm partial sums: records A then records B, each
+                                        // [m_tiles*4 (32-row windows)][out_ld][2] fp32 (sum, sumsq)
+  int64_t stats_b_off;                  // float offset of the B records
   int32_t debug_skip_epilogue;          // measurement only: epilogue warps drain nothing (main-loop ceiling)
   int64_t rows;
   int32_t Hp, Wp, H, W;

@@ -53,13 +53,13 @@ class Act:
 
     def __init__(self, t, H, C, phases, rows):
         self.t, self.H, self.C, self.phases, self.rows = t, H, C, phases, rows
-        self.stats = None          # fp32 [ceil(rows/128), 3, C, 2] GroupNorm partial sums (written by conv epilogues)
+        self.stats = None          # fp32 [2, ceil(rows/128)*4, C, 2] GroupNorm window partial sums (conv epilogues)
         self.has_stats = False     # True while `stats` describes the current contents of `t`
 
     def stats_buffer(self) -> torch.Tensor:
         if self.stats is None:
             tiles = (self.rows + 127) // 128
-            self.stats = torch.zeros(tiles * 3 * self.C * 2, dtype=torch.float32, device=self.t.device)
+            self.stats = torch.zeros(2 * tiles * 4 * self.C * 2, dtype=torch.float32, device=self.t.device)
         return self.stats
 
 
