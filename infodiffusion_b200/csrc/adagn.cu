@@ -47,6 +47,7 @@ struct AdaGNParams {
   const float* stats1;
   int slice_rows;        // rows per CTA of the streaming variant
   long long stats_b_windows;   // number of 32-row window records (offset of the B records, in records)
+  int block_rows;              // rows per ring stage of the streaming variant
 };
 
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier
@@ -227,7 +228,12 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_kernel(const AdaGNParams p)
 // fold partials -> (A, B) per channel, then y = silu(A*x + B) with 16-byte loads / stores, 4 in flight.
 // No clusters, no barriers in the hot loop, one HBM read + one HBM write.
 // ---------------------------------------------------------------------------------------------------
+constexpr int kRing = 3;            // bulk-copy stages per CTA (3 x 16 KB: three CTAs per SM, 144 KB in flight)
+constexpr int kRingStageBytes = 16384;
+
 __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNParams p) {
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  __shared__ __align__(8) uint64_t s_full[kRing];
   __shared__ float2 s_sub[4][kMaxC];
   __shared__ float s_tot[2 * kMaxC];
   __shared__ float s_mean[32], s_rstd[32];
@@ -308,52 +314,79 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
   }
   __syncthreads();
 
+  // ---------------------------------------------------------------- streaming sweep
+  // The slice is pulled through a ring of kRing shared-memory stages by bulk-async copies (one per
+  // source per stage, issued by thread 0, completion on an mbarrier), so ~48-64 KB per CTA are in
+  // flight regardless of register pressure; threads read 16-byte vectors from the stage, apply
+  // y = silu(A*x + B) and store straight to global memory (coalesced 16-byte stores).
   const int VPR = C >> 3;
   const int rpp = kAdaThreads / VPR;
-  if (t >= rpp * VPR) return;
+  const bool active = t < rpp * VPR;
   const int vl = t % VPR;
   const int rsub = t / VPR;
   const int v0 = p.c0 >> 3;
   float A[8], B[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { const float2 ab = s_ab[vl * 8 + j]; A[j] = ab.x; B[j] = ab.y; }
+  for (int j = 0; j < 8; ++j) { const float2 ab = s_ab[(active ? vl : 0) * 8 + j]; A[j] = ab.x; B[j] = ab.y; }
   const bool do_silu = p.apply_silu != 0;
   const bool from0 = vl < v0;
-  const bf16* src = from0 ? (p.src0 + vl * 8) : (p.src1 + (vl - v0) * 8);
-  const int pitch = from0 ? p.c0 : p.c1;
   const long long row_base = static_cast<long long>(n) * R;
   const int r_begin = blockIdx.x * p.slice_rows;
   const int r_end = min(R, r_begin + p.slice_rows);
+  const int RB = p.block_rows;                                  // rows per stage
+  const int nblk = (r_end - r_begin + RB - 1) / RB;
+  const uint32_t stage_bytes = static_cast<uint32_t>(RB) * C * 2;
+  const uint32_t ring = smem_u32(ring_raw);
+  const uint32_t my_off = from0 ? static_cast<uint32_t>(vl * 16) : static_cast<uint32_t>(RB * p.c0 * 2 + (vl - v0) * 16);
+  const uint32_t my_pitch = from0 ? p.c0 * 2 : p.c1 * 2;
   const float inv_wp = 1.0f / static_cast<float>(p.Wp);
-  for (int r = r_begin + rsub; r < r_end; r += kUnroll * rpp) {
-    uint4 u[kUnroll];
-    bool ok[kUnroll];
+
+  auto issue = [&](int blk) {                                   // thread 0 only
+    const int st = blk % kRing;
+    const int r0 = r_begin + blk * RB;
+    const int nr = min(RB, r_end - r0);
+    const uint32_t b0 = static_cast<uint32_t>(nr) * p.c0 * 2, b1 = static_cast<uint32_t>(nr) * p.c1 * 2;
+    mbar_arrive_expect_tx(&s_full[st], b0 + b1);
+    bulk_load(ring_raw + st * stage_bytes, p.src0 + (row_base + r0) * p.c0, b0, &s_full[st]);
+    if (b1) bulk_load(ring_raw + st * stage_bytes + RB * p.c0 * 2, p.src1 + (row_base + r0) * p.c1, b1, &s_full[st]);
+  };
+  if (t == 0) {
+    for (int i = 0; i < kRing; ++i) mbar_init(&s_full[i], 1);
+    fence_mbar_init();
+    for (int b = 0; b < kRing && b < nblk; ++b) issue(b);
+  }
+  __syncthreads();
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int st = blk % kRing;
+    mbar_wait(&s_full[st], (blk / kRing) & 1u);
+    const int r0 = r_begin + blk * RB;
+    const int nr = min(RB, r_end - r0);
+    if (active) {
+      const uint32_t base = ring + st * stage_bytes + my_off;
+#pragma unroll 4
+      for (int lr = rsub; lr < nr; lr += rpp) {
+        const int rr = r0 + lr;
+        const int y = __float2int_rd((static_cast<float>(rr) + 0.5f) * inv_wp);
+        const int x = rr - y * p.Wp;
+        if (x >= p.W || y >= p.H) continue;                     // pad rows: never written
+        const uint4 u = lds128(base + lr * my_pitch);
+        const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+        float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
 #pragma unroll
-    for (int k = 0; k < kUnroll; ++k) {          // all loads first (memory-level parallelism)
-      const int rr = r + k * rpp;
-      const int y = __float2int_rd((static_cast<float>(rr) + 0.5f) * inv_wp);
-      const int x = rr - y * p.Wp;
-      ok[k] = (rr < r_end) && (x < p.W) && (y < p.H);      // pad rows: neither read nor written
-      if (ok[k]) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (row_base + rr) * pitch));
-    }
-#pragma unroll
-    for (int k = 0; k < kUnroll; ++k) {
-      if (!ok[k]) continue;
-      const float2 a0 = unpack_bf16x2(u[k].x), a1 = unpack_bf16x2(u[k].y), a2 = unpack_bf16x2(u[k].z),
-                   a3 = unpack_bf16x2(u[k].w);
-      float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float v = fmaf(f[j], A[j], B[j]);
-        f[j] = do_silu ? silu_fast(v) : v;
+        for (int j = 0; j < 8; ++j) {
+          const float v = fmaf(f[j], A[j], B[j]);
+          f[j] = do_silu ? silu_fast(v) : v;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]);
+        o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]);
+        o.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(p.out + (row_base + rr) * C + vl * 8) = o;
       }
-      uint4 o;
-      o.x = pack_bf16x2(f[0], f[1]);
-      o.y = pack_bf16x2(f[2], f[3]);
-      o.z = pack_bf16x2(f[4], f[5]);
-      o.w = pack_bf16x2(f[6], f[7]);
-      *reinterpret_cast<uint4*>(p.out + (row_base + r + k * rpp) * C + vl * 8) = o;
     }
+    __syncthreads();                                            // everyone is done reading this stage
+    if (t == 0 && blk + kRing < nblk) issue(blk + kRing);
   }
 }
 
@@ -387,7 +420,16 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
     while (static_cast<long long>(slices) * a.batch < 600 && slices < max_slices) ++slices;
     p.slice_rows = (p.rows_per_img + slices - 1) / slices;
     slices = (p.rows_per_img + p.slice_rows - 1) / p.slice_rows;
-    adagn_apply_kernel<<<dim3(slices, a.batch, 1), kAdaThreads, 0, stream>>>(p);
+    p.block_rows = kRingStageBytes / (p.C * 2);
+    const size_t ring_bytes = static_cast<size_t>(kRing) * p.block_rows * p.C * 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(adagn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kRing * kRingStageBytes);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    adagn_apply_kernel<<<dim3(slices, a.batch, 1), kAdaThreads, ring_bytes, stream>>>(p);
     return cudaGetLastError();
   }
 
