@@ -243,6 +243,28 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
   const int C = p.C;
   const int R = p.rows_per_img;
 
+  // ---- start streaming the slice right away: the ring fills while the coefficients are computed
+  const long long row_base = static_cast<long long>(n) * R;
+  const int r_begin = blockIdx.x * p.slice_rows;
+  const int r_end = min(R, r_begin + p.slice_rows);
+  const int RB = p.block_rows;                                  // rows per stage
+  const int nblk = (r_end - r_begin + RB - 1) / RB;
+  const uint32_t stage_bytes = static_cast<uint32_t>(RB) * C * 2;
+  auto issue = [&](int blk) {                                   // thread 0 only
+    const int st = blk % kRing;
+    const int r0 = r_begin + blk * RB;
+    const int nr = min(RB, r_end - r0);
+    const uint32_t b0 = static_cast<uint32_t>(nr) * p.c0 * 2, b1 = static_cast<uint32_t>(nr) * p.c1 * 2;
+    mbar_arrive_expect_tx(&s_full[st], b0 + b1);
+    bulk_load(ring_raw + st * stage_bytes, p.src0 + (row_base + r0) * p.c0, b0, &s_full[st]);
+    if (b1) bulk_load(ring_raw + st * stage_bytes + RB * p.c0 * 2, p.src1 + (row_base + r0) * p.c1, b1, &s_full[st]);
+  };
+  if (t == 0) {
+    for (int i = 0; i < kRing; ++i) mbar_init(&s_full[i], 1);
+    fence_mbar_init();
+    for (int b = 0; b < kRing && b < nblk; ++b) issue(b);
+  }
+
   // per-channel totals over the 32-row window records that intersect image n.  All 256 threads take
   // part: thread -> (channel, sub-sequence of windows), loads issued four at a time; the order of every
   // addition is a function of (n, geometry) only, so the result is deterministic.
@@ -262,10 +284,11 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
     };
     float sx = 0.f, sq = 0.f;
     int w = w_first + sub;
-    for (; w + 3 * nsub <= w_last; w += 4 * nsub) {
+    for (; w + 7 * nsub <= w_last; w += 8 * nsub) {
       const float2 v0 = part(w), v1 = part(w + nsub), v2 = part(w + 2 * nsub), v3 = part(w + 3 * nsub);
-      sx += (v0.x + v1.x) + (v2.x + v3.x);
-      sq += (v0.y + v1.y) + (v2.y + v3.y);
+      const float2 v4 = part(w + 4 * nsub), v5 = part(w + 5 * nsub), v6 = part(w + 6 * nsub), v7 = part(w + 7 * nsub);
+      sx += ((v0.x + v1.x) + (v2.x + v3.x)) + ((v4.x + v5.x) + (v6.x + v7.x));
+      sq += ((v0.y + v1.y) + (v2.y + v3.y)) + ((v4.y + v5.y) + (v6.y + v7.y));
     }
     for (; w <= w_last; w += nsub) {
       const float2 v = part(w);
@@ -330,32 +353,10 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
   for (int j = 0; j < 8; ++j) { const float2 ab = s_ab[(active ? vl : 0) * 8 + j]; A[j] = ab.x; B[j] = ab.y; }
   const bool do_silu = p.apply_silu != 0;
   const bool from0 = vl < v0;
-  const long long row_base = static_cast<long long>(n) * R;
-  const int r_begin = blockIdx.x * p.slice_rows;
-  const int r_end = min(R, r_begin + p.slice_rows);
-  const int RB = p.block_rows;                                  // rows per stage
-  const int nblk = (r_end - r_begin + RB - 1) / RB;
-  const uint32_t stage_bytes = static_cast<uint32_t>(RB) * C * 2;
   const uint32_t ring = smem_u32(ring_raw);
   const uint32_t my_off = from0 ? static_cast<uint32_t>(vl * 16) : static_cast<uint32_t>(RB * p.c0 * 2 + (vl - v0) * 16);
   const uint32_t my_pitch = from0 ? p.c0 * 2 : p.c1 * 2;
   const float inv_wp = 1.0f / static_cast<float>(p.Wp);
-
-  auto issue = [&](int blk) {                                   // thread 0 only
-    const int st = blk % kRing;
-    const int r0 = r_begin + blk * RB;
-    const int nr = min(RB, r_end - r0);
-    const uint32_t b0 = static_cast<uint32_t>(nr) * p.c0 * 2, b1 = static_cast<uint32_t>(nr) * p.c1 * 2;
-    mbar_arrive_expect_tx(&s_full[st], b0 + b1);
-    bulk_load(ring_raw + st * stage_bytes, p.src0 + (row_base + r0) * p.c0, b0, &s_full[st]);
-    if (b1) bulk_load(ring_raw + st * stage_bytes + RB * p.c0 * 2, p.src1 + (row_base + r0) * p.c1, b1, &s_full[st]);
-  };
-  if (t == 0) {
-    for (int i = 0; i < kRing; ++i) mbar_init(&s_full[i], 1);
-    fence_mbar_init();
-    for (int b = 0; b < kRing && b < nblk; ++b) issue(b);
-  }
-  __syncthreads();
   for (int blk = 0; blk < nblk; ++blk) {
     const int st = blk % kRing;
     mbar_wait(&s_full[st], (blk / kRing) & 1u);
@@ -411,13 +412,13 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
   p.slice_rows = 0;
   p.stats_b_windows = (static_cast<long long>(a.batch) * p.rows_per_img + kBM - 1) / kBM * 4;
   if (p.stats0 != nullptr && (p.c1 == 0 || p.stats1 != nullptr)) {
-    // streaming variant: large slices amortise the per-CTA coefficient prologue (~192 KB of rows per CTA),
-    // but keep at least ~600 CTAs in the grid when the tensor allows 32 KB slices
+    // streaming variant: bytes in flight come from the per-CTA ring, not from occupancy, so a few hundred
+    // CTAs suffice; large slices amortise the per-CTA coefficient prologue
     const long long bytes_s = static_cast<long long>(p.rows_per_img) * p.C * 2;
-    int slices = static_cast<int>((bytes_s + 196607) / 196608);
-    if (slices < 1) slices = 1;
     const int max_slices = static_cast<int>((bytes_s + 32767) / 32768);
-    while (static_cast<long long>(slices) * a.batch < 600 && slices < max_slices) ++slices;
+    int slices = (400 + a.batch - 1) / a.batch;
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
     p.slice_rows = (p.rows_per_img + slices - 1) / slices;
     slices = (p.rows_per_img + p.slice_rows - 1) / p.slice_rows;
     p.block_rows = kRingStageBytes / (p.C * 2);
