@@ -114,6 +114,23 @@ int idf_conv_run(const idf_conv_plan* plan, idf_stream_t stream);
 int64_t idf_conv_plan_tiles(const idf_conv_plan* plan);
 
 /* ------------------------------------------------------------------------------------------
+ * Convolution weight gradient (autograd of nn.Conv2d w.r.t. weight), tcgen05, split-K with atomics:
+ *   dW[co, t, ci] += sum_r dY[r, co] * X[r + tap_off[t], ci]       dW fp32 [cout, n_taps, cin]
+ * dY: bf16 pad-flat [rows, cout] (pad rows zero), X: bf16 [x_rows, cin] (cin multiple of 64).
+ * The data gradient needs no kernel of its own: it is idf_conv_run over dY with transposed weights.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* dy; int64_t rows; int32_t cout;
+  const void* x; int64_t x_rows; int32_t cin;
+  int32_t n_taps; int32_t tap_off[9];
+  float* dw;
+} idf_wgrad_desc;
+typedef struct idf_wgrad_plan idf_wgrad_plan;
+int idf_wgrad_plan_create(const idf_wgrad_desc* desc, idf_wgrad_plan** plan);
+int idf_wgrad_plan_destroy(idf_wgrad_plan* plan);
+int idf_wgrad_run(const idf_wgrad_plan* plan, idf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused AdaGN: GroupNorm(32) statistics + affine + timestep scale/shift + latent-z scale/shift
  * + SiLU, one HBM read and one HBM write.  Replaces nn.GroupNorm + the modulation chain + nn.SiLU
  * at modules.py:214-215, 219-221, 225-227, 249-253, 265-266, 278-280, 284-286, 312-319, 335-336,
@@ -137,8 +154,27 @@ typedef struct {
   /* optional: per-tile partial sums written by the producing convolution (idf_conv_desc.stats_out).
    * When given for every source the kernel is a single streaming sweep (no statistics pass).     */
   const float* stats0; const float* stats1;
+  /* training only: inverted dropout applied after SiLU (nn.Dropout at modules.py:221,227,280,286,342).
+   * keep-mask = hash(*dropout_seed, dropout_layer, element index) >= p; 0 disables.               */
+  float dropout_p; const uint64_t* dropout_seed; uint32_t dropout_layer;
 } idf_adagn_args;
 int idf_adagn_silu_fwd(const idf_adagn_args* args, idf_stream_t stream);
+
+/* Backward of idf_adagn_silu_fwd (streaming variant: stats0/stats1 required).
+ *   dx0 / dx1 : gradient w.r.t. the sources (bf16 pad-flat; added to the buffer if acc0 / acc1)
+ *   sums      : fp32 [batch, C, 2] = (sum_hw dv, sum_hw dv * xhat) with dv = dL/d(pre-activation) -- every
+ *               parameter / modulation gradient of the op is a closed form of these (see models.py mirror)
+ *   ws        : fp32 workspace, idf_adagn_bwd_ws_floats(batch, C) floats                            */
+typedef struct {
+  idf_adagn_args f;
+  const void* dy;
+  void* dx0; void* dx1;
+  int32_t acc0, acc1;
+  float* sums;
+  float* ws;
+} idf_adagn_bwd_args;
+int64_t idf_adagn_bwd_ws_floats(int32_t batch, int32_t C);
+int idf_adagn_silu_bwd(const idf_adagn_bwd_args* args, idf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused single-head self attention (QK^T -> softmax -> PV on tcgen05), S = H*W tokens, d = 128.

@@ -46,6 +46,15 @@ class ConvDesc(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("dy", C.c_void_p), ("rows", C.c_int64), ("cout", C.c_int32),
+        ("x", C.c_void_p), ("x_rows", C.c_int64), ("cin", C.c_int32),
+        ("n_taps", C.c_int32), ("tap_off", C.c_int32 * 9),
+        ("dw", C.c_void_p),
+    ]
+
+
 class AdaGNArgs(C.Structure):
     _fields_ = [
         ("src0", C.c_void_p), ("c0", C.c_int32),
@@ -59,6 +68,18 @@ class AdaGNArgs(C.Structure):
         ("step_ptr", C.c_void_p),
         ("apply_silu", C.c_int32),
         ("stats0", C.c_void_p), ("stats1", C.c_void_p),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_void_p), ("dropout_layer", C.c_uint32),
+    ]
+
+
+class AdaGNBwdArgs(C.Structure):
+    _fields_ = [
+        ("f", AdaGNArgs),
+        ("dy", C.c_void_p),
+        ("dx0", C.c_void_p), ("dx1", C.c_void_p),
+        ("acc0", C.c_int32), ("acc1", C.c_int32),
+        ("sums", C.c_void_p),
+        ("ws", C.c_void_p),
     ]
 
 
@@ -72,7 +93,12 @@ SIGNATURES = {
     "idf_conv_plan_destroy": (C.c_int, [C.c_void_p]),
     "idf_conv_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "idf_conv_plan_tiles": (C.c_int64, [C.c_void_p]),
+    "idf_wgrad_plan_create": (C.c_int, [C.POINTER(WgradDesc), C.POINTER(C.c_void_p)]),
+    "idf_wgrad_plan_destroy": (C.c_int, [C.c_void_p]),
+    "idf_wgrad_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "idf_adagn_silu_fwd": (C.c_int, [C.POINTER(AdaGNArgs), C.c_void_p]),
+    "idf_adagn_bwd_ws_floats": (C.c_int64, [C.c_int32, C.c_int32]),
+    "idf_adagn_silu_bwd": (C.c_int, [C.POINTER(AdaGNBwdArgs), C.c_void_p]),
     "idf_attn_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                C.c_void_p]),
     "idf_linear_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,

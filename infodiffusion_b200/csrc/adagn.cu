@@ -48,6 +48,10 @@ struct AdaGNParams {
   int slice_rows;        // rows per CTA of the streaming variant
   long long stats_b_windows;   // number of 32-row window records (offset of the B records, in records)
   int block_rows;              // rows per ring stage of the streaming variant
+  unsigned drop_thr16;         // dropout: drop iff 16 random bits < thr16 (0 = off)
+  float drop_scale;            // 1 / (1 - p)
+  const unsigned long long* drop_seed;
+  unsigned drop_layer;
 };
 
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier
@@ -357,6 +361,7 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
   const uint32_t my_off = from0 ? static_cast<uint32_t>(vl * 16) : static_cast<uint32_t>(RB * p.c0 * 2 + (vl - v0) * 16);
   const uint32_t my_pitch = from0 ? p.c0 * 2 : p.c1 * 2;
   const float inv_wp = 1.0f / static_cast<float>(p.Wp);
+  const uint64_t drop_seed = (p.drop_thr16 != 0 && p.drop_seed != nullptr) ? *p.drop_seed : 0ull;
   for (int blk = 0; blk < nblk; ++blk) {
     const int st = blk % kRing;
     mbar_wait(&s_full[st], (blk / kRing) & 1u);
@@ -377,6 +382,12 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
         for (int j = 0; j < 8; ++j) {
           const float v = fmaf(f[j], A[j], B[j]);
           f[j] = do_silu ? silu_fast(v) : v;
+        }
+        if (p.drop_thr16 != 0) {
+          const uint32_t keep = dropout_keep8(drop_seed, p.drop_layer,
+                                              static_cast<uint64_t>(row_base + rr) * VPR + vl, p.drop_thr16);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * p.drop_scale : 0.f;
         }
         uint4 o;
         o.x = pack_bf16x2(f[0], f[1]);
@@ -410,6 +421,13 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
   p.stats0 = a.stats0;
   p.stats1 = a.stats1;
   p.slice_rows = 0;
+  p.drop_thr16 = 0; p.drop_scale = 1.f; p.drop_seed = reinterpret_cast<const unsigned long long*>(a.dropout_seed);
+  p.drop_layer = a.dropout_layer;
+  if (a.dropout_p > 0.f) {
+    if (a.stats0 == nullptr) return cudaErrorInvalidValue;     // dropout lives in the streaming variant only
+    p.drop_thr16 = static_cast<unsigned>(a.dropout_p * 65536.f + 0.5f);
+    p.drop_scale = 65536.f / (65536.f - static_cast<float>(p.drop_thr16));
+  }
   p.stats_b_windows = (static_cast<long long>(a.batch) * p.rows_per_img + kBM - 1) / kBM * 4;
   if (p.stats0 != nullptr && (p.c1 == 0 || p.stats1 != nullptr)) {
     // streaming variant: bytes in flight come from the per-CTA ring, not from occupancy, so a few hundred

@@ -270,10 +270,87 @@ int idf_conv_run(const idf_conv_plan* plan, idf_stream_t stream) {
   return IDF_OK;
 }
 
+struct idf_wgrad_plan {
+  WgradKernelParams params;
+  int grid;
+};
+
+int idf_wgrad_plan_create(const idf_wgrad_desc* d, idf_wgrad_plan** out_plan) {
+  if (d == nullptr || out_plan == nullptr) return fail(IDF_ERR_ARG, "null argument");
+  int rc = ensure_init();
+  if (rc != IDF_OK) return rc;
+  if (d->dy == nullptr || d->x == nullptr || d->dw == nullptr) return fail(IDF_ERR_ARG, "null tensor");
+  if (d->cin % 64 != 0 || d->cout % 8 != 0 || d->n_taps < 1 || d->n_taps > 9) return fail(IDF_ERR_ARG, "bad wgrad shape");
+  idf_wgrad_plan* pl = new (std::nothrow) idf_wgrad_plan;
+  if (pl == nullptr) return fail(IDF_ERR_NOMEM, "out of host memory");
+  std::memset(pl, 0, sizeof(*pl));
+  WgradKernelParams& p = pl->params;
+  // tap clusters: taps whose offsets lie within 8 rows share one X halo (the kx = 0,1,2 taps of a kernel row)
+  std::vector<std::pair<int, int>> taps;   // (offset, tap id)
+  for (int t = 0; t < d->n_taps; ++t) taps.push_back({d->tap_off[t], t});
+  std::sort(taps.begin(), taps.end());
+  struct Cl { int base; int n; int rel[3]; int id[3]; };
+  std::vector<Cl> cls;
+  for (auto& t : taps) {
+    if (!cls.empty() && cls.back().n < 3 && t.first - cls.back().base < 8) {
+      Cl& c = cls.back();
+      c.rel[c.n] = t.first - c.base; c.id[c.n] = t.second; c.n++;
+    } else {
+      Cl c{}; c.base = t.first; c.n = 1; c.rel[0] = 0; c.id[0] = t.second;
+      cls.push_back(c);
+    }
+  }
+  const int ci_step = d->cin >= 128 ? 128 : 64;
+  p.n_units = 0;
+  for (int co0 = 0; co0 < d->cout; co0 += 128)
+    for (int ci0 = 0; ci0 < d->cin; ci0 += ci_step)
+      for (auto& c : cls) {
+        if (p.n_units == kWgMaxUnits) { delete pl; return fail(IDF_ERR_ARG, "too many wgrad units"); }
+        const int u = p.n_units++;
+        p.u_co0[u] = co0; p.u_ci0[u] = ci0; p.u_cin[u] = std::min(ci_step, d->cin - ci0);
+        p.u_ntap[u] = c.n; p.u_base[u] = c.base;
+        for (int k = 0; k < c.n; ++k) { p.u_rel[u * 3 + k] = c.rel[k]; p.u_tap[u * 3 + k] = c.id[k]; }
+      }
+  p.n_kb = static_cast<int32_t>((d->rows + 127) / 128);
+  int slabs = (2 * g_num_sms + p.n_units - 1) / p.n_units;
+  if (slabs > p.n_kb) slabs = p.n_kb;
+  if (slabs < 1) slabs = 1;
+  p.kb_per_slab = (p.n_kb + slabs - 1) / slabs;
+  slabs = (p.n_kb + p.kb_per_slab - 1) / p.kb_per_slab;
+  p.cout = d->cout; p.cin = d->cin; p.ntaps = d->n_taps; p.dw = d->dw;
+  rc = encode_2d(&p.tmDY, d->dy, d->rows, d->cout, 128);
+  if (rc == IDF_OK) rc = encode_2d(&p.tmX, d->x, d->x_rows, d->cin, 136);
+  if (rc != IDF_OK) { delete pl; return rc; }
+  pl->grid = p.n_units * slabs;
+  *out_plan = pl;
+  return IDF_OK;
+}
+
+int idf_wgrad_plan_destroy(idf_wgrad_plan* plan) {
+  delete plan;
+  return IDF_OK;
+}
+
+int idf_wgrad_run(const idf_wgrad_plan* plan, idf_stream_t stream) {
+  if (plan == nullptr) return fail(IDF_ERR_ARG, "null plan");
+  cudaError_t e = launch_wgrad(plan->params, plan->grid, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "wgrad launch");
+  return IDF_OK;
+}
+
 int idf_adagn_silu_fwd(const idf_adagn_args* a, idf_stream_t stream) {
   if (a == nullptr || a->src0 == nullptr || a->out == nullptr) return fail(IDF_ERR_ARG, "null argument");
   cudaError_t e = launch_adagn(*a, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "adagn launch");
+  return IDF_OK;
+}
+
+int64_t idf_adagn_bwd_ws_floats(int32_t batch, int32_t C) { return adagn_bwd_ws_floats(batch, C); }
+
+int idf_adagn_silu_bwd(const idf_adagn_bwd_args* b, idf_stream_t stream) {
+  if (b == nullptr) return fail(IDF_ERR_ARG, "null argument");
+  cudaError_t e = launch_adagn_bwd(*b, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "adagn backward launch (needs stats0/stats1, dy, dx, sums, ws)");
   return IDF_OK;
 }
 

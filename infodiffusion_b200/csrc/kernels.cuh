@@ -50,9 +50,24 @@ struct alignas(64) ConvKernelParams {
   const int32_t* step_ptr;
 };
 
+constexpr int kWgMaxUnits = 64;
+struct alignas(64) WgradKernelParams {
+  CUtensorMap tmDY;                 // dY [rows, Cout]  box {64, 128}
+  CUtensorMap tmX;                  // X  [rowsX, Cin]  box {64, 136}
+  int32_t n_units;
+  int32_t u_co0[kWgMaxUnits], u_ci0[kWgMaxUnits], u_cin[kWgMaxUnits], u_ntap[kWgMaxUnits], u_base[kWgMaxUnits];
+  int32_t u_rel[kWgMaxUnits * 3], u_tap[kWgMaxUnits * 3];
+  int32_t n_kb, kb_per_slab;
+  int32_t cout, cin, ntaps;
+  float* dw;                        // fp32 [Cout, ntaps, Cin], accumulated with atomics
+};
+cudaError_t launch_wgrad(const WgradKernelParams& p, int grid, cudaStream_t stream);
+
 cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, int grid, cudaStream_t stream);
 uint32_t conv_config_smem(int block_n, int a_stage_bytes);
 cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream);
+cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, cudaStream_t stream);
+int64_t adagn_bwd_ws_floats(int batch, int C);
 cudaError_t launch_attn(const bf16* qkv, bf16* out, int batch, int H, int W, int d, float scale, cudaStream_t stream);
 cudaError_t launch_attn_v2(const CUtensorMap& tm, bf16* out, int batch, int H, int W, int d, float scale,
                            cudaStream_t stream);

@@ -265,4 +265,26 @@ __device__ __forceinline__ float silu_fast(float x) {
   return fmaf(h, t, h);
 }
 
+// ---------------------------------------------------------------------------------------------
+// counter-based dropout mask: 8 keep bits for the 8 elements of one 16-byte granule.
+// 16 random bits per element (two splitmix64 finalisers per granule); keep iff bits >= thr16.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z ^= z >> 30; z *= 0xbf58476d1ce4e5b9ull;
+  z ^= z >> 27; z *= 0x94d049bb133111ebull;
+  z ^= z >> 31;
+  return z;
+}
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t layer, uint64_t granule, uint32_t thr16) {
+  const uint64_t k = seed ^ (static_cast<uint64_t>(layer) * 0x9E3779B97F4A7C15ull) ^ (granule * 0xD1B54A32D192ED03ull);
+  const uint64_t h0 = mix64(k), h1 = mix64(k ^ 0xA24BAED4963EE407ull);
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m |= (((h0 >> (16 * j)) & 0xffffu) >= thr16 ? 1u : 0u) << j;
+    m |= (((h1 >> (16 * j)) & 0xffffu) >= thr16 ? 1u : 0u) << (4 + j);
+  }
+  return m;
+}
+
 }  // namespace idf

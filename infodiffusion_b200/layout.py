@@ -53,6 +53,26 @@ def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
     return w.detach().permute(0, 2, 3, 1).reshape(co, 9 * ci)
 
 
+def tap_offsets3x3(H: int, W: int) -> List[int]:
+    """Row offset of each of the 9 taps (tap = ky*3 + kx) in the pad-flat layout."""
+    return [(t // 3 - 1) * (W + 1) + (t % 3 - 1) for t in range(9)]
+
+
+def taps3x3_dgrad(cout: int, H: int, W: int, src: int = 0) -> List[KBlock]:
+    """K-blocks of the DATA gradient of a 3x3 / stride 1 / pad 1 conv: the same implicit GEMM run over dY
+    with negated tap offsets (dX[r] = sum_t dY[r - off_t] . W_t^T), K ordered (tap, cout)."""
+    kb: List[KBlock] = []
+    for off in tap_offsets3x3(H, W):
+        kb += [(src, c0, -off) for c0 in range(0, cout, 64)]
+    return kb
+
+
+def pack_conv3x3_dgrad(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> [Cin, 9*Cout] with k = (ky*3+kx)*Cout + co (weights of the data-gradient GEMM)."""
+    co, ci = w.shape[0], w.shape[1]
+    return w.detach().permute(1, 2, 3, 0).reshape(ci, 9 * co)
+
+
 def pack_conv1x1(w: torch.Tensor) -> torch.Tensor:
     return w.detach().reshape(w.shape[0], w.shape[1])
 

@@ -200,6 +200,49 @@ def test_conv_epilogue_groupnorm_partials(lib, cin, cout, H, B, mt):
     assert_close(stats, ref, rel_l2=1e-5, max_rel=1e-5, what="conv epilogue GroupNorm partials")
 
 
+@pytest.mark.parametrize("cin,cout,H,B", [(64, 64, 16, 3), (128, 128, 8, 5), (64, 128, 16, 2), (256, 128, 8, 3),
+                                           (128, 64, 32, 2)])
+def test_conv_data_gradient_through_forward_kernel(lib, cin, cout, H, B):
+    """dX = conv2d_input(dY, W): the forward implicit GEMM over dY with negated taps and transposed weights."""
+    from infodiffusion_b200 import layout
+    g = torch.Generator(device=DEV).manual_seed(400 + cin + cout + H)
+    dy = rbf(torch.randn(B, cout, H, H, device=DEV, generator=g))
+    w = rbf(torch.randn(cout, cin, 3, 3, device=DEV, generator=g) * (2.0 / (9 * cin)) ** 0.5)
+    ref = torch.nn.grad.conv2d_input((B, cin, H, H), w.double(), dy.double(), padding=1)
+    out = run_conv(lib, [pf(dy)], layout.taps3x3_dgrad(cout, H, H), layout.pack_conv3x3_dgrad(w).to(BF).contiguous(),
+                   torch.zeros(cin, device=DEV), B, H, cin, 128 if cin % 128 == 0 else 64)
+    assert pad_is_zero(out, B, H, H)
+    assert_close(unpf(out, B, H, H), ref, what=f"dgrad {cin}<-{cout}@{H}")
+
+
+@pytest.mark.parametrize("cin,cout,H,B", [(64, 64, 16, 3), (128, 128, 8, 5), (64, 128, 16, 2), (256, 128, 8, 3),
+                                           (128, 64, 32, 2), (192, 64, 8, 2)])
+def test_conv_weight_gradient(lib, cin, cout, H, B):
+    """dW = conv2d_weight(X, dY) on tcgen05 (pixels as K, MN-major operands, row-shifted tap views)."""
+    from infodiffusion_b200 import layout
+    from infodiffusion_b200._lib import WgradDesc
+    g = torch.Generator(device=DEV).manual_seed(500 + cin + cout + H)
+    x = rbf(torch.randn(B, cin, H, H, device=DEV, generator=g))
+    dy = rbf(torch.randn(B, cout, H, H, device=DEV, generator=g))
+    ref = torch.nn.grad.conv2d_weight(x.double(), (cout, cin, 3, 3), dy.double(), padding=1)
+    xs, dys = pf(x), pf(dy)
+    dw = torch.zeros(cout, 9, cin, device=DEV)
+    d = WgradDesc()
+    d.dy, d.rows, d.cout = dys.data_ptr(), dys.shape[0], cout
+    d.x, d.x_rows, d.cin = xs.data_ptr(), xs.shape[0], cin
+    d.n_taps = 9
+    for t, off in enumerate(layout.tap_offsets3x3(H, H)):
+        d.tap_off[t] = off
+    d.dw = dw.data_ptr()
+    h = C.c_void_p()
+    check(lib.idf_wgrad_plan_create(C.byref(d), C.byref(h)))
+    check(lib.idf_wgrad_run(h, stream()))
+    torch.cuda.synchronize()
+    lib.idf_wgrad_plan_destroy(h)
+    got = dw.reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    assert_close(got, ref, rel_l2=1e-4, max_rel=1e-3, what=f"wgrad {cin}->{cout}@{H}")   # fp32 accumulation only
+
+
 def test_conv1x1_qkv(lib):
     from infodiffusion_b200 import layout
     g = torch.Generator(device=DEV).manual_seed(5)
@@ -351,6 +394,100 @@ def test_adagn(lib, c0, c1, H, B, mod, silu):
     torch.cuda.synchronize()
     assert pad_is_zero(out2, B, H, H)
     assert_close(unpf(out2, B, H, H), ref, rel_l2=3e-3, max_rel=8e-3, what=f"adagn (streaming) C={c0}+{c1}@{H}")
+
+
+@pytest.mark.parametrize("c0,c1,H,B,mod,silu,drop", [
+    (64, 0, 32, 2, False, True, 0.0), (128, 0, 16, 3, True, True, 0.0), (128, 64, 16, 2, False, True, 0.0),
+    (128, 128, 8, 3, True, True, 0.0), (128, 0, 8, 4, False, False, 0.0), (128, 0, 16, 3, True, True, 0.1)])
+def test_adagn_backward(lib, c0, c1, H, B, mod, silu, drop):
+    """dx and the (S1, S2) sums of idf_adagn_silu_bwd against torch autograd of the same expression
+    (with dropout: the keep-mask is read off the forward output, the hash is the kernel's own)."""
+    from infodiffusion_b200._lib import AdaGNArgs, AdaGNBwdArgs
+    from infodiffusion_b200.train import adagn_param_grads
+    g = torch.Generator(device=DEV).manual_seed(700 + c0 + c1 + H)
+    Cc = c0 + c1
+    x0 = rbf(torch.randn(B, c0, H, H, device=DEV, generator=g) * 1.5 + 0.3)
+    x1 = rbf(torch.randn(B, c1, H, H, device=DEV, generator=g) * 0.7 - 0.2) if c1 else None
+    gamma = (1 + 0.1 * torch.randn(Cc, device=DEV, generator=g)).requires_grad_(True)
+    beta = (0.1 * torch.randn(Cc, device=DEV, generator=g)).requires_grad_(True)
+    dy = rbf(torch.randn(B, Cc, H, H, device=DEV, generator=g))
+    xin = (torch.cat([x0, x1], 1) if c1 else x0).clone().requires_grad_(True)
+    st = bt = sz = bz = None
+    if mod:
+        st, bt, sz, bz = (0.3 * torch.randn(B, Cc, device=DEV, generator=g) for _ in range(4))
+        for v in (st, bt, sz, bz):
+            v.requires_grad_(True)
+    s0 = pf(x0)
+    s1 = pf(x1) if c1 else None
+    a = AdaGNArgs()
+    a.src0, a.c0 = s0.data_ptr(), c0
+    if c1:
+        a.src1, a.c1 = s1.data_ptr(), c1
+    out = torch.zeros(B * (H + 1) * (H + 1), Cc, device=DEV, dtype=BF)
+    a.out, a.batch, a.H, a.W = out.data_ptr(), B, H, H
+    gam_d, bet_d = gamma.detach().clone(), beta.detach().clone()
+    a.gamma, a.beta, a.eps = gam_d.data_ptr(), bet_d.data_ptr(), 1e-5
+    if mod:
+        mt = torch.cat([st, bt], 1).detach().contiguous()      # per-sample rows (scale | shift)
+        mz = torch.cat([sz, bz], 1).detach().contiguous()
+        a.mod_t, a.mod_t_step_stride, a.mod_t_batch_stride = mt.data_ptr(), 0, 2 * Cc
+        a.mod_z, a.mod_z_step_stride, a.mod_z_batch_stride = mz.data_ptr(), 0, 2 * Cc
+    a.apply_silu = 1 if silu else 0
+    st0 = tile_partials(s0, B, H, H)
+    a.stats0 = st0.data_ptr()
+    if c1:
+        st1 = tile_partials(s1, B, H, H)
+        a.stats1 = st1.data_ptr()
+    seed = torch.tensor([0x1234567], dtype=torch.int64, device=DEV)
+    if drop > 0:
+        a.dropout_p, a.dropout_seed, a.dropout_layer = drop, seed.data_ptr(), 7
+    check(lib.idf_adagn_silu_fwd(C.byref(a), stream()))
+    torch.cuda.synchronize()
+    # reference expression under autograd (fp64)
+    v = F.group_norm(xin.double(), 32, gamma.double(), beta.double(), 1e-5)
+    if mod:
+        v = v * (1 + st.double())[:, :, None, None] + bt.double()[:, :, None, None]
+        v = v * (1 + sz.double())[:, :, None, None] + bz.double()[:, :, None, None]
+    y = F.silu(v) if silu else v
+    got_y = unpf(out, B, H, H).double()
+    if drop > 0:
+        keep = (got_y != 0)
+        frac = 1.0 - keep.double().mean().item()
+        assert abs(frac - drop) < 0.01, f"dropped fraction {frac}"
+        thr = round(drop * 65536)
+        y = y * keep * (65536.0 / (65536 - thr))
+    assert_close(got_y, y.detach(), rel_l2=4e-3, max_rel=1e-2, what="adagn forward (train)")
+    y.backward(dy.double())
+    # kernel backward
+    b = AdaGNBwdArgs()
+    b.f = a
+    dys = pf(dy)
+    dx0 = torch.zeros_like(s0)
+    dx1 = torch.zeros_like(s1) if c1 else None
+    sums = torch.zeros(B, Cc, 2, device=DEV)
+    ws = torch.zeros(lib.idf_adagn_bwd_ws_floats(B, Cc), device=DEV)
+    b.dy, b.dx0, b.sums, b.ws = dys.data_ptr(), dx0.data_ptr(), sums.data_ptr(), ws.data_ptr()
+    if c1:
+        b.dx1 = dx1.data_ptr()
+    check(lib.idf_adagn_silu_bwd(C.byref(b), stream()))
+    torch.cuda.synchronize()
+    dx_ref = xin.grad
+    assert_close(unpf(dx0, B, H, H), dx_ref[:, :c0], rel_l2=6e-3, max_rel=2e-2, what="adagn dx0")
+    if c1:
+        assert_close(unpf(dx1, B, H, H), dx_ref[:, c0:], rel_l2=6e-3, max_rel=2e-2, what="adagn dx1")
+    gr = adagn_param_grads(sums, gam_d, bet_d, *(t.detach() if t is not None else None for t in (st, bt, sz, bz)))
+    assert_close(gr["gamma"], gamma.grad, rel_l2=2e-3, max_rel=1e-2, what="d gamma")
+    assert_close(gr["beta"], beta.grad, rel_l2=2e-3, max_rel=1e-2, what="d beta")
+    if mod:
+        for name, t in (("s_t", st), ("b_t", bt), ("s_z", sz), ("b_z", bz)):
+            assert_close(gr[name], t.grad, rel_l2=2e-3, max_rel=1e-2, what="d " + name)
+    # accumulation flag: running again with acc0 adds the same gradient on top
+    b.acc0 = 1
+    if c1:
+        b.acc1 = 1
+    check(lib.idf_adagn_silu_bwd(C.byref(b), stream()))
+    torch.cuda.synchronize()
+    assert_close(unpf(dx0, B, H, H), 2 * dx_ref[:, :c0], rel_l2=8e-3, max_rel=3e-2, what="adagn dx0 accumulate")
 
 
 @pytest.mark.parametrize("H,B", [(16, 3), (8, 5)])
