@@ -210,6 +210,16 @@ int idf_nchw_to_padflat(const float* x, void* out, int32_t batch, int32_t C, int
                         idf_stream_t stream);
 int idf_padflat_to_nchw(const void* in, float* y, int32_t batch, int32_t C, int32_t H, int32_t W,
                         idf_stream_t stream);
+/* same as idf_nchw_to_padflat but into rows of `ld` >= C channels (the extra channels are left untouched) */
+int idf_nchw_to_padflat_ld(const float* x, void* out, int32_t batch, int32_t C, int32_t H, int32_t W, int32_t ld,
+                           idf_stream_t stream);
+/* backward of the layout ops (training): gradients are bf16 pad-flat; `accumulate` adds into the target */
+int idf_upsample2x_bwd(const void* dout, void* din, int32_t batch, int32_t H, int32_t W, int32_t C, int32_t accumulate,
+                       idf_stream_t stream);   /* H, W: INPUT (low) resolution */
+int idf_depth_to_space(const void* dphases, void* din, int32_t batch, int32_t H, int32_t W, int32_t C, int32_t accumulate,
+                       idf_stream_t stream);   /* H, W: full resolution; inverse of idf_space_to_depth */
+/* out[c] += sum_r m[r, c]  (bias gradient of a conv: column sums of dY), fp32 atomics */
+int idf_colsum_bf16(const void* m, float* out, int64_t rows, int32_t C, idf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Stand-alone sampler update (the unfused variant of IDF_EPI_SAMPLER):

@@ -410,8 +410,38 @@ int idf_space_to_depth(const void* in, void* out, int32_t batch, int32_t H, int3
 
 int idf_nchw_to_padflat(const float* x, void* out, int32_t batch, int32_t C, int32_t H, int32_t W,
                         idf_stream_t stream) {
-  cudaError_t e = launch_nchw_to_padflat(x, static_cast<bf16*>(out), batch, C, H, W, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_nchw_to_padflat(x, static_cast<bf16*>(out), batch, C, H, W, C, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "nchw_to_padflat launch");
+  return IDF_OK;
+}
+
+int idf_nchw_to_padflat_ld(const float* x, void* out, int32_t batch, int32_t C, int32_t H, int32_t W, int32_t ld,
+                           idf_stream_t stream) {
+  if (ld < C) return fail(IDF_ERR_ARG, "ld < C");
+  cudaError_t e = launch_nchw_to_padflat(x, static_cast<bf16*>(out), batch, C, H, W, ld, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "nchw_to_padflat launch");
+  return IDF_OK;
+}
+
+int idf_upsample2x_bwd(const void* dout, void* din, int32_t batch, int32_t H, int32_t W, int32_t C, int32_t accumulate,
+                       idf_stream_t stream) {
+  cudaError_t e = launch_upsample2x_bwd(static_cast<const bf16*>(dout), static_cast<bf16*>(din), batch, H, W, C, accumulate,
+                                        reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "upsample2x_bwd launch");
+  return IDF_OK;
+}
+
+int idf_depth_to_space(const void* dphases, void* din, int32_t batch, int32_t H, int32_t W, int32_t C, int32_t accumulate,
+                       idf_stream_t stream) {
+  cudaError_t e = launch_depth_to_space(static_cast<const bf16*>(dphases), static_cast<bf16*>(din), batch, H, W, C,
+                                        accumulate, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "depth_to_space launch");
+  return IDF_OK;
+}
+
+int idf_colsum_bf16(const void* m, float* out, int64_t rows, int32_t C, idf_stream_t stream) {
+  cudaError_t e = launch_colsum(static_cast<const bf16*>(m), out, rows, C, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "colsum launch");
   return IDF_OK;
 }
 

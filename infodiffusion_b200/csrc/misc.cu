@@ -113,7 +113,7 @@ cudaError_t launch_space_to_depth(const bf16* in, bf16* out, int batch, int H, i
 // NCHW fp32 <-> pad-flat bf16 (boundary / test helpers).  Tiled through shared memory so that both
 // sides are coalesced: a tile is 32 pixels (along W) x 32 channels.
 // ----------------------------------------------------------------------------------------------
-__global__ void nchw_to_padflat_kernel(const float* __restrict__ x, bf16* __restrict__ out, int C, int H, int W) {
+__global__ void nchw_to_padflat_kernel(const float* __restrict__ x, bf16* __restrict__ out, int C, int H, int W, int ld) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * 32;
@@ -132,7 +132,7 @@ __global__ void nchw_to_padflat_kernel(const float* __restrict__ x, bf16* __rest
     if (p < HW && c < C) {
       const int yy = static_cast<int>(p / W), xx = static_cast<int>(p % W);
       const long long row = (static_cast<long long>(n) * (H + 1) + yy) * (W + 1) + xx;
-      out[row * C + c] = __float2bfloat16(tile[tx][j]);
+      out[row * ld + c] = __float2bfloat16(tile[tx][j]);
     }
   }
 }
@@ -162,14 +162,124 @@ __global__ void padflat_to_nchw_kernel(const bf16* __restrict__ in, float* __res
   }
 }
 
-cudaError_t launch_nchw_to_padflat(const float* x, bf16* out, int batch, int C, int H, int W, cudaStream_t stream) {
+cudaError_t launch_nchw_to_padflat(const float* x, bf16* out, int batch, int C, int H, int W, int ld,
+                                   cudaStream_t stream) {
   dim3 grid(static_cast<unsigned>((static_cast<long long>(H) * W + 31) / 32), (C + 31) / 32, batch);
-  nchw_to_padflat_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, out, C, H, W);
+  nchw_to_padflat_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, out, C, H, W, ld);
   return cudaGetLastError();
 }
 cudaError_t launch_padflat_to_nchw(const bf16* in, float* y, int batch, int C, int H, int W, cudaStream_t stream) {
   dim3 grid(static_cast<unsigned>((static_cast<long long>(H) * W + 31) / 32), (C + 31) / 32, batch);
   padflat_to_nchw_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, y, C, H, W);
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------
+// backward helpers of the layout ops (training)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 add_bf16x8(const uint4& a, const uint4& b) {
+  const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+  const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
+  uint4 o;
+  o.x = pack_bf16x2(a0.x + b0.x, a0.y + b0.y);
+  o.y = pack_bf16x2(a1.x + b1.x, a1.y + b1.y);
+  o.z = pack_bf16x2(a2.x + b2.x, a2.y + b2.y);
+  o.w = pack_bf16x2(a3.x + b3.x, a3.y + b3.y);
+  return o;
+}
+
+// d(nearest x2 upsample): din[n,y,x] (+)= sum_{a,b} dout[n, 2y+a, 2x+b]; one thread = one INPUT pixel x granule
+__global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ din, int batch, int H, int W,
+                                      int C, int accumulate) {
+  const int V = C >> 3;
+  const long long total = static_cast<long long>(batch) * H * W * V;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % V);
+  const long long pix = i / V;
+  const int x = static_cast<int>(pix % W);
+  const int y = static_cast<int>((pix / W) % H);
+  const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  const int Ho = 2 * H, Wo = 2 * W;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const long long ro = (static_cast<long long>(n) * (Ho + 1) + 2 * y + a) * (Wo + 1) + 2 * x + b;
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(dout + ro * C + v * 8));
+      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y; acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+    }
+  const long long ri = (static_cast<long long>(n) * (H + 1) + y) * (W + 1) + x;
+  uint4* dst = reinterpret_cast<uint4*>(din + ri * C + v * 8);
+  uint4 o;
+  o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]); o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+  *dst = accumulate ? add_bf16x8(*dst, o) : o;
+}
+cudaError_t launch_upsample2x_bwd(const bf16* dout, bf16* din, int batch, int H, int W, int C, int accumulate,
+                                  cudaStream_t stream) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const long long total = static_cast<long long>(batch) * H * W * (C >> 3);
+  upsample2x_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(dout, din, batch, H, W, C, accumulate);
+  return cudaGetLastError();
+}
+
+// inverse of space_to_depth: din[n,y,x] (+)= dphase[(y&1)*2+(x&1)][n, y/2, x/2]
+__global__ void depth_to_space_kernel(const bf16* __restrict__ dph, bf16* __restrict__ din, int batch, int H, int W,
+                                      int C, int accumulate) {
+  const int V = C >> 3;
+  const long long total = static_cast<long long>(batch) * H * W * V;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % V);
+  const long long pix = i / V;
+  const int x = static_cast<int>(pix % W);
+  const int y = static_cast<int>((pix / W) % H);
+  const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long rows_o = static_cast<long long>(batch) * (Ho + 1) * (Wo + 1);
+  const int phase = (y & 1) * 2 + (x & 1);
+  const long long rp = phase * rows_o + (static_cast<long long>(n) * (Ho + 1) + (y >> 1)) * (Wo + 1) + (x >> 1);
+  const long long ri = (static_cast<long long>(n) * (H + 1) + y) * (W + 1) + x;
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(dph + rp * C + v * 8));
+  uint4* dst = reinterpret_cast<uint4*>(din + ri * C + v * 8);
+  *dst = accumulate ? add_bf16x8(*dst, u) : u;
+}
+cudaError_t launch_depth_to_space(const bf16* dph, bf16* din, int batch, int H, int W, int C, int accumulate,
+                                  cudaStream_t stream) {
+  if ((C % 8) || (H & 1) || (W & 1)) return cudaErrorInvalidValue;
+  const long long total = static_cast<long long>(batch) * H * W * (C >> 3);
+  depth_to_space_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(dph, din, batch, H, W, C, accumulate);
+  return cudaGetLastError();
+}
+
+// bias gradient: out[c] += sum_r m[r, c]   (m bf16 [rows, C]); block = 32 channel-pairs x 8 row lanes
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ m, float* __restrict__ out, long long rows,
+                                                     int C) {
+  __shared__ float2 red[8][32];
+  const int cp = blockIdx.x * 32 + (threadIdx.x & 31);        // channel pair index
+  const int rl = threadIdx.x >> 5;
+  float2 acc = make_float2(0.f, 0.f);
+  if (2 * cp < C) {
+    for (long long r = blockIdx.y * 8 + rl; r < rows; r += 8ll * gridDim.y) {
+      const float2 v = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(m + r * C) + cp));
+      acc.x += v.x; acc.y += v.y;
+    }
+  }
+  red[rl][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rl == 0 && 2 * cp < C) {
+    float2 t = red[0][threadIdx.x];
+    for (int k = 1; k < 8; ++k) { t.x += red[k][threadIdx.x].x; t.y += red[k][threadIdx.x].y; }
+    atomicAdd(out + 2 * cp, t.x);
+    atomicAdd(out + 2 * cp + 1, t.y);
+  }
+}
+cudaError_t launch_colsum(const bf16* m, float* out, long long rows, int C, cudaStream_t stream) {
+  if (C % 2) return cudaErrorInvalidValue;
+  dim3 grid((C / 2 + 31) / 32, 64, 1);
+  colsum_kernel<<<grid, 256, 0, stream>>>(m, out, rows, C);
   return cudaGetLastError();
 }
 
