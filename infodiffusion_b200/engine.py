@@ -68,8 +68,9 @@ class Workspace:
     (H, C, phases) geometry, so the zero border written at allocation time is never disturbed
     (kernels write interior rows only)."""
 
-    def __init__(self, batch: int, device):
+    def __init__(self, batch: int, device, recycle: bool = True):
         self.batch, self.device = batch, device
+        self.recycle = recycle       # training keeps every activation alive for the backward pass
         self.free_lists: Dict[Tuple[int, int, int], List[Act]] = {}
         self.bytes = 0
 
@@ -86,7 +87,8 @@ class Workspace:
         return Act(t, H, C_, phases, rows)
 
     def free(self, a: Act) -> None:
-        self.free_lists.setdefault((a.H, a.C, a.phases), []).append(a)
+        if self.recycle:
+            self.free_lists.setdefault((a.H, a.C, a.phases), []).append(a)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -95,12 +97,18 @@ class Workspace:
 class Plan:
     """Ordered list of kernel launches + everything they reference."""
 
-    def __init__(self, batch: int, device, ws: Optional[Workspace] = None):
+    def __init__(self, batch: int, device, ws: Optional[Workspace] = None, training: bool = False):
         self.lib = _lib.load()
         _lib.check(self.lib.idf_init())
         self.B = batch
         self.device = device
-        self.ws = ws if ws is not None else Workspace(batch, device)
+        self.training = training
+        self.ws = ws if ws is not None else Workspace(batch, device, recycle=not training)
+        self.tape: List = []         # training: backward emitters, one per forward composite, replayed in reverse
+        self.refresh: List = []      # training: (dst tensor, recipe) pairs re-evaluated before every forward
+        self.dropout_p = 0.0
+        self.dropout_seed = None     # device int64 scalar
+        self._drop_layers = 0
         self.ops: List = []          # (callable, args tuple); last arg slot is the stream
         self.meta: List[dict] = []   # per op: kernel class, algorithmic flops / bytes
         self.keep: List = []         # tensors / ctypes structs that must outlive the plan
@@ -145,15 +153,28 @@ class Plan:
         _lib.count_launch(len(self.ops))
 
     # ---- op emitters ---------------------------------------------------------------------------
-    def weight(self, m: torch.Tensor) -> torch.Tensor:
-        t = m.to(device=self.device, dtype=BF16).contiguous()
+    def weight(self, m) -> torch.Tensor:
+        """bf16 device copy of a packed weight.  `m` may be a recipe (callable returning the fp32 tensor): a
+        training plan re-evaluates recipes before every forward so the kernels see the current parameters."""
+        src = m() if callable(m) else m
+        t = src.detach().to(device=self.device, dtype=BF16).contiguous()
         self.keep.append(t)
+        if callable(m) and self.training:
+            self.refresh.append((t, m))
         return t
 
-    def f32(self, m: torch.Tensor) -> torch.Tensor:
-        t = m.detach().to(device=self.device, dtype=torch.float32).contiguous()
+    def f32(self, m) -> torch.Tensor:
+        src = m() if callable(m) else m
+        t = src.detach().to(device=self.device, dtype=torch.float32).contiguous()
         self.keep.append(t)
+        if callable(m) and self.training:
+            self.refresh.append((t, m))
         return t
+
+    def refresh_weights(self) -> None:
+        with torch.no_grad():
+            for dst, recipe in self.refresh:
+                dst.copy_(recipe().detach())
 
     def conv(self, srcs: Sequence[Act], kblocks: Sequence[Tuple[int, int, int]], wp: torch.Tensor,
              bias: torch.Tensor, H: int, cout: int, block_n: int, out: Optional[Act] = None,
@@ -196,14 +217,17 @@ class Plan:
         self._emit("conv_igemm", self.lib.idf_conv_run, (h,), flops=2 * self.B * H * H * macs)
 
     def adagn(self, src0: Act, src1: Optional[Act], out: Act, gn: nn.GroupNorm, silu: bool, mod_t=None, mod_z=None,
-              step=None) -> None:
+              step=None, dropout: bool = False, mod_cols: Optional[int] = None) -> None:
+        """Fused AdaGN.  mod_t / mod_z = (pointer, step stride, batch stride) of this block's (scale | shift)
+        columns; `dropout` applies inverted dropout after the SiLU (training plans only)."""
         a = AdaGNArgs()
         a.src0, a.c0 = src0.t.data_ptr(), src0.C
         if src1 is not None:
             a.src1, a.c1 = src1.t.data_ptr(), src1.C
         a.out = out.t.data_ptr()
         a.batch, a.H, a.W = self.B, src0.H, src0.H
-        a.gamma, a.beta = self.f32(gn.weight).data_ptr(), self.f32(gn.bias).data_ptr()
+        gamma, beta = self.f32(lambda: gn.weight), self.f32(lambda: gn.bias)
+        a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
         a.eps = float(gn.eps)
         if mod_t is not None:
             a.mod_t, a.mod_t_step_stride, a.mod_t_batch_stride = mod_t
@@ -215,14 +239,23 @@ class Plan:
             a.stats0 = src0.stats.data_ptr()
             if src1 is not None:
                 a.stats1 = src1.stats.data_ptr()
+        if dropout and self.training and self.dropout_p > 0:
+            self._drop_layers += 1
+            a.dropout_p, a.dropout_seed, a.dropout_layer = self.dropout_p, self.dropout_seed.data_ptr(), self._drop_layers
         out.has_stats = False
         self.keep.append(a)
         self._emit("adagn", self.lib.idf_adagn_silu_fwd, (C.byref(a),), nbytes=2 * 2 * self.B * src0.H * src0.H * out.C)
+        if self.training:
+            from . import train
+            self.tape.append(lambda: train.bwd_adagn(self, a, src0, src1, out, gn, gamma, beta, mod_cols))
 
     def attention(self, qkv: Act, out: Act, d: int) -> None:
         S = qkv.H * qkv.H
         self._emit("attention", self.lib.idf_attn_fwd, (qkv.t.data_ptr(), out.t.data_ptr(), self.B, qkv.H, qkv.H, d,
                                                         float(d) ** -0.5), flops=self.B * 4 * S * S * d)
+        if self.training:
+            from . import train
+            self.tape.append(lambda: train.bwd_attention(self, qkv, out, d))
 
     def linear(self, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], y: torch.Tensor, silu_in: bool) -> None:
         M, K = x.shape
@@ -236,34 +269,55 @@ class Plan:
     def taps3x3(cin: int, H: int, src: int = 0):
         return taps3x3(cin, H, H, src)
 
+    @staticmethod
+    def _bn(cout: int) -> int:
+        return 128 if cout % 128 == 0 else 64
+
     def conv3x3(self, src: Act, conv: nn.Conv2d, residual: Optional[Act] = None,
                 shortcut: Optional[Tuple[nn.Conv2d, Sequence[Act]]] = None) -> Act:
         """3x3 / stride 1 / pad 1 conv (+ residual, or + 1x1 shortcut conv over raw sources as extra K-blocks)."""
         cin, cout, H = src.C, conv.out_channels, src.H
         assert conv.in_channels == cin and cout % 64 == 0
         kb = self.taps3x3(cin, H)
-        wp = pack_conv3x3(conv.weight)
-        bias = conv.bias.detach().float()
         srcs = [src]
-        if shortcut is not None:
+        if shortcut is None:
+            wp = lambda: pack_conv3x3(conv.weight)
+            bias = lambda: conv.bias
+        else:
             sc_conv, raws = shortcut
-            wp = torch.cat([wp, pack_conv1x1(sc_conv.weight)], dim=1)
-            bias = bias + sc_conv.bias.detach().float()
+            wp = lambda: torch.cat([pack_conv3x3(conv.weight), pack_conv1x1(sc_conv.weight)], dim=1)
+            bias = lambda: conv.bias + sc_conv.bias
             for r in raws:
                 srcs.append(r)
                 kb += [(len(srcs) - 1, c0, 0) for c0 in range(0, r.C, 64)]
         out = self.ws.alloc(H, cout)
-        self.conv(srcs, kb, self.weight(wp), self.f32(bias), H, cout, 128 if cout % 128 == 0 else 64, out=out,
-                  residual=residual)
+        self.conv(srcs, kb, self.weight(wp), self.f32(bias), H, cout, self._bn(cout), out=out, residual=residual)
+        if self.training:
+            from . import train
+            parts = [train.Part(src, conv.weight, "3x3", None)]
+            biases = [conv.bias]
+            if shortcut is not None:
+                c = 0
+                for r in shortcut[1]:
+                    parts.append(train.Part(r, shortcut[0].weight, "1x1", (c, c + r.C)))
+                    c += r.C
+                biases.append(shortcut[0].bias)
+            self.tape.append(lambda: train.bwd_conv(self, parts, biases, out, residual))
         return out
 
-    def conv1x1(self, src: Act, w: torch.Tensor, b: torch.Tensor, residual: Optional[Act] = None,
+    def conv1x1(self, src: Act, convs: Sequence[nn.Conv2d], residual: Optional[Act] = None,
                 want_stats: bool = True) -> Act:
-        cout = w.shape[0]
+        """1x1 conv; several convs over the same input are stacked along N (q, k, v -> one GEMM)."""
+        cout = sum(m.out_channels for m in convs)
         kb = taps1x1(src.C)
         out = self.ws.alloc(src.H, cout)
-        self.conv([src], kb, self.weight(_pad_cols(w, 64 * len(kb))), self.f32(b), src.H, cout,
-                  128 if cout % 128 == 0 else 64, out=out, residual=residual, want_stats=want_stats)
+        wp = lambda: _pad_cols(torch.cat([pack_conv1x1(m.weight) for m in convs], dim=0), 64 * len(kb))
+        bias = lambda: torch.cat([m.bias for m in convs], dim=0)
+        self.conv([src], kb, self.weight(wp), self.f32(bias), src.H, cout, self._bn(cout), out=out, residual=residual,
+                  want_stats=want_stats)
+        if self.training:
+            from . import train
+            self.tape.append(lambda: train.bwd_conv1x1_stack(self, src, list(convs), out, residual))
         return out
 
     def downsample(self, src: Act, conv: nn.Conv2d) -> Act:
@@ -273,14 +327,20 @@ class Plan:
         self._emit("space_to_depth", self.lib.idf_space_to_depth, (src.t.data_ptr(), ph.t.data_ptr(), self.B, H, H, Cc))
         kb = taps_stride2(Cc, Ho, Ho, ph.rows)
         out = self.ws.alloc(Ho, conv.out_channels)
-        self.conv([ph], kb, self.weight(pack_conv3x3(conv.weight)), self.f32(conv.bias), Ho, conv.out_channels,
-                  128 if conv.out_channels % 128 == 0 else 64, out=out)
+        self.conv([ph], kb, self.weight(lambda: pack_conv3x3(conv.weight)), self.f32(lambda: conv.bias), Ho,
+                  conv.out_channels, self._bn(conv.out_channels), out=out)
+        if self.training:
+            from . import train
+            self.tape.append(lambda: train.bwd_downsample(self, src, ph, conv, out))
         self.ws.free(ph)
         return out
 
     def upsample(self, src: Act, conv: nn.Conv2d) -> Act:
         up = self.ws.alloc(src.H * 2, src.C)
         self._emit("upsample2x", self.lib.idf_upsample2x, (src.t.data_ptr(), up.t.data_ptr(), self.B, src.H, src.H, src.C))
+        if self.training:
+            from . import train
+            self.tape.append(lambda: train.bwd_upsample(self, src, up))
         out = self.conv3x3(up, conv)
         self.ws.free(up)
         return out
@@ -290,19 +350,18 @@ class Plan:
         Cc = x.C
         an = self.ws.alloc(x.H, Cc)
         self.adagn(x, None, an, blk.group_norm, silu=False)
-        wqkv = torch.cat([pack_conv1x1(m.weight) for m in (blk.proj_q, blk.proj_k, blk.proj_v)], dim=0)
-        bqkv = torch.cat([m.bias.detach() for m in (blk.proj_q, blk.proj_k, blk.proj_v)], dim=0)
-        qkv = self.conv1x1(an, wqkv, bqkv, want_stats=False)
+        qkv = self.conv1x1(an, [blk.proj_q, blk.proj_k, blk.proj_v], want_stats=False)
         self.ws.free(an)
         ao = self.ws.alloc(x.H, Cc)
         self.attention(qkv, ao, Cc)
         self.ws.free(qkv)
-        out = self.conv1x1(ao, pack_conv1x1(blk.proj.weight), blk.proj.bias.detach(), residual=x)
+        out = self.conv1x1(ao, [blk.proj], residual=x)
         self.ws.free(ao)
         self.ws.free(x)
         return out
 
-    def res_block(self, xs: Sequence[Act], blk, mod_t=None, mod_z=None, step=None, free_inputs=True) -> Act:
+    def res_block(self, xs: Sequence[Act], blk, mod_t=None, mod_z=None, step=None, free_inputs=True,
+                  mod_cols: Optional[int] = None) -> Act:
         """AuxResBlock / ResBlock / ResBlock_encoder over one or two (concatenated) inputs."""
         H = xs[0].H
         cin = sum(x.C for x in xs)
@@ -314,7 +373,8 @@ class Plan:
         h = self.conv3x3(a1, blk.block1[-1])
         self.ws.free(a1)
         a2 = self.ws.alloc(H, cout)
-        self.adagn(h, None, a2, blk.block2[0], silu=True, mod_t=mod_t, mod_z=mod_z, step=step)
+        self.adagn(h, None, a2, blk.block2[0], silu=True, mod_t=mod_t, mod_z=mod_z, step=step, dropout=True,
+                   mod_cols=mod_cols)
         self.ws.free(h)
         last_in = a2
         has_block3 = hasattr(blk, "block3")
@@ -322,7 +382,7 @@ class Plan:
             h = self.conv3x3(a2, blk.block2[-1])
             self.ws.free(a2)
             a3 = self.ws.alloc(H, cout)
-            self.adagn(h, None, a3, blk.block3[0], silu=True)
+            self.adagn(h, None, a3, blk.block3[0], silu=True, dropout=True)
             self.ws.free(h)
             last_in = a3
         last_conv = blk.block3[-1] if has_block3 else blk.block2[-1]
@@ -338,6 +398,33 @@ class Plan:
         if isinstance(blk.attn, AttnBlock):
             out = self.attn_block(out, blk.attn)
         return out
+
+    def head(self, x_src: torch.Tensor, conv: nn.Conv2d, Cimg: int, H: int) -> Act:
+        """head conv as im2col + K=64 GEMM (reference models.py:246,304,431)."""
+        patches = self.ws.alloc(H, 64)
+        self._emit("im2col_head", self.lib.idf_im2col_head, (x_src.data_ptr(), patches.t.data_ptr(), self.B, Cimg, H, H))
+        cout = conv.out_channels
+        h = self.ws.alloc(H, cout)
+        self.conv([patches], [(0, 0, 0)], self.weight(lambda: _pad_cols(pack_conv3x3(conv.weight), 64)),
+                  self.f32(lambda: conv.bias), H, cout, self._bn(cout), out=h, real_macs_per_row=9 * Cimg * cout)
+        if self.training:
+            from . import train
+            self.tape.append(lambda: train.bwd_head(self, patches, conv, h, Cimg))
+        self.ws.free(patches)
+        return h
+
+    def tail(self, h: Act, gn: nn.GroupNorm, tconv: nn.Conv2d, H: int, cout: int, epilogue: int, out_f32, **extra) -> None:
+        """tail: AdaGN + 3x3 conv to `cout` (<= 16) channels, fp32 NCHW out or fused sampler update."""
+        ta = self.ws.alloc(H, h.C)
+        self.adagn(h, None, ta, gn, silu=True)
+        self.ws.free(h)
+        self.conv([ta], self.taps3x3(ta.C, H), self.weight(lambda: _pad_rows(pack_conv3x3(tconv.weight), 16)),
+                  self.f32(lambda: _pad_rows(tconv.bias.float(), 16)), H, cout, 16, epilogue=epilogue, out_f32=out_f32,
+                  **extra)
+        if self.training:
+            from . import train
+            self.tape.append(lambda: train.bwd_tail(self, ta, tconv, out_f32, cout))
+        self.ws.free(ta)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -384,15 +471,19 @@ class BackbonePlan(Plan):
     mode 'sampler' : x_io is updated in place, x <- cx*x + ce*eps + cn*noise with (cx,ce,cn) = coef[*step];
                      the timestep modulation is a precomputed [T, ncol] table indexed by *step, the z
                      modulation [B, ncol] is computed once per sampling call by `set_latent`.
+    mode 'train'   : x_in and the modulation rows mod_t / mod_z [B, ncol] are inputs (the tiny MLPs that produce
+                     them stay in torch autograd); every activation is kept, dropout is on, and the plan
+                     records a backward tape (infodiffusion_b200.train).
     """
 
     def __init__(self, net, batch: int, device, mode: str = "eps", ws: Optional[Workspace] = None,
                  x_io: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
                  coef: Optional[torch.Tensor] = None, step: Optional[torch.Tensor] = None,
                  mod_t_table: Optional[torch.Tensor] = None, mod_z: Optional[torch.Tensor] = None,
-                 eps_out: Optional[torch.Tensor] = None, pack: Optional[ModulationPack] = None):
-        super().__init__(batch, device, ws)
-        assert mode in ("eps", "sampler")
+                 eps_out: Optional[torch.Tensor] = None, pack: Optional[ModulationPack] = None,
+                 dropout_p: float = 0.0):
+        super().__init__(batch, device, ws, training=(mode == "train"))
+        assert mode in ("eps", "sampler", "train")
         self.mode = mode
         Cimg, H, W = net.shape
         assert H == W, "square images only"
@@ -403,15 +494,22 @@ class BackbonePlan(Plan):
         self.pack = pack if pack is not None else ModulationPack(conditioned_blocks(net), device)
         ncol = self.pack.ncol
         self.step = step
-        if mode == "eps":
+        if mode == "train":
+            self.dropout_p = dropout_p
+            self.dropout_seed = torch.zeros(1, dtype=torch.int64, device=device)
+        if mode in ("eps", "train"):
             self.x_in = torch.zeros(B, Cimg, H, W, **f32)
-            self.t_idx = torch.zeros(B, dtype=torch.long, device=device)
-            self.a_in = torch.zeros(B, net.a_dim, **f32)
             self.eps_out = torch.zeros(B, Cimg, H, W, **f32)
             self.mod_t = torch.zeros(B, ncol, **f32)
             self.mod_z = torch.zeros(B, ncol, **f32)
-            self._emit_time_mlp(self.t_idx, self.mod_t)
-            self._emit_latent_mlp(self.a_in, self.mod_z)
+            if mode == "eps":
+                self.t_idx = torch.zeros(B, dtype=torch.long, device=device)
+                self.a_in = torch.zeros(B, net.a_dim, **f32)
+                self._emit_time_mlp(self.t_idx, self.mod_t)
+                self._emit_latent_mlp(self.a_in, self.mod_z)
+            else:
+                self.d_mod_t = torch.zeros(B, ncol, **f32)
+                self.d_mod_z = torch.zeros(B, ncol, **f32)
             mod_t_arg = (self.mod_t.data_ptr(), 0, ncol)
             x_src = self.x_in
         else:
@@ -424,35 +522,27 @@ class BackbonePlan(Plan):
         mod_z_arg = (self.mod_z.data_ptr(), 0, ncol)
 
         def mods(blk):
-            off = self.pack.offsets[id(blk)] * 4
+            col = self.pack.offsets[id(blk)]
+            off = col * 4
             mt = (mod_t_arg[0] + off, mod_t_arg[1], mod_t_arg[2])
             mz = (mod_z_arg[0] + off, mod_z_arg[1], mod_z_arg[2]) if hasattr(blk, "aemb_proj") else None
-            return mt, mz
+            return mt, mz, col
 
-        # ---- head: im2col + K=64 GEMM
         ws = self.ws
-        patches = ws.alloc(H, 64)
-        self._emit("im2col_head", self.lib.idf_im2col_head, (x_src.data_ptr(), patches.t.data_ptr(), B, Cimg, H, W))
-        hw = _pad_cols(pack_conv3x3(net.head.weight), 64)
-        h = ws.alloc(H, net.head.out_channels)
-        self.conv([patches], [(0, 0, 0)], self.weight(hw), self.f32(net.head.bias), H, net.head.out_channels,
-                  128 if net.head.out_channels % 128 == 0 else 64, out=h,
-                  real_macs_per_row=9 * Cimg * net.head.out_channels)
-        ws.free(patches)
-
+        h = self.head(x_src, net.head, Cimg, H)
         skips = [h]
         for layer in net.downblocks:
             if isinstance(layer, DownSample):
                 h = self.downsample(h, layer.main)
             else:
-                mt, mz = mods(layer)
-                h = self.res_block([h], layer, mod_t=mt, mod_z=mz, step=self.step, free_inputs=False)
+                mt, mz, col = mods(layer)
+                h = self.res_block([h], layer, mod_t=mt, mod_z=mz, step=self.step, free_inputs=False, mod_cols=col)
             skips.append(h)
         first = True
         for layer in net.middleblocks:
-            mt, mz = mods(layer)
+            mt, mz, col = mods(layer)
             # the first middle block reads the last skip tensor, which must stay alive for the up path
-            h = self.res_block([h], layer, mod_t=mt, mod_z=mz, step=self.step, free_inputs=not first)
+            h = self.res_block([h], layer, mod_t=mt, mod_z=mz, step=self.step, free_inputs=not first, mod_cols=col)
             first = False
         for layer in net.upblocks:
             if isinstance(layer, UpSample):
@@ -460,24 +550,15 @@ class BackbonePlan(Plan):
                 ws.free(h)
                 h = h2
             else:
-                mt, mz = mods(layer)
-                h = self.res_block([h, skips.pop()], layer, mod_t=mt, mod_z=mz, step=self.step, free_inputs=True)
+                mt, mz, col = mods(layer)
+                h = self.res_block([h, skips.pop()], layer, mod_t=mt, mod_z=mz, step=self.step, free_inputs=True,
+                                   mod_cols=col)
         assert not skips
-        # ---- tail: AdaGN + 3x3 conv to Cimg channels, fp32 NCHW out or fused sampler update
-        ta = ws.alloc(H, h.C)
-        self.adagn(h, None, ta, net.tail[0], silu=True)
-        ws.free(h)
-        tconv = net.tail[-1]
-        wp = _pad_rows(pack_conv3x3(tconv.weight), 16)
-        bias = _pad_rows(tconv.bias.detach().float(), 16)
-        kb = self.taps3x3(ta.C, H)
-        if mode == "eps":
-            self.conv([ta], kb, self.weight(wp), self.f32(bias), H, Cimg, 16, epilogue=EPI_F32_NCHW,
-                      out_f32=self.eps_out)
+        if mode in ("eps", "train"):
+            self.tail(h, net.tail[0], net.tail[-1], H, Cimg, EPI_F32_NCHW, self.eps_out)
         else:
-            self.conv([ta], kb, self.weight(wp), self.f32(bias), H, Cimg, 16, epilogue=EPI_SAMPLER,
-                      out_f32=self.eps_out, x_io=x_io, noise=noise, coef=coef, step=step)
-        ws.free(ta)
+            self.tail(h, net.tail[0], net.tail[-1], H, Cimg, EPI_SAMPLER, self.eps_out, x_io=x_io, noise=noise,
+                      coef=coef, step=step)
 
     # modulation MLPs ------------------------------------------------------------------------------
     def _emit_time_mlp(self, t_idx: torch.Tensor, out: torch.Tensor) -> None:
@@ -527,27 +608,27 @@ class ModulationTables(Plan):
 # encoder plan
 # ------------------------------------------------------------------------------------------------
 class EncoderPlan(Plan):
-    """(a, mu, log_var) = Encoder(x) for a fixed batch (reference models.py:488-518)."""
+    """(a, mu, log_var) = Encoder(x) for a fixed batch (reference models.py:488-518).  With training=True only
+    the conv stack runs here (x -> 1-channel map, tape recorded); fc_a / fc_mu / fc_var stay in torch autograd."""
 
-    def __init__(self, net, batch: int, device, ws: Optional[Workspace] = None, x_in: Optional[torch.Tensor] = None):
-        super().__init__(batch, device, ws)
+    def __init__(self, net, batch: int, device, ws: Optional[Workspace] = None, x_in: Optional[torch.Tensor] = None,
+                 training: bool = False, dropout_p: float = 0.0):
+        super().__init__(batch, device, ws, training=training)
         Cimg, H, W = net.shape
         assert H == W and H in (32, 64)
         B = batch
         f32 = dict(dtype=torch.float32, device=device)
+        if training:
+            self.dropout_p = dropout_p
+            self.dropout_seed = torch.zeros(1, dtype=torch.int64, device=device)
+        self.net = net
         self.x_in = x_in if x_in is not None else torch.zeros(B, Cimg, H, W, **f32)
         self.map_out = torch.zeros(B, 1, H, W, **f32)
         self.a = torch.zeros(B, net.a_dim, **f32)
         self.mu = torch.zeros(B, net.a_dim, **f32)
         self.log_var = torch.zeros(B, net.a_dim, **f32)
         ws = self.ws
-        patches = ws.alloc(H, 64)
-        self._emit("im2col_head", self.lib.idf_im2col_head, (self.x_in.data_ptr(), patches.t.data_ptr(), B, Cimg, H, W))
-        h = ws.alloc(H, net.head.out_channels)
-        self.conv([patches], [(0, 0, 0)], self.weight(_pad_cols(pack_conv3x3(net.head.weight), 64)),
-                  self.f32(net.head.bias), H, net.head.out_channels, 128 if net.head.out_channels % 128 == 0 else 64,
-                  out=h, real_macs_per_row=9 * Cimg * net.head.out_channels)
-        ws.free(patches)
+        h = self.head(self.x_in, net.head, Cimg, H)
         skips = [h]
         for layer in net.downblocks:
             if isinstance(layer, DownSample):
@@ -567,18 +648,12 @@ class EncoderPlan(Plan):
             else:
                 h = self.res_block([h, skips.pop()], layer, free_inputs=True)
         assert not skips
-        ta = ws.alloc(H, h.C)
-        self.adagn(h, None, ta, net.tail[0], silu=True)
-        ws.free(h)
-        tconv = net.tail[-1]
-        self.conv([ta], self.taps3x3(ta.C, H), self.weight(_pad_rows(pack_conv3x3(tconv.weight), 16)),
-                  self.f32(_pad_rows(tconv.bias.detach().float(), 16)), H, 1, 16, epilogue=EPI_F32_NCHW,
-                  out_f32=self.map_out)
-        ws.free(ta)
-        flat = self.map_out.view(B, H * W)
-        self.linear(flat, self.f32(net.fc_a.weight), self.f32(net.fc_a.bias), self.a, silu_in=False)
-        self.linear(self.a, self.f32(net.fc_mu.weight), self.f32(net.fc_mu.bias), self.mu, silu_in=False)
-        self.linear(self.a, self.f32(net.fc_var.weight), self.f32(net.fc_var.bias), self.log_var, silu_in=False)
+        self.tail(h, net.tail[0], net.tail[-1], H, 1, EPI_F32_NCHW, self.map_out)
+        if not training:
+            flat = self.map_out.view(B, H * W)
+            self.linear(flat, self.f32(net.fc_a.weight), self.f32(net.fc_a.bias), self.a, silu_in=False)
+            self.linear(self.a, self.f32(net.fc_mu.weight), self.f32(net.fc_mu.bias), self.mu, silu_in=False)
+            self.linear(self.a, self.f32(net.fc_var.weight), self.f32(net.fc_var.bias), self.log_var, silu_in=False)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -587,8 +662,8 @@ class EncoderPlan(Plan):
 def _check_eval(net) -> None:
     if net.training:
         raise RuntimeError(
-            "the sm_100a path implements the inference forward (Dropout = identity); call .eval() first. "
-            "Training through these kernels (dropout masks + backward) is a later SURVEY section-8 row.")
+            "this is the inference forward (Dropout = identity): call .eval() first, or enable grad so that the "
+            "training path (dropout + backward kernels, infodiffusion_b200.train) is taken.")
 
 
 @torch.no_grad()

@@ -73,6 +73,7 @@ class AuxiliaryUNet(_EngineNet):
         assert all(i < len(ch_mult) for i in attn), 'attn index out of bound'
         tdim = ch * 4
         self.a_dim = a_dim
+        self.dropout_p = float(dropout)
         self.T, self.ch, self.ch_mult, self.shape = T, ch, list(ch_mult), tuple(shape)
         self.time_embedding = TimeEmbedding(T, ch, tdim)
         self.fc_a = nn.Linear(a_dim, tdim)
@@ -91,7 +92,12 @@ class AuxiliaryUNet(_EngineNet):
         init.zeros_(self.tail[-1].bias)
 
     def forward(self, x, t, a):
-        """x [B,C,H,W] fp32, t int64 [B], a [B,a_dim] -> eps [B,C,H,W] fp32 (reference models.py:296)."""
+        """x [B,C,H,W] fp32, t int64 [B], a [B,a_dim] -> eps [B,C,H,W] fp32 (reference models.py:296).
+        eval(): inference plan.  train(): dropout on and autograd through the kernels' backward."""
+        if self.training and torch.is_grad_enabled():
+            from .train import backbone_train_forward
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            return backbone_train_forward(self, x, t, a, seed, self.dropout_p)
         from .engine import backbone_forward
         return backbone_forward(self, x, t, a)
 
@@ -104,6 +110,7 @@ class Encoder(_EngineNet):
         assert all(i < len(ch_mult) for i in attn), 'attn index out of bound'
         self.shape = shape
         self.a_dim = a_dim
+        self.dropout_p = float(dropout)
         self.ch, self.ch_mult = ch, list(ch_mult)
         self.head = nn.Conv2d(shape[0], ch, kernel_size=3, stride=1, padding=1)
         self.downblocks, self.middleblocks, self.upblocks, cur = _unet_stacks(
@@ -122,6 +129,10 @@ class Encoder(_EngineNet):
         init.zeros_(self.tail[-1].bias)
 
     def forward(self, x):
+        if self.training and torch.is_grad_enabled():
+            from .train import encoder_train_forward
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            return encoder_train_forward(self, x, seed, self.dropout_p)
         from .engine import encoder_forward
         return encoder_forward(self, x)
 
@@ -170,9 +181,9 @@ class InfoDiff(nn.Module):
         return (output, epsilon, a, mu, log_var) if get_target else output
 
     def loss_fn(self, args, x, idx=None, curr_epoch=0):
-        """Forward value of the training objective (reference models.py:632-696), prior='regular'.
-        The backward pass through the sm_100a kernels is a later row of SURVEY section 8 and is not
-        built yet; the returned tensor carries no autograd graph."""
+        """Training objective (reference models.py:632-696), prior='regular'.  In train() mode the returned
+        scalar carries an autograd graph whose heavy nodes are the sm_100a backward kernels
+        (infodiffusion_b200.train); in eval() mode it is the forward value only."""
         output, epsilon, a, mu, log_var = self.forward(x, idx=idx, get_target=True)
         loss = (output - epsilon).square().mean()
         x_0 = torch.sqrt(1 / self.alphas[0]) * (x - self.betas[0] / torch.sqrt(1 - self.alpha_bars[0]) * output)

@@ -204,3 +204,57 @@ def test_loss_fn_forward_value(m1000, golden_dir):
     gold = float(np.load(golden_dir / "loss_a32.npz")["loss"])
     print(f"\n[parity] loss_fn: cuda {float(loss):.6f} vs reference {gold:.6f}")
     assert abs(float(loss) - gold) / abs(gold) < 2e-2
+
+
+def test_training_step_gradients_match_oracle_autograd(m1000):
+    """InfoDiff.loss_fn in train() mode (dropout forced to 0 for parity): the loss value and the
+    gradient of every parameter that receives one, against torch autograd through the fp32 CPU oracle."""
+    args, m, sd = m1000
+    gl = torch.Generator().manual_seed(21)
+    B = 4
+    xb = torch.rand(B, 3, 64, 64, generator=gl) * 2 - 1
+    idx = torch.randint(0, 1000, (B,), generator=gl)
+    eps = torch.randn(B, 3, 64, 64, generator=gl)
+    encn = torch.randn(B, 32, generator=gl)
+    prior = torch.randn(B, 32, generator=gl)
+    # oracle gradients
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point() and "timembedding.0" not in k) for k, v in sd.items()}
+    sch = orc.Schedule.make(args.beta1, args.betaT, args.diffusion_steps)
+    terms = orc.infodiff_loss(sdg, sch, xb, idx, eps, encn, prior, args.mmd_weight, args.kld_weight, args.diffusion_steps)
+    terms["loss"].backward()
+    # CUDA path
+    m.train()
+    m.backbone.dropout_p = 0.0
+    m.encoder.dropout_p = 0.0
+    m.zero_grad(set_to_none=True)
+    try:
+        with _patched_draws(idx.to(DEV), [eps.clone(), encn.clone(), prior.clone()]):
+            loss = m.loss_fn(args, xb.to(DEV))
+        loss.backward()
+    finally:
+        m.eval()
+    print(f"\n[parity] train loss: cuda {float(loss):.6f} vs oracle {float(terms['loss']):.6f}")
+    assert abs(float(loss) - float(terms["loss"])) / abs(float(terms["loss"])) < 2e-2
+    worst = []
+    n_checked = 0
+    for name, p in m.named_parameters():
+        g_ref = sdg[name].grad
+        if g_ref is None or float(g_ref.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) < 1e-6 or "crossattn" in name, name
+            continue
+        assert p.grad is not None, f"no gradient for {name}"
+        g = p.grad.detach().cpu().double().flatten()
+        r = g_ref.double().flatten()
+        cos = float((g @ r) / (g.norm() * r.norm()).clamp_min(1e-30))
+        rel = float((g - r).norm() / r.norm().clamp_min(1e-30))
+        worst.append((rel, cos, name))
+        n_checked += 1
+    worst.sort(reverse=True)
+    print(f"[parity] gradients checked: {n_checked}; worst rel-L2 / cosine:")
+    for rel, cos, name in worst[:8]:
+        print(f"    {rel:.3e}  cos {cos:.5f}  {name}")
+    med = sorted(w[0] for w in worst)[len(worst) // 2]
+    print(f"[parity] median rel-L2 {med:.3e}")
+    assert n_checked > 700
+    assert med < 5e-2
+    assert all(cos > 0.98 for _, cos, _ in worst), worst[0]

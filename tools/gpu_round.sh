@@ -11,6 +11,6 @@ for t in test_layout_kernels test_conv3x3 test_conv3x3_forced_tiles_per_cta test
   TAILN=6 run ops_$t python -m pytest tests/test_gpu_ops.py -q --no-header -p no:cacheprovider -k "$t" -m gpu
 done
 for t in test_backbone_eps test_encoder test_sampler_trajectory test_reverse_ddim_both_variants \
-         test_graph_replay_equals_eager_and_is_deterministic test_full_size_batch_independence_and_chunking test_loss_fn_forward_value; do
+         test_graph_replay_equals_eager_and_is_deterministic test_full_size_batch_independence_and_chunking test_loss_fn_forward_value test_training_step_gradients; do
   TAILN=14 run net_$t python -m pytest tests/test_gpu_network.py -q --no-header -p no:cacheprovider -s -k "$t" -m gpu
 done
