@@ -96,7 +96,7 @@ class AuxiliaryUNet(_EngineNet):
         eval(): inference plan.  train(): dropout on and autograd through the kernels' backward."""
         if self.training and torch.is_grad_enabled():
             from .train import backbone_train_forward
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())   # CPU generator: follows torch.manual_seed
             return backbone_train_forward(self, x, t, a, seed, self.dropout_p)
         from .engine import backbone_forward
         return backbone_forward(self, x, t, a)
@@ -131,7 +131,7 @@ class Encoder(_EngineNet):
     def forward(self, x):
         if self.training and torch.is_grad_enabled():
             from .train import encoder_train_forward
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())   # CPU generator: follows torch.manual_seed
             return encoder_train_forward(self, x, seed, self.dropout_p)
         from .engine import encoder_forward
         return encoder_forward(self, x)
