@@ -242,6 +242,8 @@ def test_training_step_gradients_match_oracle_autograd(m1000):
         if g_ref is None or float(g_ref.abs().max()) == 0.0:
             assert p.grad is None or float(p.grad.abs().max()) < 1e-6 or "crossattn" in name, name
             continue
+        if name.endswith("attn.proj_k.bias"):
+            continue    # softmax is invariant to a per-row shift of the scores: this gradient is exactly 0 in theory
         assert p.grad is not None, f"no gradient for {name}"
         g = p.grad.detach().cpu().double().flatten()
         r = g_ref.double().flatten()
@@ -251,7 +253,7 @@ def test_training_step_gradients_match_oracle_autograd(m1000):
         n_checked += 1
     worst.sort(reverse=True)
     print(f"[parity] gradients checked: {n_checked}; worst rel-L2 / cosine:")
-    for rel, cos, name in worst[:8]:
+    for rel, cos, name in worst[:12]:
         print(f"    {rel:.3e}  cos {cos:.5f}  {name}")
     med = sorted(w[0] for w in worst)[len(worst) // 2]
     print(f"[parity] median rel-L2 {med:.3e}")
