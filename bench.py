@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("IDF_SAMPLE_CHUNK", "0")) or None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-throughput measurement")
+    ap.add_argument("--train-batch", type=int, default=32)
     return ap.parse_args()
 
 
@@ -153,6 +155,64 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------
+# training throughput (secondary metric)
+# ------------------------------------------------------------------------------------------------
+def train_throughput(a, dev, world, rank, steps=6, warmup=3):
+    import torch.distributed as dist
+    from infodiffusion_b200 import _lib
+    from infodiffusion_b200.models import InfoDiff
+    from infodiffusion_b200.train import allreduce_gradients
+    B = a.train_batch
+    args = make_args_ns(1000)
+    args.mode = "train"
+    torch.manual_seed(64)
+    model = InfoDiff(args, "cpu", (3, 64, 64)).to(dev)
+    model.device = dev
+    for n in ("alpha_bars", "betas", "alphas", "alpha_prev_bars"):
+        setattr(model, n, getattr(model, n).to(dev))
+    model.train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-5, fused=True)
+    g = torch.Generator().manual_seed(7 + rank)
+    x_h = (torch.rand(B, 3, 64, 64, generator=g) * 2 - 1).pin_memory()
+
+    def step():
+        x = x_h.to(dev, non_blocking=True)
+        loss = model.loss_fn(args, x)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            allreduce_gradients(params, world)
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = _lib.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    flops = 3 * (15.318e9 + 11.774e9) * B * world * steps      # fwd + bwd ~ 3 x fwd
+    return {"metric": "train_samples_per_sec", "value": world * B * steps / (ms / 1000.0), "unit": "samples/s",
+            "ms_per_step": ms / steps, "batch_per_gpu": B, "n_gpus": world, "final_loss": float(loss),
+            "tflops": flops / (ms / 1000.0) / 1e12, "idf_launches_per_step": (_lib.launches() - l0) // steps,
+            "config": "InfoDiff a_dim 256, T=1000, bf16 kernels / fp32 params, dropout 0.1, AdamW(1e-4, wd 1e-5), "
+                      "clip 1.0, data-parallel all-reduce" + (" (NCCL)" if world > 1 else " (single GPU)")}
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU path
 # ------------------------------------------------------------------------------------------------
 def run_ours(a):
@@ -256,6 +316,11 @@ def run_ours(a):
         gbs = g_["bytes"] / (g_["ms"] * 1e-3) / 1e9
         breakdown = {k: {"ms_per_unet_eval": v["ms"] / reps, "launches": v["n"] // reps} for k, v in acc.items()}
         breakdown["adagn"].update({"bound": "hbm", "achieved_GBps": gbs, "peak_GBps": pk["hbm"], "frac": gbs / pk["hbm"]})
+    # ---- secondary metric: training throughput (BASELINE configs[2]: a_dim 256, T=1000, batch 32/GPU,
+    #      loss_fn + backward + grad all-reduce + clip_grad_norm + AdamW), through the public API
+    train = None
+    if not a.no_train:
+        train = train_throughput(a, dev, world, rank)
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
         v, cores, sample = cpu_ddim_rate(16, 10.0, 8)
@@ -275,7 +340,7 @@ def run_ours(a):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": xT_h.numel() * 4 + a_h.numel() * 4,
                     "d2h_bytes_per_step": out_h.numel() * 4},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "kernel_breakdown": breakdown,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "train": train,
         }))
     if world > 1:
         dist.destroy_process_group()

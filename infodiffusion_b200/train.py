@@ -506,3 +506,18 @@ def encoder_train_forward(net, x: torch.Tensor, seed: int, dropout_p: float):
     log_var = net.fc_var(a)
     a_q = mu + torch.randn_like(mu) * torch.exp(0.5 * log_var)
     return a, a_q, mu, log_var
+
+
+def allreduce_gradients(params: Sequence[nn.Parameter], world: int) -> None:
+    """Data-parallel gradient exchange: one NCCL all-reduce (average) over a flat fp32 buffer of every
+    gradient that exists; parameters that never receive a gradient (dead crossattn.*, frozen table) are
+    skipped exactly like the single-process optimizer skips them."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(world)
+    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)
