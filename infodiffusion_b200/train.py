@@ -421,19 +421,43 @@ def collect_param_grads(plan) -> Dict[nn.Parameter, torch.Tensor]:
 # ------------------------------------------------------------------------------------------------
 # autograd bridge
 # ------------------------------------------------------------------------------------------------
+USE_GRAPHS = True
+
+
+def _replay(plan, slot: str, body: Callable[[], None]) -> None:
+    """Run `body` (a fixed sequence of launches over static buffers: weight re-packing + forward plan, or
+    the backward op list incl. its few torch ops).  First call: eager (also sets kernel attributes); second
+    call: captured into a CUDA graph; afterwards a single graph replay -- the ~1000 launches of a step cost
+    one launch on the host."""
+    state = getattr(plan, slot, None)
+    if not USE_GRAPHS:
+        body()
+    elif state is None:
+        body()
+        setattr(plan, slot, "warm")
+    elif state == "warm":
+        torch.cuda.synchronize(plan.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        setattr(plan, slot, g)
+        g.replay()
+        _lib.count_launch(len(plan.ops) if slot == "_g_fwd" else len(_state(plan).ops))
+    else:
+        state.replay()
+        _lib.count_launch(len(plan.ops) if slot == "_g_fwd" else len(_state(plan).ops))
 class _ConvStackFn(torch.autograd.Function):
     """out = plan(x, mod_t, mod_z); parameters are passed so that autograd routes their gradients."""
 
     @staticmethod
     def forward(ctx, plan, x, mod_t, mod_z, seed, *params):
-        plan.refresh_weights()
         plan.x_in.copy_(x)
         if mod_t is not None:
             plan.mod_t.copy_(mod_t)
             plan.mod_z.copy_(mod_z)
         if plan.dropout_seed is not None:
             plan.dropout_seed.fill_(int(seed))
-        plan.run()
+        _replay(plan, "_g_fwd", lambda: (plan.refresh_weights(), plan.run()))
         ctx.plan = plan
         ctx.params = params
         ctx.has_mod = mod_t is not None
@@ -445,7 +469,7 @@ class _ConvStackFn(torch.autograd.Function):
         plan = ctx.plan
         finalize_backward(plan)
         plan.d_out.copy_(d_out)
-        run_backward(plan)
+        _replay(plan, "_g_bwd", lambda: run_backward(plan))
         pg = collect_param_grads(plan)
         grads = []
         for prm in ctx.params:
