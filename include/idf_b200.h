@@ -172,6 +172,10 @@ typedef struct {
   int32_t acc0, acc1;
   float* sums;
   float* ws;
+  /* optional fused parameter gradients (closed forms of S1, S2; any pointer may be NULL):
+   *   d_mod_t / d_mod_z : fp32 rows laid out like mod_t / mod_z of the forward args (same strides), receive
+   *                       (d scale | d shift) of this op;  dgamma / dbeta : fp32 [C], accumulated (atomics) */
+  float* d_mod_t; float* d_mod_z; float* dgamma; float* dbeta;
 } idf_adagn_bwd_args;
 int64_t idf_adagn_bwd_ws_floats(int32_t batch, int32_t C);
 int idf_adagn_silu_bwd(const idf_adagn_bwd_args* args, idf_stream_t stream);

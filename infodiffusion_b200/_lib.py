@@ -80,6 +80,7 @@ class AdaGNBwdArgs(C.Structure):
         ("acc0", C.c_int32), ("acc1", C.c_int32),
         ("sums", C.c_void_p),
         ("ws", C.c_void_p),
+        ("d_mod_t", C.c_void_p), ("d_mod_z", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
     ]
 
 

@@ -15,7 +15,7 @@ namespace idf {
 
 constexpr int kBT = 256;       // threads
 constexpr int kBMaxC = 256;
-constexpr int kBSlices = 4;    // row slices per sample in the stats sweep
+constexpr int kBSlices = 16;   // max row slices per sample (the launcher uses fewer for large batches / small maps)
 
 struct AdaGNBwdParams {
   const bf16* src0; const bf16* src1;
@@ -30,7 +30,9 @@ struct AdaGNBwdParams {
   const bf16* dy;
   bf16* dx0; bf16* dx1; int acc0, acc1;
   float* sums; float* ws;
+  float* d_mod_t; float* d_mod_z; float* dgamma; float* dbeta;
   int slice_rows;
+  int n_slices;
 };
 
 struct BwdShared {
@@ -183,11 +185,30 @@ __global__ void __launch_bounds__(kBT) adagn_bwd_apply_kernel(const AdaGNBwdPara
   for (int i = t; i < 2 * C; i += kBT) {
     const int which = i / C, ch = i - which * C;
     float acc = 0.f;
-    for (int s = 0; s < kBSlices; ++s) acc += p.ws[((static_cast<long long>(n) * kBSlices + s) * C + ch) * 2 + which];
+    for (int s = 0; s < p.n_slices; ++s) acc += p.ws[((static_cast<long long>(n) * kBSlices + s) * C + ch) * 2 + which];
     s_S[i] = acc;
     if (blockIdx.x == 0) p.sums[(static_cast<long long>(n) * C + ch) * 2 + which] = acc;
   }
   __syncthreads();
+  if (blockIdx.x == 0) {
+    // closed-form gradients of gamma / beta / modulation rows from (S1, S2):
+    //   v = ((xhat g + b)(1+s_t) + b_t)(1+s_z) + b_z,  q = g S2 + b S1,  T = 1+s_t,  Z = 1+s_z
+    const int step = p.step_ptr ? *p.step_ptr : 0;
+    const long long off_t = step * p.mod_t_step_stride + n * p.mod_t_batch_stride;
+    const long long off_z = step * p.mod_z_step_stride + n * p.mod_z_batch_stride;
+    for (int ch = t; ch < C; ch += kBT) {
+      const float S1 = s_S[ch], S2 = s_S[C + ch];
+      const float g = p.gamma[ch], b = p.beta[ch];
+      const float q = g * S2 + b * S1;
+      float T = 1.f, Z = 1.f, bt = 0.f;
+      if (p.mod_t != nullptr) { T = 1.f + p.mod_t[off_t + ch]; bt = p.mod_t[off_t + C + ch]; }
+      if (p.mod_z != nullptr) Z = 1.f + p.mod_z[off_z + ch];
+      if (p.d_mod_t != nullptr) { p.d_mod_t[off_t + ch] = Z * q; p.d_mod_t[off_t + C + ch] = Z * S1; }
+      if (p.d_mod_z != nullptr) { p.d_mod_z[off_z + ch] = T * q + bt * S1; p.d_mod_z[off_z + C + ch] = S1; }
+      if (p.dgamma != nullptr) atomicAdd(p.dgamma + ch, T * Z * S2);
+      if (p.dbeta != nullptr) atomicAdd(p.dbeta + ch, T * Z * S1);
+    }
+  }
   if (t < 32) {
     float g1 = 0.f, g2 = 0.f;
     for (int j = 0; j < cpg; ++j) {
@@ -265,12 +286,19 @@ cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, cudaStream_t stream) {
   p.dy = static_cast<const bf16*>(b.dy);
   p.dx0 = static_cast<bf16*>(b.dx0); p.dx1 = static_cast<bf16*>(b.dx1); p.acc0 = b.acc0; p.acc1 = b.acc1;
   p.sums = b.sums; p.ws = b.ws;
+  p.d_mod_t = b.d_mod_t; p.d_mod_z = b.d_mod_z; p.dgamma = b.dgamma; p.dbeta = b.dbeta;
   if (p.C > kBMaxC || p.C % 32 != 0 || p.c0 % 8 != 0 || p.c1 % 8 != 0 || a.batch <= 0) return cudaErrorInvalidValue;
   if (p.stats0 == nullptr || (p.c1 != 0 && (p.stats1 == nullptr || p.dx1 == nullptr)) || p.dx0 == nullptr ||
       p.dy == nullptr || p.sums == nullptr || p.ws == nullptr)
     return cudaErrorInvalidValue;
-  p.slice_rows = (p.R + kBSlices - 1) / kBSlices;
-  const dim3 grid(kBSlices, a.batch, 1);
+  // enough CTAs to fill the machine (~600), but at least 64 rows per slice
+  int ns = (600 + a.batch - 1) / a.batch;
+  if (ns > kBSlices) ns = kBSlices;
+  if (ns > (p.R + 63) / 64) ns = (p.R + 63) / 64;
+  if (ns < 1) ns = 1;
+  p.slice_rows = (p.R + ns - 1) / ns;
+  p.n_slices = (p.R + p.slice_rows - 1) / p.slice_rows;
+  const dim3 grid(p.n_slices, a.batch, 1);
   adagn_bwd_stats_kernel<<<grid, kBT, 0, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

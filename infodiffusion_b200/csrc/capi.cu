@@ -312,7 +312,7 @@ int idf_wgrad_plan_create(const idf_wgrad_desc* d, idf_wgrad_plan** out_plan) {
         for (int k = 0; k < c.n; ++k) { p.u_rel[u * 3 + k] = c.rel[k]; p.u_tap[u * 3 + k] = c.id[k]; }
       }
   p.n_kb = static_cast<int32_t>((d->rows + 127) / 128);
-  int slabs = (2 * g_num_sms + p.n_units - 1) / p.n_units;
+  int slabs = (g_num_sms + p.n_units - 1) / p.n_units;   // one wave of CTAs: split-K only as far as needed
   if (slabs > p.n_kb) slabs = p.n_kb;
   if (slabs < 1) slabs = 1;
   p.kb_per_slab = (p.n_kb + slabs - 1) / slabs;

@@ -77,6 +77,7 @@ class BwdState:
         self.param_grads: List[Tuple[nn.Parameter, Callable[[], torch.Tensor]]] = []
         self.keep: List = []
         self.wplans: List = []
+        self.late: List[Callable[[], None]] = []        # pointer fix-ups once the fp32 arena exists
 
     # ---- fp32 arena (weight / bias gradients), zeroed once per step
     def arena(self, shape) -> Callable[[], torch.Tensor]:
@@ -325,31 +326,16 @@ def bwd_adagn(plan, a, src0, src1, out, gn: nn.GroupNorm, gamma: torch.Tensor, b
     ws = torch.zeros(int(plan.lib.idf_adagn_bwd_ws_floats(plan.B, Cc)), dtype=torch.float32, device=plan.device)
     b.sums, b.ws = sums.data_ptr(), ws.data_ptr()
     st.keep += [b, sums, ws]
+    # gamma / beta / modulation gradients: closed forms of (S1, S2), fused into the kernel
+    gget, bget = st.arena((Cc,)), st.arena((Cc,))
+    if a.mod_t:
+        b.d_mod_t = plan.d_mod_t.data_ptr() + 4 * mod_cols
+    if a.mod_z:
+        b.d_mod_z = plan.d_mod_z.data_ptr() + 4 * mod_cols
+    st.late.append(lambda: (setattr(b, "dgamma", gget().data_ptr()), setattr(b, "dbeta", bget().data_ptr())))
     st.kernel(plan.lib.idf_adagn_silu_bwd, C.byref(b))
-    has_t = bool(a.mod_t)
-    has_z = bool(a.mod_z)
-    res: Dict[str, torch.Tensor] = {}
-
-    def closed_forms():
-        st_, bt_, sz_, bz_ = None, None, None, None
-        if has_t:
-            st_ = plan.mod_t[:, mod_cols:mod_cols + Cc]
-            bt_ = plan.mod_t[:, mod_cols + Cc:mod_cols + 2 * Cc]
-        if has_z:
-            sz_ = plan.mod_z[:, mod_cols:mod_cols + Cc]
-            bz_ = plan.mod_z[:, mod_cols + Cc:mod_cols + 2 * Cc]
-        r = adagn_param_grads(sums, gamma, beta, st_, bt_, sz_, bz_)
-        res.clear()
-        res.update(r)
-        if has_t:
-            plan.d_mod_t[:, mod_cols:mod_cols + Cc] = r["s_t"]
-            plan.d_mod_t[:, mod_cols + Cc:mod_cols + 2 * Cc] = r["b_t"]
-        if has_z:
-            plan.d_mod_z[:, mod_cols:mod_cols + Cc] = r["s_z"]
-            plan.d_mod_z[:, mod_cols + Cc:mod_cols + 2 * Cc] = r["b_z"]
-    st.ops.append(closed_forms)
-    st.param_grads.append((gn.weight, lambda: res["gamma"]))
-    st.param_grads.append((gn.bias, lambda: res["beta"]))
+    st.param_grads.append((gn.weight, gget))
+    st.param_grads.append((gn.bias, bget))
 
 
 def bwd_attention(plan, qkv, out, d: int) -> None:
@@ -391,6 +377,8 @@ def finalize_backward(plan) -> BwdState:
     for emit in reversed(plan.tape):
         emit()
     st.flat = torch.zeros(max(st.flat_size, 4), dtype=torch.float32, device=plan.device)
+    for fix in st.late:
+        fix()
     for d, h, get in st.wplans:
         d.dw = get().data_ptr()
         _lib.check(plan.lib.idf_wgrad_plan_create(C.byref(d), C.byref(h)))

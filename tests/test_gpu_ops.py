@@ -469,8 +469,19 @@ def test_adagn_backward(lib, c0, c1, H, B, mod, silu, drop):
     b.dy, b.dx0, b.sums, b.ws = dys.data_ptr(), dx0.data_ptr(), sums.data_ptr(), ws.data_ptr()
     if c1:
         b.dx1 = dx1.data_ptr()
+    # fused closed forms: gamma / beta accumulate over samples, modulation rows are written per sample
+    dgam, dbet = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
+    b.dgamma, b.dbeta = dgam.data_ptr(), dbet.data_ptr()
+    if mod:
+        dmt, dmz = torch.zeros(B, 2 * Cc, device=DEV), torch.zeros(B, 2 * Cc, device=DEV)
+        b.d_mod_t, b.d_mod_z = dmt.data_ptr(), dmz.data_ptr()
     check(lib.idf_adagn_silu_bwd(C.byref(b), stream()))
     torch.cuda.synchronize()
+    assert_close(dgam, gamma.grad, rel_l2=2e-3, max_rel=1e-2, what="fused d gamma")
+    assert_close(dbet, beta.grad, rel_l2=2e-3, max_rel=1e-2, what="fused d beta")
+    if mod:
+        for name, got, t in (("s_t", dmt[:, :Cc], st), ("b_t", dmt[:, Cc:], bt), ("s_z", dmz[:, :Cc], sz), ("b_z", dmz[:, Cc:], bz)):
+            assert_close(got, t.grad, rel_l2=2e-3, max_rel=1e-2, what="fused d " + name)
     dx_ref = xin.grad
     assert_close(unpf(dx0, B, H, H), dx_ref[:, :c0], rel_l2=6e-3, max_rel=2e-2, what="adagn dx0")
     if c1:
