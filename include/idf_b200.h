@@ -196,6 +196,12 @@ int idf_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, 
                    int32_t N, int32_t K, int32_t silu_in, idf_stream_t stream);
 /* y[m, :] = table[idx[m], :]  (nn.Embedding lookup, modules.py:23,37) */
 int idf_gather_rows_f32(const float* table, const int64_t* idx, float* y, int32_t M, int32_t N, idf_stream_t stream);
+/* dst[i] (+)= src[idx[i]-1] (+ src[idx2[i]-1]);  index 0 = literal zero, idx2 may be NULL, n % 4 == 0.
+ * Training only: one launch re-packs all fp32 parameters into the bf16 GEMM operand layouts that the
+ * reference obtains implicitly from nn.Conv2d.weight (modules.py:66,81,133-136,216-231), another assembles
+ * parameter-shaped gradients from the weight-gradient arena (what autograd does per parameter). */
+int idf_gather_elems(const float* src, const int32_t* idx, const int32_t* idx2, void* dst, int64_t n, int32_t dst_bf16,
+                     int32_t accumulate, idf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layout / data-movement kernels

@@ -387,6 +387,18 @@ int idf_gather_rows_f32(const float* table, const int64_t* idx, float* y, int32_
   return IDF_OK;
 }
 
+int idf_gather_elems(const float* src, const int32_t* idx, const int32_t* idx2, void* dst, int64_t n, int32_t dst_bf16,
+                     int32_t accumulate, idf_stream_t stream) {
+  if (n < 0 || (n & 3) != 0) return fail(IDF_ERR_ARG, "gather_elems: n must be a non-negative multiple of 4");
+  if (dst_bf16 && accumulate) return fail(IDF_ERR_ARG, "gather_elems: accumulation needs an fp32 destination");
+  if ((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(idx2) | reinterpret_cast<uintptr_t>(dst)) & 15)
+    return fail(IDF_ERR_ARG, "gather_elems: idx / dst must be 16-byte aligned");
+  cudaError_t e = launch_gather_elems(src, idx, idx2, dst, n, dst_bf16 != 0, accumulate != 0, g_num_sms,
+                                      reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "gather_elems launch");
+  return IDF_OK;
+}
+
 int idf_im2col_head(const float* x, void* out, int32_t batch, int32_t C, int32_t H, int32_t W, idf_stream_t stream) {
   cudaError_t e = launch_im2col_head(x, static_cast<bf16*>(out), batch, C, H, W, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "im2col_head launch (needs 9*C <= 64)");

@@ -73,6 +73,8 @@ cudaError_t launch_attn_v2(const CUtensorMap& tm, bf16* out, int batch, int H, i
                            cudaStream_t stream);
 cudaError_t launch_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy,
                               int M, int N, int K, int silu_in, cudaStream_t stream);
+cudaError_t launch_gather_elems(const float* src, const int* idx, const int* idx2, void* dst, long long n, bool dst_bf16,
+                                bool accumulate, int num_sms, cudaStream_t stream);
 cudaError_t launch_gather_rows(const float* table, const int64_t* idx, float* y, int M, int N, cudaStream_t stream);
 cudaError_t launch_im2col_head(const float* x, bf16* out, int batch, int C, int H, int W, cudaStream_t stream);
 cudaError_t launch_upsample2x(const bf16* in, bf16* out, int batch, int H, int W, int C, cudaStream_t stream);

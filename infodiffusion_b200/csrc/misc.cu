@@ -384,6 +384,52 @@ cudaError_t launch_gather_rows(const float* table, const int64_t* idx, float* y,
 }
 
 // ----------------------------------------------------------------------------------------------
+// Element gather (training): dst[i] (+)= src[idx[i]-1] (+ src[idx2[i]-1]), index 0 = literal zero.
+// One launch re-packs every fp32 parameter into the bf16 GEMM operand layouts (forward and data-gradient
+// packings) or assembles the parameter-shaped gradients from the weight-gradient arena.  n % 4 == 0.
+// ----------------------------------------------------------------------------------------------
+template <bool kBf16, bool kAcc>
+__global__ void __launch_bounds__(256) gather_elems_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                                           const int* __restrict__ idx2, void* __restrict__ dst,
+                                                           long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int4 a = reinterpret_cast<const int4*>(idx)[i];
+    float v0 = a.x ? src[a.x - 1] : 0.f, v1 = a.y ? src[a.y - 1] : 0.f;
+    float v2 = a.z ? src[a.z - 1] : 0.f, v3 = a.w ? src[a.w - 1] : 0.f;
+    if (idx2 != nullptr) {
+      const int4 b = reinterpret_cast<const int4*>(idx2)[i];
+      v0 += b.x ? src[b.x - 1] : 0.f; v1 += b.y ? src[b.y - 1] : 0.f;
+      v2 += b.z ? src[b.z - 1] : 0.f; v3 += b.w ? src[b.w - 1] : 0.f;
+    }
+    if constexpr (kBf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&lo);
+      o.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(dst)[i] = o;
+    } else {
+      float4* d = reinterpret_cast<float4*>(dst) + i;
+      if constexpr (kAcc) {
+        const float4 o = *d;
+        v0 += o.x; v1 += o.y; v2 += o.z; v3 += o.w;
+      }
+      *d = make_float4(v0, v1, v2, v3);
+    }
+  }
+}
+cudaError_t launch_gather_elems(const float* src, const int* idx, const int* idx2, void* dst, long long n, bool dst_bf16,
+                                bool accumulate, int num_sms, cudaStream_t stream) {
+  const long long n4 = n / 4;
+  if (n4 == 0) return cudaSuccess;
+  const int grid = static_cast<int>(min(static_cast<long long>(num_sms) * 8, (n4 + 255) / 256));
+  if (dst_bf16) gather_elems_kernel<true, false><<<grid, 256, 0, stream>>>(src, idx, idx2, dst, n4);
+  else if (accumulate) gather_elems_kernel<false, true><<<grid, 256, 0, stream>>>(src, idx, idx2, dst, n4);
+  else gather_elems_kernel<false, false><<<grid, 256, 0, stream>>>(src, idx, idx2, dst, n4);
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------
 // MMD (utils.py:74-90): loss = mean k(x,x) + mean k(y,y) - 2 mean k(x,y), k(u,v)=exp(-|u-v|^2/D^2)
 // One block per column index j: accumulates sum_i [k(x_i,x_j) + k(y_i,y_j) - 2 k(x_i,y_j)] and
 // d loss / d y_j.  The per-block partial is added to *loss with one atomicAdd (loss must be zeroed).

@@ -29,7 +29,8 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import EPI_BF16, EPI_F32_NCHW, EPI_SAMPLER, AdaGNArgs, ConvDesc
-from .layout import pack_conv1x1, pack_conv3x3, pad_cols as _pad_cols, pad_rows as _pad_rows, taps1x1, taps3x3, taps_stride2
+from .layout import (ParamIndex, pack_conv1x1, pack_conv3x3, pad_cols as _pad_cols, pad_rows as _pad_rows, probing, pv,
+                     taps1x1, taps3x3, taps_stride2)
 from .modules import AttnBlock, AuxResBlock, DownSample, ResBlock, ResBlock_encoder, UpSample
 
 BF16 = torch.bfloat16
@@ -94,6 +95,45 @@ class Workspace:
 # ------------------------------------------------------------------------------------------------
 # plan builder
 # ------------------------------------------------------------------------------------------------
+class _GatherArena:
+    """Bump allocator for packed training operands: tensors are slices of a few large buffers, and each
+    buffer carries the int32 gather map (1-based indices into Plan.flat_params, 0 = zero) that re-packs it."""
+
+    def __init__(self, dtype, capacity: int, device):
+        self.dtype, self.capacity, self.device = dtype, capacity, device
+        self._chunks: List[dict] = []
+
+    def alloc(self, shape, idx: List[torch.Tensor]) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= d
+        span = (n + 127) // 128 * 128                       # 256-byte alignment for bf16 (TMA base), 512 for fp32
+        ch = self._chunks[-1] if self._chunks else None
+        if ch is None or ch["used"] + span > ch["buf"].numel():
+            cap = max(self.capacity if ch is None else self.capacity // 2, span)
+            ch = dict(buf=torch.zeros(cap, dtype=self.dtype, device=self.device), used=0, parts=[], maps=None)
+            self._chunks.append(ch)
+        off = ch["used"]
+        ch["used"] += span
+        ch["parts"].append((off, n, idx))
+        ch["maps"] = None
+        return ch["buf"][off:off + n].view(*shape)
+
+    def chunks(self):
+        for ch in self._chunks:
+            if ch["maps"] is None:
+                i1 = torch.zeros(ch["used"], dtype=torch.int32, device=self.device)
+                i2 = None
+                for off, n, idx in ch["parts"]:
+                    i1[off:off + n] = idx[0]
+                    if len(idx) > 1:
+                        if i2 is None:
+                            i2 = torch.zeros(ch["used"], dtype=torch.int32, device=self.device)
+                        i2[off:off + n] = idx[1]
+                ch["maps"] = (i1, i2)
+            yield ch["buf"], ch["maps"][0], ch["maps"][1], ch["used"]
+
+
 class Plan:
     """Ordered list of kernel launches + everything they reference."""
 
@@ -105,7 +145,8 @@ class Plan:
         self.training = training
         self.ws = ws if ws is not None else Workspace(batch, device, recycle=not training)
         self.tape: List = []         # training: backward emitters, one per forward composite, replayed in reverse
-        self.refresh: List = []      # training: (dst tensor, recipe) pairs re-evaluated before every forward
+        self.pindex: Optional[ParamIndex] = None   # training: flat parameter layout the packing gathers read
+        self.recipes: List = []      # training: (packed tensor, recipe) pairs (kept for verification)
         self.dropout_p = 0.0
         self.dropout_seed = None     # device int64 scalar
         self._drop_layers = 0
@@ -154,27 +195,58 @@ class Plan:
 
     # ---- op emitters ---------------------------------------------------------------------------
     def weight(self, m) -> torch.Tensor:
-        """bf16 device copy of a packed weight.  `m` may be a recipe (callable returning the fp32 tensor): a
-        training plan re-evaluates recipes before every forward so the kernels see the current parameters."""
-        src = m() if callable(m) else m
-        t = src.detach().to(device=self.device, dtype=BF16).contiguous()
-        self.keep.append(t)
-        if callable(m) and self.training:
-            self.refresh.append((t, m))
-        return t
+        """bf16 device copy of a packed weight.  `m` may be a recipe (callable returning the fp32 tensor, reading
+        parameters through layout.pv): a training plan re-packs all recipes before every forward with one
+        gather launch so the kernels see the current parameters."""
+        return self._packed(m, BF16)
 
     def f32(self, m) -> torch.Tensor:
+        """fp32 device copy (biases, GroupNorm affine); a recipe may return a tuple of tensors to be summed."""
+        return self._packed(m, torch.float32)
+
+    def _packed(self, m, dtype) -> torch.Tensor:
         src = m() if callable(m) else m
-        t = src.detach().to(device=self.device, dtype=torch.float32).contiguous()
-        self.keep.append(t)
-        if callable(m) and self.training:
-            self.refresh.append((t, m))
+        if isinstance(src, tuple):
+            src = sum(x.detach().double() for x in src)
+        if not (callable(m) and self.training):
+            t = src.detach().to(device=self.device, dtype=dtype).contiguous()
+            self.keep.append(t)
+            return t
+        assert self.pindex is not None, "training plan: bind_params() before the first weight"
+        with probing(self.pindex):
+            idx = m()
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        assert len(idx) <= 2 and all(i.dtype == torch.int64 for i in idx), "recipe must be a pure re-ordering of parameters"
+        arena = self._arena_bf16 if dtype == BF16 else self._arena_f32
+        t = arena.alloc(src.shape, [i.reshape(-1).to(torch.int32) for i in idx])
+        t.copy_(src.detach())
+        self.recipes.append((t, m))
         return t
 
+    def bind_params(self, params) -> None:
+        """Training plans: the parameters the recipes read, in a fixed flat fp32 layout."""
+        self.pindex = ParamIndex(params, self.device)
+        self.flat_params = torch.zeros(self.pindex.total, dtype=torch.float32, device=self.device)
+        self._flat_views = self.pindex.views(self.flat_params)
+        total = self.pindex.total
+        self._arena_bf16 = _GatherArena(BF16, int(2.3 * total) + (4 << 20), self.device)
+        self._arena_f32 = _GatherArena(torch.float32, 1 << 20, self.device)
+
     def refresh_weights(self) -> None:
+        """flat_params <- parameters (one multi-tensor copy), then one gather launch per arena chunk."""
+        if self.pindex is None:
+            return
         with torch.no_grad():
-            for dst, recipe in self.refresh:
-                dst.copy_(recipe().detach())
+            torch._foreach_copy_(self._flat_views, [p.detach() for p in self.pindex.params])
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        n = 0
+        for arena in (self._arena_bf16, self._arena_f32):
+            for buf, idx, idx2, used in arena.chunks():
+                _lib.check(self.lib.idf_gather_elems(self.flat_params.data_ptr(), idx.data_ptr(),
+                                                     idx2.data_ptr() if idx2 is not None else None, buf.data_ptr(),
+                                                     used, 1 if arena.dtype == BF16 else 0, 0, stream))
+                n += 1
+        _lib.count_launch(n)
 
     def conv(self, srcs: Sequence[Act], kblocks: Sequence[Tuple[int, int, int]], wp: torch.Tensor,
              bias: torch.Tensor, H: int, cout: int, block_n: int, out: Optional[Act] = None,
@@ -226,7 +298,7 @@ class Plan:
             a.src1, a.c1 = src1.t.data_ptr(), src1.C
         a.out = out.t.data_ptr()
         a.batch, a.H, a.W = self.B, src0.H, src0.H
-        gamma, beta = self.f32(lambda: gn.weight), self.f32(lambda: gn.bias)
+        gamma, beta = self.f32(lambda: pv(gn.weight)), self.f32(lambda: pv(gn.bias))
         a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
         a.eps = float(gn.eps)
         if mod_t is not None:
@@ -281,12 +353,12 @@ class Plan:
         kb = self.taps3x3(cin, H)
         srcs = [src]
         if shortcut is None:
-            wp = lambda: pack_conv3x3(conv.weight)
-            bias = lambda: conv.bias
+            wp = lambda: pack_conv3x3(pv(conv.weight))
+            bias = lambda: pv(conv.bias)
         else:
             sc_conv, raws = shortcut
-            wp = lambda: torch.cat([pack_conv3x3(conv.weight), pack_conv1x1(sc_conv.weight)], dim=1)
-            bias = lambda: conv.bias + sc_conv.bias
+            wp = lambda: torch.cat([pack_conv3x3(pv(conv.weight)), pack_conv1x1(pv(sc_conv.weight))], dim=1)
+            bias = lambda: (pv(conv.bias), pv(sc_conv.bias))                      # summed by f32()
             for r in raws:
                 srcs.append(r)
                 kb += [(len(srcs) - 1, c0, 0) for c0 in range(0, r.C, 64)]
@@ -311,8 +383,8 @@ class Plan:
         cout = sum(m.out_channels for m in convs)
         kb = taps1x1(src.C)
         out = self.ws.alloc(src.H, cout)
-        wp = lambda: _pad_cols(torch.cat([pack_conv1x1(m.weight) for m in convs], dim=0), 64 * len(kb))
-        bias = lambda: torch.cat([m.bias for m in convs], dim=0)
+        wp = lambda: _pad_cols(torch.cat([pack_conv1x1(pv(m.weight)) for m in convs], dim=0), 64 * len(kb))
+        bias = lambda: torch.cat([pv(m.bias) for m in convs], dim=0)
         self.conv([src], kb, self.weight(wp), self.f32(bias), src.H, cout, self._bn(cout), out=out, residual=residual,
                   want_stats=want_stats)
         if self.training:
@@ -327,7 +399,7 @@ class Plan:
         self._emit("space_to_depth", self.lib.idf_space_to_depth, (src.t.data_ptr(), ph.t.data_ptr(), self.B, H, H, Cc))
         kb = taps_stride2(Cc, Ho, Ho, ph.rows)
         out = self.ws.alloc(Ho, conv.out_channels)
-        self.conv([ph], kb, self.weight(lambda: pack_conv3x3(conv.weight)), self.f32(lambda: conv.bias), Ho,
+        self.conv([ph], kb, self.weight(lambda: pack_conv3x3(pv(conv.weight))), self.f32(lambda: pv(conv.bias)), Ho,
                   conv.out_channels, self._bn(conv.out_channels), out=out)
         if self.training:
             from . import train
@@ -405,8 +477,8 @@ class Plan:
         self._emit("im2col_head", self.lib.idf_im2col_head, (x_src.data_ptr(), patches.t.data_ptr(), self.B, Cimg, H, H))
         cout = conv.out_channels
         h = self.ws.alloc(H, cout)
-        self.conv([patches], [(0, 0, 0)], self.weight(lambda: _pad_cols(pack_conv3x3(conv.weight), 64)),
-                  self.f32(lambda: conv.bias), H, cout, self._bn(cout), out=h, real_macs_per_row=9 * Cimg * cout)
+        self.conv([patches], [(0, 0, 0)], self.weight(lambda: _pad_cols(pack_conv3x3(pv(conv.weight)), 64)),
+                  self.f32(lambda: pv(conv.bias)), H, cout, self._bn(cout), out=h, real_macs_per_row=9 * Cimg * cout)
         if self.training:
             from . import train
             self.tape.append(lambda: train.bwd_head(self, patches, conv, h, Cimg))
@@ -418,8 +490,8 @@ class Plan:
         ta = self.ws.alloc(H, h.C)
         self.adagn(h, None, ta, gn, silu=True)
         self.ws.free(h)
-        self.conv([ta], self.taps3x3(ta.C, H), self.weight(lambda: _pad_rows(pack_conv3x3(tconv.weight), 16)),
-                  self.f32(lambda: _pad_rows(tconv.bias.float(), 16)), H, cout, 16, epilogue=epilogue, out_f32=out_f32,
+        self.conv([ta], self.taps3x3(ta.C, H), self.weight(lambda: _pad_rows(pack_conv3x3(pv(tconv.weight)), 16)),
+                  self.f32(lambda: _pad_rows(pv(tconv.bias), 16)), H, cout, 16, epilogue=epilogue, out_f32=out_f32,
                   **extra)
         if self.training:
             from . import train
@@ -489,6 +561,9 @@ class BackbonePlan(Plan):
         assert H == W, "square images only"
         assert H in (32, 64), "the sm_100a plan supports 32x32 / 64x64 inputs (attention at 16x16 / 8x8)"
         self.net = net
+        if mode == "train":
+            from .train import stack_params
+            self.bind_params(stack_params(net))
         B = batch
         f32 = dict(dtype=torch.float32, device=device)
         self.pack = pack if pack is not None else ModulationPack(conditioned_blocks(net), device)
@@ -622,6 +697,9 @@ class EncoderPlan(Plan):
             self.dropout_p = dropout_p
             self.dropout_seed = torch.zeros(1, dtype=torch.int64, device=device)
         self.net = net
+        if training:
+            from .train import stack_params
+            self.bind_params(stack_params(net))
         self.x_in = x_in if x_in is not None else torch.zeros(B, Cimg, H, W, **f32)
         self.map_out = torch.zeros(B, 1, H, W, **f32)
         self.a = torch.zeros(B, net.a_dim, **f32)

@@ -93,6 +93,51 @@ def pad_cols(m: torch.Tensor, cols: int) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# parameter index probing (training): packing recipes are pure re-orderings (permute / reshape / cat / zero
+# pad), so running one over "1 + flat index" tensors instead of values yields the gather map of the packing.
+# ------------------------------------------------------------------------------------------------
+class ParamIndex:
+    """Flat fp32 layout of a parameter list: parameter i occupies [offset[i], offset[i] + numel) (4-aligned)."""
+
+    def __init__(self, params: Sequence[torch.Tensor], device):
+        self.params = list(params)
+        self.device = device
+        self.offset = {}
+        off = 0
+        for p in self.params:
+            self.offset[id(p)] = off
+            off += (p.numel() + 3) // 4 * 4
+        self.total = max(off, 4)
+
+    def index_of(self, p) -> torch.Tensor:
+        off = self.offset[id(p)]
+        return torch.arange(off + 1, off + 1 + p.numel(), dtype=torch.int64, device=self.device).view(p.shape)
+
+    def views(self, flat: torch.Tensor) -> List[torch.Tensor]:
+        return [flat[self.offset[id(p)]: self.offset[id(p)] + p.numel()].view(p.shape) for p in self.params]
+
+
+_probe: List[ParamIndex] = []
+
+
+def pv(p):
+    """Value of parameter `p` inside a packing recipe: the tensor itself, or -- while probing -- the int64
+    tensor of its 1-based flat indices."""
+    return _probe[-1].index_of(p) if _probe else p
+
+
+class probing:
+    def __init__(self, pindex: ParamIndex):
+        self.pindex = pindex
+
+    def __enter__(self):
+        _probe.append(self.pindex)
+
+    def __exit__(self, *exc):
+        _probe.pop()
+
+
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous batch shard of `total` independent samples for `rank` (sampling / encoding are
     per-sample independent: GroupNorm and attention never mix samples)."""

@@ -58,6 +58,7 @@ class _EngineNet(nn.Module):
     def invalidate_plans(self):
         """Drop packed bf16 weights / workspaces (call after the fp32 parameters change)."""
         self._plans().clear()
+        self.__dict__.pop("_idf_stack_params", None)
 
     def load_state_dict(self, *a, **k):
         out = super().load_state_dict(*a, **k)

@@ -26,7 +26,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import AdaGNBwdArgs, WgradDesc
-from .layout import tap_offsets3x3, taps_stride2
+from .layout import pv, tap_offsets3x3, taps_stride2
 
 BF16 = torch.bfloat16
 
@@ -190,13 +190,13 @@ def bwd_conv(plan, parts: Sequence[Part], biases: Sequence[nn.Parameter], out, r
             kb = []
             for off in offs:
                 kb += [(0, c0, -off) for c0 in range(0, cout, 64)]
-            _dgrad(plan, st, dout, src, kb, lambda w=w: w.permute(1, 2, 3, 0).reshape(w.shape[1], 9 * w.shape[0]), src.C)
+            _dgrad(plan, st, dout, src, kb, lambda w=w: pv(w).permute(1, 2, 3, 0).reshape(w.shape[1], 9 * w.shape[0]), src.C)
             get = _wgrad(plan, st, dout, src, src.t.shape[0], src.C, cout, offs)
             st.param_grads.append((w, lambda get=get, w=w: get().view(w.shape[0], 3, 3, w.shape[1]).permute(0, 3, 1, 2)))
         else:
             c0s, c1s = prt.cslice
             kb = [(0, c0, 0) for c0 in range(0, cout, 64)]
-            _dgrad(plan, st, dout, src, kb, lambda w=w, a=c0s, b=c1s: w[:, a:b, 0, 0].t(), src.C)
+            _dgrad(plan, st, dout, src, kb, lambda w=w, a=c0s, b=c1s: pv(w)[:, a:b, 0, 0].t(), src.C)
             sc_dw.append((prt, _wgrad(plan, st, dout, src, src.t.shape[0], src.C, cout, [0])))
     if sc_dw:
         w = sc_dw[0][0].weight
@@ -214,7 +214,7 @@ def bwd_conv1x1_stack(plan, src, convs: Sequence[nn.Conv2d], out, residual) -> N
     dout = st.grad(out)
     cout, cin = out.C, src.C
     kb = [(0, c0, 0) for c0 in range(0, cout, 64)]
-    _dgrad(plan, st, dout, src, kb, lambda: torch.cat([m.weight[:, :, 0, 0] for m in convs], dim=0).t(), cin)
+    _dgrad(plan, st, dout, src, kb, lambda: torch.cat([pv(m.weight)[:, :, 0, 0] for m in convs], dim=0).t(), cin)
     get = _wgrad(plan, st, dout, src, src.t.shape[0], cin, cout, [0])
     bget = _bias_grad(plan, st, dout, cout)
     o = 0
@@ -252,7 +252,7 @@ def bwd_tail(plan, ta, tconv: nn.Conv2d, out_f32: torch.Tensor, cout: int) -> No
     kb = [(0, 0, -off) for off in offs]
 
     def wt():
-        w = tconv.weight                                           # [cout, cin, 3, 3]
+        w = pv(tconv.weight)                                       # [cout, cin, 3, 3]
         full = torch.zeros(cin, 9, 64, dtype=w.dtype, device=w.device)
         full[:, :, :cout] = w.permute(1, 2, 3, 0).reshape(cin, 9, cout)
         return full.reshape(cin, 9 * 64)
@@ -287,7 +287,7 @@ def bwd_downsample(plan, src, ph, conv: nn.Conv2d, out) -> None:
             st.grads[id(tgt)] = tgt              # the phase slice IS the gradient buffer of this pseudo-activation
             st.written[id(tgt)] = False
             _dgrad(plan, st, dout, tgt, kb,
-                   lambda taps=taps: torch.cat([w[:, :, ky, kx].t() for ky, kx in taps], dim=1), Cc)
+                   lambda taps=taps: torch.cat([pv(w)[:, :, ky, kx].t() for ky, kx in taps], dim=1), Cc)
     g = st.grad(src)
     st.kernel(plan.lib.idf_depth_to_space, dph_t.data_ptr(), g.t.data_ptr(), plan.B, src.H, src.H, Cc,
               1 if st.is_written(src) else 0)
@@ -382,8 +382,33 @@ def finalize_backward(plan) -> BwdState:
     for d, h, get in st.wplans:
         d.dw = get().data_ptr()
         _lib.check(plan.lib.idf_wgrad_plan_create(C.byref(d), C.byref(h)))
+    _build_grad_maps(plan, st)
     st._final = True
     return st
+
+
+def _build_grad_maps(plan, st: BwdState) -> None:
+    """Gather maps arena -> parameter-shaped gradients.  Every entry of st.param_grads is a pure view / cat of
+    arena buffers, so evaluating it over an arena of 1-based indices gives the map; pass k holds the k-th
+    contribution of each parameter (a parameter used by several GEMM segments is summed over passes)."""
+    pindex = plan.pindex
+    values = st.flat
+    st.flat = torch.arange(1, values.numel() + 1, dtype=torch.int64, device=plan.device)
+    passes: List[torch.Tensor] = []
+    seen: Dict[int, int] = {}
+    try:
+        for prm, get in st.param_grads:
+            k = seen.get(id(prm), 0)
+            seen[id(prm)] = k + 1
+            if k == len(passes):
+                passes.append(torch.zeros(pindex.total, dtype=torch.int32, device=plan.device))
+            off = pindex.offset[id(prm)]
+            passes[k][off:off + prm.numel()] = get().reshape(-1).to(torch.int32)
+    finally:
+        st.flat = values
+    st.grad_maps = passes
+    st.grad_flat = torch.zeros(pindex.total, dtype=torch.float32, device=plan.device)
+    st.has_grad = [id(p) in seen for p in pindex.params]
 
 
 def run_backward(plan) -> None:
@@ -391,6 +416,20 @@ def run_backward(plan) -> None:
     st.flat.zero_()
     for op in st.ops:
         op()
+    stream = torch.cuda.current_stream(plan.device).cuda_stream
+    for k, m in enumerate(st.grad_maps):         # parameter-shaped gradients, one gather launch per pass
+        _lib.check(plan.lib.idf_gather_elems(st.flat.data_ptr(), m.data_ptr(), None, st.grad_flat.data_ptr(),
+                                             m.numel(), 0, 1 if k else 0, stream))
+    _lib.count_launch(len(st.grad_maps))
+
+
+def fused_param_grads(plan) -> List[Optional[torch.Tensor]]:
+    """Gradients of plan.pindex.params (None where the conv stack contributes nothing), as views of a fresh
+    copy of the flat gradient buffer."""
+    st = _state(plan)
+    flat = st.grad_flat.clone()
+    views = plan.pindex.views(flat)
+    return [v if has else None for v, has in zip(views, st.has_grad)]
 
 
 def collect_param_grads(plan) -> Dict[nn.Parameter, torch.Tensor]:
@@ -458,11 +497,7 @@ class _ConvStackFn(torch.autograd.Function):
         finalize_backward(plan)
         plan.d_out.copy_(d_out)
         _replay(plan, "_g_bwd", lambda: run_backward(plan))
-        pg = collect_param_grads(plan)
-        grads = []
-        for prm in ctx.params:
-            g = pg.get(prm)
-            grads.append(None if g is None else g.reshape(prm.shape).to(prm.dtype))
+        grads = fused_param_grads(plan)            # same order as ctx.params (= plan.pindex.params)
         dmt = plan.d_mod_t.clone() if ctx.has_mod else None
         dmz = plan.d_mod_z.clone() if ctx.has_mod else None
         return (None, None, dmt, dmz, None, *grads)
@@ -470,8 +505,12 @@ class _ConvStackFn(torch.autograd.Function):
 
 def stack_params(net) -> List[nn.Parameter]:
     """Parameters whose gradients come from the conv-stack kernels (everything spatial: convs, GroupNorms)."""
-    skip = ("time_embedding", "fc_a", "fc_mu", "fc_var", "temb_proj", "aemb_proj", "crossattn")
-    return [p for n, p in net.named_parameters() if p.requires_grad and not any(s in n for s in skip)]
+    cached = net.__dict__.get("_idf_stack_params")
+    if cached is None:
+        skip = ("time_embedding", "fc_a", "fc_mu", "fc_var", "temb_proj", "aemb_proj", "crossattn")
+        cached = [p for n, p in net.named_parameters() if not any(s in n for s in skip)]
+        net.__dict__["_idf_stack_params"] = cached
+    return cached
 
 
 def backbone_train_forward(net, x_t: torch.Tensor, t: torch.Tensor, a: torch.Tensor, seed: int,

@@ -260,3 +260,59 @@ def test_training_step_gradients_match_oracle_autograd(m1000):
     assert n_checked > 700
     assert med < 5e-2
     assert all(cos > 0.98 for _, cos, _ in worst), worst[0]
+
+
+def test_training_packing_and_gradient_gathers_are_exact(m1000):
+    """The two gather launches of a training step are pure re-orderings: (1) the bf16 / fp32 operand arenas
+    equal the per-tensor packing recipes evaluated on the current parameters, also after the parameters
+    change in place; (2) the parameter-shaped gradients equal the per-parameter view assembly of the arena."""
+    from infodiffusion_b200 import train as T
+    args, m, sd = m1000
+    net = m.backbone
+    B = 2
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 3, 64, 64, generator=g).to(DEV)
+    t = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+    a = torch.randn(B, 32, generator=g).to(DEV)
+    m.train()
+    try:
+        for it in range(3):                      # eager, capture, replay
+            m.zero_grad(set_to_none=True)
+            out = net(x, t, a)
+            out.square().mean().backward()
+        plan = next(p for k, p in net._plans().items() if k[0] == "train" and k[1] == B)
+        st = T._state(plan)
+        ref = T.collect_param_grads(plan)
+        n = 0
+        for prm, has in zip(plan.pindex.params, st.has_grad):
+            assert has == (prm in ref)
+            if has:
+                assert torch.equal(prm.grad, ref[prm].reshape(prm.shape)), "fused gradient gather differs"
+                n += 1
+        assert n > 300
+        # in-place parameter update, then a forward: packed operands must follow
+        with torch.no_grad():
+            for prm in plan.pindex.params:
+                prm.mul_(1.01)
+        net(x, t, a)
+        torch.cuda.synchronize()
+        for packed, recipe in plan.recipes:      # the gather maps reproduce every packing recipe
+            want = recipe()
+            want = sum(want) if isinstance(want, tuple) else want
+            assert torch.equal(packed, want.detach().to(packed.dtype)), "gather map differs from its recipe"
+        assert len(plan.recipes) > 300
+        checked = 0
+        for arena in (plan._arena_bf16, plan._arena_f32):
+            for buf, idx, idx2, used in arena.chunks():
+                want = torch.where(idx > 0, plan.flat_params[(idx.long() - 1).clamp_min(0)], torch.zeros((), device=DEV))
+                if idx2 is not None:
+                    want = want + torch.where(idx2 > 0, plan.flat_params[(idx2.long() - 1).clamp_min(0)], torch.zeros((), device=DEV))
+                assert torch.equal(buf[:used], want.to(buf.dtype))
+                checked += used
+        assert checked > 1_000_000
+        flat_now = torch.cat([torch.nn.functional.pad(p.detach().reshape(-1), (0, (-p.numel()) % 4)) for p in plan.pindex.params])
+        assert torch.equal(plan.flat_params[:flat_now.numel()], flat_now)
+    finally:
+        with torch.no_grad():
+            m.load_state_dict(sd)
+        m.eval()
