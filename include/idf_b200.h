@@ -157,6 +157,9 @@ typedef struct {
   /* training only: inverted dropout applied after SiLU (nn.Dropout at modules.py:221,227,280,286,342).
    * keep-mask = hash(*dropout_seed, dropout_layer, element index) >= p; 0 disables.               */
   float dropout_p; const uint64_t* dropout_seed; uint32_t dropout_layer;
+  /* training only, optional: fp32 [batch, C, 4] = (A, B, group mean, group rstd) per sample and channel with
+   * v = A*x + B, written by the forward (streaming variant) and read back by idf_adagn_silu_bwd. */
+  float* save_coef;
 } idf_adagn_args;
 int idf_adagn_silu_fwd(const idf_adagn_args* args, idf_stream_t stream);
 

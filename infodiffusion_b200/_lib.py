@@ -69,6 +69,7 @@ class AdaGNArgs(C.Structure):
         ("apply_silu", C.c_int32),
         ("stats0", C.c_void_p), ("stats1", C.c_void_p),
         ("dropout_p", C.c_float), ("dropout_seed", C.c_void_p), ("dropout_layer", C.c_uint32),
+        ("save_coef", C.c_void_p),
     ]
 
 

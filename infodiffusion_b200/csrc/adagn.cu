@@ -52,6 +52,7 @@ struct AdaGNParams {
   float drop_scale;            // 1 / (1 - p)
   const unsigned long long* drop_seed;
   unsigned drop_layer;
+  float* save_coef;            // training: [batch, C, 4] = (A, B, mean, rstd)
 };
 
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier
@@ -338,6 +339,8 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
       B = B * sc + sh;
     }
     s_ab[ch] = make_float2(A, B);
+    if (p.save_coef != nullptr && blockIdx.x == 0)
+      reinterpret_cast<float4*>(p.save_coef)[static_cast<long long>(n) * C + ch] = make_float4(A, B, s_mean[g], s_rstd[g]);
   }
   __syncthreads();
 
@@ -423,6 +426,7 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
   p.slice_rows = 0;
   p.drop_thr16 = 0; p.drop_scale = 1.f; p.drop_seed = reinterpret_cast<const unsigned long long*>(a.dropout_seed);
   p.drop_layer = a.dropout_layer;
+  p.save_coef = a.save_coef;
   if (a.dropout_p > 0.f) {
     if (a.stats0 == nullptr) return cudaErrorInvalidValue;     // dropout lives in the streaming variant only
     p.drop_thr16 = static_cast<unsigned>(a.dropout_p * 65536.f + 0.5f);

@@ -29,6 +29,7 @@ struct AdaGNBwdParams {
   unsigned drop_thr16; float drop_scale; const unsigned long long* drop_seed; unsigned drop_layer;
   const bf16* dy;
   bf16* dx0; bf16* dx1; int acc0, acc1;
+  const float* save_coef;
   float* sums; float* ws;
   float* d_mod_t; float* d_mod_z; float* dgamma; float* dbeta;
   int slice_rows;
@@ -45,6 +46,16 @@ struct BwdShared {
 // Forward statistics + folded coefficients for sample n (same arithmetic, same order as adagn_apply_kernel).
 __device__ void bwd_prologue(const AdaGNBwdParams& p, int n, BwdShared& sh) {
   const int t = threadIdx.x, C = p.C, R = p.R;
+  if (p.save_coef != nullptr) {               // coefficients saved by the forward kernel
+    const int cpg = C / 32;
+    for (int ch = t; ch < C; ch += kBT) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.save_coef) + static_cast<long long>(n) * C + ch);
+      sh.ab[ch] = make_float2(v.x, v.y);
+      if (ch % cpg == 0) { sh.mean[ch / cpg] = v.z; sh.rstd[ch / cpg] = v.w; }
+    }
+    __syncthreads();
+    return;
+  }
   const int w_first = (n * R) / 32, w_last = ((n + 1) * R - 1) / 32;
   const bool first_straddles = (w_first * 32) < n * R;
   const int nsub = (kBT / C) > 0 ? (kBT / C) : 1;
@@ -285,7 +296,7 @@ cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, cudaStream_t stream) {
   }
   p.dy = static_cast<const bf16*>(b.dy);
   p.dx0 = static_cast<bf16*>(b.dx0); p.dx1 = static_cast<bf16*>(b.dx1); p.acc0 = b.acc0; p.acc1 = b.acc1;
-  p.sums = b.sums; p.ws = b.ws;
+  p.sums = b.sums; p.ws = b.ws; p.save_coef = a.save_coef;
   p.d_mod_t = b.d_mod_t; p.d_mod_z = b.d_mod_z; p.dgamma = b.dgamma; p.dbeta = b.dbeta;
   if (p.C > kBMaxC || p.C % 32 != 0 || p.c0 % 8 != 0 || p.c1 % 8 != 0 || a.batch <= 0) return cudaErrorInvalidValue;
   if (p.stats0 == nullptr || (p.c1 != 0 && (p.stats1 == nullptr || p.dx1 == nullptr)) || p.dx0 == nullptr ||

@@ -314,6 +314,10 @@ class Plan:
         if dropout and self.training and self.dropout_p > 0:
             self._drop_layers += 1
             a.dropout_p, a.dropout_seed, a.dropout_layer = self.dropout_p, self.dropout_seed.data_ptr(), self._drop_layers
+        if self.training and a.stats0:
+            coef = torch.zeros(self.B, out.C, 4, dtype=torch.float32, device=self.device)
+            self.keep.append(coef)
+            a.save_coef = coef.data_ptr()
         out.has_stats = False
         self.keep.append(a)
         self._emit("adagn", self.lib.idf_adagn_silu_fwd, (C.byref(a),), nbytes=2 * 2 * self.B * src0.H * src0.H * out.C)

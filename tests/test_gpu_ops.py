@@ -396,10 +396,11 @@ def test_adagn(lib, c0, c1, H, B, mod, silu):
     assert_close(unpf(out2, B, H, H), ref, rel_l2=3e-3, max_rel=8e-3, what=f"adagn (streaming) C={c0}+{c1}@{H}")
 
 
+@pytest.mark.parametrize("save", [False, True])
 @pytest.mark.parametrize("c0,c1,H,B,mod,silu,drop", [
     (64, 0, 32, 2, False, True, 0.0), (128, 0, 16, 3, True, True, 0.0), (128, 64, 16, 2, False, True, 0.0),
     (128, 128, 8, 3, True, True, 0.0), (128, 0, 8, 4, False, False, 0.0), (128, 0, 16, 3, True, True, 0.1)])
-def test_adagn_backward(lib, c0, c1, H, B, mod, silu, drop):
+def test_adagn_backward(lib, c0, c1, H, B, mod, silu, drop, save):
     """dx and the (S1, S2) sums of idf_adagn_silu_bwd against torch autograd of the same expression
     (with dropout: the keep-mask is read off the forward output, the hash is the kernel's own)."""
     from infodiffusion_b200._lib import AdaGNArgs, AdaGNBwdArgs
@@ -441,6 +442,9 @@ def test_adagn_backward(lib, c0, c1, H, B, mod, silu, drop):
     seed = torch.tensor([0x1234567], dtype=torch.int64, device=DEV)
     if drop > 0:
         a.dropout_p, a.dropout_seed, a.dropout_layer = drop, seed.data_ptr(), 7
+    coef = torch.zeros(B, Cc, 4, device=DEV)
+    if save:
+        a.save_coef = coef.data_ptr()       # backward reads the forward's coefficients instead of the records
     check(lib.idf_adagn_silu_fwd(C.byref(a), stream()))
     torch.cuda.synchronize()
     # reference expression under autograd (fp64)
