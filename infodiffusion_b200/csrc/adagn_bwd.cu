@@ -36,6 +36,8 @@ struct AdaGNBwdParams {
   int n_slices;
 };
 
+constexpr int kUn = 4;            // rows in flight per thread
+
 struct BwdShared {
   float2 sub[4][kBMaxC];
   float tot[2 * kBMaxC];
@@ -163,16 +165,30 @@ __global__ void __launch_bounds__(kBT) adagn_bwd_stats_kernel(const AdaGNBwdPara
   const float inv_wp = 1.0f / static_cast<float>(p.Wp);
   const uint64_t seed = (p.drop_thr16 != 0 && p.drop_seed != nullptr) ? *p.drop_seed : 0ull;
   if (active) {
-    for (int r = r_begin + rsub; r < r_end; r += rpp) {
-      const int y = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_wp);
-      const int xw = r - y * p.Wp;
-      if (xw >= p.W || y >= p.H) continue;
-      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(src + (row_base + r) * pitch));
-      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(p.dy + (row_base + r) * C + vl * 8));
-      float x[8], dv[8];
-      granule_dv(p, ux, ud, A, B, seed, static_cast<uint64_t>(row_base + r) * VPR + vl, x, dv);
+    // kUn rows per trip, all loads issued before the arithmetic (memory-level parallelism)
+    for (int rb = r_begin + rsub; rb < r_end; rb += kUn * rpp) {
+      uint4 ux[kUn], ud[kUn];
+      bool ok[kUn];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s1[j] += dv[j]; s2[j] = fmaf(dv[j], (x[j] - mean[j]) * rstd[j], s2[j]); }
+      for (int u = 0; u < kUn; ++u) {
+        const int r = rb + u * rpp;
+        const int y = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_wp);
+        const int xw = r - y * p.Wp;
+        ok[u] = r < r_end && xw < p.W && y < p.H;
+        if (ok[u]) {
+          ux[u] = __ldg(reinterpret_cast<const uint4*>(src + (row_base + r) * pitch));
+          ud[u] = __ldg(reinterpret_cast<const uint4*>(p.dy + (row_base + r) * C + vl * 8));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUn; ++u) {
+        if (!ok[u]) continue;
+        const int r = rb + u * rpp;
+        float x[8], dv[8];
+        granule_dv(p, ux[u], ud[u], A, B, seed, static_cast<uint64_t>(row_base + r) * VPR + vl, x, dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] += dv[j]; s2[j] = fmaf(dv[j], (x[j] - mean[j]) * rstd[j], s2[j]); }
+      }
     }
   }
 #pragma unroll
@@ -252,25 +268,38 @@ __global__ void __launch_bounds__(kBT) adagn_bwd_apply_kernel(const AdaGNBwdPara
   const int r_begin = blockIdx.x * p.slice_rows, r_end = min(R, r_begin + p.slice_rows);
   const float inv_wp = 1.0f / static_cast<float>(p.Wp);
   const uint64_t seed = (p.drop_thr16 != 0 && p.drop_seed != nullptr) ? *p.drop_seed : 0ull;
-  for (int r = r_begin + rsub; r < r_end; r += rpp) {
-    const int y = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_wp);
-    const int xw = r - y * p.Wp;
-    if (xw >= p.W || y >= p.H) continue;                    // pad rows keep a zero gradient
-    const uint4 ux = __ldg(reinterpret_cast<const uint4*>(src + (row_base + r) * pitch));
-    const uint4 ud = __ldg(reinterpret_cast<const uint4*>(p.dy + (row_base + r) * C + vl * 8));
-    float x[8], dv[8], o[8];
-    granule_dv(p, ux, ud, A, B, seed, static_cast<uint64_t>(row_base + r) * VPR + vl, x, dv);
+  for (int rb = r_begin + rsub; rb < r_end; rb += kUn * rpp) {
+    uint4 ux[kUn], ud[kUn], uo[kUn];
+    bool ok[kUn];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dv[j], -(G1[j] + (x[j] - mean[j]) * rstd[j] * G2[j]));
-    uint4* op = reinterpret_cast<uint4*>(dst + (row_base + r) * pitch);
-    if (acc) {
-      const uint4 u = *op;
-      const float2 e0 = unpack_bf16x2(u.x), e1 = unpack_bf16x2(u.y), e2 = unpack_bf16x2(u.z), e3 = unpack_bf16x2(u.w);
-      o[0] += e0.x; o[1] += e0.y; o[2] += e1.x; o[3] += e1.y; o[4] += e2.x; o[5] += e2.y; o[6] += e3.x; o[7] += e3.y;
+    for (int u = 0; u < kUn; ++u) {
+      const int r = rb + u * rpp;
+      const int y = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_wp);
+      const int xw = r - y * p.Wp;
+      ok[u] = r < r_end && xw < p.W && y < p.H;              // pad rows keep a zero gradient
+      if (ok[u]) {
+        ux[u] = __ldg(reinterpret_cast<const uint4*>(src + (row_base + r) * pitch));
+        ud[u] = __ldg(reinterpret_cast<const uint4*>(p.dy + (row_base + r) * C + vl * 8));
+        if (acc) uo[u] = *reinterpret_cast<const uint4*>(dst + (row_base + r) * pitch);
+      }
     }
-    uint4 w;
-    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
-    *op = w;
+#pragma unroll
+    for (int u = 0; u < kUn; ++u) {
+      if (!ok[u]) continue;
+      const int r = rb + u * rpp;
+      float x[8], dv[8], o[8];
+      granule_dv(p, ux[u], ud[u], A, B, seed, static_cast<uint64_t>(row_base + r) * VPR + vl, x, dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dv[j], -(G1[j] + (x[j] - mean[j]) * rstd[j] * G2[j]));
+      if (acc) {
+        const uint4 e = uo[u];
+        const float2 e0 = unpack_bf16x2(e.x), e1 = unpack_bf16x2(e.y), e2 = unpack_bf16x2(e.z), e3 = unpack_bf16x2(e.w);
+        o[0] += e0.x; o[1] += e0.y; o[2] += e1.x; o[3] += e1.y; o[4] += e2.x; o[5] += e2.y; o[6] += e3.x; o[7] += e3.y;
+      }
+      uint4 w;
+      w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dst + (row_base + r) * pitch) = w;
+    }
   }
 }
 

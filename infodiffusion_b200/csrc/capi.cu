@@ -452,7 +452,7 @@ int idf_depth_to_space(const void* dphases, void* din, int32_t batch, int32_t H,
 }
 
 int idf_colsum_bf16(const void* m, float* out, int64_t rows, int32_t C, idf_stream_t stream) {
-  cudaError_t e = launch_colsum(static_cast<const bf16*>(m), out, rows, C, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_colsum(static_cast<const bf16*>(m), out, rows, C, g_num_sms, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "colsum launch");
   return IDF_OK;
 }

@@ -82,7 +82,7 @@ cudaError_t launch_space_to_depth(const bf16* in, bf16* out, int batch, int H, i
 cudaError_t launch_nchw_to_padflat(const float* x, bf16* out, int batch, int C, int H, int W, int ld, cudaStream_t stream);
 cudaError_t launch_upsample2x_bwd(const bf16* dout, bf16* din, int batch, int H, int W, int C, int accumulate, cudaStream_t stream);
 cudaError_t launch_depth_to_space(const bf16* dph, bf16* din, int batch, int H, int W, int C, int accumulate, cudaStream_t stream);
-cudaError_t launch_colsum(const bf16* m, float* out, long long rows, int C, cudaStream_t stream);
+cudaError_t launch_colsum(const bf16* m, float* out, long long rows, int C, int num_sms, cudaStream_t stream);
 cudaError_t launch_padflat_to_nchw(const bf16* in, float* y, int batch, int C, int H, int W, cudaStream_t stream);
 cudaError_t launch_sampler_update(float* x, const float* eps, const float* noise, const float* coef,
                                   const int32_t* step_ptr, int64_t n, cudaStream_t stream);

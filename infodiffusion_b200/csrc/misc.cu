@@ -254,32 +254,49 @@ cudaError_t launch_depth_to_space(const bf16* dph, bf16* din, int batch, int H, 
   return cudaGetLastError();
 }
 
-// bias gradient: out[c] += sum_r m[r, c]   (m bf16 [rows, C]); block = 32 channel-pairs x 8 row lanes
+// bias gradient: out[c] += sum_r m[r, c]   (m bf16 [rows, C], C % 8 == 0, C <= 2048).  Thread = one 16-byte
+// granule (8 channels) of every rpp-th row, four rows in flight; block partials combined in shared memory,
+// one atomicAdd per channel and block.
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ m, float* __restrict__ out, long long rows,
                                                      int C) {
-  __shared__ float2 red[8][32];
-  const int cp = blockIdx.x * 32 + (threadIdx.x & 31);        // channel pair index
-  const int rl = threadIdx.x >> 5;
-  float2 acc = make_float2(0.f, 0.f);
-  if (2 * cp < C) {
-    for (long long r = blockIdx.y * 8 + rl; r < rows; r += 8ll * gridDim.y) {
-      const float2 v = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(m + r * C) + cp));
-      acc.x += v.x; acc.y += v.y;
+  __shared__ float red[256][9];
+  const int VPR = C >> 3, rpp = 256 / VPR;
+  const int t = threadIdx.x, vl = t % VPR, rsub = t / VPR;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (t < rpp * VPR) {
+    const long long stride = static_cast<long long>(gridDim.x) * rpp;
+    for (long long r = static_cast<long long>(blockIdx.x) * rpp + rsub; r < rows; r += 4 * stride) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + u * stride;
+        v[u] = rr < rows ? __ldg(reinterpret_cast<const uint4*>(m + rr * C) + vl) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 a0 = unpack_bf16x2(v[u].x), a1 = unpack_bf16x2(v[u].y), a2 = unpack_bf16x2(v[u].z), a3 = unpack_bf16x2(v[u].w);
+        acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
+        acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+      }
     }
   }
-  red[rl][threadIdx.x & 31] = acc;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[t][j] = acc[j];
   __syncthreads();
-  if (rl == 0 && 2 * cp < C) {
-    float2 t = red[0][threadIdx.x];
-    for (int k = 1; k < 8; ++k) { t.x += red[k][threadIdx.x].x; t.y += red[k][threadIdx.x].y; }
-    atomicAdd(out + 2 * cp, t.x);
-    atomicAdd(out + 2 * cp + 1, t.y);
+  for (int ch = t; ch < C; ch += 256) {
+    const int cvl = ch >> 3, j = ch & 7;
+    float sum = 0.f;
+    for (int rs = 0; rs < rpp; ++rs) sum += red[rs * VPR + cvl][j];
+    atomicAdd(out + ch, sum);
   }
 }
-cudaError_t launch_colsum(const bf16* m, float* out, long long rows, int C, cudaStream_t stream) {
-  if (C % 2) return cudaErrorInvalidValue;
-  dim3 grid((C / 2 + 31) / 32, 64, 1);
-  colsum_kernel<<<grid, 256, 0, stream>>>(m, out, rows, C);
+cudaError_t launch_colsum(const bf16* m, float* out, long long rows, int C, int num_sms, cudaStream_t stream) {
+  if (C % 8 || C > 2048 || C <= 0) return cudaErrorInvalidValue;
+  const int rpp = 256 / (C / 8);
+  long long grid = (rows + 16ll * rpp - 1) / (16ll * rpp);          // >= 16 rows per thread
+  if (grid > 4ll * num_sms) grid = 4ll * num_sms;
+  if (grid < 1) grid = 1;
+  colsum_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(m, out, rows, C);
   return cudaGetLastError();
 }
 

@@ -580,3 +580,15 @@ def test_mmd_against_oracle_and_golden(lib, golden_dir):
         assert abs(float(vg) - float(vo)) < 5e-6, f"mmd value D={D}: {float(vg)} vs {float(vo)}"
         assert_close(gg.cpu(), go, rel_l2=1e-4, max_rel=1e-3, what=f"mmd grad D={D}")
         assert abs(float(vg) - float(gold[f"v{D}"])) < 5e-6, "mmd vs golden"
+
+
+@pytest.mark.parametrize("rows,Cc", [(1, 64), (4225 * 3, 64), (1089 * 5, 128), (289 * 2, 384), (77, 8)])
+def test_colsum_bias_gradient(lib, rows, Cc):
+    """idf_colsum_bf16 accumulates the column sums of a bf16 matrix into an fp32 vector (conv bias gradient)."""
+    g = torch.Generator(device=DEV).manual_seed(rows + Cc)
+    mth = (torch.randn(rows, Cc, device=DEV, generator=g)).to(BF)
+    out = torch.full((Cc,), 0.5, device=DEV)
+    check(lib.idf_colsum_bf16(mth.data_ptr(), out.data_ptr(), rows, Cc, stream()))
+    torch.cuda.synchronize()
+    want = mth.double().sum(0) + 0.5
+    assert_close(out, want, rel_l2=1e-5, max_rel=1e-4, what="colsum")
