@@ -142,7 +142,7 @@ __device__ __forceinline__ void granule_dv(const AdaGNBwdParams& p, const uint4&
   }
 }
 
-__global__ void __launch_bounds__(kBT) adagn_bwd_stats_kernel(const AdaGNBwdParams p) {
+__global__ void __launch_bounds__(kBT, 2) adagn_bwd_stats_kernel(const AdaGNBwdParams p) {
   __shared__ BwdShared sh;
   __shared__ float s_part[kBT][17];
   const int n = blockIdx.y, t = threadIdx.x, C = p.C, R = p.R;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kBT) adagn_bwd_stats_kernel(const AdaGNBwdPara
   }
 }
 
-__global__ void __launch_bounds__(kBT) adagn_bwd_apply_kernel(const AdaGNBwdParams p) {
+__global__ void __launch_bounds__(kBT, 2) adagn_bwd_apply_kernel(const AdaGNBwdParams p) {
   __shared__ BwdShared sh;
   __shared__ float s_S[2 * kBMaxC];
   __shared__ float s_G[64];
@@ -211,8 +211,13 @@ __global__ void __launch_bounds__(kBT) adagn_bwd_apply_kernel(const AdaGNBwdPara
   const int cpg = C / 32;
   for (int i = t; i < 2 * C; i += kBT) {
     const int which = i / C, ch = i - which * C;
+    float part[kBSlices];
+#pragma unroll
+    for (int s = 0; s < kBSlices; ++s)           // independent loads, fixed summation order
+      part[s] = s < p.n_slices ? p.ws[((static_cast<long long>(n) * kBSlices + s) * C + ch) * 2 + which] : 0.f;
     float acc = 0.f;
-    for (int s = 0; s < p.n_slices; ++s) acc += p.ws[((static_cast<long long>(n) * kBSlices + s) * C + ch) * 2 + which];
+#pragma unroll
+    for (int s = 0; s < kBSlices; ++s) acc += part[s];
     s_S[i] = acc;
     if (blockIdx.x == 0) p.sums[(static_cast<long long>(n) * C + ch) * 2 + which] = acc;
   }
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(kBT) adagn_bwd_apply_kernel(const AdaGNBwdPara
 
 int64_t adagn_bwd_ws_floats(int batch, int C) { return static_cast<int64_t>(batch) * kBSlices * C * 2; }
 
-cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, cudaStream_t stream) {
+cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, int num_sms, cudaStream_t stream) {
   const idf_adagn_args& a = b.f;
   AdaGNBwdParams p;
   p.src0 = static_cast<const bf16*>(a.src0); p.src1 = static_cast<const bf16*>(a.src1);
@@ -331,8 +336,8 @@ cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, cudaStream_t stream) {
   if (p.stats0 == nullptr || (p.c1 != 0 && (p.stats1 == nullptr || p.dx1 == nullptr)) || p.dx0 == nullptr ||
       p.dy == nullptr || p.sums == nullptr || p.ws == nullptr)
     return cudaErrorInvalidValue;
-  // enough CTAs to fill the machine (~600), but at least 64 rows per slice
-  int ns = (600 + a.batch - 1) / a.batch;
+  // one wave of CTAs (2 resident per SM), but at least 64 rows per slice
+  int ns = (2 * num_sms) / a.batch;
   if (ns > kBSlices) ns = kBSlices;
   if (ns > (p.R + 63) / 64) ns = (p.R + 63) / 64;
   if (ns < 1) ns = 1;

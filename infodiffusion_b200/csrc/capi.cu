@@ -349,7 +349,7 @@ int64_t idf_adagn_bwd_ws_floats(int32_t batch, int32_t C) { return adagn_bwd_ws_
 
 int idf_adagn_silu_bwd(const idf_adagn_bwd_args* b, idf_stream_t stream) {
   if (b == nullptr) return fail(IDF_ERR_ARG, "null argument");
-  cudaError_t e = launch_adagn_bwd(*b, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_adagn_bwd(*b, g_num_sms, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "adagn backward launch (needs stats0/stats1, dy, dx, sums, ws)");
   return IDF_OK;
 }
