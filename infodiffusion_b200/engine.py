@@ -583,9 +583,10 @@ class BackbonePlan(Plan):
             self.mod_z = torch.zeros(B, ncol, **f32)
             if mode == "eps":
                 self.t_idx = torch.zeros(B, dtype=torch.long, device=device)
-                self.a_in = torch.zeros(B, net.a_dim, **f32)
                 self._emit_time_mlp(self.t_idx, self.mod_t)
-                self._emit_latent_mlp(self.a_in, self.mod_z)
+                if hasattr(net, "fc_a"):                      # UNet (models.py:7) has no latent input
+                    self.a_in = torch.zeros(B, net.a_dim, **f32)
+                    self._emit_latent_mlp(self.a_in, self.mod_z)
             else:
                 self.d_mod_t = torch.zeros(B, ncol, **f32)
                 self.d_mod_z = torch.zeros(B, ncol, **f32)
@@ -659,9 +660,12 @@ class BackbonePlan(Plan):
     def _emit_latent_mlp(self, a_in: torch.Tensor, out: torch.Tensor) -> None:
         """out[n] = concat_blocks aemb_proj(SiLU(fc_a(a[n])))  (models.py:298; modules.py:316)."""
         fc = self.net.fc_a
+        pre_silu = isinstance(fc, nn.Sequential)      # BottleneckAuxUNet: fc_a = SiLU -> Linear (models.py:336-339)
+        if pre_silu:
+            fc = fc[1]
         aemb = torch.zeros(a_in.shape[0], fc.out_features, dtype=torch.float32, device=self.device)
         self.keep.append(aemb)
-        self.linear(a_in, self.f32(fc.weight), self.f32(fc.bias), aemb, silu_in=False)
+        self.linear(a_in, self.f32(fc.weight), self.f32(fc.bias), aemb, silu_in=pre_silu)
         self.linear(aemb, self.pack.w_z, self.pack.b_z, out, silu_in=True)
 
 
@@ -676,6 +680,8 @@ class ModulationTables(Plan):
         BackbonePlan._emit_time_mlp(self, self.t_all, self.table)
 
     def latent_rows(self, a: torch.Tensor, out: torch.Tensor) -> None:
+        if not hasattr(self.net, "fc_a"):
+            return
         p = Plan(1, self.device)
         p.net, p.pack = self.net, self.pack
         BackbonePlan._emit_latent_mlp(p, a, out)
@@ -749,7 +755,7 @@ def _check_eval(net) -> None:
 
 
 @torch.no_grad()
-def backbone_forward(net, x: torch.Tensor, t: torch.Tensor, a: torch.Tensor) -> torch.Tensor:
+def backbone_forward(net, x: torch.Tensor, t: torch.Tensor, a: Optional[torch.Tensor]) -> torch.Tensor:
     _require_cuda(x, "x")
     _check_eval(net)
     B = x.shape[0]
@@ -760,7 +766,8 @@ def backbone_forward(net, x: torch.Tensor, t: torch.Tensor, a: torch.Tensor) -> 
     p: BackbonePlan = plans[key]
     p.x_in.copy_(x)
     p.t_idx.copy_(t.to(torch.long))
-    p.a_in.copy_(a)
+    if hasattr(net, "fc_a"):
+        p.a_in.copy_(a)
     p.run()
     return p.eps_out.clone()
 

@@ -103,6 +103,75 @@ class AuxiliaryUNet(_EngineNet):
         return backbone_forward(self, x, t, a)
 
 
+class UNet(_EngineNet):
+    """Unconditional eps-network of the vanilla diffusion model (reference models.py:7-88).  The reference's
+    constructor crashes at HEAD (it passes crossattn= to ResBlock, models.py:32-33); here ResBlock accepts and
+    ignores the keyword, everything else -- names, init order, forward(x, t) -- is the reference's."""
+
+    def __init__(self, T, ch=64, ch_mult=[1, 2, 4, 8], attn=[2], num_res_blocks=2, dropout=0.1, shape=None):
+        super().__init__()
+        assert all(i < len(ch_mult) for i in attn), 'attn index out of bound'
+        tdim = ch * 4
+        self.dropout_p = float(dropout)
+        self.T, self.ch, self.ch_mult, self.shape = T, ch, list(ch_mult), tuple(shape)
+        self.time_embedding = TimeEmbedding(T, ch, tdim)
+        self.head = nn.Conv2d(shape[0], ch, kernel_size=3, stride=1, padding=1)
+        self.downblocks, self.middleblocks, self.upblocks, cur = _unet_stacks(
+            lambda i, o, at: ResBlock(in_ch=i, out_ch=o, tdim=tdim, dropout=dropout, attn=at),
+            ch, ch_mult, attn, num_res_blocks,
+            lambda c: nn.ModuleList([ResBlock(c, c, tdim, dropout, attn=True, crossattn=False),
+                                     ResBlock(c, c, tdim, dropout, attn=False, crossattn=False)]))
+        self.tail = _tail(cur, shape[0])
+        init.xavier_uniform_(self.head.weight)
+        init.zeros_(self.head.bias)
+        init.xavier_uniform_(self.tail[-1].weight, gain=1e-5)
+        init.zeros_(self.tail[-1].bias)
+
+    def forward(self, x, t):
+        """x [B,C,H,W] fp32, t int64 [B] -> eps (reference models.py:62)."""
+        if self.training and torch.is_grad_enabled():
+            from .train import backbone_train_forward
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
+            return backbone_train_forward(self, x, t, None, seed, self.dropout_p)
+        from .engine import backbone_forward
+        return backbone_forward(self, x, t, None)
+
+
+class BottleneckAuxUNet(_EngineNet):
+    """eps-network whose only latent-conditioned blocks are the two middle AuxResBlocks; down / up blocks are
+    plain ResBlocks and fc_a = SiLU -> Linear with kaiming init (reference models.py:329-421)."""
+
+    def __init__(self, T, ch=64, ch_mult=[1, 2, 4, 8], attn=[2], num_res_blocks=2, dropout=0.1, a_dim=32, shape=None):
+        super().__init__()
+        assert all(i < len(ch_mult) for i in attn), 'attn index out of bound'
+        tdim = ch * 4
+        self.a_dim = a_dim
+        self.dropout_p = float(dropout)
+        self.T, self.ch, self.ch_mult, self.shape = T, ch, list(ch_mult), tuple(shape)
+        self.time_embedding = TimeEmbedding(T, ch, tdim)
+        self.fc_a = nn.Sequential(nn.SiLU(), nn.Linear(self.a_dim, tdim))
+        self.head = nn.Conv2d(shape[0], ch, kernel_size=3, stride=1, padding=1)
+        self.downblocks, self.middleblocks, self.upblocks, cur = _unet_stacks(
+            lambda i, o, at: ResBlock(in_ch=i, out_ch=o, tdim=tdim, dropout=dropout, attn=at),
+            ch, ch_mult, attn, num_res_blocks,
+            lambda c: nn.ModuleList([AuxResBlock(c, c, tdim, dropout, attn=True, crossattn=False),
+                                     AuxResBlock(c, c, tdim, dropout, attn=False, crossattn=False)]))
+        self.tail = _tail(cur, shape[0])
+        init.xavier_uniform_(self.head.weight)
+        init.zeros_(self.head.bias)
+        init.kaiming_normal_(self.fc_a[1].weight, a=0, nonlinearity='relu')
+        init.xavier_uniform_(self.tail[-1].weight, gain=1e-5)
+        init.zeros_(self.tail[-1].bias)
+
+    def forward(self, x, t, a):
+        if self.training and torch.is_grad_enabled():
+            from .train import backbone_train_forward
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
+            return backbone_train_forward(self, x, t, a, seed, self.dropout_p)
+        from .engine import backbone_forward
+        return backbone_forward(self, x, t, a)
+
+
 class Encoder(_EngineNet):
     """UNet-shaped encoder x -> (a, a_q, mu, log_var) (reference models.py:424-518)."""
 
@@ -150,10 +219,9 @@ class InfoDiff(nn.Module):
         self.alphas = 1 - self.betas
         self.alpha_prev_bars = torch.cat([torch.Tensor([1]).to(device=device), self.alpha_bars[:-1]])
         ch_mult = [1, 2, 4] if args.input_size == 28 else [1, 2, 2, 2]
-        if getattr(args, "is_bottleneck", False):
-            raise NotImplementedError("BottleneckAuxUNet is a later SURVEY section-8f row; not built yet")
-        self.backbone = AuxiliaryUNet(ch_mult=ch_mult, T=args.diffusion_steps, ch=args.unets_channels,
-                                      a_dim=args.a_dim, shape=shape)
+        net_cls = BottleneckAuxUNet if getattr(args, "is_bottleneck", False) else AuxiliaryUNet   # models.py:623-626
+        self.backbone = net_cls(ch_mult=ch_mult, T=args.diffusion_steps, ch=args.unets_channels,
+                                a_dim=args.a_dim, shape=shape)
         self.encoder = Encoder(ch_mult=ch_mult, ch=args.encoder_channels, a_dim=args.a_dim, shape=shape)
         self.mmd_weight: float = args.mmd_weight
         self.kld_weight: float = args.kld_weight
@@ -203,3 +271,42 @@ class InfoDiff(nn.Module):
             else:
                 loss = loss + args.kld_weight * kld
         return loss
+
+
+class Diff(nn.Module):
+    """Plain DDPM wrapper: eps-MSE loss only; UNet backbone over images or LatentUNet over z
+    (reference models.py:726-779)."""
+
+    def __init__(self, args, device, shape):
+        super().__init__()
+        self.device = device
+        lin = lambda: torch.linspace(start=args.beta1, end=args.betaT, steps=args.diffusion_steps)
+        self.alpha_bars = torch.cumprod(1 - lin(), dim=0).to(device=device)
+        self.betas = lin().to(device=device)
+        self.alphas = 1 - self.betas
+        self.alpha_prev_bars = torch.cat([torch.Tensor([1]).to(device=device), self.alpha_bars[:-1]])
+        self.is_latent = bool(args.is_latent) or args.mode == "train_latent_ddim"
+        ch_mult = [1, 2, 4] if args.input_size == 28 else [1, 2, 4, 8]
+        if self.is_latent:
+            self.backbone = LatentUNet(T=args.diffusion_steps, num_layers=10, dropout=0.1, shape=shape, activation='silu')
+        else:
+            self.backbone = UNet(ch_mult=ch_mult, T=args.diffusion_steps, ch=args.unets_channels, shape=shape)
+        self.to(device)
+
+    def loss_fn(self, args, x, idx=None, curr_epoch=0):
+        output, epsilon = self.forward(x, idx=idx, get_target=True)
+        return (output - epsilon).square().mean()
+
+    def forward(self, x, idx=None, get_target=False):
+        epsilon = None
+        if idx is None:
+            idx = torch.randint(0, len(self.alpha_bars), (x.size(0),)).to(device=self.device)
+            used = self.alpha_bars[idx][:, None] if self.is_latent else self.alpha_bars[idx][:, None, None, None]
+            epsilon = torch.randn_like(x)
+            x_tilde = torch.sqrt(used) * x + torch.sqrt(1 - used) * epsilon
+        else:
+            if not torch.is_tensor(idx):
+                idx = torch.full((x.size(0),), int(idx), dtype=torch.long, device=self.device)
+            x_tilde = x
+        output = self.backbone(x_tilde, idx)
+        return (output, epsilon) if get_target else output

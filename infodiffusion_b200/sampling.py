@@ -170,40 +170,66 @@ class DiffusionProcess():
 
     # ------------------------------------------------------------------------------------------
     def _sampler(self, kind: str, batch: int, record_eps: bool = False, with_encoder: bool = False) -> _FusedSampler:
-        if self.model == 'vanilla' or not hasattr(self.diffusion_fn, "backbone"):
-            raise NotImplementedError("only the InfoDiff (--model diff) sampler path is built so far")
-        if self.diffusion_fn.backbone.training:
+        net = getattr(self.diffusion_fn, "backbone", None)
+        if net is None or not hasattr(net, "head"):
+            raise NotImplementedError("DiffusionProcess drives the image UNets (InfoDiff / Diff over a UNet backbone); "
+                                      "use LatentDiffusionProcess for a LatentUNet")
+        if net.training:
             raise RuntimeError("sampling runs the inference forward; call model.eval() first")
         key = (kind, batch, record_eps, with_encoder)
         if key not in self._samplers:
             self._samplers[key] = _FusedSampler(self, kind, batch, self.chunk, record_eps, with_encoder)
         return self._samplers[key]
 
-    def _run(self, kind: str, x: torch.Tensor, a: Optional[torch.Tensor], trace=None) -> torch.Tensor:
+    def _iter(self, kind: str, x: torch.Tensor, a: Optional[torch.Tensor], record_eps: bool = False):
+        """Generator over the steps of one trajectory: yields (idx, sampler) after every update; sampler.x is the
+        live x buffer (clone it to keep a step)."""
         B = x.shape[0]
         T = len(self.alpha_bars)
-        with_encoder = (kind == "reverse") and (a is None)
-        s = self._sampler(kind, B, record_eps=trace is not None, with_encoder=with_encoder)
+        vanilla = self.model == 'vanilla'                  # diffusion_fn(x, idx): no latent (sampling.py:31-32)
+        with_encoder = (kind == "reverse") and (a is None) and not vanilla
+        s = self._sampler(kind, B, record_eps=record_eps, with_encoder=with_encoder)
         s.x.copy_(x)
-        if a is not None:
+        if a is not None and not vanilla:
             s.set_latent(a)
         if kind == "reverse":
             order = range(1, T - 1)                     # idx 0 yields x unchanged (sampling.py:64-65)
         else:
             order = reversed(range(T))
         for idx in order:
-            if kind == "ddpm":
-                if idx > 0:
-                    self.noise_fn(idx, s.noise)         # drawn BEFORE the model call (sampling.py:29)
-            elif kind == "ddim":
-                if idx > 0:
-                    self.noise_fn(idx, s.noise)         # reference draws it after the model call (sampling.py:56);
-                                                        # the model call consumes no random numbers, so the
-                                                        # generator stream is identical
+            if kind != "reverse" and idx > 0:
+                # ddpm: drawn BEFORE the model call (sampling.py:29); ddim: the reference draws it after the model
+                # call (sampling.py:56) -- the model call consumes no random numbers, so the stream is identical
+                self.noise_fn(idx, s.noise)
             s.run_step(idx, use_graph=self.use_graph)
+            yield idx, s
+
+    def _run(self, kind: str, x: torch.Tensor, a: Optional[torch.Tensor], trace=None) -> torch.Tensor:
+        s = None
+        for idx, s in self._iter(kind, x, a, record_eps=trace is not None):
             if trace is not None:
                 trace.append((idx, s.eps.clone(), s.x.clone()))
-        return s.x.clone()
+        return s.x.clone() if s is not None else x.clone()
+
+    # ---- the reference's generator methods: one x per step (sampling.py:23-79) --------------------------
+    @torch.no_grad()
+    def _ddpm_one_diffusion_step(self, x, a=None):
+        for _, s in self._iter("ddpm", x, a):
+            yield s.x.clone()
+
+    @torch.no_grad()
+    def _ddim_one_diffusion_step(self, x, a=None):
+        for _, s in self._iter("ddim", x, a):
+            yield s.x.clone()
+
+    @torch.no_grad()
+    def _ddim_one_reverse_diffusion_step(self, x, a=None):
+        yield x                                          # idx == 0 (sampling.py:64-65)
+        for _, s in self._iter("reverse", x, a):
+            yield s.x.clone()
+
+    def _one_diffusion_step(self, sample, a=None, deterministic=False):
+        return self._ddim_one_diffusion_step(sample, a) if deterministic else self._ddpm_one_diffusion_step(sample, a)
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -223,3 +249,62 @@ class DiffusionProcess():
         if a is None:
             a = torch.randn([sampling_number, self.a_dim]).to(device=self.device)
         return self._run("ddim" if self.deterministic else "ddpm", xT, a, trace)
+
+
+class TwoPhaseDiffusionProcess():
+    """Drop-in for the reference's TwoPhaseDiffusionProcess (sampling.py:104-204): diffusion_fn_1 is the InfoDiff
+    model (x, idx, a), diffusion_fn_2 the vanilla Diff model (x, idx).
+
+    Bug compatibility: the reference hands the step counter to its generators by value when they
+    are created (t = 0, sampling.py:198-201), so `t <= split_step` never changes and diffusion_fn_2 runs every
+    step whenever split_step >= 0.  That is the default here.  `args.two_phase_fix = True` makes the counter
+    advance: steps with t <= split_step use diffusion_fn_2, later steps diffusion_fn_1."""
+
+    def __init__(self, args, diffusion_fn_1, diffusion_fn_2, device, shape):
+        import copy
+        self.split_step = args.split_step
+        self.deterministic = args.deterministic
+        self.a_dim = args.a_dim
+        self.shape = shape
+        self.device = device
+        self.fix = bool(getattr(args, "two_phase_fix", False))
+        a1, a2 = copy.copy(args), copy.copy(args)
+        a1.model, a2.model = "diff", "vanilla"
+        self.p1 = DiffusionProcess(a1, diffusion_fn_1, device, shape)
+        self.p2 = DiffusionProcess(a2, diffusion_fn_2, device, shape)
+        self.diffusion_fn_1, self.diffusion_fn_2 = self.p1.diffusion_fn, self.p2.diffusion_fn
+        self.betas, self.alphas = self.p1.betas, self.p1.alphas
+        self.alpha_bars, self.alpha_prev_bars = self.p1.alpha_bars, self.p1.alpha_prev_bars
+        self.noise_fn = lambda idx, out: out.normal_()
+
+    @torch.no_grad()
+    def sampling(self, sampling_number=16, xT=None, a=None):
+        if xT is None:
+            xT = torch.randn([sampling_number, *self.shape]).to(device=self.device)
+        if a is None:
+            a = torch.randn([sampling_number, self.a_dim]).to(device=self.device)
+        kind = "ddim" if self.deterministic else "ddpm"
+        self.p1.noise_fn = self.p2.noise_fn = self.noise_fn
+        if not self.fix:
+            proc = self.p2 if 0 <= self.split_step else self.p1
+            return proc._run(kind, xT, a)
+        # intended behaviour: switch networks along the trajectory; x moves between the two samplers' buffers
+        B, T = xT.shape[0], len(self.alpha_bars)
+        s1, s2 = self.p1._sampler(kind, B), self.p2._sampler(kind, B)
+        s1.set_latent(a)
+        cur = None
+        x = xT
+        for t, idx in enumerate(reversed(range(T))):
+            s, proc = (s2, self.p2) if t <= self.split_step else (s1, self.p1)
+            if s is not cur:
+                s.x.copy_(x if cur is None else cur.x)
+                cur = s
+            if idx > 0:
+                self.noise_fn(idx, s.noise)
+            s.run_step(idx, use_graph=proc.use_graph)
+        return cur.x.clone()
+
+    @torch.no_grad()
+    def reverse_sampling(self, x0, a=None):
+        """reference sampling.py:189-195: diffusion_fn_1 with a dropped (the encoder is re-run every step)."""
+        return self.p1.reverse_sampling(x0, None)

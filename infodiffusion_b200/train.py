@@ -526,16 +526,19 @@ def backbone_train_forward(net, x_t: torch.Tensor, t: torch.Tensor, a: torch.Ten
     # modulation rows through torch autograd (tiny GEMMs): temb -> all blocks' temb_proj, a -> fc_a -> aemb_proj
     te = net.time_embedding.timembedding
     temb = te[3](torch.nn.functional.silu(te[1](te[0].weight[t])))
-    aemb = net.fc_a(a)
     blocks = conditioned_blocks(net)
     w_t = torch.cat([b.temb_proj[1].weight for b in blocks], 0)
     b_t = torch.cat([b.temb_proj[1].bias for b in blocks], 0)
     mod_t = torch.nn.functional.linear(torch.nn.functional.silu(temb), w_t, b_t)
-    w_z = torch.cat([b.aemb_proj[1].weight if hasattr(b, "aemb_proj") else torch.zeros_like(b.temb_proj[1].weight)
-                     for b in blocks], 0)
-    b_z = torch.cat([b.aemb_proj[1].bias if hasattr(b, "aemb_proj") else torch.zeros_like(b.temb_proj[1].bias)
-                     for b in blocks], 0)
-    mod_z = torch.nn.functional.linear(torch.nn.functional.silu(aemb), w_z, b_z)
+    if hasattr(net, "fc_a"):
+        aemb = net.fc_a(a)                       # Linear (AuxiliaryUNet) or SiLU -> Linear (BottleneckAuxUNet)
+        w_z = torch.cat([b.aemb_proj[1].weight if hasattr(b, "aemb_proj") else torch.zeros_like(b.temb_proj[1].weight)
+                         for b in blocks], 0)
+        b_z = torch.cat([b.aemb_proj[1].bias if hasattr(b, "aemb_proj") else torch.zeros_like(b.temb_proj[1].bias)
+                         for b in blocks], 0)
+        mod_z = torch.nn.functional.linear(torch.nn.functional.silu(aemb), w_z, b_z)
+    else:
+        mod_z = torch.zeros_like(mod_t)          # UNet: no block reads it
     params = stack_params(net)
     return _ConvStackFn.apply(plan, x_t, mod_t, mod_z, seed, *params)
 

@@ -114,7 +114,7 @@ def aux_res_block(sd: SD, pfx: str, x: Tensor, temb: Tensor, aemb: Optional[Tens
     t_out = _lin(F.silu(temb), sd, pfx + "temb_proj.1")[:, :, None, None]
     scale, shift = torch.chunk(t_out, 2, dim=1)
     h = _gn(h, sd, pfx + "block2.0") * (1 + scale) + shift
-    if aemb is not None:
+    if aemb is not None and pfx + "aemb_proj.1.weight" in sd:     # plain ResBlock has no aemb_proj (modules.py:206-258)
         a_out = _lin(F.silu(aemb), sd, pfx + "aemb_proj.1")[:, :, None, None]
         scale, shift = torch.chunk(a_out, 2, dim=1)
         h = h * (1 + scale) + shift
@@ -144,11 +144,10 @@ def _count(sd: SD, pfx: str) -> int:
 # --------------------------------------------------------------------------------------
 # networks
 # --------------------------------------------------------------------------------------
-def aux_unet_forward(sd: SD, x: Tensor, t: Tensor, a: Tensor, pfx: str = "backbone.",
-                     trace: Optional[Dict[str, Tensor]] = None) -> Tensor:
-    """AuxiliaryUNet.forward(x, t, a) -> eps -- models.py:296-326."""
-    aemb = _lin(a, sd, pfx + "fc_a")                       # models.py:298 (no activation before)
-    temb = time_embedding(sd, pfx + "time_embedding.", t)  # models.py:301
+def _unet_body(sd: SD, pfx: str, x: Tensor, temb: Tensor, aemb: Optional[Tensor],
+               trace: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """head -> down -> middle -> up (cat skip) -> tail, shared by UNet / AuxiliaryUNet / BottleneckAuxUNet
+    (models.py:62-88, 296-326, 391-421).  Blocks without `aemb_proj` ignore `aemb`."""
     h = _conv(x, sd, pfx + "head")
     hs = [h]
     if trace is not None:
@@ -177,8 +176,29 @@ def aux_unet_forward(sd: SD, x: Tensor, t: Tensor, a: Tensor, pfx: str = "backbo
         if trace is not None:
             trace[f"up{i}"] = h
     assert len(hs) == 0
-    h = _conv(F.silu(_gn(h, sd, pfx + "tail.0")), sd, pfx + "tail.2")  # models.py:280-284, 323
-    return h
+    return _conv(F.silu(_gn(h, sd, pfx + "tail.0")), sd, pfx + "tail.2")  # models.py:280-284, 323
+
+
+def aux_unet_forward(sd: SD, x: Tensor, t: Tensor, a: Tensor, pfx: str = "backbone.",
+                     trace: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """AuxiliaryUNet.forward(x, t, a) -> eps -- models.py:296-326."""
+    aemb = _lin(a, sd, pfx + "fc_a")                       # models.py:298 (no activation before)
+    temb = time_embedding(sd, pfx + "time_embedding.", t)  # models.py:301
+    return _unet_body(sd, pfx, x, temb, aemb, trace)
+
+
+def bottleneck_unet_forward(sd: SD, x: Tensor, t: Tensor, a: Tensor, pfx: str = "backbone.") -> Tensor:
+    """BottleneckAuxUNet.forward(x, t, a) -> eps -- models.py:391-421: fc_a = SiLU -> Linear (336-339); only the
+    two middle AuxResBlocks see aemb, down / up blocks are plain ResBlocks."""
+    aemb = _lin(F.silu(a), sd, pfx + "fc_a.1")
+    temb = time_embedding(sd, pfx + "time_embedding.", t)
+    return _unet_body(sd, pfx, x, temb, aemb)
+
+
+def unet_forward(sd: SD, x: Tensor, t: Tensor, pfx: str = "backbone.") -> Tensor:
+    """UNet.forward(x, t) -> eps -- models.py:62-88 (unconditional; plain ResBlocks everywhere)."""
+    temb = time_embedding(sd, pfx + "time_embedding.", t)
+    return _unet_body(sd, pfx, x, temb, None)
 
 
 def encoder_forward(sd: SD, x: Tensor, pfx: str = "encoder.",
@@ -404,6 +424,62 @@ def reverse_sample(sd: SD, sch: Schedule, x0: Tensor, a: Optional[Tensor] = None
     (bug-compatible) behaviour; passing ``a`` gives the a-honouring variant."""
     x = x0
     for idx, eps, x in ddim_reverse_steps(sch, infodiff_eps_fn(sd, a, enc_noise_fn), x0):
+        if record is not None:
+            record.append((idx, eps, x))
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# other samplers
+# --------------------------------------------------------------------------------------
+@torch.no_grad()
+def two_phase_sample(eps_fn_1, eps_fn_2, sch: Schedule, xT: Tensor, deterministic: bool, split_step: int,
+                     noise_fn: NoiseFn = _randn, fixed: bool = False, record: Optional[List] = None) -> Tensor:
+    """TwoPhaseDiffusionProcess.sampling -- sampling.py:127-204.
+
+    eps_fn_1(x, idx) is the InfoDiff branch (a bound by the caller), eps_fn_2(x, idx) the vanilla branch.
+    The reference passes the step counter ``t`` into the generator BY VALUE when the generator is created
+    (``t = 0``; sampling.py:198-201), so ``t <= split_step`` is evaluated with t == 0 at every step and
+    diffusion_fn_2 is used throughout whenever split_step >= 0.  ``fixed=True`` gives the
+    evidently intended behaviour: the counter advances, steps with t <= split_step use fn_2, later ones fn_1.
+    """
+    steps = ddim_steps if deterministic else ddpm_steps
+    counter = {"t": 0}
+
+    def eps_fn(x: Tensor, idx: int) -> Tensor:
+        t = counter["t"] if fixed else 0
+        counter["t"] += 1
+        return eps_fn_2(x, idx) if t <= split_step else eps_fn_1(x, idx)
+    x = xT
+    for idx, eps, x in steps(sch, eps_fn, xT, noise_fn):
+        if record is not None:
+            record.append((idx, eps, x))
+    return x
+
+
+def latent_eps_fn(sd: SD, pfx: str = "backbone."):
+    """Diff.forward(x, idx:int) with a LatentUNet backbone -- models.py:764-779."""
+    def fn(x: Tensor, idx: int) -> Tensor:
+        t = torch.full((x.shape[0],), idx, dtype=torch.long)
+        return latent_unet_forward(sd, x, t, pfx)
+    return fn
+
+
+def vanilla_eps_fn(sd: SD, pfx: str = "backbone."):
+    """Diff.forward(x, idx:int) with a UNet backbone -- models.py:764-779."""
+    def fn(x: Tensor, idx: int) -> Tensor:
+        t = torch.full((x.shape[0],), idx, dtype=torch.long)
+        return unet_forward(sd, x, t, pfx)
+    return fn
+
+
+@torch.no_grad()
+def latent_sample(sd: SD, sch: Schedule, zT: Tensor, deterministic: bool, noise_fn: NoiseFn = _randn,
+                  record: Optional[List] = None) -> Tensor:
+    """LatentDiffusionProcess.sampling -- sampling.py:232-291 (same step formulas over [B, a_dim])."""
+    steps = ddim_steps if deterministic else ddpm_steps
+    x = zT
+    for idx, eps, x in steps(sch, latent_eps_fn(sd), zT, noise_fn):
         if record is not None:
             record.append((idx, eps, x))
     return x

@@ -98,3 +98,38 @@ def test_reverse_ddim(golden_dir):
     xTa = orc.reverse_sample(sd, sch, x0, a=a)
     assert rel_l2(xTa, torch.from_numpy(g["xT_given_a"])) < 2e-6
     assert rel_l2(xTa, xT) > 1e-4      # the two variants really differ
+
+
+def test_variant_goldens_and_constructor_digests(golden_dir):
+    """Bottleneck / vanilla UNet / Diff / two-phase / latent: the product's constructors reproduce the reference's
+    initial state bit for bit (digests minted by oracle/make_golden_variants.py) and the oracle reproduces the
+    reference's outputs on the regenerated weights."""
+    import json
+    from infodiffusion_b200 import models
+    from oracle.golden_util import state_digest
+    meta = json.loads((golden_dir / "meta.json").read_text())
+    x, t, a = rand_inputs(2, 32, 1000)
+
+    args = make_args(a_dim=32, diffusion_steps=1000, is_bottleneck=True)
+    torch.manual_seed(SEED)
+    m = models.InfoDiff(args, "cpu", (3, 64, 64))
+    assert state_digest(m.state_dict()) == meta["state_bottleneck_a32_T1000"]["digest"]
+    sd = perturb_state_dict(m.state_dict())
+    with torch.no_grad():
+        eps = orc.bottleneck_unet_forward(sd, x, t, a)
+    assert rel_l2(eps, torch.from_numpy(np.load(golden_dir / "bottleneck_a32_T1000.npz")["eps"])) < 1e-6
+
+    torch.manual_seed(SEED)
+    u = models.UNet(T=1000, ch=64, ch_mult=[1, 2, 2, 2], shape=(3, 64, 64))
+    assert state_digest(u.state_dict()) == meta["state_unet_1222_T1000"]["digest"]
+    sdu = perturb_state_dict({"backbone." + k: v for k, v in u.state_dict().items()})
+    with torch.no_grad():
+        eps = orc.unet_forward(sdu, x, t)
+    assert rel_l2(eps, torch.from_numpy(np.load(golden_dir / "unet_1222_T1000.npz")["eps"])) < 1e-6
+
+    args6 = make_args(a_dim=32, diffusion_steps=6, model="vanilla", split_step=2)
+    torch.manual_seed(SEED + 1)
+    van = models.Diff(args6, "cpu", (3, 64, 64))
+    torch.manual_seed(SEED + 1)
+    van.backbone = models.UNet(T=6, ch=64, ch_mult=[1, 2, 2, 2], shape=(3, 64, 64))
+    assert state_digest(van.state_dict()) == meta["state_diff_unet_1222_T6_seed65"]["digest"]
