@@ -199,6 +199,18 @@ int idf_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, 
                    int32_t N, int32_t K, int32_t silu_in, idf_stream_t stream);
 /* y[m, :] = table[idx[m], :]  (nn.Embedding lookup, modules.py:23,37) */
 int idf_gather_rows_f32(const float* table, const int64_t* idx, float* y, int32_t M, int32_t N, idf_stream_t stream);
+/* LatentUNet layer tail, MLPLNAct.forward (models.py:147-163) after the Linear: out[m, :] = SiLU(LayerNorm(y[m, :] *
+ * (1 + cond[m, :]))), condition_bias = 1 (models.py:219).  cond may be NULL (no modulation) or one broadcast row
+ * (cond_row_stride = 0); with step_ptr the row block starts at cond + *step_ptr * cond_step_stride (per-timestep
+ * table inside a captured sampler graph); gamma/beta NULL = no affine; apply_silu = 0 for an activation-less
+ * layer. fp32, N <= 8192. */
+int idf_scale_layernorm_silu(const float* y, int64_t ldy, const float* cond, int64_t cond_row_stride,
+                             int64_t cond_step_stride, const int32_t* step_ptr, const float* gamma, const float* beta,
+                             float eps, float* out, int64_t ldo, int32_t M, int32_t N, int32_t apply_silu,
+                             idf_stream_t stream);
+/* dst[m, n] = src[m, n] for an M x N fp32 block with row pitches lds / ldd: places x next to h for the skip
+ * concatenation cat([h, x]) of LatentUNet (models.py:230-232). */
+int idf_copy2d_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int32_t M, int32_t N, idf_stream_t stream);
 /* dst[i] (+)= src[idx[i]-1] (+ src[idx2[i]-1]);  index 0 = literal zero, idx2 may be NULL, n % 4 == 0.
  * Training only: one launch re-packs all fp32 parameters into the bf16 GEMM operand layouts that the
  * reference obtains implicitly from nn.Conv2d.weight (modules.py:66,81,133-136,216-231), another assembles

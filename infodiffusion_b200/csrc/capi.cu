@@ -387,6 +387,24 @@ int idf_gather_rows_f32(const float* table, const int64_t* idx, float* y, int32_
   return IDF_OK;
 }
 
+int idf_copy2d_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int32_t M, int32_t N, idf_stream_t stream) {
+  if (src == nullptr || dst == nullptr) return fail(IDF_ERR_ARG, "copy2d: null argument");
+  cudaError_t e = launch_copy2d_f32(src, lds, dst, ldd, M, N, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "copy2d launch");
+  return IDF_OK;
+}
+
+int idf_scale_layernorm_silu(const float* y, int64_t ldy, const float* cond, int64_t cond_row_stride,
+                             int64_t cond_step_stride, const int32_t* step_ptr, const float* gamma, const float* beta,
+                             float eps, float* out, int64_t ldo, int32_t M, int32_t N, int32_t apply_silu,
+                             idf_stream_t stream) {
+  if (y == nullptr || out == nullptr || (gamma == nullptr) != (beta == nullptr)) return fail(IDF_ERR_ARG, "scale_layernorm_silu: bad pointers");
+  cudaError_t e = launch_scale_ln_silu(y, ldy, cond, cond_row_stride, cond_step_stride, step_ptr, gamma, beta, eps, out, ldo,
+                                       M, N, apply_silu, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "scale_layernorm_silu launch (N <= 8192)");
+  return IDF_OK;
+}
+
 int idf_gather_elems(const float* src, const int32_t* idx, const int32_t* idx2, void* dst, int64_t n, int32_t dst_bf16,
                      int32_t accumulate, idf_stream_t stream) {
   if (n < 0 || (n & 3) != 0) return fail(IDF_ERR_ARG, "gather_elems: n must be a non-negative multiple of 4");

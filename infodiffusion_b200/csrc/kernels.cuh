@@ -73,6 +73,10 @@ cudaError_t launch_attn_v2(const CUtensorMap& tm, bf16* out, int batch, int H, i
                            cudaStream_t stream);
 cudaError_t launch_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy,
                               int M, int N, int K, int silu_in, cudaStream_t stream);
+cudaError_t launch_scale_ln_silu(const float* y, long long ldy, const float* cond, long long cond_stride,
+                                 long long cond_step_stride, const int* step_ptr, const float* gamma, const float* beta,
+                                 float eps, float* out, long long ldo, int M, int N, int apply_silu, cudaStream_t stream);
+cudaError_t launch_copy2d_f32(const float* src, long long lds, float* dst, long long ldd, int M, int N, cudaStream_t stream);
 cudaError_t launch_gather_elems(const float* src, const int* idx, const int* idx2, void* dst, long long n, bool dst_bf16,
                                 bool accumulate, int num_sms, cudaStream_t stream);
 cudaError_t launch_gather_rows(const float* table, const int64_t* idx, float* y, int M, int N, cudaStream_t stream);

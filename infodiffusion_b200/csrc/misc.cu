@@ -382,8 +382,61 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
   }
 }
 
+// larger batches (LatentUNet at sampling batch sizes): 64x64 output tile, 4x4 accumulators per thread, K in
+// chunks of 16 staged k-major so the inner loop reads two float4 per 16 FMAs.  Same fp32 FMA order over k.
+__global__ void __launch_bounds__(256) linear_f32_tile64_kernel(const float* __restrict__ x, long long ldx,
+                                                                const float* __restrict__ w, const float* __restrict__ b,
+                                                                float* __restrict__ y, long long ldy, int M, int N, int K,
+                                                                int silu_in) {
+  __shared__ __align__(16) float xs[16][68];
+  __shared__ __align__(16) float ws[16][68];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int t = threadIdx.x;
+  const int tm = (t >> 4) * 4, tn = (t & 15) * 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = t; i < 64 * 16; i += 256) {
+      const int r = i >> 4, c = i & 15;
+      float v = 0.f;
+      if (m0 + r < M && k0 + c < K) {
+        v = x[(m0 + r) * ldx + k0 + c];
+        if (silu_in) v = v / (1.0f + expf(-v));
+      }
+      xs[c][r] = v;
+      ws[c][r] = (n0 + r < N && k0 + c < K) ? w[static_cast<long long>(n0 + r) * K + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 xv = *reinterpret_cast<const float4*>(&xs[c][tm]);
+      const float4 wv = *reinterpret_cast<const float4*>(&ws[c][tn]);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, wa[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], wa[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + tm + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tn + j;
+      if (n < N) y[m * ldy + n] = acc[i][j] + (b ? b[n] : 0.f);
+    }
+  }
+}
+
 cudaError_t launch_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy,
                               int M, int N, int K, int silu_in, cudaStream_t stream) {
+  if (M >= 64) {
+    dim3 grid64((N + 63) / 64, (M + 63) / 64, 1);
+    linear_f32_tile64_kernel<<<grid64, 256, 0, stream>>>(x, ldx, w, b, y, ldy, M, N, K, silu_in);
+    return cudaGetLastError();
+  }
   dim3 grid((N + 63) / 64, (M + 15) / 16, 1);
   linear_f32_kernel<<<grid, 256, 0, stream>>>(x, ldx, w, b, y, ldy, M, N, K, silu_in);
   return cudaGetLastError();
@@ -397,6 +450,76 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, const int64_
 }
 cudaError_t launch_gather_rows(const float* table, const int64_t* idx, float* y, int M, int N, cudaStream_t stream) {
   gather_rows_kernel<<<M, 128, 0, stream>>>(table, idx, y, N);
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------
+// LatentUNet layer tail (models.py:147-163): out = SiLU(LayerNorm(y * (1 + cond))) over rows of N features.
+// One CTA per row; the modulated row is staged in shared memory, mean and variance are two separate
+// passes (as ATen's layer_norm), cond may be a single broadcast row (sampling: every sample shares t).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_128(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return (red[0] + red[1]) + (red[2] + red[3]);
+}
+__global__ void __launch_bounds__(128) scale_ln_silu_kernel(const float* __restrict__ y, long long ldy,
+                                                            const float* __restrict__ cond, long long cond_stride,
+                                                            long long cond_step_stride, const int* __restrict__ step_ptr,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float eps, float* __restrict__ out, long long ldo, int N,
+                                                            int apply_silu) {
+  extern __shared__ float row[];
+  __shared__ float red[4];
+  const long long m = blockIdx.x;
+  const float* yr = y + m * ldy;
+  const float* cr = cond ? cond + m * cond_stride + (step_ptr ? *step_ptr * cond_step_stride : 0) : nullptr;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < N; i += 128) {
+    float v = yr[i];
+    if (cr) v *= 1.0f + cr[i];
+    row[i] = v;
+    s += v;
+  }
+  const float mean = block_sum_128(s, red) / static_cast<float>(N);
+  float q = 0.f;
+  for (int i = threadIdx.x; i < N; i += 128) { const float d = row[i] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(block_sum_128(q, red) / static_cast<float>(N) + eps);
+  for (int i = threadIdx.x; i < N; i += 128) {
+    float v = (row[i] - mean) * rstd;
+    if (gamma) v = fmaf(v, gamma[i], beta[i]);
+    if (apply_silu) v = v / (1.0f + __expf(-v));
+    out[m * ldo + i] = v;
+  }
+}
+cudaError_t launch_scale_ln_silu(const float* y, long long ldy, const float* cond, long long cond_stride,
+                                 long long cond_step_stride, const int* step_ptr, const float* gamma, const float* beta,
+                                 float eps, float* out, long long ldo, int M, int N, int apply_silu, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || N > 8192) return cudaErrorInvalidValue;
+  scale_ln_silu_kernel<<<M, 128, N * sizeof(float), stream>>>(y, ldy, cond, cond_stride, cond_step_stride, step_ptr, gamma,
+                                                              beta, eps, out, ldo, N, apply_silu);
+  return cudaGetLastError();
+}
+
+__global__ void copy2d_f32_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
+                                  int M, int N) {
+  const long long total = static_cast<long long>(M) * N;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / N, n = i - m * N;
+    dst[m * ldd + n] = src[m * lds + n];
+  }
+}
+cudaError_t launch_copy2d_f32(const float* src, long long lds, float* dst, long long ldd, int M, int N, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return cudaErrorInvalidValue;
+  const long long total = static_cast<long long>(M) * N;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  const int grid = static_cast<int>(blocks);
+  copy2d_f32_kernel<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, M, N);
   return cudaGetLastError();
 }
 

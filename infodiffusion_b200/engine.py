@@ -787,3 +787,120 @@ def encoder_forward(net, x: torch.Tensor):
     a, mu, log_var = p.a.clone(), p.mu.clone(), p.log_var.clone()
     a_q = mu + torch.randn_like(mu) * torch.exp(0.5 * log_var)      # reference models.py:515
     return a, a_q, mu, log_var
+
+
+# ------------------------------------------------------------------------------------------------
+# latent eps-network (LatentUNet, reference models.py:166-234)
+# ------------------------------------------------------------------------------------------------
+class LatentPlan(Plan):
+    """eps = LatentUNet(z, t) for a fixed batch: per layer one fp32 GEMM (idf_linear_f32) and one fused
+    (1 + cond) scale -> LayerNorm -> SiLU kernel that writes straight into the [h | z] concatenation buffer the
+    next layer reads (models.py:230-232).  Weight-bandwidth-bound: 13.5 M parameters for a_dim = 256.
+
+    mode 'eps'     : z_in [B, D], t_idx [B] -> eps_out; the per-sample condition rows are computed per call.
+    mode 'sampler' : z_io is updated in place by idf_sampler_update with coef[*step]; every sample shares the
+                     timestep, so the condition rows come from a precomputed [T, n_cond * 4D] table."""
+
+    def __init__(self, net, batch: int, device, mode: str = "eps", T: Optional[int] = None,
+                 z_io: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                 coef: Optional[torch.Tensor] = None, step: Optional[torch.Tensor] = None,
+                 eps_out: Optional[torch.Tensor] = None):
+        super().__init__(batch, device)
+        assert mode in ("eps", "sampler")
+        self.net, self.mode = net, mode
+        B = batch
+        f32 = dict(dtype=torch.float32, device=device)
+        layers = list(net.layers)
+        D = layers[0].linear.in_features
+        Hd = layers[0].linear.out_features
+        assert all(l.use_cond and isinstance(l.norm, nn.LayerNorm) for l in layers[:-1]) and not layers[-1].use_cond
+        assert all(l.condition_bias == 1 for l in layers[:-1]), "kernel folds condition_bias = 1 (models.py:219)"
+        n_cond = len(layers) - 1
+        self.z_in = z_io if z_io is not None else torch.zeros(B, D, **f32)
+        self.eps_out = eps_out if eps_out is not None else torch.zeros(B, D, **f32)
+        self.hcat = torch.zeros(B, Hd + D, **f32)          # [h | z]: layer i >= 1 reads cat([h, z])
+        self.ybuf = torch.zeros(B, Hd, **f32)
+        w_cond = self.f32(torch.cat([l.linear_emb.weight for l in layers[:-1]], 0))
+        b_cond = self.f32(torch.cat([l.linear_emb.bias for l in layers[:-1]], 0))
+        te = net.time_embed
+        C_t = net.num_time_emb_channels
+        if mode == "eps":
+            assert T is not None, "LatentPlan needs the number of diffusion steps for its sinusoid table"
+            from .modules import timestep_embedding
+            self.t_idx = torch.zeros(B, dtype=torch.long, device=device)
+            table = timestep_embedding(torch.arange(T, device=device), C_t).contiguous()      # modules.py:41-60
+            e0, e1, e2 = torch.zeros(B, C_t, **f32), torch.zeros(B, D, **f32), torch.zeros(B, D, **f32)
+            self.cond = torch.zeros(B, n_cond * Hd, **f32)
+            self.keep += [table, e0, e1, e2]
+            self._emit("gather_rows", self.lib.idf_gather_rows_f32, (table.data_ptr(), self.t_idx.data_ptr(), e0.data_ptr(), B, C_t))
+            self.linear(e0, self.f32(te[0].weight), self.f32(te[0].bias), e1, silu_in=False)
+            self.linear(e1, self.f32(te[2].weight), self.f32(te[2].bias), e2, silu_in=True)
+            self.linear(e2, w_cond, b_cond, self.cond, silu_in=True)           # cond_layers = act -> linear_emb
+            cond_arg = lambda i: (self.cond.data_ptr() + 4 * i * Hd, n_cond * Hd, 0, None)
+        else:
+            assert z_io is not None and coef is not None and step is not None and T is not None
+            from .modules import timestep_embedding
+            tp = Plan(1, device)                                               # one-off: the [T, n_cond * Hd] table
+            e0 = timestep_embedding(torch.arange(T, device=device), C_t).contiguous()
+            e1, e2 = torch.zeros(T, D, **f32), torch.zeros(T, D, **f32)
+            self.cond = torch.zeros(T, n_cond * Hd, **f32)
+            tp.linear(e0, tp.f32(te[0].weight), tp.f32(te[0].bias), e1, silu_in=False)
+            tp.linear(e1, tp.f32(te[2].weight), tp.f32(te[2].bias), e2, silu_in=True)
+            tp.linear(e2, w_cond, b_cond, self.cond, silu_in=True)
+            tp.run()
+            torch.cuda.current_stream(device).synchronize()
+            cond_arg = lambda i: (self.cond.data_ptr() + 4 * i * Hd, 0, n_cond * Hd, step.data_ptr())
+        ld = Hd + D
+        self._emit("copy2d", self.lib.idf_copy2d_f32, (self.z_in.data_ptr(), self.z_in.stride(0),
+                                                       self.hcat.data_ptr() + 4 * Hd, ld, B, D))
+        for i, l in enumerate(layers):
+            src = self.z_in if i == 0 else self.hcat
+            w, b = self.f32(l.linear.weight), self.f32(l.linear.bias)
+            if i == len(layers) - 1:
+                self.linear(src, w, b, self.eps_out, silu_in=False)            # plain Linear (models.py:195-200)
+                break
+            self.linear(src, w, b, self.ybuf, silu_in=False)
+            cptr, crow, cstep, sptr = cond_arg(i)
+            self._emit("scale_ln_silu", self.lib.idf_scale_layernorm_silu,
+                       (self.ybuf.data_ptr(), Hd, cptr, crow, cstep, sptr, self.f32(l.norm.weight).data_ptr(),
+                        self.f32(l.norm.bias).data_ptr(), float(l.norm.eps), self.hcat.data_ptr(), ld, B, Hd,
+                        1 if l.activation is not None else 0))
+        if mode == "sampler":
+            self._emit("sampler_update", self.lib.idf_sampler_update,
+                       (self.z_in.data_ptr(), self.eps_out.data_ptr(), _ptr(noise), coef.data_ptr(), step.data_ptr(), B * D))
+
+
+@torch.no_grad()
+def latent_forward(net, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x, "x")
+    _check_eval(net)
+    B = x.shape[0]
+    T = int(getattr(net, "T", 0)) or None
+    key = ("latent_eps", B, x.device.index)
+    plans = net._plans()
+    if key not in plans:
+        if T is None:
+            raise RuntimeError("LatentUNet was built without T; pass T= to the constructor")
+        plans[key] = LatentPlan(net, B, x.device, mode="eps", T=T)
+    p: LatentPlan = plans[key]
+    p.z_in.copy_(x)
+    p.t_idx.copy_(t.to(torch.long))
+    p.run()
+    return p.eps_out.clone()
+
+
+def latent_forward_autograd(net, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    """Training-mode LatentUNet forward (reference models.py:223-234, 147-163) as a torch autograd composite on
+    the GPU: train_latent_ddim is not on the measured hot path and has no backward kernels of its own."""
+    from .modules import timestep_embedding
+    _require_cuda(x, "x")
+    temb = net.time_embed(timestep_embedding(t, net.num_time_emb_channels))
+    h = x
+    for i, layer in enumerate(net.layers):
+        if i in net.skip_layers:
+            h = torch.cat([h, x], dim=1)
+        h = layer.linear(h)
+        if layer.use_cond:
+            h = h * (layer.condition_bias + layer.cond_layers(temb))
+        h = layer.dropout(layer.act(layer.norm(h)))
+    return h

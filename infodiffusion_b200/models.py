@@ -207,6 +207,75 @@ class Encoder(_EngineNet):
         return encoder_forward(self, x)
 
 
+class MLPLNAct(nn.Module):
+    """Linear -> x * (condition_bias + Linear(act(cond))) -> LayerNorm -> act -> Dropout: one layer of the latent
+    eps-network (reference models.py:91-163).  Parameter container; `linear_emb` is registered twice (also as
+    cond_layers.1) exactly like the reference, so the state_dict carries both aliases."""
+
+    def __init__(self, in_channels, out_channels, norm, use_cond, activation=None, cond_channels=None,
+                 condition_bias=0, dropout=0):
+        super().__init__()
+        self.activation = activation
+        self.act = nn.SiLU() if activation is not None else nn.Identity()
+        self.condition_bias = condition_bias
+        self.use_cond = use_cond
+        self.linear = nn.Linear(in_channels, out_channels)
+        if self.use_cond:
+            self.linear_emb = nn.Linear(cond_channels, out_channels)
+            self.cond_layers = nn.Sequential(self.act, self.linear_emb)
+        self.norm = nn.LayerNorm(out_channels) if norm else nn.Identity()
+        self.dropout = nn.Dropout(dropout) if dropout > 0 else nn.Identity()
+        gains = {'relu': (0, 'relu'), 'leaky_relu': (0.2, 'leaky_relu'), 'silu': (0, 'relu')}
+        if activation in gains:                       # reference init_weights (models.py:127-145)
+            a, nl = gains[activation]
+            for module in self.modules():
+                if isinstance(module, nn.Linear):
+                    init.kaiming_normal_(module.weight, a=a, nonlinearity=nl)
+
+    def forward(self, x, cond=None):
+        raise RuntimeError("MLPLNAct is a parameter container; it runs inside LatentUNet.forward")
+
+
+class LatentUNet(_EngineNet):
+    """10-layer skip-MLP eps-network over the latent z (reference models.py:166-234): layer i >= 1 reads
+    cat([h, x]); time embedding = Linear(SiLU(Linear(sinusoid(t))))."""
+
+    def __init__(self, T, num_layers=10, dropout=0.1, shape=None, activation='silu', num_time_emb_channels: int = 64,
+                 num_time_layers: int = 2):
+        super().__init__()
+        self.num_time_emb_channels = num_time_emb_channels
+        self.shape = shape
+        self.T = T
+        D = shape[-1]
+        layers = []
+        for i in range(num_time_layers):
+            layers.append(nn.Linear(num_time_emb_channels if i == 0 else D, D))
+            if i < num_time_layers - 1:
+                layers.append(nn.SiLU())
+        self.time_embed = nn.Sequential(*layers)
+        self.skip_layers = list(range(1, num_layers))
+        self.layers = nn.ModuleList([])
+        for i in range(num_layers):
+            if i == 0:
+                act, norm, cond, (a, b), drop = activation, True, True, (D, D * 4), dropout
+            elif i == num_layers - 1:
+                act, norm, cond, (a, b), drop = None, False, False, (D * 4, D), 0
+            else:
+                act, norm, cond, (a, b), drop = 'silu', True, True, (D * 4, D * 4), dropout
+            if i in self.skip_layers:
+                a += D
+            self.layers.append(MLPLNAct(a, b, norm=norm, activation=act, cond_channels=D, use_cond=cond,
+                                        condition_bias=1, dropout=drop))
+
+    def forward(self, x, t):
+        """x [B, D] fp32, t int64 [B] -> eps [B, D] (reference models.py:223).  eval(): fused kernels
+        (engine.LatentPlan); train() with grad: the same arithmetic as a torch autograd composite on the GPU."""
+        from .engine import latent_forward, latent_forward_autograd
+        if self.training and torch.is_grad_enabled():
+            return latent_forward_autograd(self, x, t)
+        return latent_forward(self, x, t)
+
+
 class InfoDiff(nn.Module):
     """Model wrapper: noise schedule, q(x_t|x_0), z routing and losses (reference models.py:605-723)."""
 

@@ -308,3 +308,114 @@ class TwoPhaseDiffusionProcess():
     def reverse_sampling(self, x0, a=None):
         """reference sampling.py:189-195: diffusion_fn_1 with a dropped (the encoder is re-run every step)."""
         return self.p1.reverse_sampling(x0, None)
+
+
+class LatentDiffusionProcess():
+    """Drop-in for the reference's LatentDiffusionProcess (sampling.py:207-291): DDPM / DDIM / reverse DDIM over the
+    latent z [B, a_dim] with diffusion_fn(z, idx) = Diff over a LatentUNet.  One CUDA graph per (kind, batch): 20
+    launches of the MLP plus the fused z update, the timestep entering through a device-side step counter."""
+
+    def __init__(self, args, diffusion_fn, device):
+        self.betas, self.alphas, ab, apb = make_schedule(args.beta1, args.betaT, args.diffusion_steps)
+        self.alpha_bars = ab.to(device=device)
+        self.alpha_prev_bars = apb.to(device=device)
+        self.deterministic = args.deterministic
+        self.a_dim = args.a_dim
+        self.model = args.model
+        self.diffusion_fn = diffusion_fn.to(device=device)
+        self.device = device
+        self.use_graph = getattr(args, "cuda_graph", True)
+        self.noise_fn = lambda idx, out: out.normal_()
+        self._samplers = {}
+
+    def _sampler(self, kind: str, batch: int):
+        from .engine import LatentPlan
+        net = self.diffusion_fn.backbone
+        if net.training:
+            raise RuntimeError("sampling runs the inference forward; call model.eval() first")
+        key = (kind, batch)
+        if key not in self._samplers:
+            dev = self.device
+            T = len(self.alpha_bars)
+            D = net.layers[0].linear.in_features
+            s = type("LatentSampler", (), {})()
+            s.x = torch.zeros(batch, D, dtype=torch.float32, device=dev)
+            s.noise = torch.zeros_like(s.x) if kind != "reverse" else None
+            s.eps = torch.zeros_like(s.x)
+            s.step = torch.zeros(1, dtype=torch.int32, device=dev)
+            s.coef = step_coefficients(kind, self.betas.cpu(), self.alphas.cpu(), self.alpha_bars.cpu(),
+                                       self.alpha_prev_bars.cpu()).to(dev).contiguous()
+            s.plan = LatentPlan(net, batch, dev, mode="sampler", T=T, z_io=s.x, noise=s.noise, coef=s.coef, step=s.step,
+                                eps_out=s.eps)
+            s.graph = None
+            self._samplers[key] = s
+        return self._samplers[key]
+
+    def _step(self, s, idx: int) -> None:
+        s.step.fill_(idx)
+        if not self.use_graph:
+            s.plan.run()
+            return
+        if s.graph is None:
+            keep = s.x.clone()
+            torch.cuda.synchronize(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                s.plan.run()                         # warm-up outside capture
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                s.plan.run()
+            s.graph = g
+            s.x.copy_(keep)
+            s.step.fill_(idx)
+        s.graph.replay()
+        _lib.count_launch(len(s.plan.ops))
+
+    def _iter(self, kind: str, x: torch.Tensor):
+        T = len(self.alpha_bars)
+        s = self._sampler(kind, x.shape[0])
+        s.x.copy_(x)
+        order = range(1, T - 1) if kind == "reverse" else reversed(range(T))
+        for idx in order:
+            if kind != "reverse" and idx > 0:
+                self.noise_fn(idx, s.noise)
+            self._step(s, idx)
+            yield idx, s
+
+    @torch.no_grad()
+    def _ddpm_one_diffusion_step(self, x):
+        for _, s in self._iter("ddpm", x):
+            yield s.x.clone()
+
+    @torch.no_grad()
+    def _ddim_one_diffusion_step(self, x):
+        for _, s in self._iter("ddim", x):
+            yield s.x.clone()
+
+    @torch.no_grad()
+    def _ddim_one_reverse_diffusion_step(self, x):
+        yield x
+        for _, s in self._iter("reverse", x):
+            yield s.x.clone()
+
+    def _one_diffusion_step(self, sample, deterministic=False):
+        return self._ddim_one_diffusion_step(sample) if deterministic else self._ddpm_one_diffusion_step(sample)
+
+    @torch.no_grad()
+    def reverse_sampling(self, x0):
+        s = None
+        for _, s in self._iter("reverse", x0):
+            pass
+        return s.x.clone() if s is not None else x0.clone()
+
+    @torch.no_grad()
+    def sampling(self, sampling_number=16, xT=None):
+        if xT is None:
+            xT = torch.randn([sampling_number, self.a_dim]).to(device=self.device)
+        s = None
+        for _, s in self._iter("ddim" if self.deterministic else "ddpm", xT):
+            pass
+        return s.x.clone()

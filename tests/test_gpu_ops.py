@@ -592,3 +592,25 @@ def test_colsum_bias_gradient(lib, rows, Cc):
     torch.cuda.synchronize()
     want = mth.double().sum(0) + 0.5
     assert_close(out, want, rel_l2=1e-5, max_rel=1e-4, what="colsum")
+
+
+@pytest.mark.parametrize("M,N,bcast,silu,affine", [(5, 128, False, True, True), (70, 1024, True, True, True),
+                                                   (3, 1000, False, False, False), (1, 32, False, True, True)])
+def test_scale_layernorm_silu(lib, M, N, bcast, silu, affine):
+    """LatentUNet layer tail (reference models.py:147-163): SiLU(LayerNorm(y * (1 + cond)))."""
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + N)
+    ld = N + 8
+    ybuf = torch.randn(M, ld, device=DEV, generator=g)
+    cond = torch.randn(1 if bcast else M, N, device=DEV, generator=g) * 0.3
+    gamma = 1 + 0.1 * torch.randn(N, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(N, device=DEV, generator=g)
+    out = torch.zeros(M, ld, device=DEV)
+    check(lib.idf_scale_layernorm_silu(ybuf.data_ptr(), ld, cond.data_ptr(), 0 if bcast else N, 0, None,
+                                       gamma.data_ptr() if affine else None, beta.data_ptr() if affine else None, 1e-5,
+                                       out.data_ptr(), ld, M, N, int(silu), stream()))
+    torch.cuda.synchronize()
+    v = ybuf[:, :N].double() * (1 + cond.double())
+    v = F.layer_norm(v, (N,), gamma.double() if affine else None, beta.double() if affine else None, 1e-5)
+    want = F.silu(v) if silu else v
+    assert_close(out[:, :N], want, rel_l2=2e-6, max_rel=2e-4, what="scale_layernorm_silu")
+    assert float(out[:, N:].abs().max()) == 0.0
