@@ -208,6 +208,20 @@ int idf_scale_layernorm_silu(const float* y, int64_t ldy, const float* cond, int
                              int64_t cond_step_stride, const int32_t* step_ptr, const float* gamma, const float* beta,
                              float eps, float* out, int64_t ldo, int32_t M, int32_t N, int32_t apply_silu,
                              idf_stream_t stream);
+/* Train-step tail: torch.nn.utils.clip_grad_norm_(params, max_norm) + torch.optim.AdamW.step() (run.py:199-200, 177)
+ * over all parameter tensors in three launches.  Tables live in device memory: one pointer per tensor and one
+ * (tensor, offset / 4096) pair per 4096-element chunk.  fp32 everywhere.  norm_out[0] = total gradient norm (what
+ * clip_grad_norm_ returns), norm_out[1] = applied clip coefficient.  Gradients are scaled on the fly, not written
+ * back.  max_norm <= 0 disables clipping.  bias_correctionK = 1 - betaK^step (host-side, like torch). */
+typedef struct {
+  void* const* params; const void* const* grads; void* const* exp_avg; void* const* exp_avg_sq;
+  const int64_t* numel; const int32_t* chunk_tensor; const int32_t* chunk_offset;
+  int32_t n_chunks;
+  float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, max_norm;
+  float* partial;      /* [n_chunks] scratch */
+  float* norm_out;     /* [2] */
+} idf_clip_adamw_args;
+int idf_clip_adamw(const idf_clip_adamw_args* args, idf_stream_t stream);
 /* dst[m, n] = src[m, n] for an M x N fp32 block with row pitches lds / ldd: places x next to h for the skip
  * concatenation cat([h, x]) of LatentUNet (models.py:230-232). */
 int idf_copy2d_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int32_t M, int32_t N, idf_stream_t stream);

@@ -73,6 +73,17 @@ class AdaGNArgs(C.Structure):
     ]
 
 
+class ClipAdamWArgs(C.Structure):
+    _fields_ = [
+        ("params", C.c_void_p), ("grads", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+        ("numel", C.c_void_p), ("chunk_tensor", C.c_void_p), ("chunk_offset", C.c_void_p),
+        ("n_chunks", C.c_int32),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+        ("bias_correction1", C.c_float), ("bias_correction2", C.c_float), ("max_norm", C.c_float),
+        ("partial", C.c_void_p), ("norm_out", C.c_void_p),
+    ]
+
+
 class AdaGNBwdArgs(C.Structure):
     _fields_ = [
         ("f", AdaGNArgs),
@@ -108,6 +119,7 @@ SIGNATURES = {
     "idf_scale_layernorm_silu": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_void_p]),
+    "idf_clip_adamw": (C.c_int, [C.c_void_p, C.c_void_p]),
     "idf_copy2d_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "idf_gather_elems": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "idf_gather_rows_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

@@ -387,6 +387,24 @@ int idf_gather_rows_f32(const float* table, const int64_t* idx, float* y, int32_
   return IDF_OK;
 }
 
+int idf_clip_adamw(const idf_clip_adamw_args* a, idf_stream_t stream) {
+  if (a == nullptr) return fail(IDF_ERR_ARG, "clip_adamw: null argument");
+  if (a->n_chunks < 0 || (a->n_chunks > 0 && (!a->params || !a->grads || !a->exp_avg || !a->exp_avg_sq || !a->numel ||
+                                              !a->chunk_tensor || !a->chunk_offset || !a->partial || !a->norm_out)))
+    return fail(IDF_ERR_ARG, "clip_adamw: bad tables");
+  if (!(a->bias_correction1 > 0.f) || !(a->bias_correction2 > 0.f)) return fail(IDF_ERR_ARG, "clip_adamw: bias corrections must be > 0");
+  ClipAdamWParams p;
+  p.params = a->params; p.grads = a->grads; p.exp_avg = a->exp_avg; p.exp_avg_sq = a->exp_avg_sq;
+  p.numel = reinterpret_cast<const long long*>(a->numel); p.chunk_tensor = a->chunk_tensor; p.chunk_offset = a->chunk_offset;
+  p.n_chunks = a->n_chunks;
+  p.lr = a->lr; p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps; p.weight_decay = a->weight_decay;
+  p.bias_correction1 = a->bias_correction1; p.bias_correction2 = a->bias_correction2; p.max_norm = a->max_norm;
+  p.partial = a->partial; p.norm_out = a->norm_out;
+  cudaError_t e = launch_clip_adamw(p, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "clip_adamw launch");
+  return IDF_OK;
+}
+
 int idf_copy2d_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int32_t M, int32_t N, idf_stream_t stream) {
   if (src == nullptr || dst == nullptr) return fail(IDF_ERR_ARG, "copy2d: null argument");
   cudaError_t e = launch_copy2d_f32(src, lds, dst, ldd, M, N, reinterpret_cast<cudaStream_t>(stream));

@@ -73,6 +73,14 @@ cudaError_t launch_attn_v2(const CUtensorMap& tm, bf16* out, int batch, int H, i
                            cudaStream_t stream);
 cudaError_t launch_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy,
                               int M, int N, int K, int silu_in, cudaStream_t stream);
+struct ClipAdamWParams {
+  void* const* params; const void* const* grads; void* const* exp_avg; void* const* exp_avg_sq;
+  const long long* numel; const int* chunk_tensor; const int* chunk_offset;
+  int n_chunks;
+  float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, max_norm;
+  float* partial; float* norm_out;
+};
+cudaError_t launch_clip_adamw(const ClipAdamWParams& p, cudaStream_t stream);
 cudaError_t launch_scale_ln_silu(const float* y, long long ldy, const float* cond, long long cond_stride,
                                  long long cond_step_stride, const int* step_ptr, const float* gamma, const float* beta,
                                  float eps, float* out, long long ldo, int M, int N, int apply_silu, cudaStream_t stream);

@@ -1,0 +1,100 @@
+"""Fused train-step tail: gradient-norm clipping + AdamW over every parameter in three kernel launches
+(reference run.py:177, 199-200: ``clip_grad_norm_(model.parameters(), 1.)`` then ``AdamW.step()``).
+
+``ClipAdamW`` is a ``torch.optim.Optimizer`` (param_groups, ``lr`` per group, ``zero_grad``), so the reference's
+LR schedulers (CosineAnnealingLR wrapped by GradualWarmupScheduler, run.py:182-185) drive it unchanged.  The
+update rule and its defaults are torch.optim.AdamW's; the clip coefficient is clip_grad_norm_'s
+``min(1, max_norm / (total_norm + 1e-6))`` with the L2 norm taken over all parameters of all groups.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import torch
+
+from . import _lib
+from ._lib import ClipAdamWArgs
+
+_CHUNK = 4096
+
+
+class ClipAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_norm=1.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.max_norm = float(max_norm)
+        self.total_norm = None         # device scalar after step(): what clip_grad_norm_ returns
+        self._tables = {}
+
+    def _group_tables(self, gi: int, ps: List[torch.Tensor]):
+        """Static per-group tables (parameter / moment pointers, sizes, chunk map); gradients change per step."""
+        key = (gi, tuple(id(p) for p in ps))
+        tb = self._tables.get(gi)
+        if tb is not None and tb["key"] == key:
+            return tb
+        dev = ps[0].device
+        for p in ps:
+            if p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous():
+                raise RuntimeError("ClipAdamW needs contiguous fp32 CUDA parameters")
+            st = self.state[p]
+            if "exp_avg" not in st:
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        ct, co = [], []
+        for i, p in enumerate(ps):
+            n = (p.numel() + _CHUNK - 1) // _CHUNK
+            ct += [i] * n
+            co += list(range(n))
+        i64 = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+        tb = dict(key=key, n=len(ct),
+                  params=i64([p.data_ptr() for p in ps]),
+                  m=i64([self.state[p]["exp_avg"].data_ptr() for p in ps]),
+                  v=i64([self.state[p]["exp_avg_sq"].data_ptr() for p in ps]),
+                  numel=i64([p.numel() for p in ps]), ct=i32(ct), co=i32(co),
+                  partial=torch.zeros(max(len(ct), 1), dtype=torch.float32, device=dev),
+                  grads_host=torch.zeros(len(ps), dtype=torch.int64).pin_memory(),
+                  grads=torch.zeros(len(ps), dtype=torch.int64, device=dev))
+        self._tables[gi] = tb
+        return tb
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        lib = _lib.load()
+        groups = []
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.grad is not None]
+            if ps:
+                groups.append((gi, group, ps))
+        if not groups:
+            return loss
+        dev = groups[0][2][0].device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if len(groups) > 1 and self.max_norm > 0:
+            raise NotImplementedError("global-norm clipping across several param groups")
+        for gi, group, ps in groups:
+            tb = self._group_tables(gi, ps)
+            gh = tb["grads_host"]
+            for i, p in enumerate(ps):
+                g = p.grad
+                if g.dtype != torch.float32 or not g.is_contiguous():
+                    g = p.grad = g.float().contiguous()
+                gh[i] = g.data_ptr()
+            tb["grads"].copy_(gh, non_blocking=True)
+            group["step"] = int(group.get("step", 0)) + 1
+            b1, b2 = group["betas"]
+            norm_out = torch.empty(2, dtype=torch.float32, device=dev)
+            a = ClipAdamWArgs()
+            a.params, a.grads, a.exp_avg, a.exp_avg_sq = (tb[k].data_ptr() for k in ("params", "grads", "m", "v"))
+            a.numel, a.chunk_tensor, a.chunk_offset = tb["numel"].data_ptr(), tb["ct"].data_ptr(), tb["co"].data_ptr()
+            a.n_chunks = tb["n"]
+            a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = group["lr"], b1, b2, group["eps"], group["weight_decay"]
+            a.bias_correction1 = 1.0 - b1 ** group["step"]
+            a.bias_correction2 = 1.0 - b2 ** group["step"]
+            a.max_norm = self.max_norm
+            a.partial, a.norm_out = tb["partial"].data_ptr(), norm_out.data_ptr()
+            _lib.check(lib.idf_clip_adamw(C.byref(a), stream))
+            _lib.count_launch(3)
+            self.total_norm = norm_out[0]
+        return loss

@@ -614,3 +614,37 @@ def test_scale_layernorm_silu(lib, M, N, bcast, silu, affine):
     want = F.silu(v) if silu else v
     assert_close(out[:, :N], want, rel_l2=2e-6, max_rel=2e-4, what="scale_layernorm_silu")
     assert float(out[:, N:].abs().max()) == 0.0
+
+
+def test_clip_adamw_matches_torch():
+    """ClipAdamW.step() == clip_grad_norm_(params, 1.) + torch.optim.AdamW.step() (reference run.py:199-200, 177),
+    over several steps, ragged tensor sizes, a parameter without gradient and a gradient view with an odd offset."""
+    from infodiffusion_b200.optim import ClipAdamW
+    g = torch.Generator(device=DEV).manual_seed(5)
+    shapes = [(64, 64, 3, 3), (4097,), (3,), (128, 9), (5000, 3), (7,)]
+    ref = [torch.nn.Parameter(torch.randn(s, device=DEV, generator=g)) for s in shapes]
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    o_ref = torch.optim.AdamW(ref, lr=3e-3, weight_decay=1e-2)
+    o_mine = ClipAdamW(mine, lr=3e-3, weight_decay=1e-2, max_norm=1.0)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(o_mine, T_max=5)
+    sched_ref = torch.optim.lr_scheduler.CosineAnnealingLR(o_ref, T_max=5)
+    for it in range(4):
+        scale = 10.0 if it % 2 == 0 else 0.01          # clipping active / inactive
+        flat = torch.randn(sum(p.numel() for p in ref) + 1, device=DEV, generator=g) * scale
+        off = 1                                        # odd offset: unaligned gradient views
+        for i, (pr, pm) in enumerate(zip(ref, mine)):
+            if i == 2 and it == 0:
+                pr.grad = pm.grad = None               # skipped like torch skips it
+                continue
+            gv = flat[off:off + pr.numel()].view(pr.shape)
+            off += pr.numel()
+            pr.grad = gv.clone()
+            pm.grad = gv
+        want_norm = torch.nn.utils.clip_grad_norm_([p for p in ref if p.grad is not None], 1.0)
+        o_ref.step()
+        o_mine.step()
+        sched.step(); sched_ref.step()
+        torch.cuda.synchronize()
+        assert abs(float(o_mine.total_norm) - float(want_norm)) <= 1e-5 * float(want_norm)
+        for pr, pm in zip(ref, mine):
+            assert_close(pm.detach(), pr.detach(), rel_l2=1e-6, max_rel=1e-4, what=f"adamw step {it}")
