@@ -161,7 +161,8 @@ def train_throughput(a, dev, world, rank, steps=6, warmup=3):
     import torch.distributed as dist
     from infodiffusion_b200 import _lib
     from infodiffusion_b200.models import InfoDiff
-    from infodiffusion_b200.train import allreduce_gradients
+    from infodiffusion_b200.optim import ClipAdamW
+    from infodiffusion_b200.train import GradSync, set_grad_sync
     B = a.train_batch
     args = make_args_ns(1000)
     args.mode = "train"
@@ -172,7 +173,9 @@ def train_throughput(a, dev, world, rank, steps=6, warmup=3):
         setattr(model, n, getattr(model, n).to(dev))
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-5, fused=True)
+    opt = ClipAdamW(params, lr=1e-4, weight_decay=1e-5, max_norm=1.0)     # clip_grad_norm_(1.0) + AdamW (run.py:199-200)
+    sync = GradSync(world) if world > 1 else None
+    set_grad_sync(sync)
     g = torch.Generator().manual_seed(7 + rank)
     x_h = (torch.rand(B, 3, 64, 64, generator=g) * 2 - 1).pin_memory()
 
@@ -181,9 +184,8 @@ def train_throughput(a, dev, world, rank, steps=6, warmup=3):
         loss = model.loss_fn(args, x)
         opt.zero_grad(set_to_none=True)
         loss.backward()
-        if world > 1:
-            allreduce_gradients(params, world)
-        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        if sync is not None:
+            sync.finish(params)                  # all-reduces were started inside backward
         opt.step()
         return loss
 
@@ -204,12 +206,13 @@ def train_throughput(a, dev, world, rank, steps=6, warmup=3):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    set_grad_sync(None)
     flops = 3 * (15.318e9 + 11.774e9) * B * world * steps      # fwd + bwd ~ 3 x fwd
     return {"metric": "train_samples_per_sec", "value": world * B * steps / (ms / 1000.0), "unit": "samples/s",
             "ms_per_step": ms / steps, "batch_per_gpu": B, "n_gpus": world, "final_loss": float(loss),
             "tflops": flops / (ms / 1000.0) / 1e12, "idf_launches_per_step": (_lib.launches() - l0) // steps,
-            "config": "InfoDiff a_dim 256, T=1000, bf16 kernels / fp32 params, dropout 0.1, AdamW(1e-4, wd 1e-5), "
-                      "clip 1.0, data-parallel all-reduce" + (" (NCCL)" if world > 1 else " (single GPU)")}
+            "config": "InfoDiff a_dim 256, T=1000, bf16 kernels / fp32 params, dropout 0.1, fused clip(1.0)+AdamW(1e-4, "
+                      "wd 1e-5), data-parallel all-reduce overlapped with backward" + (" (NCCL)" if world > 1 else " (single GPU)")}
 
 
 # ------------------------------------------------------------------------------------------------

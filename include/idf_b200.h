@@ -212,12 +212,14 @@ int idf_scale_layernorm_silu(const float* y, int64_t ldy, const float* cond, int
  * over all parameter tensors in three launches.  Tables live in device memory: one pointer per tensor and one
  * (tensor, offset / 4096) pair per 4096-element chunk.  fp32 everywhere.  norm_out[0] = total gradient norm (what
  * clip_grad_norm_ returns), norm_out[1] = applied clip coefficient.  Gradients are scaled on the fly, not written
- * back.  max_norm <= 0 disables clipping.  bias_correctionK = 1 - betaK^step (host-side, like torch). */
+ * back.  max_norm <= 0 disables clipping.  bias_corrections[2*i + k-1] = 1 - betaK^step_i for tensor i (torch keeps
+ * one step count per parameter; a parameter that skipped steps has its own). */
 typedef struct {
   void* const* params; const void* const* grads; void* const* exp_avg; void* const* exp_avg_sq;
   const int64_t* numel; const int32_t* chunk_tensor; const int32_t* chunk_offset;
   int32_t n_chunks;
-  float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, max_norm;
+  const float* bias_corrections;   /* device, [n_tensors][2] */
+  float lr, beta1, beta2, eps, weight_decay, max_norm;
   float* partial;      /* [n_chunks] scratch */
   float* norm_out;     /* [2] */
 } idf_clip_adamw_args;

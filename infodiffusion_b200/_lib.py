@@ -78,8 +78,9 @@ class ClipAdamWArgs(C.Structure):
         ("params", C.c_void_p), ("grads", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
         ("numel", C.c_void_p), ("chunk_tensor", C.c_void_p), ("chunk_offset", C.c_void_p),
         ("n_chunks", C.c_int32),
+        ("bias_corrections", C.c_void_p),
         ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
-        ("bias_correction1", C.c_float), ("bias_correction2", C.c_float), ("max_norm", C.c_float),
+        ("max_norm", C.c_float),
         ("partial", C.c_void_p), ("norm_out", C.c_void_p),
     ]
 

@@ -392,13 +392,13 @@ int idf_clip_adamw(const idf_clip_adamw_args* a, idf_stream_t stream) {
   if (a->n_chunks < 0 || (a->n_chunks > 0 && (!a->params || !a->grads || !a->exp_avg || !a->exp_avg_sq || !a->numel ||
                                               !a->chunk_tensor || !a->chunk_offset || !a->partial || !a->norm_out)))
     return fail(IDF_ERR_ARG, "clip_adamw: bad tables");
-  if (!(a->bias_correction1 > 0.f) || !(a->bias_correction2 > 0.f)) return fail(IDF_ERR_ARG, "clip_adamw: bias corrections must be > 0");
+  if (a->n_chunks > 0 && a->bias_corrections == nullptr) return fail(IDF_ERR_ARG, "clip_adamw: bias_corrections table missing");
   ClipAdamWParams p;
   p.params = a->params; p.grads = a->grads; p.exp_avg = a->exp_avg; p.exp_avg_sq = a->exp_avg_sq;
   p.numel = reinterpret_cast<const long long*>(a->numel); p.chunk_tensor = a->chunk_tensor; p.chunk_offset = a->chunk_offset;
   p.n_chunks = a->n_chunks;
   p.lr = a->lr; p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps; p.weight_decay = a->weight_decay;
-  p.bias_correction1 = a->bias_correction1; p.bias_correction2 = a->bias_correction2; p.max_norm = a->max_norm;
+  p.bias_corrections = a->bias_corrections; p.max_norm = a->max_norm;
   p.partial = a->partial; p.norm_out = a->norm_out;
   cudaError_t e = launch_clip_adamw(p, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "clip_adamw launch");

@@ -77,7 +77,8 @@ struct ClipAdamWParams {
   void* const* params; const void* const* grads; void* const* exp_avg; void* const* exp_avg_sq;
   const long long* numel; const int* chunk_tensor; const int* chunk_offset;
   int n_chunks;
-  float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, max_norm;
+  const float* bias_corrections;
+  float lr, beta1, beta2, eps, weight_decay, max_norm;
   float* partial; float* norm_out;
 };
 cudaError_t launch_clip_adamw(const ClipAdamWParams& p, cudaStream_t stream);

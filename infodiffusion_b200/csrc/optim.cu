@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(kOptThreads) adamw_kernel(const ClipAdamWParam
   float* v = static_cast<float*>(p.exp_avg_sq[ti]) + off;
   const float coef = p.norm_out[1];
   const float decay = 1.0f - p.lr * p.weight_decay;
-  const float step_size = p.lr / p.bias_correction1;
-  const float inv_sqrt_bc2 = rsqrtf(p.bias_correction2);
+  const float step_size = p.lr / p.bias_corrections[2 * ti];          // per tensor: torch keeps one step count per parameter
+  const float inv_sqrt_bc2 = rsqrtf(p.bias_corrections[2 * ti + 1]);
   auto upd = [&](float gi, float& mi, float& vi, float& wi) {
     gi *= coef;
     mi = fmaf(p.beta1, mi, (1.0f - p.beta1) * gi);

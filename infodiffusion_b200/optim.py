@@ -54,7 +54,9 @@ class ClipAdamW(torch.optim.Optimizer):
                   numel=i64([p.numel() for p in ps]), ct=i32(ct), co=i32(co),
                   partial=torch.zeros(max(len(ct), 1), dtype=torch.float32, device=dev),
                   grads_host=torch.zeros(len(ps), dtype=torch.int64).pin_memory(),
-                  grads=torch.zeros(len(ps), dtype=torch.int64, device=dev))
+                  grads=torch.zeros(len(ps), dtype=torch.int64, device=dev),
+                  bc_host=torch.zeros(len(ps), 2, dtype=torch.float32).pin_memory(),
+                  bc=torch.zeros(len(ps), 2, dtype=torch.float32, device=dev))
         self._tables[gi] = tb
         return tb
 
@@ -75,6 +77,8 @@ class ClipAdamW(torch.optim.Optimizer):
             raise NotImplementedError("global-norm clipping across several param groups")
         for gi, group, ps in groups:
             tb = self._group_tables(gi, ps)
+            if tb.get("staged") is not None:
+                tb["staged"].synchronize()                # the previous step's async copies read the pinned tables
             gh = tb["grads_host"]
             for i, p in enumerate(ps):
                 g = p.grad
@@ -82,16 +86,28 @@ class ClipAdamW(torch.optim.Optimizer):
                     g = p.grad = g.float().contiguous()
                 gh[i] = g.data_ptr()
             tb["grads"].copy_(gh, non_blocking=True)
-            group["step"] = int(group.get("step", 0)) + 1
             b1, b2 = group["betas"]
+            steps = []
+            for p in ps:                                   # one step count per parameter, like torch.optim.AdamW
+                st = self.state[p]
+                st["step"] = st.get("step", 0) + 1
+                steps.append(st["step"])
+            bch = tb["bc_host"]
+            if min(steps) == max(steps):
+                bch[:, 0] = 1.0 - b1 ** steps[0]
+                bch[:, 1] = 1.0 - b2 ** steps[0]
+            else:
+                bch.copy_(torch.tensor([[1.0 - b1 ** k, 1.0 - b2 ** k] for k in steps], dtype=torch.float32))
+            tb["bc"].copy_(bch, non_blocking=True)
+            tb["staged"] = torch.cuda.Event()
+            tb["staged"].record(torch.cuda.current_stream(dev))
             norm_out = torch.empty(2, dtype=torch.float32, device=dev)
             a = ClipAdamWArgs()
             a.params, a.grads, a.exp_avg, a.exp_avg_sq = (tb[k].data_ptr() for k in ("params", "grads", "m", "v"))
             a.numel, a.chunk_tensor, a.chunk_offset = tb["numel"].data_ptr(), tb["ct"].data_ptr(), tb["co"].data_ptr()
             a.n_chunks = tb["n"]
             a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = group["lr"], b1, b2, group["eps"], group["weight_decay"]
-            a.bias_correction1 = 1.0 - b1 ** group["step"]
-            a.bias_correction2 = 1.0 - b2 ** group["step"]
+            a.bias_corrections = tb["bc"].data_ptr()
             a.max_norm = self.max_norm
             a.partial, a.norm_out = tb["partial"].data_ptr(), norm_out.data_ptr()
             _lib.check(lib.idf_clip_adamw(C.byref(a), stream))

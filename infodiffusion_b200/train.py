@@ -425,11 +425,60 @@ def run_backward(plan) -> None:
 
 def fused_param_grads(plan) -> List[Optional[torch.Tensor]]:
     """Gradients of plan.pindex.params (None where the conv stack contributes nothing), as views of a fresh
-    copy of the flat gradient buffer."""
+    copy of the flat gradient buffer.  With a GradSync installed the flat buffer's all-reduce is started here,
+    i.e. the backbone's gradients travel over NVLink while the encoder's backward kernels are still running."""
     st = _state(plan)
     flat = st.grad_flat.clone()
     views = plan.pindex.views(flat)
+    if _grad_sync is not None:
+        _grad_sync.reduce(flat, [p for p, has in zip(plan.pindex.params, st.has_grad) if has])
     return [v if has else None for v, has in zip(views, st.has_grad)]
+
+
+class GradSync:
+    """Data-parallel gradient exchange overlapped with the backward pass (training row).
+
+    Every conv-stack backward hands its flat fp32 gradient buffer to `reduce`, which launches one asynchronous
+    all-reduce (average) on it; `finish` waits for those and all-reduces the few remaining gradients (time / latent
+    MLPs, fc heads) in one more flat buffer.  Gradient clipping and the optimizer run after `finish`, so the
+    global norm is identical on all ranks with no further collective."""
+
+    def __init__(self, world: int):
+        import torch.distributed as dist
+        self.world = world
+        self.avg = dist.get_backend() == "nccl"            # gloo has no AVG: sum, then divide
+        self.pending: List = []
+        self.covered: set = set()
+
+    def reduce(self, flat: torch.Tensor, params: Sequence[nn.Parameter]) -> None:
+        import torch.distributed as dist
+        op = dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM
+        self.pending.append((dist.all_reduce(flat, op=op, async_op=True), flat))
+        self.covered.update(id(p) for p in params)
+
+    def finish(self, params: Sequence[nn.Parameter]) -> None:
+        import torch.distributed as dist
+        rest = [p.grad for p in params if p.grad is not None and id(p) not in self.covered]
+        if rest:
+            buf = torch._utils._flatten_dense_tensors(rest)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            buf.div_(self.world)
+            for g, f in zip(rest, torch._utils._unflatten_dense_tensors(buf, rest)):
+                g.copy_(f)
+        for work, flat in self.pending:
+            work.wait()
+            if not self.avg:
+                flat.div_(self.world)
+        self.pending.clear()
+        self.covered.clear()
+
+
+_grad_sync: Optional[GradSync] = None
+
+
+def set_grad_sync(sync: Optional[GradSync]) -> None:
+    global _grad_sync
+    _grad_sync = sync
 
 
 def collect_param_grads(plan) -> Dict[nn.Parameter, torch.Tensor]:

@@ -59,6 +59,19 @@ def _worker(rank: int, world: int, port: int, total: int, tmp: str):
         assert torch.allclose(ps[0].grad, torch.full((3, 2), mean))
         assert ps[1].grad is None
         assert torch.allclose(ps[2].grad, torch.arange(2.0) * mean)
+        # overlapped variant: the conv-stack backward hands its flat buffer to GradSync.reduce, finish() covers the rest
+        from infodiffusion_b200.train import GradSync
+        sync = GradSync(world)
+        qs = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(2, 2)), torch.nn.Parameter(torch.zeros(3))]
+        flat = torch.arange(8.0) * (rank + 1)
+        qs[0].grad, qs[1].grad = flat[:4], flat[4:].view(2, 2)
+        qs[2].grad = torch.full((3,), 10.0 * (rank + 1))
+        sync.reduce(flat, qs[:2])
+        sync.finish(qs)
+        assert torch.allclose(qs[0].grad, torch.arange(4.0) * mean)
+        assert torch.allclose(qs[1].grad, (torch.arange(4.0) + 4).view(2, 2) * mean)
+        assert torch.allclose(qs[2].grad, torch.full((3,), 10.0 * mean))
+        assert not sync.pending and not sync.covered
         with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:
