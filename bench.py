@@ -209,7 +209,7 @@ def train_throughput(a, dev, world, rank, steps=6, warmup=3):
     set_grad_sync(None)
     flops = 3 * (15.318e9 + 11.774e9) * B * world * steps      # fwd + bwd ~ 3 x fwd
     return {"metric": "train_samples_per_sec", "value": world * B * steps / (ms / 1000.0), "unit": "samples/s",
-            "ms_per_step": ms / steps, "batch_per_gpu": B, "n_gpus": world, "final_loss": float(loss),
+            "ms_per_step": ms / steps, "batch_per_gpu": B, "n_gpus": world, "final_loss": float(loss.detach()),
             "tflops": flops / (ms / 1000.0) / 1e12, "idf_launches_per_step": (_lib.launches() - l0) // steps,
             "config": "InfoDiff a_dim 256, T=1000, bf16 kernels / fp32 params, dropout 0.1, fused clip(1.0)+AdamW(1e-4, "
                       "wd 1e-5), data-parallel all-reduce overlapped with backward" + (" (NCCL)" if world > 1 else " (single GPU)")}
