@@ -104,6 +104,15 @@ typedef struct {
    *   B[k][c] = the same over its rows in the following image (only written if the window straddles).
    * Consumed by idf_adagn_silu_fwd (stats0 / stats1).                                             */
   float* stats_out;
+  /* optional: AdaGN (+SiLU) of the CONSUMED activation fused into the A-operand path (inference): k-blocks with
+   * kb_xf[k] >= 0 are read as bf16(act(A*x + B)), (A, B) = xf_coef[image][kb_xf[k] + channel - kb_c0[k]], act = SiLU
+   * if xf_silu.  xf_coef: fp32 [batch][xf_ctot][2] written by idf_adagn_coef.  Pad rows stay zero.  k-blocks of the
+   * same (source, slice) must agree.  xf_coef == NULL disables (kb_xf ignored).  Replaces the separate
+   * GroupNorm/modulate/SiLU pass in front of every conv of modules.py:214-231, 265-291, 335-345, 132-136. */
+  const float* xf_coef;
+  int32_t xf_ctot;
+  int32_t xf_silu;
+  int32_t kb_xf[IDF_CONV_MAX_KB];
 } idf_conv_desc;
 
 typedef struct idf_conv_plan idf_conv_plan;
@@ -162,6 +171,10 @@ typedef struct {
   float* save_coef;
 } idf_adagn_args;
 int idf_adagn_silu_fwd(const idf_adagn_args* args, idf_stream_t stream);
+/* Coefficients only: coef_out[n][c] = (A, B) with AdaGN(x)[n, c, :, :] = A*x + B (before the activation), from the
+ * producers' window records (stats0 / stats1 required).  Feeds idf_conv_desc.xf_coef; out / src pointers of
+ * `args` are not dereferenced. */
+int idf_adagn_coef(const idf_adagn_args* args, float* coef_out, idf_stream_t stream);
 
 /* Backward of idf_adagn_silu_fwd (streaming variant: stats0/stats1 required).
  *   dx0 / dx1 : gradient w.r.t. the sources (bf16 pad-flat; added to the buffer if acc0 / acc1)

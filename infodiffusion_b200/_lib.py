@@ -43,6 +43,7 @@ class ConvDesc(C.Structure):
         ("coef", C.c_void_p),
         ("step_ptr", C.c_void_p),
         ("stats_out", C.c_void_p),
+        ("xf_coef", C.c_void_p), ("xf_ctot", C.c_int32), ("xf_silu", C.c_int32), ("kb_xf", C.c_int32 * IDF_CONV_MAX_KB),
     ]
 
 
@@ -110,6 +111,7 @@ SIGNATURES = {
     "idf_wgrad_plan_create": (C.c_int, [C.POINTER(WgradDesc), C.POINTER(C.c_void_p)]),
     "idf_wgrad_plan_destroy": (C.c_int, [C.c_void_p]),
     "idf_wgrad_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "idf_adagn_coef": (C.c_int, [C.POINTER(AdaGNArgs), C.c_void_p, C.c_void_p]),
     "idf_adagn_silu_fwd": (C.c_int, [C.POINTER(AdaGNArgs), C.c_void_p]),
     "idf_adagn_bwd_ws_floats": (C.c_int64, [C.c_int32, C.c_int32]),
     "idf_adagn_silu_bwd": (C.c_int, [C.POINTER(AdaGNBwdArgs), C.c_void_p]),

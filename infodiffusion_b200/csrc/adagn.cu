@@ -236,40 +236,23 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_kernel(const AdaGNParams p)
 constexpr int kRing = 3;            // bulk-copy stages per CTA (3 x 16 KB: three CTAs per SM, 144 KB in flight)
 constexpr int kRingStageBytes = 16384;
 
-__global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNParams p) {
-  extern __shared__ __align__(128) uint8_t ring_raw[];
-  __shared__ __align__(8) uint64_t s_full[kRing];
-  __shared__ float2 s_sub[4][kMaxC];
-  __shared__ float s_tot[2 * kMaxC];
-  __shared__ float s_mean[32], s_rstd[32];
-  __shared__ float2 s_ab[kMaxC];
-  const int n = blockIdx.y;
+// Per-channel coefficients of image n: GroupNorm statistics from the producers' 32-row window records, folded with
+// gamma / beta and the two modulations into y = A*x + B.  All kAdaThreads threads of the block take part.
+struct CoefShared {
+  float2 sub[4][kMaxC];
+  float tot[2 * kMaxC];
+  float mean[32], rstd[32];
+  float2 ab[kMaxC];
+};
+__device__ __forceinline__ void fold_coefficients(const AdaGNParams& p, int n, CoefShared& sh, bool save) {
   const int t = threadIdx.x;
   const int C = p.C;
   const int R = p.rows_per_img;
-
-  // ---- start streaming the slice right away: the ring fills while the coefficients are computed
-  const long long row_base = static_cast<long long>(n) * R;
-  const int r_begin = blockIdx.x * p.slice_rows;
-  const int r_end = min(R, r_begin + p.slice_rows);
-  const int RB = p.block_rows;                                  // rows per stage
-  const int nblk = (r_end - r_begin + RB - 1) / RB;
-  const uint32_t stage_bytes = static_cast<uint32_t>(RB) * C * 2;
-  auto issue = [&](int blk) {                                   // thread 0 only
-    const int st = blk % kRing;
-    const int r0 = r_begin + blk * RB;
-    const int nr = min(RB, r_end - r0);
-    const uint32_t b0 = static_cast<uint32_t>(nr) * p.c0 * 2, b1 = static_cast<uint32_t>(nr) * p.c1 * 2;
-    mbar_arrive_expect_tx(&s_full[st], b0 + b1);
-    bulk_load(ring_raw + st * stage_bytes, p.src0 + (row_base + r0) * p.c0, b0, &s_full[st]);
-    if (b1) bulk_load(ring_raw + st * stage_bytes + RB * p.c0 * 2, p.src1 + (row_base + r0) * p.c1, b1, &s_full[st]);
-  };
-  if (t == 0) {
-    for (int i = 0; i < kRing; ++i) mbar_init(&s_full[i], 1);
-    fence_mbar_init();
-    for (int b = 0; b < kRing && b < nblk; ++b) issue(b);
-  }
-
+  float2 (&s_sub)[4][kMaxC] = sh.sub;
+  float (&s_tot)[2 * kMaxC] = sh.tot;
+  float (&s_mean)[32] = sh.mean;
+  float (&s_rstd)[32] = sh.rstd;
+  float2 (&s_ab)[kMaxC] = sh.ab;
   // per-channel totals over the 32-row window records that intersect image n.  All 256 threads take
   // part: thread -> (channel, sub-sequence of windows), loads issued four at a time; the order of every
   // addition is a function of (n, geometry) only, so the result is deterministic.
@@ -339,10 +322,54 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
       B = B * sc + sh;
     }
     s_ab[ch] = make_float2(A, B);
-    if (p.save_coef != nullptr && blockIdx.x == 0)
+    if (p.save_coef != nullptr && save)
       reinterpret_cast<float4*>(p.save_coef)[static_cast<long long>(n) * C + ch] = make_float4(A, B, s_mean[g], s_rstd[g]);
   }
   __syncthreads();
+
+}
+
+// coefficients only (consumer convolution applies them to its A operand): one block per image
+__global__ void __launch_bounds__(kAdaThreads) adagn_coef_kernel(const AdaGNParams p, float2* __restrict__ coef_out) {
+  __shared__ CoefShared sh;
+  const int n = blockIdx.x;
+  fold_coefficients(p, n, sh, true);
+  for (int ch = threadIdx.x; ch < p.C; ch += kAdaThreads) coef_out[static_cast<long long>(n) * p.C + ch] = sh.ab[ch];
+}
+
+__global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNParams p) {
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  __shared__ __align__(8) uint64_t s_full[kRing];
+  __shared__ CoefShared sh;
+  const int n = blockIdx.y;
+  const int t = threadIdx.x;
+  const int C = p.C;
+  const int R = p.rows_per_img;
+
+  // ---- start streaming the slice right away: the ring fills while the coefficients are computed
+  const long long row_base = static_cast<long long>(n) * R;
+  const int r_begin = blockIdx.x * p.slice_rows;
+  const int r_end = min(R, r_begin + p.slice_rows);
+  const int RB = p.block_rows;                                  // rows per stage
+  const int nblk = (r_end - r_begin + RB - 1) / RB;
+  const uint32_t stage_bytes = static_cast<uint32_t>(RB) * C * 2;
+  auto issue = [&](int blk) {                                   // thread 0 only
+    const int st = blk % kRing;
+    const int r0 = r_begin + blk * RB;
+    const int nr = min(RB, r_end - r0);
+    const uint32_t b0 = static_cast<uint32_t>(nr) * p.c0 * 2, b1 = static_cast<uint32_t>(nr) * p.c1 * 2;
+    mbar_arrive_expect_tx(&s_full[st], b0 + b1);
+    bulk_load(ring_raw + st * stage_bytes, p.src0 + (row_base + r0) * p.c0, b0, &s_full[st]);
+    if (b1) bulk_load(ring_raw + st * stage_bytes + RB * p.c0 * 2, p.src1 + (row_base + r0) * p.c1, b1, &s_full[st]);
+  };
+  if (t == 0) {
+    for (int i = 0; i < kRing; ++i) mbar_init(&s_full[i], 1);
+    fence_mbar_init();
+    for (int b = 0; b < kRing && b < nblk; ++b) issue(b);
+  }
+
+  fold_coefficients(p, n, sh, blockIdx.x == 0);
+  const float2 (&s_ab)[kMaxC] = sh.ab;
 
   // ---------------------------------------------------------------- streaming sweep
   // The slice is pulled through a ring of kRing shared-memory stages by bulk-async copies (one per
@@ -403,6 +430,43 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
     __syncthreads();                                            // everyone is done reading this stage
     if (t == 0 && blk + kRing < nblk) issue(blk + kRing);
   }
+}
+
+static cudaError_t fill_params(const idf_adagn_args& a, AdaGNParams& p);
+
+cudaError_t launch_adagn_coef(const idf_adagn_args& a, float* coef_out, cudaStream_t stream) {
+  AdaGNParams p;
+  cudaError_t e = fill_params(a, p);
+  if (e != cudaSuccess) return e;
+  if (p.stats0 == nullptr || (p.c1 != 0 && p.stats1 == nullptr) || a.dropout_p > 0.f) return cudaErrorInvalidValue;
+  p.save_coef = nullptr;
+  adagn_coef_kernel<<<a.batch, kAdaThreads, 0, stream>>>(p, reinterpret_cast<float2*>(coef_out));
+  return cudaGetLastError();
+}
+
+static cudaError_t fill_params(const idf_adagn_args& a, AdaGNParams& p) {
+  p.src0 = static_cast<const bf16*>(a.src0);
+  p.src1 = static_cast<const bf16*>(a.src1);
+  p.out = static_cast<bf16*>(a.out);
+  p.c0 = a.c0;
+  p.c1 = (a.src1 || a.stats1) ? a.c1 : 0;
+  p.C = p.c0 + p.c1;
+  p.H = a.H; p.W = a.W; p.Hp = a.H + 1; p.Wp = a.W + 1;
+  p.rows_per_img = p.Hp * p.Wp;
+  p.gamma = a.gamma; p.beta = a.beta; p.eps = a.eps;
+  p.mod_t = a.mod_t; p.mod_t_step_stride = a.mod_t_step_stride; p.mod_t_batch_stride = a.mod_t_batch_stride;
+  p.mod_z = a.mod_z; p.mod_z_step_stride = a.mod_z_step_stride; p.mod_z_batch_stride = a.mod_z_batch_stride;
+  p.step_ptr = a.step_ptr;
+  p.apply_silu = a.apply_silu;
+  if (p.C > kMaxC || p.C % 32 != 0 || p.c0 % 8 != 0 || p.c1 % 8 != 0 || a.batch <= 0) return cudaErrorInvalidValue;
+  p.stats0 = a.stats0;
+  p.stats1 = a.stats1;
+  p.slice_rows = 0;
+  p.drop_thr16 = 0; p.drop_scale = 1.f; p.drop_seed = reinterpret_cast<const unsigned long long*>(a.dropout_seed);
+  p.drop_layer = a.dropout_layer;
+  p.save_coef = a.save_coef;
+  p.stats_b_windows = (static_cast<long long>(a.batch) * p.rows_per_img + kBM - 1) / kBM * 4;
+  return cudaSuccess;
 }
 
 cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {

@@ -78,6 +78,7 @@ struct idf_conv_plan {
   int block_n;
   int mt;      // 128-row tiles per CTA work unit
   int grid;
+  bool xform;  // some halo group carries a fused AdaGN: launch the variant with transform warps
   int64_t tiles;
 };
 
@@ -141,7 +142,9 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   // ---- K-block table -> groups: per (source, 64-channel slice), taps whose row offsets lie within a
   //      few hundred rows of each other share one halo load (3x3 taps; the phases of a stride-2 conv
   //      are far apart and form separate groups).
-  struct Tap { int src, c0, off, kb; };
+  struct Tap { int src, c0, off, kb, xf; };
+  const bool use_xf = d->xf_coef != nullptr;
+  if (use_xf && (d->xf_ctot <= 0 || d->xf_ctot % 8 != 0)) { delete pl; return fail(IDF_ERR_ARG, "xf_ctot must be a positive multiple of 8"); }
   std::vector<Tap> taps;
   for (int k = 0; k < d->num_kb; ++k) {
     if (d->kb_src[k] < 0 || d->kb_src[k] >= d->n_src || d->kb_c0[k] < 0 || d->kb_c0[k] % 64 != 0 ||
@@ -149,7 +152,9 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
       delete pl;
       return fail(IDF_ERR_ARG, "k-block %d out of range", k);
     }
-    taps.push_back({d->kb_src[k], d->kb_c0[k], d->kb_rowoff[k], k});
+    const int xf = use_xf ? d->kb_xf[k] : -1;
+    if (xf >= 0 && (xf % 8 != 0 || xf + kBK > d->xf_ctot)) { delete pl; return fail(IDF_ERR_ARG, "k-block %d: kb_xf out of range", k); }
+    taps.push_back({d->kb_src[k], d->kb_c0[k], d->kb_rowoff[k], k, xf < 0 ? -1 : xf});
   }
   std::stable_sort(taps.begin(), taps.end(), [](const Tap& a, const Tap& b) {
     if (a.src != b.src) return a.src < b.src;
@@ -167,8 +172,9 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
     if (!same) {
       if (p.n_groups == kMaxGroups) { delete pl; return fail(IDF_ERR_ARG, "too many halo groups"); }
       g = p.n_groups++;
-      p.g_src[g] = t.src; p.g_c0[g] = t.c0; p.g_lo[g] = t.off; p.g_ntaps[g] = 0;
+      p.g_src[g] = t.src; p.g_c0[g] = t.c0; p.g_lo[g] = t.off; p.g_ntaps[g] = 0; p.g_xf[g] = t.xf;
     }
+    if (p.g_xf[g] != t.xf) { delete pl; return fail(IDF_ERR_ARG, "k-blocks of one (source, slice) disagree on kb_xf"); }
     p.t_rel[p.n_taps] = t.off - p.g_lo[g];
     p.t_kb[p.n_taps] = t.kb;
     p.n_taps++;
@@ -244,6 +250,11 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   p.noise = d->noise;
   p.coef = d->coef;
   p.step_ptr = d->step_ptr;
+  p.xf_coef = reinterpret_cast<const float2*>(d->xf_coef);
+  p.xf_ctot = d->xf_ctot;
+  p.xf_silu = d->xf_silu;
+  pl->xform = false;
+  for (int g = 0; g < p.n_groups; ++g) pl->xform = pl->xform || p.g_xf[g] >= 0;
   if (p.bias == nullptr) { delete pl; return fail(IDF_ERR_ARG, "bias is null"); }
   pl->block_n = d->block_n;
   pl->mt = mt;
@@ -265,7 +276,7 @@ int64_t idf_conv_plan_tiles(const idf_conv_plan* plan) {
 
 int idf_conv_run(const idf_conv_plan* plan, idf_stream_t stream) {
   if (plan == nullptr) return fail(IDF_ERR_ARG, "null plan");
-  cudaError_t e = launch_conv_igemm(plan->params, plan->block_n, plan->mt, plan->grid, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_conv_igemm(plan->params, plan->block_n, plan->mt, plan->xform, plan->grid, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "conv_igemm launch");
   return IDF_OK;
 }
@@ -335,6 +346,13 @@ int idf_wgrad_run(const idf_wgrad_plan* plan, idf_stream_t stream) {
   if (plan == nullptr) return fail(IDF_ERR_ARG, "null plan");
   cudaError_t e = launch_wgrad(plan->params, plan->grid, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "wgrad launch");
+  return IDF_OK;
+}
+
+int idf_adagn_coef(const idf_adagn_args* a, float* coef_out, idf_stream_t stream) {
+  if (a == nullptr || coef_out == nullptr) return fail(IDF_ERR_ARG, "null argument");
+  cudaError_t e = launch_adagn_coef(*a, coef_out, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "adagn_coef launch (needs stats0/stats1, C <= 256, C % 32 == 0)");
   return IDF_OK;
 }
 

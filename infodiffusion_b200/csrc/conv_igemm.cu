@@ -57,7 +57,7 @@ struct HaloCfg {
   static constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64
                                         : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
   static_assert(2 * ACC_COLS <= 512, "accumulators do not fit in TMEM");
-  static constexpr int NBARS = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int NBARS = 3 * A_STAGES + 2 * B_STAGES + 4;
   static constexpr int NI = (MT >= 2) ? 2 : 1;                        // UMMA issuing threads (accumulators split)
 };
 
@@ -194,8 +194,11 @@ __device__ __forceinline__ void epilogue_narrow(const ConvKernelParams& p, const
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <int BN, int MT>
-__global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant__ ConvKernelParams p) {
+// XF = true adds four "transform" warps (threads 384..511) between the A producer and the UMMA issuers: they
+// apply the consumer-side AdaGN (y = act(A*x + B), coefficients per image and channel) to the halo in place, so
+// the normalised activation is never written to or read from HBM.
+template <int BN, int MT, bool XF>
+__global__ void __launch_bounds__(XF ? 512 : 384, 1) conv_halo_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = HaloCfg<BN, MT>;
   constexpr int AS = Cfg::A_STAGES, BS = Cfg::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -208,7 +211,8 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
   uint64_t* b_empty = b_full + BS;
   uint64_t* tfull = b_empty + BS;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* a_ready = tempty + 2;                                 // XF: halo transformed (one arrive per transform warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + AS);
   const uint32_t tap_sa = smem_u32(a_full) + 512;               // per-tap descriptor offsets
   const uint32_t stage_sa = tap_sa + 256;                       // epilogue staging tiles
   const uint32_t bias_sa = stage_sa + kStageBytes;              // bias vector
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
     tma_prefetch_desc(&p.tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, Cfg::NI); }
+    for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, Cfg::NI); mbar_init(a_ready + s, 4); }
     for (int s = 0; s < BS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, Cfg::NI); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, Cfg::NI); mbar_init(tempty + a, 256); }
     fence_mbar_init();
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
-  if (warp >= 4) {   // bias -> shared memory
+  if (warp >= 4 && warp < 12) {   // bias -> shared memory
     const int nb = p.n_tiles * BN;
     for (int i = threadIdx.x - 128; i < nb; i += 256) sts32(bias_sa + 4 * i, __float_as_uint(__ldg(p.bias + i)));
   }
@@ -306,7 +310,8 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
         int t = 0;
         uint32_t rel = lds32(tap_sa);
         for (int g = 0; g < p.n_groups; ++g) {
-          mbar_wait(a_full + sa, pa);
+          mbar_wait((XF ? a_ready : a_full) + sa, pa);
+          if constexpr (XF) tc_fence_after();
           const uint32_t a_lo0 = umma_desc_lo(smem_u32(smA + sa * p.a_stage_bytes)) +
                                  static_cast<uint32_t>(m_begin * (kBM * 128 / 16));
           const int t_end = t + p.g_ntaps[g];
@@ -329,7 +334,70 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
         umma_commit(tfull + as);
       }
     }
-  } else if (warp >= 4) {
+  } else if (XF && warp >= 12) {
+    // ------------------------------------------------------------------ transform warps (fused AdaGN + SiLU)
+    // thread -> one physical 16-byte granule column gi and the rows rs, rs + 16, ...; all its rows share
+    // (row & 7), so under the 128-byte swizzle it always holds the same logical 8 channels gl = gi ^ (rs & 7).
+    const int tt = threadIdx.x - 384;
+    const int gi = tt & 7, rs = tt >> 3;
+    const int gl = gi ^ (rs & 7);
+    const float inv_wp = 1.0f / static_cast<float>(p.Wp), inv_hp = 1.0f / static_cast<float>(p.Hp);
+    const bool do_silu = p.xf_silu != 0;
+    int sa = 0;
+    uint32_t pa = 0;
+    for (int st = blockIdx.x; st < total; st += gridDim.x) {
+      const int ms = st / p.n_tiles;
+      const int64_t row0 = static_cast<int64_t>(ms) * (MT * kBM);
+      for (int g = 0; g < p.n_groups; ++g) {
+        const int cb = p.g_xf[g];
+        mbar_wait(a_full + sa, pa);
+        if (cb >= 0) {
+          const int nrows = MT * kBM + p.extra_rows[p.g_src[g]];
+          const int64_t rbase = row0 + p.g_lo[g];
+          const uint32_t base = smem_u32(smA + sa * p.a_stage_bytes) + static_cast<uint32_t>(gi * 16);
+          const float2* ctab = p.xf_coef + cb + gl * 8;
+          int cur = -1;
+          float A[8], B[8];
+#pragma unroll 2
+          for (int i = rs; i < nrows; i += 16) {
+            const int64_t r = rbase + i;
+            if (r < 0 || r >= p.rows) continue;                      // outside the tensor: TMA wrote zeros
+            const int rq = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_wp);
+            const int x = static_cast<int>(r) - rq * p.Wp;
+            const int img = __float2int_rd((static_cast<float>(rq) + 0.5f) * inv_hp);
+            const int y = rq - img * p.Hp;
+            if (x >= p.W || y >= p.H) continue;                      // pad row: holds zeros and must keep them
+            if (img != cur) {
+              cur = img;
+              const float4* c4 = reinterpret_cast<const float4*>(ctab + static_cast<int64_t>(img) * p.xf_ctot);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 c = __ldg(c4 + j);
+                A[2 * j] = c.x; B[2 * j] = c.y; A[2 * j + 1] = c.z; B[2 * j + 1] = c.w;
+              }
+            }
+            const uint32_t addr = base + static_cast<uint32_t>(i) * 128u;
+            const uint4 u = lds128(addr);
+            const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+            float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float v = fmaf(f[j], A[j], B[j]);
+              f[j] = do_silu ? silu_fast(v) : v;
+            }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+            sts128(addr, o);
+          }
+          fence_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready + sa);
+        if (++sa == AS) { sa = 0; pa ^= 1u; }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
     // ------------------------------------------------------------------ epilogue (8 warps)
     const int e = warp - 4;
     const int q = e & 3;      // TMEM lane quarter (== warp % 4)
@@ -426,33 +494,38 @@ __global__ void __launch_bounds__(384, 1) conv_halo_kernel(const __grid_constant
   }
 }
 
-template <int BN, int MT>
+template <int BN, int MT, bool XF>
 static cudaError_t launch_cfg(const ConvKernelParams& p, int grid, cudaStream_t stream) {
   using Cfg = HaloCfg<BN, MT>;
   const uint32_t smem = conv_smem_bytes(p.a_stage_bytes, Cfg::A_STAGES, Cfg::B_STAGES, Cfg::B_BYTES);
   static uint32_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, MT, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     attr_smem = smem;
   }
-  conv_halo_kernel<BN, MT><<<grid, 384, smem, stream>>>(p);
+  conv_halo_kernel<BN, MT, XF><<<grid, XF ? 512 : 384, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, int grid, cudaStream_t stream) {
+template <bool XF>
+static cudaError_t launch_sel(const ConvKernelParams& p, int block_n, int mt, int grid, cudaStream_t stream) {
   const int key = block_n * 10 + mt;
   switch (key) {
-    case 1281: return launch_cfg<128, 1>(p, grid, stream);
-    case 1282: return launch_cfg<128, 2>(p, grid, stream);
-    case 641: return launch_cfg<64, 1>(p, grid, stream);
-    case 642: return launch_cfg<64, 2>(p, grid, stream);
-    case 644: return launch_cfg<64, 4>(p, grid, stream);
-    case 161: return launch_cfg<16, 1>(p, grid, stream);
-    case 164: return launch_cfg<16, 4>(p, grid, stream);
+    case 1281: return launch_cfg<128, 1, XF>(p, grid, stream);
+    case 1282: return launch_cfg<128, 2, XF>(p, grid, stream);
+    case 641: return launch_cfg<64, 1, XF>(p, grid, stream);
+    case 642: return launch_cfg<64, 2, XF>(p, grid, stream);
+    case 644: return launch_cfg<64, 4, XF>(p, grid, stream);
+    case 161: return launch_cfg<16, 1, XF>(p, grid, stream);
+    case 164: return launch_cfg<16, 4, XF>(p, grid, stream);
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, bool xform, int grid, cudaStream_t stream) {
+  return xform ? launch_sel<true>(p, block_n, mt, grid, stream) : launch_sel<false>(p, block_n, mt, grid, stream);
 }
 
 // shared-memory need of a configuration (host side, for plan validation)

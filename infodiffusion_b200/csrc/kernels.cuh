@@ -48,6 +48,12 @@ struct alignas(64) ConvKernelParams {
   const float* noise;
   const float* coef;
   const int32_t* step_ptr;
+  // fused AdaGN (+SiLU) on the A operand: halo groups with g_xf[g] >= 0 are rewritten in shared memory as
+  // bf16(act(A*x + B)) with (A, B) = xf_coef[image][g_xf[g] + channel] before the MMAs read them
+  const float2* xf_coef;                // [batch][xf_ctot] (A, B)
+  int32_t xf_ctot;
+  int32_t xf_silu;
+  int32_t g_xf[kMaxGroups];             // channel base of the group's 64-channel slice in xf_coef, or -1
 };
 
 constexpr int kWgMaxUnits = 64;
@@ -63,7 +69,8 @@ struct alignas(64) WgradKernelParams {
 };
 cudaError_t launch_wgrad(const WgradKernelParams& p, int grid, cudaStream_t stream);
 
-cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, int grid, cudaStream_t stream);
+cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, bool xform, int grid, cudaStream_t stream);
+cudaError_t launch_adagn_coef(const idf_adagn_args& a, float* coef_out, cudaStream_t stream);
 uint32_t conv_config_smem(int block_n, int a_stage_bytes);
 cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream);
 cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, int num_sms, cudaStream_t stream);

@@ -64,6 +64,18 @@ class Act:
         return self.stats
 
 
+class VAct:
+    """The output of an AdaGN (+SiLU) that is never materialised: the raw source activation(s) plus per-image
+    (A, B) coefficients [B, C, 2]; the consuming conv applies bf16(act(A*x + B)) to its A operand in shared memory."""
+    __slots__ = ("srcs", "coef", "silu", "H", "C")
+
+    def __init__(self, srcs, coef, silu, H, C):
+        self.srcs, self.coef, self.silu, self.H, self.C = srcs, coef, silu, H, C
+
+
+FUSE_ADAGN = True      # inference plans: fold every AdaGN into its consumer conv (False: separate AdaGN kernels)
+
+
 class Workspace:
     """Pool of zero-initialised pad-flat buffers.  Buffers are only ever recycled for the same
     (H, C, phases) geometry, so the zero border written at allocation time is never disturbed
@@ -143,6 +155,7 @@ class Plan:
         self.B = batch
         self.device = device
         self.training = training
+        self.fuse_adagn = FUSE_ADAGN and not training
         self.ws = ws if ws is not None else Workspace(batch, device, recycle=not training)
         self.tape: List = []         # training: backward emitters, one per forward composite, replayed in reverse
         self.pindex: Optional[ParamIndex] = None   # training: flat parameter layout the packing gathers read
@@ -251,7 +264,9 @@ class Plan:
     def conv(self, srcs: Sequence[Act], kblocks: Sequence[Tuple[int, int, int]], wp: torch.Tensor,
              bias: torch.Tensor, H: int, cout: int, block_n: int, out: Optional[Act] = None,
              residual: Optional[Act] = None, epilogue: int = EPI_BF16, out_f32=None, x_io=None, noise=None,
-             coef=None, step=None, real_macs_per_row: Optional[int] = None, want_stats: bool = True) -> None:
+             coef=None, step=None, real_macs_per_row: Optional[int] = None, want_stats: bool = True,
+             xf: Optional[Tuple[torch.Tensor, bool, Sequence[int]]] = None) -> None:
+        """`xf` = (coefficients [B, Ctot, 2], silu?, per-k-block channel base or -1): fused AdaGN on the A operand."""
         d = ConvDesc()
         d.n_src = len(srcs)
         for i, s in enumerate(srcs):
@@ -280,6 +295,12 @@ class Plan:
             assert residual.H == H and residual.C == cout
             d.residual, d.res_ld = residual.t.data_ptr(), residual.C
         d.out_f32, d.x_io, d.noise, d.coef, d.step_ptr = _ptr(out_f32), _ptr(x_io), _ptr(noise), _ptr(coef), _ptr(step)
+        if xf is not None:
+            ctab, xsilu, kb_xf = xf
+            assert len(kb_xf) == len(kblocks) and ctab.shape[0] == self.B
+            d.xf_coef, d.xf_ctot, d.xf_silu = ctab.data_ptr(), ctab.shape[1], 1 if xsilu else 0
+            for k, v in enumerate(kb_xf):
+                d.kb_xf[k] = v
         h = C.c_void_p()
         _lib.check(self.lib.idf_conv_plan_create(C.byref(d), C.byref(h)))
         self.conv_plans.append(h)
@@ -287,6 +308,55 @@ class Plan:
         self.conv_tiles += int(self.lib.idf_conv_plan_tiles(h))
         macs = real_macs_per_row if real_macs_per_row is not None else 64 * len(kblocks) * cout
         self._emit("conv_igemm", self.lib.idf_conv_run, (h,), flops=2 * self.B * H * H * macs)
+
+    def norm(self, src0: Act, src1: Optional[Act], gn: nn.GroupNorm, silu: bool, mod_t=None, mod_z=None, step=None,
+             dropout: bool = False, mod_cols: Optional[int] = None):
+        """AdaGN of one or two (channel-concatenated) activations for a following conv.  Inference plans return a
+        VAct (coefficients only, applied inside the conv); otherwise the activation is materialised."""
+        if self.fuse_adagn and src0.has_stats and (src1 is None or src1.has_stats):
+            Cc = src0.C + (src1.C if src1 is not None else 0)
+            a = AdaGNArgs()
+            a.c0 = src0.C
+            a.stats0 = src0.stats.data_ptr()
+            if src1 is not None:
+                a.c1, a.stats1 = src1.C, src1.stats.data_ptr()
+            a.batch, a.H, a.W = self.B, src0.H, src0.H
+            gamma, beta = self.f32(lambda: pv(gn.weight)), self.f32(lambda: pv(gn.bias))
+            a.gamma, a.beta, a.eps = gamma.data_ptr(), beta.data_ptr(), float(gn.eps)
+            if mod_t is not None:
+                a.mod_t, a.mod_t_step_stride, a.mod_t_batch_stride = mod_t
+            if mod_z is not None:
+                a.mod_z, a.mod_z_step_stride, a.mod_z_batch_stride = mod_z
+            a.step_ptr = _ptr(step)
+            a.apply_silu = 1 if silu else 0
+            ctab = torch.zeros(self.B, Cc, 2, dtype=torch.float32, device=self.device)
+            self.keep += [a, ctab]
+            self._emit("adagn_coef", self.lib.idf_adagn_coef, (C.byref(a), ctab.data_ptr()))
+            return VAct([src0] if src1 is None else [src0, src1], ctab, silu, src0.H, Cc)
+        out = self.ws.alloc(src0.H, src0.C + (src1.C if src1 is not None else 0))
+        self.adagn(src0, src1, out, gn, silu, mod_t=mod_t, mod_z=mod_z, step=step, dropout=dropout, mod_cols=mod_cols)
+        return out
+
+    def done(self, a) -> None:
+        """Release a norm() result once its consumer conv has been emitted."""
+        if isinstance(a, Act):
+            self.ws.free(a)
+
+    @staticmethod
+    def _operand(src, offsets: Sequence[int]):
+        """(sources, k-blocks, kb_xf) of a conv over `src` (Act or VAct), K ordered (tap, concatenated channel)."""
+        parts = src.srcs if isinstance(src, VAct) else [src]
+        kb, kx = [], []
+        for off in offsets:
+            base = 0
+            for si, part in enumerate(parts):
+                assert part.C % 64 == 0
+                for c0 in range(0, part.C, 64):
+                    kb.append((si, c0, off))
+                    kx.append(base + c0)
+                base += part.C
+        xf = (src.coef, src.silu, kx) if isinstance(src, VAct) else None
+        return list(parts), kb, xf
 
     def adagn(self, src0: Act, src1: Optional[Act], out: Act, gn: nn.GroupNorm, silu: bool, mod_t=None, mod_z=None,
               step=None, dropout: bool = False, mod_cols: Optional[int] = None) -> None:
@@ -354,8 +424,8 @@ class Plan:
         """3x3 / stride 1 / pad 1 conv (+ residual, or + 1x1 shortcut conv over raw sources as extra K-blocks)."""
         cin, cout, H = src.C, conv.out_channels, src.H
         assert conv.in_channels == cin and cout % 64 == 0
-        kb = self.taps3x3(cin, H)
-        srcs = [src]
+        from .layout import tap_offsets3x3
+        srcs, kb, xf = self._operand(src, tap_offsets3x3(H, H))
         if shortcut is None:
             wp = lambda: pack_conv3x3(pv(conv.weight))
             bias = lambda: pv(conv.bias)
@@ -364,10 +434,15 @@ class Plan:
             wp = lambda: torch.cat([pack_conv3x3(pv(conv.weight)), pack_conv1x1(pv(sc_conv.weight))], dim=1)
             bias = lambda: (pv(conv.bias), pv(sc_conv.bias))                      # summed by f32()
             for r in raws:
-                srcs.append(r)
-                kb += [(len(srcs) - 1, c0, 0) for c0 in range(0, r.C, 64)]
+                si = next((i for i, s_ in enumerate(srcs) if s_ is r), None)   # a raw source may already be an operand
+                if si is None:
+                    srcs.append(r)
+                    si = len(srcs) - 1
+                kb += [(si, c0, 0) for c0 in range(0, r.C, 64)]
+                if xf is not None:
+                    xf[2].extend([-1] * (r.C // 64))
         out = self.ws.alloc(H, cout)
-        self.conv(srcs, kb, self.weight(wp), self.f32(bias), H, cout, self._bn(cout), out=out, residual=residual)
+        self.conv(srcs, kb, self.weight(wp), self.f32(bias), H, cout, self._bn(cout), out=out, residual=residual, xf=xf)
         if self.training:
             from . import train
             parts = [train.Part(src, conv.weight, "3x3", None)]
@@ -385,12 +460,12 @@ class Plan:
                 want_stats: bool = True) -> Act:
         """1x1 conv; several convs over the same input are stacked along N (q, k, v -> one GEMM)."""
         cout = sum(m.out_channels for m in convs)
-        kb = taps1x1(src.C)
+        srcs, kb, xf = self._operand(src, [0])
         out = self.ws.alloc(src.H, cout)
         wp = lambda: _pad_cols(torch.cat([pack_conv1x1(pv(m.weight)) for m in convs], dim=0), 64 * len(kb))
         bias = lambda: torch.cat([pv(m.bias) for m in convs], dim=0)
-        self.conv([src], kb, self.weight(wp), self.f32(bias), src.H, cout, self._bn(cout), out=out, residual=residual,
-                  want_stats=want_stats)
+        self.conv(srcs, kb, self.weight(wp), self.f32(bias), src.H, cout, self._bn(cout), out=out, residual=residual,
+                  want_stats=want_stats, xf=xf)
         if self.training:
             from . import train
             self.tape.append(lambda: train.bwd_conv1x1_stack(self, src, list(convs), out, residual))
@@ -424,10 +499,9 @@ class Plan:
     def attn_block(self, x: Act, blk: AttnBlock) -> Act:
         """GroupNorm -> fused qkv GEMM -> attention -> proj GEMM + residual (reference modules.py:145-164)."""
         Cc = x.C
-        an = self.ws.alloc(x.H, Cc)
-        self.adagn(x, None, an, blk.group_norm, silu=False)
+        an = self.norm(x, None, blk.group_norm, silu=False)
         qkv = self.conv1x1(an, [blk.proj_q, blk.proj_k, blk.proj_v], want_stats=False)
-        self.ws.free(an)
+        self.done(an)
         ao = self.ws.alloc(x.H, Cc)
         self.attention(qkv, ao, Cc)
         self.ws.free(qkv)
@@ -444,30 +518,27 @@ class Plan:
         assert cin == blk.in_ch
         cout = blk.out_ch
         x1 = xs[1] if len(xs) > 1 else None
-        a1 = self.ws.alloc(H, cin)
-        self.adagn(xs[0], x1, a1, blk.block1[0], silu=True)
+        a1 = self.norm(xs[0], x1, blk.block1[0], silu=True)
         h = self.conv3x3(a1, blk.block1[-1])
-        self.ws.free(a1)
-        a2 = self.ws.alloc(H, cout)
-        self.adagn(h, None, a2, blk.block2[0], silu=True, mod_t=mod_t, mod_z=mod_z, step=step, dropout=True,
-                   mod_cols=mod_cols)
-        self.ws.free(h)
-        last_in = a2
+        self.done(a1)
+        a2 = self.norm(h, None, blk.block2[0], silu=True, mod_t=mod_t, mod_z=mod_z, step=step, dropout=True,
+                       mod_cols=mod_cols)
+        last_in, last_raw = a2, h
         has_block3 = hasattr(blk, "block3")
         if has_block3:
-            h = self.conv3x3(a2, blk.block2[-1])
-            self.ws.free(a2)
-            a3 = self.ws.alloc(H, cout)
-            self.adagn(h, None, a3, blk.block3[0], silu=True, dropout=True)
-            self.ws.free(h)
-            last_in = a3
+            h2 = self.conv3x3(a2, blk.block2[-1])
+            self.done(a2)
+            self.ws.free(h)                       # raw input of a2 (a VAct reads it inside the conv just emitted)
+            a3 = self.norm(h2, None, blk.block3[0], silu=True, dropout=True)
+            last_in, last_raw = a3, h2
         last_conv = blk.block3[-1] if has_block3 else blk.block2[-1]
         if isinstance(blk.shortcut, nn.Conv2d):
             out = self.conv3x3(last_in, last_conv, shortcut=(blk.shortcut, list(xs)))
         else:
             assert len(xs) == 1
             out = self.conv3x3(last_in, last_conv, residual=xs[0])
-        self.ws.free(last_in)
+        self.done(last_in)
+        self.ws.free(last_raw)
         if free_inputs:
             for x in xs:
                 self.ws.free(x)
@@ -491,16 +562,17 @@ class Plan:
 
     def tail(self, h: Act, gn: nn.GroupNorm, tconv: nn.Conv2d, H: int, cout: int, epilogue: int, out_f32, **extra) -> None:
         """tail: AdaGN + 3x3 conv to `cout` (<= 16) channels, fp32 NCHW out or fused sampler update."""
-        ta = self.ws.alloc(H, h.C)
-        self.adagn(h, None, ta, gn, silu=True)
-        self.ws.free(h)
-        self.conv([ta], self.taps3x3(ta.C, H), self.weight(lambda: _pad_rows(pack_conv3x3(pv(tconv.weight)), 16)),
+        from .layout import tap_offsets3x3
+        ta = self.norm(h, None, gn, silu=True)
+        srcs, kb, xf = self._operand(ta, tap_offsets3x3(H, H))
+        self.conv(srcs, kb, self.weight(lambda: _pad_rows(pack_conv3x3(pv(tconv.weight)), 16)),
                   self.f32(lambda: _pad_rows(pv(tconv.bias), 16)), H, cout, 16, epilogue=epilogue, out_f32=out_f32,
-                  **extra)
+                  xf=xf, **extra)
         if self.training:
             from . import train
             self.tape.append(lambda: train.bwd_tail(self, ta, tconv, out_f32, cout))
-        self.ws.free(ta)
+        self.done(ta)
+        self.ws.free(h)
 
 
 # ------------------------------------------------------------------------------------------------

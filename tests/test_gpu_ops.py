@@ -648,3 +648,94 @@ def test_clip_adamw_matches_torch():
         assert abs(float(o_mine.total_norm) - float(want_norm)) <= 1e-5 * float(want_norm)
         for pr, pm in zip(ref, mine):
             assert_close(pm.detach(), pr.detach(), rel_l2=1e-6, max_rel=1e-4, what=f"adamw step {it}")
+
+
+@pytest.mark.parametrize("c0,c1,cout,H,B,k,silu,mt,sc", [
+    (64, 0, 64, 16, 3, 3, True, 0, False), (128, 0, 128, 8, 5, 3, True, 0, False), (128, 64, 64, 16, 2, 3, True, 0, True),
+    (128, 128, 128, 8, 3, 3, True, 0, True), (128, 0, 384, 16, 2, 1, False, 0, False), (64, 0, 64, 32, 6, 3, True, 4, False),
+    (128, 0, 128, 16, 9, 3, True, 2, False), (64, 0, 3, 16, 3, 3, True, 0, False), (64, 0, 64, 64, 3, 3, True, 0, False)])
+def test_conv_with_fused_adagn_equals_adagn_then_conv(lib, c0, c1, cout, H, B, k, silu, mt, sc):
+    """idf_conv with xf_coef (AdaGN + SiLU applied to the A operand in shared memory) against the two-kernel path
+    idf_adagn_silu_fwd -> idf_conv on the same inputs: the transform performs the same fp32 arithmetic and the same
+    bf16 rounding, so the results are bitwise identical.  Covers concatenated sources, an untransformed 1x1
+    shortcut over the raw sources, 1x1 convs, the narrow fp32 epilogue and MT > 1 work units."""
+    from infodiffusion_b200 import layout
+    from infodiffusion_b200._lib import AdaGNArgs
+    g = torch.Generator(device=DEV).manual_seed(c0 + c1 + cout + H + k)
+    Cc = c0 + c1
+    x0 = rbf(torch.randn(B, c0, H, H, device=DEV, generator=g) * 1.5 + 0.3)
+    x1 = rbf(torch.randn(B, c1, H, H, device=DEV, generator=g) * 0.7 - 0.2) if c1 else None
+    s0, s1 = pf(x0), (pf(x1) if c1 else None)
+    gamma = 1 + 0.1 * torch.randn(Cc, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(Cc, device=DEV, generator=g)
+    zz = 0.3 * torch.randn(B, 2 * Cc, device=DEV, generator=g)
+    a = AdaGNArgs()
+    a.src0, a.c0 = s0.data_ptr(), c0
+    st0 = tile_partials(s0, B, H, H)
+    a.stats0 = st0.data_ptr()
+    if c1:
+        a.src1, a.c1 = s1.data_ptr(), c1
+        st1 = tile_partials(s1, B, H, H)
+        a.stats1 = st1.data_ptr()
+    normed = torch.zeros(B * (H + 1) * (H + 1), Cc, device=DEV, dtype=BF)
+    a.out, a.batch, a.H, a.W = normed.data_ptr(), B, H, H
+    a.gamma, a.beta, a.eps = gamma.data_ptr(), beta.data_ptr(), 1e-5
+    a.mod_z, a.mod_z_step_stride, a.mod_z_batch_stride = zz.data_ptr(), 0, 2 * Cc
+    a.apply_silu = 1 if silu else 0
+    check(lib.idf_adagn_silu_fwd(C.byref(a), stream()))
+    coef = torch.zeros(B, Cc, 2, device=DEV)
+    check(lib.idf_adagn_coef(C.byref(a), coef.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    # weights
+    cpad = 16 if cout < 64 else cout
+    w = rbf(torch.randn(cout, Cc, k, k, device=DEV, generator=g) * (2.0 / (k * k * Cc)) ** 0.5)
+    wp = layout.pack_conv3x3(w) if k == 3 else layout.pack_conv1x1(w)
+    offs = layout.tap_offsets3x3(H, H) if k == 3 else [0]
+    bias = torch.randn(cpad, device=DEV, generator=g)
+    # unfused: one materialised source
+    kb_ref = [(0, c, off) for off in offs for c in range(0, Cc, 64)]
+    srcs_ref = [normed]
+    # fused: raw sources + coefficient bases
+    srcs, kb, kx = [s0] + ([s1] if c1 else []), [], []
+    for off in offs:
+        for c in range(0, c0, 64):
+            kb.append((0, c, off)); kx.append(c)
+        for c in range(0, c1, 64):
+            kb.append((1, c, off)); kx.append(c0 + c)
+    if sc:                                   # fused 1x1 shortcut over the RAW sources: no transform on those k-blocks
+        wsc = rbf(torch.randn(cout, Cc, 1, 1, device=DEV, generator=g) * (1.0 / Cc) ** 0.5)
+        wp = torch.cat([wp, layout.pack_conv1x1(wsc)], dim=1)
+        srcs_ref = [normed, s0] + ([s1] if c1 else [])
+        for c in range(0, c0, 64):
+            kb_ref.append((1, c, 0)); kb.append((0, c, 0)); kx.append(-1)
+        for c in range(0, c1, 64):
+            kb_ref.append((2, c, 0)); kb.append((1, c, 0)); kx.append(-1)
+    wp = layout.pad_rows(wp, cpad).to(BF).contiguous()
+    bn = 16 if cout < 64 else (128 if cout % 128 == 0 else 64)
+    extra = {}
+    if cout < 64:
+        out_ref, out_fused = torch.zeros(B, cout, H, H, device=DEV), torch.zeros(B, cout, H, H, device=DEV)
+        epi = 1
+    else:
+        epi = 0
+    from infodiffusion_b200._lib import IDF_CONV_MAX_KB
+    kbx = (C.c_int32 * IDF_CONV_MAX_KB)(*(kx + [0] * (IDF_CONV_MAX_KB - len(kx))))
+    if mt:
+        check(lib.idf_set_option(b"conv_force_mt", mt))
+    try:
+        if epi == 0:
+            ref = run_conv(lib, srcs_ref, kb_ref, wp, bias, B, H, cout, bn)
+            got = run_conv(lib, srcs, kb, wp, bias, B, H, cout, bn, xf_coef=coef, xf_ctot=Cc, xf_silu=int(silu), kb_xf=kbx)
+            assert pad_is_zero(got, B, H, H)
+        else:
+            run_conv(lib, srcs_ref, kb_ref, wp, bias, B, H, cout, bn, epilogue=1, out_f32=out_ref)
+            run_conv(lib, srcs, kb, wp, bias, B, H, cout, bn, epilogue=1, out_f32=out_fused, xf_coef=coef, xf_ctot=Cc,
+                     xf_silu=int(silu), kb_xf=kbx)
+            ref, got = out_ref, out_fused
+    finally:
+        if mt:
+            check(lib.idf_set_option(b"conv_force_mt", 0))
+    assert float(ref.float().abs().max()) > 0.1
+    assert torch.equal(got, ref), f"fused != unfused: max diff {float((got.float() - ref.float()).abs().max())}"
+    # the raw sources must be untouched (the transform happens in shared memory only)
+    assert torch.equal(s0, pf(x0))
