@@ -106,8 +106,8 @@ typedef struct {
   float* stats_out;
   /* optional: AdaGN (+SiLU) of the CONSUMED activation fused into the A-operand path (inference): k-blocks with
    * kb_xf[k] >= 0 are read as bf16(act(A*x + B)), (A, B) = xf_coef[image][kb_xf[k] + channel - kb_c0[k]], act = SiLU
-   * if xf_silu.  xf_coef: fp32 [batch][xf_ctot][2] written by idf_adagn_coef.  Pad rows stay zero.  k-blocks of the
-   * same (source, slice) must agree.  xf_coef == NULL disables (kb_xf ignored).  Replaces the separate
+   * if xf_silu.  xf_coef: fp32 [batch][xf_ctot][2] written by idf_adagn_coef.  Pad rows stay zero.  A slice may be
+   * read both transformed and raw (fused 1x1 shortcut).  xf_coef == NULL disables (kb_xf ignored).  Replaces the separate
    * GroupNorm/modulate/SiLU pass in front of every conv of modules.py:214-231, 265-291, 335-345, 132-136. */
   const float* xf_coef;
   int32_t xf_ctot;

@@ -159,6 +159,7 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   std::stable_sort(taps.begin(), taps.end(), [](const Tap& a, const Tap& b) {
     if (a.src != b.src) return a.src < b.src;
     if (a.c0 != b.c0) return a.c0 < b.c0;
+    if (a.xf != b.xf) return a.xf > b.xf;      // transformed and raw reads of one slice are separate halo loads
     return a.off < b.off;
   });
   p.n_src = d->n_src;
@@ -168,13 +169,12 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   for (size_t i = 0; i < taps.size(); ++i) {
     const Tap& t = taps[i];
     int g = p.n_groups - 1;
-    const bool same = g >= 0 && p.g_src[g] == t.src && p.g_c0[g] == t.c0 && (t.off - p.g_lo[g]) <= 248;
+    const bool same = g >= 0 && p.g_src[g] == t.src && p.g_c0[g] == t.c0 && p.g_xf[g] == t.xf && (t.off - p.g_lo[g]) <= 248;
     if (!same) {
       if (p.n_groups == kMaxGroups) { delete pl; return fail(IDF_ERR_ARG, "too many halo groups"); }
       g = p.n_groups++;
       p.g_src[g] = t.src; p.g_c0[g] = t.c0; p.g_lo[g] = t.off; p.g_ntaps[g] = 0; p.g_xf[g] = t.xf;
     }
-    if (p.g_xf[g] != t.xf) { delete pl; return fail(IDF_ERR_ARG, "k-blocks of one (source, slice) disagree on kb_xf"); }
     p.t_rel[p.n_taps] = t.off - p.g_lo[g];
     p.t_kb[p.n_taps] = t.kb;
     p.n_taps++;

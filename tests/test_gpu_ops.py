@@ -736,6 +736,9 @@ def test_conv_with_fused_adagn_equals_adagn_then_conv(lib, c0, c1, cout, H, B, k
         if mt:
             check(lib.idf_set_option(b"conv_force_mt", 0))
     assert float(ref.float().abs().max()) > 0.1
-    assert torch.equal(got, ref), f"fused != unfused: max diff {float((got.float() - ref.float()).abs().max())}"
+    if sc:      # raw and transformed k-blocks interleave differently: fp32 accumulation order differs, 1 bf16 ulp at most
+        assert_close(got.float(), ref.double(), rel_l2=1e-3, max_rel=1.6e-2, what="fused conv + shortcut")
+    else:
+        assert torch.equal(got, ref), f"fused != unfused: max diff {float((got.float() - ref.float()).abs().max())}"
     # the raw sources must be untouched (the transform happens in shared memory only)
     assert torch.equal(s0, pf(x0))
