@@ -194,11 +194,11 @@ __device__ __forceinline__ void epilogue_narrow(const ConvKernelParams& p, const
 }
 
 // ---------------------------------------------------------------------------------------------------
-// XF = true adds four "transform" warps (threads 384..511) between the A producer and the UMMA issuers: they
+// XF = true adds eight "transform" warps (threads 384..639) between the A producer and the UMMA issuers: they
 // apply the consumer-side AdaGN (y = act(A*x + B), coefficients per image and channel) to the halo in place, so
 // the normalised activation is never written to or read from HBM.
 template <int BN, int MT, bool XF>
-__global__ void __launch_bounds__(XF ? 512 : 384, 1) conv_halo_kernel(const __grid_constant__ ConvKernelParams p) {
+__global__ void __launch_bounds__(XF ? 640 : 384, 1) conv_halo_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = HaloCfg<BN, MT>;
   constexpr int AS = Cfg::A_STAGES, BS = Cfg::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(XF ? 512 : 384, 1) conv_halo_kernel(const __gr
     tma_prefetch_desc(&p.tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, Cfg::NI); mbar_init(a_ready + s, 4); }
+    for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, Cfg::NI); mbar_init(a_ready + s, 8); }
     for (int s = 0; s < BS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, Cfg::NI); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, Cfg::NI); mbar_init(tempty + a, 256); }
     fence_mbar_init();
@@ -336,54 +336,72 @@ __global__ void __launch_bounds__(XF ? 512 : 384, 1) conv_halo_kernel(const __gr
     }
   } else if (XF && warp >= 12) {
     // ------------------------------------------------------------------ transform warps (fused AdaGN + SiLU)
-    // thread -> one physical 16-byte granule column gi and the rows rs, rs + 16, ...; all its rows share
-    // (row & 7), so under the 128-byte swizzle it always holds the same logical 8 channels gl = gi ^ (rs & 7).
+    // 256 threads.  thread -> one physical 16-byte granule column gi and the rows rs, rs + 32, ...; all its rows
+    // share (row & 7), so under the 128-byte swizzle it always holds the same logical 8 channels gl = gi ^ (rs & 7).
+    // The 8 lanes of a row share the row bookkeeping: lane gi == 0 computes (valid, image) and broadcasts it.
     const int tt = threadIdx.x - 384;
     const int gi = tt & 7, rs = tt >> 3;
     const int gl = gi ^ (rs & 7);
+    const unsigned grp_mask = 0xffu << (lane & 24);
+    const int grp_lead = lane & 24;
     const float inv_wp = 1.0f / static_cast<float>(p.Wp), inv_hp = 1.0f / static_cast<float>(p.Hp);
     const bool do_silu = p.xf_silu != 0;
+    const float cs = do_silu ? 0.5f : 1.0f;          // SiLU(v) = h + h*tanh(h), h = v/2: fold the 1/2 into (A, B)
+    const int rows32 = static_cast<int>(p.rows);
     int sa = 0;
     uint32_t pa = 0;
     for (int st = blockIdx.x; st < total; st += gridDim.x) {
       const int ms = st / p.n_tiles;
-      const int64_t row0 = static_cast<int64_t>(ms) * (MT * kBM);
+      const int row0 = ms * (MT * kBM);
       for (int g = 0; g < p.n_groups; ++g) {
         const int cb = p.g_xf[g];
         mbar_wait(a_full + sa, pa);
         if (cb >= 0) {
           const int nrows = MT * kBM + p.extra_rows[p.g_src[g]];
-          const int64_t rbase = row0 + p.g_lo[g];
+          const int rbase = row0 + p.g_lo[g];
           const uint32_t base = smem_u32(smA + sa * p.a_stage_bytes) + static_cast<uint32_t>(gi * 16);
           const float2* ctab = p.xf_coef + cb + gl * 8;
           int cur = -1;
           float A[8], B[8];
 #pragma unroll 2
-          for (int i = rs; i < nrows; i += 16) {
-            const int64_t r = rbase + i;
-            if (r < 0 || r >= p.rows) continue;                      // outside the tensor: TMA wrote zeros
-            const int rq = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_wp);
-            const int x = static_cast<int>(r) - rq * p.Wp;
-            const int img = __float2int_rd((static_cast<float>(rq) + 0.5f) * inv_hp);
-            const int y = rq - img * p.Hp;
-            if (x >= p.W || y >= p.H) continue;                      // pad row: holds zeros and must keep them
-            if (img != cur) {
-              cur = img;
-              const float4* c4 = reinterpret_cast<const float4*>(ctab + static_cast<int64_t>(img) * p.xf_ctot);
+          for (int i = rs; i < nrows; i += 32) {
+            int info = -1;                                           // -1: leave the row alone
+            if (gi == 0) {
+              const int r = rbase + i;
+              if (r >= 0 && r < rows32) {                            // outside the tensor: TMA wrote zeros
+                const int rq = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_wp);
+                const int x = r - rq * p.Wp;
+                const int img = __float2int_rd((static_cast<float>(rq) + 0.5f) * inv_hp);
+                const int y = rq - img * p.Hp;
+                if (x < p.W && y < p.H) info = img;                  // pad rows hold zeros and must keep them
+              }
+            }
+            info = __shfl_sync(grp_mask, info, grp_lead);
+            if (info < 0) continue;
+            if (info != cur) {
+              cur = info;
+              const float4* c4 = reinterpret_cast<const float4*>(ctab + static_cast<int64_t>(info) * p.xf_ctot);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 c = __ldg(c4 + j);
-                A[2 * j] = c.x; B[2 * j] = c.y; A[2 * j + 1] = c.z; B[2 * j + 1] = c.w;
+                A[2 * j] = c.x * cs; B[2 * j] = c.y * cs; A[2 * j + 1] = c.z * cs; B[2 * j + 1] = c.w * cs;
               }
             }
             const uint32_t addr = base + static_cast<uint32_t>(i) * 128u;
             const uint4 u = lds128(addr);
             const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
             float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+            if (do_silu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float v = fmaf(f[j], A[j], B[j]);
-              f[j] = do_silu ? silu_fast(v) : v;
+              for (int j = 0; j < 8; ++j) {
+                const float h = fmaf(f[j], A[j], B[j]);
+                float th;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));     // (tanh.approx.f16x2 still issues two MUFU ops)
+                f[j] = fmaf(h, th, h);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], A[j], B[j]);
             }
             uint4 o;
             o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
@@ -505,7 +523,7 @@ static cudaError_t launch_cfg(const ConvKernelParams& p, int grid, cudaStream_t 
     if (e != cudaSuccess) return e;
     attr_smem = smem;
   }
-  conv_halo_kernel<BN, MT, XF><<<grid, XF ? 512 : 384, smem, stream>>>(p);
+  conv_halo_kernel<BN, MT, XF><<<grid, XF ? 640 : 384, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

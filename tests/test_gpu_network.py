@@ -316,3 +316,44 @@ def test_training_packing_and_gradient_gathers_are_exact(m1000):
         with torch.no_grad():
             m.load_state_dict(sd)
         m.eval()
+
+
+def test_fused_adagn_mode_matches_default(m10):
+    """engine.FUSE_ADAGN (AdaGN + SiLU applied to the conv's A operand in shared memory) is an alternative lowering
+    of the same network: eps, encoder outputs and a DDIM trajectory agree with the default lowering to bf16
+    rounding and stay within the stated tolerance of the oracle."""
+    from infodiffusion_b200 import engine
+    args, m, sd = m10
+    x, t, a = rand_inputs(2, 32, 10)
+    xd, td, ad = x.to(DEV), t.to(DEV), a.to(DEV)
+    base_eps = m.backbone(xd, td, ad)
+    base_a = m.encoder(xd)[0]
+    xT = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(3))
+    shape = tuple(xT.shape)
+    p0 = _proc(args, m, True)
+    p0.noise_fn = lambda idx, out: out.copy_(step_noise(idx, shape))
+    base_x0 = p0.sampling(2, xT=xT.to(DEV), a=ad)
+    engine.FUSE_ADAGN = True
+    try:
+        m.backbone.invalidate_plans()
+        m.encoder.invalidate_plans()
+        f_eps = m.backbone(xd, td, ad)
+        f_a = m.encoder(xd)[0]
+        plan = next(iter(m.backbone._plans().values()))
+        assert any(mt["tag"] == "adagn_coef" for mt in plan.meta) and not any(mt["tag"] == "adagn" for mt in plan.meta)
+        p1 = _proc(args, m, True)
+        p1.noise_fn = lambda idx, out: out.copy_(step_noise(idx, shape))
+        f_x0 = p1.sampling(2, xT=xT.to(DEV), a=ad)
+    finally:
+        engine.FUSE_ADAGN = False
+        m.backbone.invalidate_plans()
+        m.encoder.invalidate_plans()
+    with torch.no_grad():
+        ref = orc.aux_unet_forward(sd, x, t, a)
+    print(f"\n[parity] fused-AdaGN lowering: eps vs default {rel_l2(f_eps.cpu(), base_eps.cpu()):.3e}, vs oracle "
+          f"{rel_l2(f_eps.cpu(), ref):.3e}; encoder a vs default {rel_l2(f_a.cpu(), base_a.cpu()):.3e}; "
+          f"DDIM-10 x0 vs default {rel_l2(f_x0.cpu(), base_x0.cpu()):.3e}")
+    assert rel_l2(f_eps.cpu(), ref) < TOL_EPS
+    assert rel_l2(f_eps.cpu(), base_eps.cpu()) < 5e-3
+    assert rel_l2(f_a.cpu(), base_a.cpu()) < 5e-3
+    assert rel_l2(f_x0.cpu(), base_x0.cpu()) < 2e-3

@@ -656,8 +656,7 @@ def test_clip_adamw_matches_torch():
     (128, 0, 128, 16, 9, 3, True, 2, False), (64, 0, 3, 16, 3, 3, True, 0, False), (64, 0, 64, 64, 3, 3, True, 0, False)])
 def test_conv_with_fused_adagn_equals_adagn_then_conv(lib, c0, c1, cout, H, B, k, silu, mt, sc):
     """idf_conv with xf_coef (AdaGN + SiLU applied to the A operand in shared memory) against the two-kernel path
-    idf_adagn_silu_fwd -> idf_conv on the same inputs: the transform performs the same fp32 arithmetic and the same
-    bf16 rounding, so the results are bitwise identical.  Covers concatenated sources, an untransformed 1x1
+    idf_adagn_silu_fwd -> idf_conv on the same inputs.  Covers concatenated sources, an untransformed 1x1
     shortcut over the raw sources, 1x1 convs, the narrow fp32 epilogue and MT > 1 work units."""
     from infodiffusion_b200 import layout
     from infodiffusion_b200._lib import AdaGNArgs
@@ -738,7 +737,7 @@ def test_conv_with_fused_adagn_equals_adagn_then_conv(lib, c0, c1, cout, H, B, k
     assert float(ref.float().abs().max()) > 0.1
     if sc:      # raw and transformed k-blocks interleave differently: fp32 accumulation order differs, 1 bf16 ulp at most
         assert_close(got.float(), ref.double(), rel_l2=1e-3, max_rel=1.6e-2, what="fused conv + shortcut")
-    else:
+    else:       # same fp32 arithmetic, same bf16 rounding of the operand: bitwise identical
         assert torch.equal(got, ref), f"fused != unfused: max diff {float((got.float() - ref.float()).abs().max())}"
     # the raw sources must be untouched (the transform happens in shared memory only)
     assert torch.equal(s0, pf(x0))
