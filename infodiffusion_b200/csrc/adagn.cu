@@ -45,9 +45,7 @@ struct AdaGNParams {
   int apply_silu;
   const float* stats0;   // per-tile partial sums from the producing conv (streaming variant)
   const float* stats1;
-  int slice_rows;        // (unused by the streaming variant)
-  long long total_rows;  // batch * rows_per_img
-  long long rows_per_cta;   // streaming variant: contiguous pad-flat rows per CTA
+  int slice_rows;        // rows per CTA of the streaming variant
   long long stats_b_windows;   // number of 32-row window records (offset of the B records, in records)
   int block_rows;              // rows per ring stage of the streaming variant
   unsigned drop_thr16;         // dropout: drop iff 16 random bits < thr16 (0 = off)
@@ -339,66 +337,54 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_coef_kernel(const AdaGNPara
   for (int ch = threadIdx.x; ch < p.C; ch += kAdaThreads) coef_out[static_cast<long long>(n) * p.C + ch] = sh.ab[ch];
 }
 
-// Persistent streaming variant.  The B*(H+1)*(W+1) pad-flat rows of the whole batch are cut into gridDim.x equal
-// contiguous ranges (grid = 3 resident CTAs per SM, so every SM streams the same number of bytes); a CTA walks its
-// range image by image in blocks of `block_rows` rows through a ring of kRing shared-memory stages filled by
-// bulk-async copies, and re-folds the coefficients whenever it enters the next image.
-struct BlockWalk {                 // identical state machine for the producer (thread 0) and the consumers
-  long long cur, seg_end, hi;
-  int R, RB;
-  __device__ void init(long long lo, long long hi_, int R_, int RB_) {
-    cur = lo; hi = hi_; R = R_; RB = RB_;
-    seg_end = min(hi, (lo / R + 1) * static_cast<long long>(R));
-  }
-  __device__ bool next(long long& r0, int& nr) {
-    if (cur >= hi) return false;
-    r0 = cur;
-    nr = static_cast<int>(min(static_cast<long long>(RB), seg_end - cur));
-    cur += nr;
-    if (cur == seg_end) seg_end = min(hi, seg_end + R);
-    return true;
-  }
-};
-
 __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNParams p) {
   extern __shared__ __align__(128) uint8_t ring_raw[];
   __shared__ __align__(8) uint64_t s_full[kRing];
   __shared__ CoefShared sh;
+  const int n = blockIdx.y;
   const int t = threadIdx.x;
   const int C = p.C;
   const int R = p.rows_per_img;
-  const int RB = p.block_rows;                                  // rows per stage
-  const long long g_lo = static_cast<long long>(blockIdx.x) * p.rows_per_cta;
-  const long long g_hi = min(p.total_rows, g_lo + p.rows_per_cta);
-  const uint32_t stage_bytes = static_cast<uint32_t>(RB) * C * 2;
 
-  // ---- producer state (thread 0): runs kRing blocks ahead of the consumers
-  BlockWalk prod;
-  int prod_blk = 0;
-  auto issue = [&]() {                                          // thread 0 only
-    long long r0; int nr;
-    if (!prod.next(r0, nr)) return;
-    const int st = prod_blk % kRing;
-    ++prod_blk;
+  // ---- start streaming the slice right away: the ring fills while the coefficients are computed
+  const long long row_base = static_cast<long long>(n) * R;
+  const int r_begin = blockIdx.x * p.slice_rows;
+  const int r_end = min(R, r_begin + p.slice_rows);
+  const int RB = p.block_rows;                                  // rows per stage
+  const int nblk = (r_end - r_begin + RB - 1) / RB;
+  const uint32_t stage_bytes = static_cast<uint32_t>(RB) * C * 2;
+  auto issue = [&](int blk) {                                   // thread 0 only
+    const int st = blk % kRing;
+    const int r0 = r_begin + blk * RB;
+    const int nr = min(RB, r_end - r0);
     const uint32_t b0 = static_cast<uint32_t>(nr) * p.c0 * 2, b1 = static_cast<uint32_t>(nr) * p.c1 * 2;
     mbar_arrive_expect_tx(&s_full[st], b0 + b1);
-    bulk_load(ring_raw + st * stage_bytes, p.src0 + r0 * p.c0, b0, &s_full[st]);
-    if (b1) bulk_load(ring_raw + st * stage_bytes + RB * p.c0 * 2, p.src1 + r0 * p.c1, b1, &s_full[st]);
+    bulk_load(ring_raw + st * stage_bytes, p.src0 + (row_base + r0) * p.c0, b0, &s_full[st]);
+    if (b1) bulk_load(ring_raw + st * stage_bytes + RB * p.c0 * 2, p.src1 + (row_base + r0) * p.c1, b1, &s_full[st]);
   };
   if (t == 0) {
     for (int i = 0; i < kRing; ++i) mbar_init(&s_full[i], 1);
     fence_mbar_init();
-    prod.init(g_lo, g_hi, R, RB);
-    for (int b = 0; b < kRing; ++b) issue();                    // the ring fills while the coefficients are folded
+    for (int b = 0; b < kRing && b < nblk; ++b) issue(b);
   }
-  __syncthreads();                                              // barrier init visible before anyone waits
 
+  fold_coefficients(p, n, sh, blockIdx.x == 0);
+  const float2 (&s_ab)[kMaxC] = sh.ab;
+
+  // ---------------------------------------------------------------- streaming sweep
+  // The slice is pulled through a ring of kRing shared-memory stages by bulk-async copies (one per
+  // source per stage, issued by thread 0, completion on an mbarrier), so ~48-64 KB per CTA are in
+  // flight regardless of register pressure; threads read 16-byte vectors from the stage, apply
+  // y = silu(A*x + B) and store straight to global memory (coalesced 16-byte stores).
   const int VPR = C >> 3;
   const int rpp = kAdaThreads / VPR;
   const bool active = t < rpp * VPR;
   const int vl = t % VPR;
   const int rsub = t / VPR;
   const int v0 = p.c0 >> 3;
+  float A[8], B[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float2 ab = s_ab[(active ? vl : 0) * 8 + j]; A[j] = ab.x; B[j] = ab.y; }
   const bool do_silu = p.apply_silu != 0;
   const bool from0 = vl < v0;
   const uint32_t ring = smem_u32(ring_raw);
@@ -406,28 +392,16 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
   const uint32_t my_pitch = from0 ? p.c0 * 2 : p.c1 * 2;
   const float inv_wp = 1.0f / static_cast<float>(p.Wp);
   const uint64_t drop_seed = (p.drop_thr16 != 0 && p.drop_seed != nullptr) ? *p.drop_seed : 0ull;
-  float A[8], B[8];
-  BlockWalk cons;
-  cons.init(g_lo, g_hi, R, RB);
-  int n_cur = -1;
-  long long r0;
-  int nr;
-  for (int blk = 0; cons.next(r0, nr); ++blk) {
-    const int n = static_cast<int>(r0 / R);                     // blocks never straddle images
-    if (n != n_cur) {
-      n_cur = n;
-      fold_coefficients(p, n, sh, r0 == static_cast<long long>(n) * R);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float2 ab = sh.ab[(active ? vl : 0) * 8 + j]; A[j] = ab.x; B[j] = ab.y; }
-    }
+  for (int blk = 0; blk < nblk; ++blk) {
     const int st = blk % kRing;
     mbar_wait(&s_full[st], (blk / kRing) & 1u);
+    const int r0 = r_begin + blk * RB;
+    const int nr = min(RB, r_end - r0);
     if (active) {
       const uint32_t base = ring + st * stage_bytes + my_off;
-      const int ri0 = static_cast<int>(r0 - static_cast<long long>(n) * R);   // first row of the block within its image
 #pragma unroll 4
       for (int lr = rsub; lr < nr; lr += rpp) {
-        const int rr = ri0 + lr;
+        const int rr = r0 + lr;
         const int y = __float2int_rd((static_cast<float>(rr) + 0.5f) * inv_wp);
         const int x = rr - y * p.Wp;
         if (x >= p.W || y >= p.H) continue;                     // pad rows: never written
@@ -440,7 +414,8 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
           f[j] = do_silu ? silu_fast(v) : v;
         }
         if (p.drop_thr16 != 0) {
-          const uint32_t keep = dropout_keep8(drop_seed, p.drop_layer, static_cast<uint64_t>(r0 + lr) * VPR + vl, p.drop_thr16);
+          const uint32_t keep = dropout_keep8(drop_seed, p.drop_layer,
+                                              static_cast<uint64_t>(row_base + rr) * VPR + vl, p.drop_thr16);
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * p.drop_scale : 0.f;
         }
@@ -449,11 +424,11 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
         o.y = pack_bf16x2(f[2], f[3]);
         o.z = pack_bf16x2(f[4], f[5]);
         o.w = pack_bf16x2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(p.out + (r0 + lr) * C + vl * 8) = o;
+        *reinterpret_cast<uint4*>(p.out + (row_base + rr) * C + vl * 8) = o;
       }
     }
     __syncthreads();                                            // everyone is done reading this stage
-    if (t == 0) issue();
+    if (t == 0 && blk + kRing < nblk) issue(blk + kRing);
   }
 }
 
@@ -494,7 +469,7 @@ static cudaError_t fill_params(const idf_adagn_args& a, AdaGNParams& p) {
   return cudaSuccess;
 }
 
-cudaError_t launch_adagn(const idf_adagn_args& a, int num_sms, cudaStream_t stream) {
+cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
   AdaGNParams p;
   p.src0 = static_cast<const bf16*>(a.src0);
   p.src1 = static_cast<const bf16*>(a.src1);
@@ -523,16 +498,16 @@ cudaError_t launch_adagn(const idf_adagn_args& a, int num_sms, cudaStream_t stre
   }
   p.stats_b_windows = (static_cast<long long>(a.batch) * p.rows_per_img + kBM - 1) / kBM * 4;
   if (p.stats0 != nullptr && (p.c1 == 0 || p.stats1 != nullptr)) {
-    // streaming variant: equal contiguous row ranges over 3 resident CTAs per SM (ring 48 KB + 12 KB static each);
-    // small maps get fewer CTAs so that every CTA still streams at least two ring stages
+    // streaming variant: bytes in flight come from the per-CTA ring, not from occupancy, so a few hundred
+    // CTAs suffice; large slices amortise the per-CTA coefficient prologue
+    const long long bytes_s = static_cast<long long>(p.rows_per_img) * p.C * 2;
+    const int max_slices = static_cast<int>((bytes_s + 32767) / 32768);
+    int slices = (400 + a.batch - 1) / a.batch;
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    p.slice_rows = (p.rows_per_img + slices - 1) / slices;
+    slices = (p.rows_per_img + p.slice_rows - 1) / p.slice_rows;
     p.block_rows = kRingStageBytes / (p.C * 2);
-    p.total_rows = static_cast<long long>(a.batch) * p.rows_per_img;
-    long long ctas = 3ll * num_sms;
-    const long long max_ctas = (p.total_rows + 2 * p.block_rows - 1) / (2 * p.block_rows);
-    if (ctas > max_ctas) ctas = max_ctas;
-    if (ctas < 1) ctas = 1;
-    p.rows_per_cta = (p.total_rows + ctas - 1) / ctas;
-    ctas = (p.total_rows + p.rows_per_cta - 1) / p.rows_per_cta;
     const size_t ring_bytes = static_cast<size_t>(kRing) * p.block_rows * p.C * 2;
     static bool attr_set = false;
     if (!attr_set) {
@@ -541,7 +516,7 @@ cudaError_t launch_adagn(const idf_adagn_args& a, int num_sms, cudaStream_t stre
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    adagn_apply_kernel<<<static_cast<unsigned>(ctas), kAdaThreads, ring_bytes, stream>>>(p);
+    adagn_apply_kernel<<<dim3(slices, a.batch, 1), kAdaThreads, ring_bytes, stream>>>(p);
     return cudaGetLastError();
   }
 

@@ -358,9 +358,7 @@ int idf_adagn_coef(const idf_adagn_args* a, float* coef_out, idf_stream_t stream
 
 int idf_adagn_silu_fwd(const idf_adagn_args* a, idf_stream_t stream) {
   if (a == nullptr || a->src0 == nullptr || a->out == nullptr) return fail(IDF_ERR_ARG, "null argument");
-  int rc = ensure_init();
-  if (rc != IDF_OK) return rc;
-  cudaError_t e = launch_adagn(*a, g_num_sms, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_adagn(*a, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "adagn launch");
   return IDF_OK;
 }

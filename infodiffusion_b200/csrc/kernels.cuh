@@ -72,7 +72,7 @@ cudaError_t launch_wgrad(const WgradKernelParams& p, int grid, cudaStream_t stre
 cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, bool xform, int grid, cudaStream_t stream);
 cudaError_t launch_adagn_coef(const idf_adagn_args& a, float* coef_out, cudaStream_t stream);
 uint32_t conv_config_smem(int block_n, int a_stage_bytes);
-cudaError_t launch_adagn(const idf_adagn_args& a, int num_sms, cudaStream_t stream);
+cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream);
 cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, int num_sms, cudaStream_t stream);
 int64_t adagn_bwd_ws_floats(int batch, int C);
 cudaError_t launch_attn(const bf16* qkv, bf16* out, int batch, int H, int W, int d, float scale, cudaStream_t stream);
