@@ -382,14 +382,17 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
   const int vl = t % VPR;
   const int rsub = t / VPR;
   const int v0 = p.c0 >> 3;
+  const bool do_silu = p.apply_silu != 0;
+  const float cs = do_silu ? 0.5f : 1.0f;       // SiLU(v) = h + h*tanh(h) with h = v/2: the 1/2 is folded into (A, B)
   float A[8], B[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { const float2 ab = s_ab[(active ? vl : 0) * 8 + j]; A[j] = ab.x; B[j] = ab.y; }
-  const bool do_silu = p.apply_silu != 0;
+  for (int j = 0; j < 8; ++j) { const float2 ab = s_ab[(active ? vl : 0) * 8 + j]; A[j] = ab.x * cs; B[j] = ab.y * cs; }
   const bool from0 = vl < v0;
   const uint32_t ring = smem_u32(ring_raw);
-  const uint32_t my_off = from0 ? static_cast<uint32_t>(vl * 16) : static_cast<uint32_t>(RB * p.c0 * 2 + (vl - v0) * 16);
-  const uint32_t my_pitch = from0 ? p.c0 * 2 : p.c1 * 2;
+  const uint32_t my_off = (from0 ? static_cast<uint32_t>(vl * 16) : static_cast<uint32_t>(RB * p.c0 * 2 + (vl - v0) * 16)) +
+                          static_cast<uint32_t>(rsub) * (from0 ? p.c0 * 2 : p.c1 * 2);
+  const uint32_t it_pitch = static_cast<uint32_t>(rpp) * (from0 ? p.c0 * 2 : p.c1 * 2);   // smem bytes between my rows
+  const long long out_it = static_cast<long long>(rpp) * C;                                // elements between my rows
   const float inv_wp = 1.0f / static_cast<float>(p.Wp);
   const uint64_t drop_seed = (p.drop_thr16 != 0 && p.drop_seed != nullptr) ? *p.drop_seed : 0ull;
   for (int blk = 0; blk < nblk; ++blk) {
@@ -399,19 +402,29 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
     const int nr = min(RB, r_end - r0);
     if (active) {
       const uint32_t base = ring + st * stage_bytes + my_off;
-#pragma unroll 4
-      for (int lr = rsub; lr < nr; lr += rpp) {
+      bf16* const optr = p.out + (row_base + r0 + rsub) * C + vl * 8;
+      // a stage holds exactly 4 * rpp rows: four rows per thread, no trip-count arithmetic
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int lr = rsub + k * rpp;
         const int rr = r0 + lr;
         const int y = __float2int_rd((static_cast<float>(rr) + 0.5f) * inv_wp);
         const int x = rr - y * p.Wp;
-        if (x >= p.W || y >= p.H) continue;                     // pad rows: never written
-        const uint4 u = lds128(base + lr * my_pitch);
+        if (lr >= nr || x >= p.W || y >= p.H) continue;         // beyond the slice / pad rows: never written
+        const uint4 u = lds128(base + k * it_pitch);
         const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
         float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+        if (do_silu) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float v = fmaf(f[j], A[j], B[j]);
-          f[j] = do_silu ? silu_fast(v) : v;
+          for (int j = 0; j < 8; ++j) {
+            const float h = fmaf(f[j], A[j], B[j]);
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+            f[j] = fmaf(h, th, h);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], A[j], B[j]);
         }
         if (p.drop_thr16 != 0) {
           const uint32_t keep = dropout_keep8(drop_seed, p.drop_layer,
@@ -424,7 +437,7 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
         o.y = pack_bf16x2(f[2], f[3]);
         o.z = pack_bf16x2(f[4], f[5]);
         o.w = pack_bf16x2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(p.out + (row_base + rr) * C + vl * 8) = o;
+        *reinterpret_cast<uint4*>(optr + k * out_it) = o;
       }
     }
     __syncthreads();                                            // everyone is done reading this stage
@@ -507,7 +520,7 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
     if (slices < 1) slices = 1;
     p.slice_rows = (p.rows_per_img + slices - 1) / slices;
     slices = (p.rows_per_img + p.slice_rows - 1) / p.slice_rows;
-    p.block_rows = kRingStageBytes / (p.C * 2);
+    p.block_rows = 4 * (kAdaThreads / (p.C / 8));            // four rows per thread and stage (<= 16 KB)
     const size_t ring_bytes = static_cast<size_t>(kRing) * p.block_rows * p.C * 2;
     static bool attr_set = false;
     if (!attr_set) {
