@@ -22,6 +22,11 @@ namespace cg = cooperative_groups;
 
 namespace idf {
 
+// tuning knobs (idf_set_option "adagn_ring" / "adagn_ctas").  Measured on B200 (tools/adagn_microbench.py): two
+// stages (five CTAs per SM) beat three or five -- the sweep is bound by resident warps, not by bytes in flight.
+int g_adagn_ring = 2;
+int g_adagn_ctas = 400;
+
 constexpr int kAdaThreads = 256;
 constexpr int kMaxC = 256;
 constexpr int kUnroll = 4;
@@ -48,6 +53,7 @@ struct AdaGNParams {
   int slice_rows;        // rows per CTA of the streaming variant
   long long stats_b_windows;   // number of 32-row window records (offset of the B records, in records)
   int block_rows;              // rows per ring stage of the streaming variant
+  int ring;                    // ring stages in use
   unsigned drop_thr16;         // dropout: drop iff 16 random bits < thr16 (0 = off)
   float drop_scale;            // 1 / (1 - p)
   const unsigned long long* drop_seed;
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_kernel(const AdaGNParams p)
 // fold partials -> (A, B) per channel, then y = silu(A*x + B) with 16-byte loads / stores, 4 in flight.
 // No clusters, no barriers in the hot loop, one HBM read + one HBM write.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kRing = 3;            // bulk-copy stages per CTA (3 x 16 KB: three CTAs per SM, 144 KB in flight)
+constexpr int kRingMax = 8;         // bulk-copy stages per CTA: p.ring of them are used (16 KB each)
 constexpr int kRingStageBytes = 16384;
 
 // Per-channel coefficients of image n: GroupNorm statistics from the producers' 32-row window records, folded with
@@ -339,7 +345,8 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_coef_kernel(const AdaGNPara
 
 __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNParams p) {
   extern __shared__ __align__(128) uint8_t ring_raw[];
-  __shared__ __align__(8) uint64_t s_full[kRing];
+  __shared__ __align__(8) uint64_t s_full[kRingMax];
+  const int kRing = p.ring;
   __shared__ CoefShared sh;
   const int n = blockIdx.y;
   const int t = threadIdx.x;
@@ -403,16 +410,22 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
     if (active) {
       const uint32_t base = ring + st * stage_bytes + my_off;
       bf16* const optr = p.out + (row_base + r0 + rsub) * C + vl * 8;
-      // a stage holds exactly 4 * rpp rows: four rows per thread, no trip-count arithmetic
+      // a stage holds exactly 4 * rpp rows: four rows per thread.  All four loads are issued first and the arithmetic
+      // is branch-free (only the store is predicated), so the four rows overlap inside one warp.
+      uint4 u[4];
+      bool ok[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int lr = rsub + k * rpp;
         const int rr = r0 + lr;
         const int y = __float2int_rd((static_cast<float>(rr) + 0.5f) * inv_wp);
         const int x = rr - y * p.Wp;
-        if (lr >= nr || x >= p.W || y >= p.H) continue;         // beyond the slice / pad rows: never written
-        const uint4 u = lds128(base + k * it_pitch);
-        const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+        ok[k] = lr < nr && x < p.W && y < p.H;                  // beyond the slice / pad rows: never written
+        u[k] = lds128(base + k * it_pitch);                     // always inside the stage
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a0 = unpack_bf16x2(u[k].x), a1 = unpack_bf16x2(u[k].y), a2 = unpack_bf16x2(u[k].z), a3 = unpack_bf16x2(u[k].w);
         float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
         if (do_silu) {
 #pragma unroll
@@ -428,7 +441,7 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
         }
         if (p.drop_thr16 != 0) {
           const uint32_t keep = dropout_keep8(drop_seed, p.drop_layer,
-                                              static_cast<uint64_t>(row_base + rr) * VPR + vl, p.drop_thr16);
+                                              static_cast<uint64_t>(row_base + r0 + rsub + k * rpp) * VPR + vl, p.drop_thr16);
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * p.drop_scale : 0.f;
         }
@@ -437,7 +450,7 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
         o.y = pack_bf16x2(f[2], f[3]);
         o.z = pack_bf16x2(f[4], f[5]);
         o.w = pack_bf16x2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(optr + k * out_it) = o;
+        if (ok[k]) *reinterpret_cast<uint4*>(optr + k * out_it) = o;
       }
     }
     __syncthreads();                                            // everyone is done reading this stage
@@ -515,17 +528,18 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
     // CTAs suffice; large slices amortise the per-CTA coefficient prologue
     const long long bytes_s = static_cast<long long>(p.rows_per_img) * p.C * 2;
     const int max_slices = static_cast<int>((bytes_s + 32767) / 32768);
-    int slices = (400 + a.batch - 1) / a.batch;
+    int slices = (g_adagn_ctas + a.batch - 1) / a.batch;
     if (slices > max_slices) slices = max_slices;
     if (slices < 1) slices = 1;
     p.slice_rows = (p.rows_per_img + slices - 1) / slices;
     slices = (p.rows_per_img + p.slice_rows - 1) / p.slice_rows;
     p.block_rows = 4 * (kAdaThreads / (p.C / 8));            // four rows per thread and stage (<= 16 KB)
-    const size_t ring_bytes = static_cast<size_t>(kRing) * p.block_rows * p.C * 2;
+    p.ring = g_adagn_ring;
+    const size_t ring_bytes = static_cast<size_t>(p.ring) * p.block_rows * p.C * 2;
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(adagn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kRing * kRingStageBytes);
+                                           kRingMax * kRingStageBytes);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }

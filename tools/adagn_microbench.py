@@ -28,8 +28,12 @@ def timeit(fn, n=20):
     return e0.elapsed_time(e1) / n * 1e3     # us
 
 
-flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-for (B, H, Cc) in [(256, 64, 64), (256, 32, 128), (256, 64, 128), (256, 16, 128), (256, 8, 128)]:
+import os
+for knob in ("adagn_ring", "adagn_ctas"):
+    if os.environ.get(knob.upper()):
+        _lib.check(lib.idf_set_option(knob.encode(), int(os.environ[knob.upper()])))
+        print(knob, "=", os.environ[knob.upper()])
+for (B, H, Cc) in [(256, 64, 64), (256, 32, 128), (256, 16, 128)]:
     rows = B * (H + 1) * (H + 1)
     x = torch.randn(rows, Cc, device=dev).to(BF)
     out = torch.zeros_like(x)
