@@ -363,32 +363,16 @@ __global__ void __launch_bounds__(XF ? 640 : 384, 1) conv_halo_kernel(const __gr
           const float2* ctab = p.xf_coef + cb + gl * 8;
           int cur = -1;
           float A[8], B[8];
-#pragma unroll 2
-          for (int i = rs; i < nrows; i += 32) {
-            int info = -1;                                           // -1: leave the row alone
-            if (gi == 0) {
-              const int r = rbase + i;
-              if (r >= 0 && r < rows32) {                            // outside the tensor: TMA wrote zeros
-                const int rq = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_wp);
-                const int x = r - rq * p.Wp;
-                const int img = __float2int_rd((static_cast<float>(rq) + 0.5f) * inv_hp);
-                const int y = rq - img * p.Hp;
-                if (x < p.W && y < p.H) info = img;                  // pad rows hold zeros and must keep them
-              }
-            }
-            info = __shfl_sync(grp_mask, info, grp_lead);
-            if (info < 0) continue;
-            if (info != cur) {
-              cur = info;
-              const float4* c4 = reinterpret_cast<const float4*>(ctab + static_cast<int64_t>(info) * p.xf_ctot);
+          auto reload = [&](int img) {
+            cur = img;
+            const float4* c4 = reinterpret_cast<const float4*>(ctab + static_cast<int64_t>(img) * p.xf_ctot);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 c = __ldg(c4 + j);
-                A[2 * j] = c.x * cs; B[2 * j] = c.y * cs; A[2 * j + 1] = c.z * cs; B[2 * j + 1] = c.w * cs;
-              }
+            for (int j = 0; j < 4; ++j) {
+              const float4 c = __ldg(c4 + j);
+              A[2 * j] = c.x * cs; B[2 * j] = c.y * cs; A[2 * j + 1] = c.z * cs; B[2 * j + 1] = c.w * cs;
             }
-            const uint32_t addr = base + static_cast<uint32_t>(i) * 128u;
-            const uint4 u = lds128(addr);
+          };
+          auto xform = [&](const uint4& u) -> uint4 {
             const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
             float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
             if (do_silu) {
@@ -396,7 +380,7 @@ __global__ void __launch_bounds__(XF ? 640 : 384, 1) conv_halo_kernel(const __gr
               for (int j = 0; j < 8; ++j) {
                 const float h = fmaf(f[j], A[j], B[j]);
                 float th;
-                asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));     // (tanh.approx.f16x2 still issues two MUFU ops)
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
                 f[j] = fmaf(h, th, h);
               }
             } else {
@@ -406,7 +390,52 @@ __global__ void __launch_bounds__(XF ? 640 : 384, 1) conv_halo_kernel(const __gr
             uint4 o;
             o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
             o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-            sts128(addr, o);
+            return o;
+          };
+          // four rows per trip: row bookkeeping and all four loads first, then branch-free arithmetic with predicated
+          // stores when the rows share one image (the common case); rows of different images fall back to one by one
+          for (int i0 = rs; i0 < nrows; i0 += 128) {
+            int info[4];
+            uint4 u[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = i0 + 32 * q;
+              int inf = -1;                                            // -1: leave the row alone
+              if (gi == 0 && i < nrows) {
+                const int r = rbase + i;
+                if (r >= 0 && r < rows32) {                            // outside the tensor: TMA wrote zeros
+                  const int rq = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_wp);
+                  const int x = r - rq * p.Wp;
+                  const int img = __float2int_rd((static_cast<float>(rq) + 0.5f) * inv_hp);
+                  const int y = rq - img * p.Hp;
+                  if (x < p.W && y < p.H) inf = img;                   // pad rows hold zeros and must keep them
+                }
+              }
+              info[q] = __shfl_sync(grp_mask, inf, grp_lead);
+              u[q] = lds128(base + static_cast<uint32_t>(min(i, nrows - 1)) * 128u);
+            }
+            int want = -1;
+#pragma unroll
+            for (int q = 3; q >= 0; --q) want = info[q] >= 0 ? info[q] : want;
+            if (want < 0) continue;
+            if (want != cur) reload(want);
+            bool uniform = true;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) uniform = uniform && (info[q] < 0 || info[q] == cur);
+            if (uniform) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 o = xform(u[q]);
+                if (info[q] >= 0) sts128(base + static_cast<uint32_t>(i0 + 32 * q) * 128u, o);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (info[q] < 0) continue;
+                if (info[q] != cur) reload(info[q]);
+                sts128(base + static_cast<uint32_t>(i0 + 32 * q) * 128u, xform(u[q]));
+              }
+            }
           }
           fence_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
         }

@@ -79,6 +79,10 @@ class VAct:
 # way and the transform competes with the epilogue warps for issue slots -- so the separate HBM-bound AdaGN kernels
 # stay the default and this is an opt-in (bench.py --fuse-adagn).
 FUSE_ADAGN = False
+# Fusing only the small maps (H <= FUSE_ADAGN_MAX_H), whose stand-alone AdaGN launches are pure latency, measured
+# worse as well (332 vs 344 img/s with 16): the coefficient kernels and the slower convs cost more than the launches
+# saved.  0 disables.
+FUSE_ADAGN_MAX_H = 0
 
 
 class Workspace:
@@ -318,7 +322,8 @@ class Plan:
              dropout: bool = False, mod_cols: Optional[int] = None):
         """AdaGN of one or two (channel-concatenated) activations for a following conv.  Inference plans return a
         VAct (coefficients only, applied inside the conv); otherwise the activation is materialised."""
-        if self.fuse_adagn and src0.has_stats and (src1 is None or src1.has_stats):
+        fuse = self.fuse_adagn or (not self.training and src0.H <= FUSE_ADAGN_MAX_H)
+        if fuse and src0.has_stats and (src1 is None or src1.has_stats):
             Cc = src0.C + (src1.C if src1 is not None else 0)
             a = AdaGNArgs()
             a.c0 = src0.C
