@@ -357,3 +357,30 @@ def test_fused_adagn_mode_matches_default(m10):
     assert rel_l2(f_eps.cpu(), base_eps.cpu()) < 5e-3
     assert rel_l2(f_a.cpu(), base_a.cpu()) < 5e-3
     assert rel_l2(f_x0.cpu(), base_x0.cpu()) < 2e-3
+
+
+def test_ddim_inversion_round_trip_at_save_latent_size():
+    """Size-independent property at BASELINE configs[3]'s per-GPU shape (64 images, T = 100): encode x0 -> z,
+    reverse DDIM x0 -> x_T with that z, then DDIM x_T -> x0' with zero injected noise.  Deterministic DDIM and its
+    inversion are mutual inverses up to the step-size error, so x0' returns to x0; a wrong coefficient table, a
+    stale latent row or a sample permuted inside the batch would break this at once."""
+    from infodiffusion_b200.sampling import DiffusionProcess
+    args, m, sd = build(256, 100)
+    args.reverse_uses_given_latent = True
+    B = 64
+    g = torch.Generator().manual_seed(11)
+    x0 = (torch.rand(B, 3, 64, 64, generator=g) * 2 - 1).to(DEV)
+    z = m.encoder(x0)[0]
+    p = DiffusionProcess(make_args(**{**vars(args), "deterministic": True}), m, DEV, (3, 64, 64))
+    p.honor_latent_in_reverse = True
+    p.noise_fn = lambda idx, out: out.zero_()
+    xT = p.reverse_sampling(x0, z)
+    assert float((xT - x0).abs().mean()) > 1e-3                     # the trajectory actually moved
+    x0r = p.sampling(B, xT=xT, a=z)
+    err = rel_l2(x0r.cpu(), x0.cpu())
+    per = ((x0r - x0).flatten(1).norm(dim=1) / x0.flatten(1).norm(dim=1)).cpu()
+    print(f"\n[property] DDIM inversion round trip, B={B}, T=100: rel-L2 {err:.3e}, worst sample {float(per.max()):.3e}")
+    assert err < 5e-2 and float(per.max()) < 1e-1
+    # a different latent must not reconstruct: the z conditioning is live
+    x0w = p.sampling(B, xT=xT, a=z.roll(1, 0))
+    assert rel_l2(x0w.cpu(), x0.cpu()) > 2 * err
