@@ -153,3 +153,25 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in idf_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     assert _lib.load().idf_version() >= 100
+
+
+def test_product_never_imports_the_oracle_and_has_no_cpu_path():
+    """The oracle is test infrastructure: nothing under infodiffusion_b200/ may import or execute it, and the
+    network forwards must refuse CPU tensors instead of falling back."""
+    import re
+    pkg = ROOT / "infodiffusion_b200"
+    for f in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
+        if f.suffix in (".py", ".cu", ".cuh"):
+            txt = f.read_text()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f"{f.name} imports the oracle"
+            assert "infodiff_oracle" not in txt, f"{f.name} references the oracle"
+    from infodiffusion_b200.models import AuxiliaryUNet, Encoder, LatentUNet, UNet
+    net = AuxiliaryUNet(T=10, ch=64, ch_mult=[1, 2, 2, 2], a_dim=8, shape=(3, 64, 64)).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 3, 64, 64), torch.zeros(1, dtype=torch.long), torch.zeros(1, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Encoder(ch=64, ch_mult=[1, 2, 2, 2], a_dim=8, shape=(3, 64, 64)).eval()(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        UNet(T=10, ch=64, ch_mult=[1, 2, 2, 2], shape=(3, 64, 64)).eval()(torch.zeros(1, 3, 64, 64), torch.zeros(1, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        LatentUNet(T=10, shape=(1, 8, 8)).eval()(torch.zeros(2, 8), torch.zeros(2, dtype=torch.long))
