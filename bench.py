@@ -52,6 +52,26 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(kind: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the captured kernel, from the newest committed
+    `ncu --set full` raw page under profiles/ (None if there is none)."""
+    import csv
+    files = sorted((ROOT / "profiles").glob(f"*_ncu_{kind}_raw.csv"))
+    if not files:
+        return None, None
+    rows = list(csv.reader(files[-1].open()))
+    if len(rows) < 3:
+        return None, None
+    hdr, units = rows[0], rows[1]
+    try:
+        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+    except ValueError:
+        return None, None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0) for r in rows[2:]]
+    return sum(vals) / len(vals), f"{files[-1].name}: mean over {len(vals)} captured launches of {rows[2][ik].split('(')[0]}"
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -312,7 +332,8 @@ def run_ours(a):
         c = acc["conv_igemm"]
         tfs = c["flops"] / (c["ms"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM)", "achieved": tfs,
-                "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": tfs / pk["tf_sus"], "traffic": None,
+                "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": tfs / pk["tf_sus"], "traffic": ncu_traffic("conv")[0],
+                "traffic_source": ncu_traffic("conv")[1],
                 "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "share_of_step": c["ms"] / tot, "launches_per_unet_eval": c["n"] // reps,
                 "avg_launch_ms": c["ms"] / c["n"]}
@@ -320,7 +341,8 @@ def run_ours(a):
         if "adagn" in acc:       # the stand-alone AdaGN kernels, HBM-bound (default; --fuse-adagn folds them into the convs)
             g_ = acc["adagn"]
             gbs = g_["bytes"] / (g_["ms"] * 1e-3) / 1e9
-            breakdown["adagn"].update({"bound": "hbm", "achieved_GBps": gbs, "peak_GBps": pk["hbm"], "frac": gbs / pk["hbm"]})
+            breakdown["adagn"].update({"bound": "hbm", "achieved_GBps": gbs, "peak_GBps": pk["hbm"], "frac": gbs / pk["hbm"],
+                                       "traffic": ncu_traffic("adagn")[0], "traffic_source": ncu_traffic("adagn")[1]})
         else:
             roof["note"] = ("AdaGN+SiLU is applied to the conv's A operand in shared memory (transform warps): the 73 "
                             "normalised activations are never written to or read from HBM; only the per-image "
