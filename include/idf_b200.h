@@ -239,6 +239,9 @@ typedef struct {
   float* norm_out;     /* [2] */
 } idf_clip_adamw_args;
 int idf_clip_adamw(const idf_clip_adamw_args* args, idf_stream_t stream);
+/* eval_fid output stage (run.py:288-295 followed by torchvision.utils.save_image): x fp32 NCHW in [-1, 1] ->
+ * uint8 NHWC, u = trunc(clamp(((clip(x,-1,1) + 1) / 2) * 255 + 0.5, 0, 255)), the bytes the reference's PNGs hold. */
+int idf_to_uint8_hwc(const float* x, uint8_t* out, int32_t batch, int32_t C, int32_t H, int32_t W, idf_stream_t stream);
 /* dst[m, n] = src[m, n] for an M x N fp32 block with row pitches lds / ldd: places x next to h for the skip
  * concatenation cat([h, x]) of LatentUNet (models.py:230-232). */
 int idf_copy2d_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int32_t M, int32_t N, idf_stream_t stream);

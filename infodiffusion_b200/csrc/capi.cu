@@ -426,6 +426,13 @@ int idf_clip_adamw(const idf_clip_adamw_args* a, idf_stream_t stream) {
   return IDF_OK;
 }
 
+int idf_to_uint8_hwc(const float* x, uint8_t* out, int32_t batch, int32_t C, int32_t H, int32_t W, idf_stream_t stream) {
+  if (x == nullptr || out == nullptr) return fail(IDF_ERR_ARG, "to_uint8_hwc: null argument");
+  cudaError_t e = launch_to_uint8_hwc(x, out, batch, C, H, W, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "to_uint8_hwc launch");
+  return IDF_OK;
+}
+
 int idf_copy2d_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int32_t M, int32_t N, idf_stream_t stream) {
   if (src == nullptr || dst == nullptr) return fail(IDF_ERR_ARG, "copy2d: null argument");
   cudaError_t e = launch_copy2d_f32(src, lds, dst, ldd, M, N, reinterpret_cast<cudaStream_t>(stream));

@@ -92,6 +92,7 @@ cudaError_t launch_clip_adamw(const ClipAdamWParams& p, cudaStream_t stream);
 cudaError_t launch_scale_ln_silu(const float* y, long long ldy, const float* cond, long long cond_stride,
                                  long long cond_step_stride, const int* step_ptr, const float* gamma, const float* beta,
                                  float eps, float* out, long long ldo, int M, int N, int apply_silu, cudaStream_t stream);
+cudaError_t launch_to_uint8_hwc(const float* x, uint8_t* out, int batch, int C, int H, int W, cudaStream_t stream);
 cudaError_t launch_copy2d_f32(const float* src, long long lds, float* dst, long long ldd, int M, int N, cudaStream_t stream);
 cudaError_t launch_gather_elems(const float* src, const int* idx, const int* idx2, void* dst, long long n, bool dst_bf16,
                                 bool accumulate, int num_sms, cudaStream_t stream);

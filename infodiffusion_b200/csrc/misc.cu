@@ -454,6 +454,34 @@ cudaError_t launch_gather_rows(const float* table, const int64_t* idx, float* y,
 }
 
 // ----------------------------------------------------------------------------------------------
+// eval_fid output stage (run.py:288-295 + torchvision.utils.save_image): per image clip(x, -1, 1) -> (x + 1) / 2 ->
+// mul 255, add 0.5, clamp(0, 255), truncate to uint8, CHW -> HWC.  Same fp32 operations in the same order (no FMA
+// contraction), so the bytes equal what the reference writes into its PNGs.
+// ----------------------------------------------------------------------------------------------
+__global__ void to_uint8_hwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int C, int HW, long long total) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / (static_cast<long long>(HW) * C);
+    const long long rem = i - n * HW * C;
+    const int pix = static_cast<int>(rem / C), c = static_cast<int>(rem - static_cast<long long>(pix) * C);
+    float v = x[(n * C + c) * HW + pix];
+    v = fminf(fmaxf(v, -1.0f), 1.0f);
+    v = __fdiv_rn(__fadd_rn(v, 1.0f), 2.0f);
+    v = __fadd_rn(__fmul_rn(v, 255.0f), 0.5f);
+    v = fminf(fmaxf(v, 0.0f), 255.0f);
+    out[i] = static_cast<uint8_t>(v);
+  }
+}
+cudaError_t launch_to_uint8_hwc(const float* x, uint8_t* out, int batch, int C, int H, int W, cudaStream_t stream) {
+  const long long total = static_cast<long long>(batch) * C * H * W;
+  if (total <= 0) return cudaErrorInvalidValue;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 2368) blocks = 2368;
+  to_uint8_hwc_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, out, C, H * W, total);
+  return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------
 // LatentUNet layer tail (models.py:147-163): out = SiLU(LayerNorm(y * (1 + cond))) over rows of N features.
 // One CTA per row; the modulated row is staged in shared memory, mean and variance are two separate
 // passes (as ATen's layer_norm), cond may be a single broadcast row (sampling: every sample shares t).

@@ -194,11 +194,15 @@ class Plan:
         self.adagn_bytes += nbytes if tag == "adagn" else 0
 
     # ---- execution -----------------------------------------------------------------------------
-    def run_timed(self) -> List[Tuple[str, float, int, int]]:
-        """Eager run with a CUDA-event pair around every launch (on the launching stream).
-        Returns [(kernel class, milliseconds, algorithmic flops, algorithmic bytes)]."""
+    def run_timed(self, run_ahead_ms: float = 8.0) -> List[Tuple[str, float, int, int]]:
+        """Eager run with a CUDA-event pair around every launch (on the launching stream).  The stream is first
+        blocked by a spin kernel of ~run_ahead_ms so that the host enqueues all launches and events ahead of the
+        GPU: the event deltas are then GPU durations, not host launch intervals (a ctypes launch costs ~10 us,
+        more than the small kernels run).  Returns [(kernel class, milliseconds, algorithmic flops, bytes)]."""
         st = torch.cuda.current_stream(self.device)
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.ops) + 1)]
+        if run_ahead_ms > 0:
+            torch.cuda._sleep(int(run_ahead_ms * 1.9e6))          # cycles at ~1.9 GHz
         evs[0].record(st)
         for i, (fn, args) in enumerate(self.ops):
             _lib.check(fn(*args, st.cuda_stream))
