@@ -182,6 +182,21 @@ def check(rc: int) -> None:
         raise IdfError(f"idf_b200 error {rc}: {msg.decode() if msg else '?'}")
 
 
+_WEIGHT_EPOCH = 0
+
+
+def bump_weight_epoch() -> None:
+    """Called by code that updates parameters behind torch's back (ClipAdamW writes them from a CUDA kernel through
+    raw pointers, so tensor._version does not move): cached inference plans hold packed bf16 copies of the weights
+    and must be rebuilt."""
+    global _WEIGHT_EPOCH
+    _WEIGHT_EPOCH += 1
+
+
+def weight_epoch() -> int:
+    return _WEIGHT_EPOCH
+
+
 def count_launch(n: int = 1) -> None:
     global _launches
     _launches += n

@@ -50,10 +50,24 @@ def _tail(cur, out_ch):
 class _EngineNet(nn.Module):
     """Common plumbing: lazily builds (and caches per batch size) the kernel plan for this network."""
 
+    def weights_signature(self):
+        """Changes whenever a parameter is updated in place (optimizer step), replaced (.to(), load_state_dict) or
+        written by the fused optimizer; inference plans hold packed bf16 copies of the weights and are keyed on it."""
+        from ._lib import weight_epoch
+        ver = ptr = 0
+        for p in self.parameters():
+            ver += p._version
+            ptr += p.data_ptr()
+        return (weight_epoch(), ver, ptr)
+
     def _plans(self):
-        if "_idf_plans" not in self.__dict__:
-            self.__dict__["_idf_plans"] = {}
-        return self.__dict__["_idf_plans"]
+        d = self.__dict__.setdefault("_idf_plans", {})
+        sig = self.weights_signature()
+        if self.__dict__.get("_idf_sig") != sig:
+            for k in [k for k in d if not str(k[0]).startswith("train")]:   # training plans re-pack every step
+                del d[k]
+            self.__dict__["_idf_sig"] = sig
+        return d
 
     def invalidate_plans(self):
         """Drop packed bf16 weights / workspaces (call after the fp32 parameters change)."""

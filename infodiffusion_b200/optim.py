@@ -112,5 +112,6 @@ class ClipAdamW(torch.optim.Optimizer):
             a.partial, a.norm_out = tb["partial"].data_ptr(), norm_out.data_ptr()
             _lib.check(lib.idf_clip_adamw(C.byref(a), stream))
             _lib.count_launch(3)
+            _lib.bump_weight_epoch()              # parameters changed without torch noticing (raw-pointer kernel)
             self.total_norm = norm_out[0]
         return loss

@@ -176,6 +176,10 @@ class DiffusionProcess():
                                       "use LatentDiffusionProcess for a LatentUNet")
         if net.training:
             raise RuntimeError("sampling runs the inference forward; call model.eval() first")
+        sig = tuple(m.weights_signature() for m in self.diffusion_fn.children() if hasattr(m, "weights_signature"))
+        if getattr(self, "_sig", None) != sig:          # the weights moved since the samplers packed them
+            self._samplers.clear()
+            self._sig = sig
         key = (kind, batch, record_eps, with_encoder)
         if key not in self._samplers:
             self._samplers[key] = _FusedSampler(self, kind, batch, self.chunk, record_eps, with_encoder)
@@ -333,6 +337,10 @@ class LatentDiffusionProcess():
         net = self.diffusion_fn.backbone
         if net.training:
             raise RuntimeError("sampling runs the inference forward; call model.eval() first")
+        sig = net.weights_signature()
+        if getattr(self, "_sig", None) != sig:
+            self._samplers.clear()
+            self._sig = sig
         key = (kind, batch)
         if key not in self._samplers:
             dev = self.device

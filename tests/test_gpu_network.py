@@ -384,3 +384,36 @@ def test_ddim_inversion_round_trip_at_save_latent_size():
     # a different latent must not reconstruct: the z conditioning is live
     x0w = p.sampling(B, xT=xT, a=z.roll(1, 0))
     assert rel_l2(x0w.cpu(), x0.cpu()) > 2 * err
+
+
+def test_inference_follows_weight_updates(m10):
+    """Inference plans and samplers hold packed bf16 copies of the weights; they must be rebuilt when the parameters
+    change -- by a torch optimizer (tensor versions move), by the fused ClipAdamW (raw-pointer kernel) or by hand."""
+    from infodiffusion_b200.optim import ClipAdamW
+    args, m, sd = m10
+    x, t, a = rand_inputs(2, 32, 10)
+    xd, td, ad = x.to(DEV), t.to(DEV), a.to(DEV)
+    w = m.backbone.head.weight
+    try:
+        e0 = m.backbone(xd, td, ad)
+        p = _proc(args, m, True)
+        p.noise_fn = lambda idx, out: out.zero_()
+        s0 = p.sampling(2, xT=xd, a=ad)
+        with torch.no_grad():
+            w.mul_(1.5)                                   # in-place edit: version counter moves
+        e1 = m.backbone(xd, td, ad)
+        assert rel_l2(e1.cpu(), e0.cpu()) > 1e-2
+        s1 = p.sampling(2, xT=xd, a=ad)
+        assert rel_l2(s1.cpu(), s0.cpu()) > 1e-4
+        opt = ClipAdamW([w], lr=1e-1, weight_decay=0.0, max_norm=0.0)
+        w.grad = torch.ones_like(w)
+        opt.step()                                        # raw-pointer update: only the epoch moves
+        e2 = m.backbone(xd, td, ad)
+        assert rel_l2(e2.cpu(), e1.cpu()) > 1e-3
+        with torch.no_grad():
+            ref = orc.aux_unet_forward({**sd, "backbone.head.weight": w.detach().cpu()}, x, t, a)
+        assert rel_l2(e2.cpu(), ref) < TOL_EPS
+    finally:
+        w.grad = None
+        with torch.no_grad():
+            m.load_state_dict(sd)
