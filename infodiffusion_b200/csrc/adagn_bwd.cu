@@ -36,7 +36,7 @@ struct AdaGNBwdParams {
   int n_slices;
 };
 
-constexpr int kUn = 4;            // rows in flight per thread
+constexpr int kUn = 2;            // rows in flight per thread (more would cost occupancy: 4 CTAs/SM at <= 64 registers)
 
 struct BwdShared {
   float2 sub[4][kBMaxC];
@@ -142,7 +142,7 @@ __device__ __forceinline__ void granule_dv(const AdaGNBwdParams& p, const uint4&
   }
 }
 
-__global__ void __launch_bounds__(kBT, 2) adagn_bwd_stats_kernel(const AdaGNBwdParams p) {
+__global__ void __launch_bounds__(kBT, 3) adagn_bwd_stats_kernel(const AdaGNBwdParams p) {
   __shared__ BwdShared sh;
   __shared__ float s_part[kBT][17];
   const int n = blockIdx.y, t = threadIdx.x, C = p.C, R = p.R;
@@ -150,11 +150,11 @@ __global__ void __launch_bounds__(kBT, 2) adagn_bwd_stats_kernel(const AdaGNBwdP
   const int VPR = C >> 3, rpp = kBT / VPR;
   const bool active = t < rpp * VPR;
   const int vl = t % VPR, rsub = t / VPR, v0 = p.c0 >> 3, cpg = C / 32;
-  float A[8], B[8], mean[8], rstd[8], s1[8], s2[8];
+  float A[8], B[8], s1[8], s2[8];          // s2 accumulates sum dv*x; the (x - mean)*rstd form is applied at the end
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int ch = (active ? vl : 0) * 8 + j;
-    A[j] = sh.ab[ch].x; B[j] = sh.ab[ch].y; mean[j] = sh.mean[ch / cpg]; rstd[j] = sh.rstd[ch / cpg];
+    A[j] = sh.ab[ch].x; B[j] = sh.ab[ch].y;
     s1[j] = 0.f; s2[j] = 0.f;
   }
   const bool from0 = vl < v0;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kBT, 2) adagn_bwd_stats_kernel(const AdaGNBwdP
         float x[8], dv[8];
         granule_dv(p, ux[u], ud[u], A, B, seed, static_cast<uint64_t>(row_base + r) * VPR + vl, x, dv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += dv[j]; s2[j] = fmaf(dv[j], (x[j] - mean[j]) * rstd[j], s2[j]); }
+        for (int j = 0; j < 8; ++j) { s1[j] += dv[j]; s2[j] = fmaf(dv[j], x[j], s2[j]); }
       }
     }
   }
@@ -198,11 +198,16 @@ __global__ void __launch_bounds__(kBT, 2) adagn_bwd_stats_kernel(const AdaGNBwdP
     const int which = i / C, ch = i - which * C, cvl = ch >> 3, j = ch & 7;
     float acc = 0.f;
     for (int rs = 0; rs < rpp; ++rs) acc += s_part[rs * VPR + cvl][which * 8 + j];
+    if (which == 1) {                       // sum dv*xhat = rstd * (sum dv*x - mean * sum dv)
+      float a1 = 0.f;
+      for (int rs = 0; rs < rpp; ++rs) a1 += s_part[rs * VPR + cvl][j];
+      acc = (acc - sh.mean[ch / cpg] * a1) * sh.rstd[ch / cpg];
+    }
     p.ws[((static_cast<long long>(n) * kBSlices + blockIdx.x) * C + ch) * 2 + which] = acc;
   }
 }
 
-__global__ void __launch_bounds__(kBT, 2) adagn_bwd_apply_kernel(const AdaGNBwdParams p) {
+__global__ void __launch_bounds__(kBT, 3) adagn_bwd_apply_kernel(const AdaGNBwdParams p) {
   __shared__ BwdShared sh;
   __shared__ float s_S[2 * kBMaxC];
   __shared__ float s_G[64];
@@ -211,13 +216,14 @@ __global__ void __launch_bounds__(kBT, 2) adagn_bwd_apply_kernel(const AdaGNBwdP
   const int cpg = C / 32;
   for (int i = t; i < 2 * C; i += kBT) {
     const int which = i / C, ch = i - which * C;
-    float part[kBSlices];
-#pragma unroll
-    for (int s = 0; s < kBSlices; ++s)           // independent loads, fixed summation order
-      part[s] = s < p.n_slices ? p.ws[((static_cast<long long>(n) * kBSlices + s) * C + ch) * 2 + which] : 0.f;
     float acc = 0.f;
+    const float* wsp = p.ws + (static_cast<long long>(n) * kBSlices * C + ch) * 2 + which;
+    for (int s0 = 0; s0 < p.n_slices; s0 += 4) {        // four independent loads per trip, fixed summation order
+      float q[4];
 #pragma unroll
-    for (int s = 0; s < kBSlices; ++s) acc += part[s];
+      for (int j = 0; j < 4; ++j) q[j] = (s0 + j < p.n_slices) ? wsp[static_cast<long long>(s0 + j) * C * 2] : 0.f;
+      acc += (q[0] + q[1]) + (q[2] + q[3]);
+    }
     s_S[i] = acc;
     if (blockIdx.x == 0) p.sums[(static_cast<long long>(n) * C + ch) * 2 + which] = acc;
   }
@@ -257,12 +263,13 @@ __global__ void __launch_bounds__(kBT, 2) adagn_bwd_apply_kernel(const AdaGNBwdP
   const int VPR = C >> 3, rpp = kBT / VPR;
   if (t >= rpp * VPR) return;
   const int vl = t % VPR, rsub = t / VPR, v0 = p.c0 >> 3;
-  float A[8], B[8], mean[8], rstd[8], G1[8], G2[8];
+  float A[8], B[8], K0[8], K1[8];           // dx = A*dv - (G1 + (x - mean)*rstd*G2) = A*dv - x*K1 + K0
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int ch = vl * 8 + j, g = ch / cpg;
-    A[j] = sh.ab[ch].x; B[j] = sh.ab[ch].y; mean[j] = sh.mean[g]; rstd[j] = sh.rstd[g];
-    G1[j] = s_G[g]; G2[j] = s_G[32 + g];
+    A[j] = sh.ab[ch].x; B[j] = sh.ab[ch].y;
+    K1[j] = sh.rstd[g] * s_G[32 + g];
+    K0[j] = sh.mean[g] * K1[j] - s_G[g];
   }
   const bool from0 = vl < v0;
   const bf16* src = from0 ? (p.src0 + vl * 8) : (p.src1 + (vl - v0) * 8);
@@ -295,7 +302,7 @@ __global__ void __launch_bounds__(kBT, 2) adagn_bwd_apply_kernel(const AdaGNBwdP
       float x[8], dv[8], o[8];
       granule_dv(p, ux[u], ud[u], A, B, seed, static_cast<uint64_t>(row_base + r) * VPR + vl, x, dv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dv[j], -(G1[j] + (x[j] - mean[j]) * rstd[j] * G2[j]));
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dv[j], fmaf(-x[j], K1[j], K0[j]));
       if (acc) {
         const uint4 e = uo[u];
         const float2 e0 = unpack_bf16x2(e.x), e1 = unpack_bf16x2(e.y), e2 = unpack_bf16x2(e.z), e3 = unpack_bf16x2(e.w);
@@ -336,8 +343,8 @@ cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, int num_sms, cudaStrea
   if (p.stats0 == nullptr || (p.c1 != 0 && (p.stats1 == nullptr || p.dx1 == nullptr)) || p.dx0 == nullptr ||
       p.dy == nullptr || p.sums == nullptr || p.ws == nullptr)
     return cudaErrorInvalidValue;
-  // one wave of CTAs (2 resident per SM), but at least 64 rows per slice
-  int ns = (2 * num_sms) / a.batch;
+  // one wave of CTAs (3 resident per SM), but at least 64 rows per slice
+  int ns = (3 * num_sms) / a.batch;
   if (ns > kBSlices) ns = kBSlices;
   if (ns > (p.R + 63) / 64) ns = (p.R + 63) / 64;
   if (ns < 1) ns = 1;
