@@ -233,3 +233,33 @@ def test_latent_training_composite_matches_kernels(latent_model):
             l.dropout = d
         net.eval()
         net.zero_grad(set_to_none=True)
+
+
+def test_run_py_modes_end_to_end(tmp_path, monkeypatch):
+    """run.py --mode train -> save_latent -> train_latent_ddim -> eval_fid (latent sampler) on synthetic 64x64 data:
+    checkpoints, the latent .npz and the PNG folder appear under the reference's names and the loss is finite."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    common = ["--model", "diff", "--prior", "regular", "--dataset", "synthetic", "--a_dim", "32", "--batch_size", "4",
+              "--epochs", "1", "--save_epochs", "1", "--diffusion_steps", "4", "--synthetic_size", "8", "--r_seed", "64",
+              "--model_folder", "./models", "--img_folder", "./imgs"]
+
+    def run(*extra):
+        r = subprocess.run([sys.executable, str(root / "run.py"), *common, *extra], cwd=tmp_path, capture_output=True, text=True,
+                           timeout=600, env={**__import__("os").environ, "PYTHONPATH": str(root)})
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return r.stdout
+    out = run("--mode", "train")
+    assert "Loss" in out and "nan" not in out.lower()
+    exp = "synthetic_32d_0.1mmd"
+    assert (tmp_path / "models" / exp / "model-1.pth").exists()
+    run("--mode", "save_latent")
+    z = np.load(tmp_path / f"diff_{exp.replace('.', '_')}_latent.npz")
+    assert z["all_a"].shape == (8, 32) and z["all_attr"].shape == (8,)
+    run("--mode", "train_latent_ddim")
+    assert (tmp_path / "models" / f"{exp}_latent" / "model-1.pth").exists()
+    run("--mode", "eval_fid", "--is_latent", "--deterministic", "--sampling_number", "6")
+    pngs = sorted((tmp_path / "imgs" / exp / "eval-fid-latent").glob("sample-*.png"))
+    assert [p.name for p in pngs] == [f"sample-{i:06d}.png" for i in range(6)]
