@@ -426,6 +426,66 @@ cudaError_t launch_attn_v2(const CUtensorMap& tm, bf16* out, int batch, int H, i
   return cudaErrorInvalidValue;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Small-map attention (S = H*W <= 64 tokens with S*d <= 8192, e.g. the 4x4 middle block of a 32x32 model):
+// far too little work for the tensor-core pipeline (131 kFLOP per sample at S=16, d=128).  One CTA per sample,
+// q, k, v in fp32 shared memory, scores / softmax / PV with plain FMAs.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_small_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int H, int W,
+                                                         int d, float scale) {
+  extern __shared__ float sm[];
+  const int S = H * W, n = blockIdx.x, t = threadIdx.x;
+  float* q = sm;
+  float* k = q + S * d;
+  float* v = k + S * d;
+  float* sc = v + S * d;                                  // [S][S]
+  const long long img_row0 = static_cast<long long>(n) * (H + 1) * (W + 1);
+  for (int i = t; i < S * 3 * d; i += 128) {
+    const int tok = i / (3 * d), c = i - tok * 3 * d;
+    const long long row = img_row0 + (tok / W) * (W + 1) + (tok % W);
+    const float val = __bfloat162float(qkv[row * 3 * d + c]);
+    (c < d ? q : (c < 2 * d ? k : v))[tok * d + (c % d)] = val;
+  }
+  __syncthreads();
+  for (int i = t; i < S * S; i += 128) {
+    const int a = i / S, b = i - a * S;
+    float acc = 0.f;
+    for (int c = 0; c < d; ++c) acc = fmaf(q[a * d + c], k[b * d + c], acc);
+    sc[i] = acc * scale;
+  }
+  __syncthreads();
+  for (int a = t; a < S; a += 128) {                      // softmax over each row (reference F.softmax, modules.py:156)
+    float m = -INFINITY;
+    for (int b = 0; b < S; ++b) m = fmaxf(m, sc[a * S + b]);
+    float sum = 0.f;
+    for (int b = 0; b < S; ++b) { const float e = __expf(sc[a * S + b] - m); sc[a * S + b] = e; sum += e; }
+    const float inv = 1.0f / sum;
+    for (int b = 0; b < S; ++b) sc[a * S + b] *= inv;
+  }
+  __syncthreads();
+  for (int i = t; i < S * d; i += 128) {
+    const int a = i / d, c = i - a * d;
+    float acc = 0.f;
+    for (int b = 0; b < S; ++b) acc = fmaf(sc[a * S + b], v[b * d + c], acc);
+    const long long row = img_row0 + (a / W) * (W + 1) + (a % W);
+    out[row * d + c] = __float2bfloat16(acc);
+  }
+}
+
+cudaError_t launch_attn_small(const bf16* qkv, bf16* out, int batch, int H, int W, int d, float scale, cudaStream_t stream) {
+  const int S = H * W;
+  if (S > 64 || S * d > 8192 || S <= 0) return cudaErrorInvalidValue;
+  const size_t smem = (3 * static_cast<size_t>(S) * d + static_cast<size_t>(S) * S) * sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    attr = smem;
+  }
+  attn_small_kernel<<<batch, 128, smem, stream>>>(qkv, out, H, W, d, scale);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_attn(const bf16* qkv, bf16* out, int batch, int H, int W, int d, float scale,
                         cudaStream_t stream) {
   if (d != kD) return cudaErrorInvalidValue;

@@ -381,6 +381,13 @@ int idf_attn_fwd(const void* qkv, void* out, int32_t batch, int32_t H, int32_t W
   int rc = ensure_init();
   if (rc != IDF_OK) return rc;
   cudaError_t e;
+  const int S_tok = H * W;
+  if (d != 128 || (S_tok != 64 && S_tok != 256)) {   // small maps (e.g. 4x4): plain-FMA kernel, one CTA per sample
+    e = launch_attn_small(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), batch, H, W, d, scale,
+                          reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "attention launch (supported: d=128 with H*W in {64,256}; or H*W <= 64 with H*W*d <= 8192)");
+    return IDF_OK;
+  }
   if (g_attn_impl == 1) {   // v1: thread-gathered operands, V transposed in shared memory
     e = launch_attn(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), batch, H, W, d, scale,
                     reinterpret_cast<cudaStream_t>(stream));

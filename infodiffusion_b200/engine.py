@@ -649,7 +649,7 @@ class BackbonePlan(Plan):
         self.mode = mode
         Cimg, H, W = net.shape
         assert H == W, "square images only"
-        assert H in (32, 64), "the sm_100a plan supports 32x32 / 64x64 inputs (attention at 16x16 / 8x8)"
+        assert H in (32, 64), "the sm_100a plans support 32x32 / 64x64 inputs"
         self.net = net
         if mode == "train":
             from .train import stack_params

@@ -100,9 +100,11 @@ def get_dataset_config(args):
     """reference data.py:63-108, restricted to what the kernels cover."""
     if args.dataset in ('celeba', 'ffhq', 'synthetic'):
         args.input_channels, args.unets_channels, args.encoder_channels, args.input_size = 3, 64, 64, 64
+    elif args.dataset == 'cifar10':
+        args.input_channels, args.unets_channels, args.encoder_channels, args.input_size = 3, 64, 64, 32
     else:
-        raise NotImplementedError(f"--dataset {args.dataset}: the sm_100a plans cover 64x64 inputs with 64-channel UNets "
-                                  "(celeba / ffhq shape); see DESIGN.md section 7")
+        raise NotImplementedError(f"--dataset {args.dataset}: the sm_100a plans cover 64x64 / 32x32 inputs with 64-channel "
+                                  "UNets (celeba / ffhq / cifar10 shapes); see DESIGN.md section 7")
     return (args.input_channels, args.input_size, args.input_size)
 
 

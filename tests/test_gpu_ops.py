@@ -741,3 +741,21 @@ def test_conv_with_fused_adagn_equals_adagn_then_conv(lib, c0, c1, cout, H, B, k
         assert torch.equal(got, ref), f"fused != unfused: max diff {float((got.float() - ref.float()).abs().max())}"
     # the raw sources must be untouched (the transform happens in shared memory only)
     assert torch.equal(s0, pf(x0))
+
+
+@pytest.mark.parametrize("H,B,d", [(4, 5, 128), (2, 3, 128), (8, 2, 64)])
+def test_attention_small_maps(lib, H, B, d):
+    """Maps below the tensor-core kernel's shapes (e.g. the 4x4 middle block of a 32x32 model): plain-FMA kernel."""
+    g = torch.Generator(device=DEV).manual_seed(31 + H + d)
+    S = H * H
+    q, k, v = (rbf(torch.randn(B, d, H, H, device=DEV, generator=g) * s) for s in (1.2, 1.2, 1.0))
+    qkv = pf(torch.cat([q, k, v], 1))
+    out = torch.zeros(B * (H + 1) * (H + 1), d, device=DEV, dtype=BF)
+    check(lib.idf_attn_fwd(qkv.data_ptr(), out.data_ptr(), B, H, H, d, d ** -0.5, stream()))
+    torch.cuda.synchronize()
+    qq = q.double().permute(0, 2, 3, 1).reshape(B, S, d)
+    kk = k.double().reshape(B, d, S)
+    vv = v.double().permute(0, 2, 3, 1).reshape(B, S, d)
+    ref = torch.bmm(torch.softmax(torch.bmm(qq, kk) * d ** -0.5, dim=-1), vv).reshape(B, H, H, d).permute(0, 3, 1, 2)
+    assert pad_is_zero(out, B, H, H)
+    assert_close(unpf(out, B, H, H), ref, rel_l2=3e-3, max_rel=1e-2, what=f"small attention S={S} d={d}")

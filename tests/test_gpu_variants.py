@@ -263,3 +263,36 @@ def test_run_py_modes_end_to_end(tmp_path, monkeypatch):
     run("--mode", "eval_fid", "--is_latent", "--deterministic", "--sampling_number", "6")
     pngs = sorted((tmp_path / "imgs" / exp / "eval-fid-latent").glob("sample-*.png"))
     assert [p.name for p in pngs] == [f"sample-{i:06d}.png" for i in range(6)]
+
+
+def test_32x32_model_cifar_shape():
+    """32x32 inputs (the reference's cifar10 configuration: 64-channel UNets, levels 32/16/8/4, attention at 8x8 and
+    in the 4x4 middle block): backbone eps, encoder and a short DDIM trajectory against the oracle."""
+    from infodiffusion_b200.models import InfoDiff
+    from infodiffusion_b200.sampling import DiffusionProcess
+    T = 6
+    args = make_args(a_dim=32, diffusion_steps=T, input_size=32)
+    torch.manual_seed(SEED)
+    m = InfoDiff(args, "cpu", (3, 32, 32))
+    sd = perturb_state_dict(m.state_dict())
+    m.load_state_dict(sd)
+    m = _to_dev(m)
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(3, 3, 32, 32, generator=g) * 2 - 1
+    t = torch.randint(0, T, (3,), generator=g)
+    a = torch.randn(3, 32, generator=g)
+    with torch.no_grad():
+        ref = orc.aux_unet_forward(sd, x, t, a)
+        a_ref, _, _, _ = orc.encoder_forward(sd, x, noise=torch.zeros(3, 32))
+    got = m.backbone(x.to(DEV), t.to(DEV), a.to(DEV)).cpu()
+    a_got = m.encoder(x.to(DEV))[0].cpu()
+    print(f"\n[parity] 32x32: eps rel-L2 {rel_l2(got, ref):.3e}, encoder a {rel_l2(a_got, a_ref):.3e}")
+    assert rel_l2(got, ref) < TOL_EPS and rel_l2(a_got, a_ref) < TOL_EPS
+    shape = (3, 3, 32, 32)
+    p = DiffusionProcess(make_args(**{**vars(args), "deterministic": True}), m, DEV, (3, 32, 32))
+    p.noise_fn = lambda idx, out: out.copy_(step_noise(idx, shape))
+    xT = torch.randn(*shape, generator=g)
+    sch = orc.Schedule.make(args.beta1, args.betaT, T)
+    want = orc.sample(sd, sch, xT, a, True, noise_fn=lambda i, like: step_noise(i, shape))
+    x0 = p.sampling(3, xT=xT.to(DEV), a=a.to(DEV)).cpu()
+    assert rel_l2(x0, want) < TOL_X
