@@ -12,41 +12,20 @@
 // Operand bytes per MMA drop 3-7x (e.g. 64->64 @64^2: 221 KB -> 33 KB + weights per 128 rows).
 //
 // Roles (384 threads): warp 0 = A (halo) TMA producer     warp 3 = B (weights) TMA producer
-//                      warp 1 = UMMA issuer (1 thread)    warp 2 = TMEM allocator
+//                      warp 1 = UMMA issuer (1 thread)    warp 2 = TMEM allocator (+ second UMMA issuer when MT >= 2)
 //                      warps 4..11 = epilogue (two warps per TMEM lane quarter)
-// Pipelines: A halo stages x2, B ring x6-8 (full/empty mbarriers), TMEM accumulator sets x2.
+//                      XF variant only: warps 12..19 = transform (fused AdaGN + SiLU on the halo, in place)
+// Pipelines: A halo stages x2, B ring x4-8 (full/empty mbarriers), TMEM accumulator sets x2.
 #include "kernels.cuh"
 
 namespace idf {
 
 __host__ __device__ constexpr int conv_b_stages(int bn) { return bn == 16 ? 8 : (bn == 64 ? 4 : 6); }
-// GroupNorm partial-statistics exchange between the 4 epilogue warps of one work item:
-// [2 halves][4 lane quarters][3 image slots][32 columns] float2 (sum, sumsq)
-constexpr uint32_t kStatScratchBytes = 2 * 4 * 3 * 32 * 8;
 // per-epilogue-warp staging tile: 32 rows x 64 B (+16 B pad per row: conflict-free for both the row-per-lane
 // and the 4-lanes-per-row access patterns)
 constexpr uint32_t kStageRowBytes = 80;
 constexpr uint32_t kStageBytes = 8 * 32 * kStageRowBytes;
 constexpr uint32_t kBiasBytes = 512 * 4;   // bias vector of the whole conv (cout_pad <= 512), staged once per CTA
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// Sum over the 32 lanes of a warp of 32 per-lane values: on return lane L holds the total of v[L] in v[0]
-// (butterfly transpose-reduce, 31 shuffles).
-__device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int j = 0; j < s; ++j) {
-      const float send = up ? v[j] : v[j + s];
-      const float keep = up ? v[j + s] : v[j];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-}
 
 template <int BN, int MT>
 struct HaloCfg {

@@ -254,7 +254,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {     // two instructions: a bf16 is the top half of an fp32
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 // SiLU through the hardware tanh: x*sigmoid(x) = h + h*tanh(h), h = x/2 -- 3 instructions, 1 MUFU.
 // tanh.approx.f32 has ~2^-11 absolute error, i.e. |error| <= |x| * 2.5e-4: below bf16 output rounding (2^-9).
 __device__ __forceinline__ float silu_fast(float x) {
