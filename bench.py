@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("IDF_SAMPLE_CHUNK", "0")) or None)
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("IDF_SAMPLE_LANES", "1")),
+                    help="streams the micro-batches of a step are spread over (needs --chunk < batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fuse-adagn", action="store_true", help="fold every AdaGN into its consumer conv (A/B comparison)")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-throughput measurement")
@@ -256,6 +258,7 @@ def run_ours(a):
     B = a.batch
     args = make_args_ns(T_STEPS)
     args.sample_chunk = a.chunk
+    args.sample_lanes = a.lanes
     torch.manual_seed(64)
     model = InfoDiff(args, "cpu", (3, 64, 64)).to(dev).eval()
     model.device = dev
@@ -357,7 +360,7 @@ def run_ours(a):
         v, cores, sample = cpu_ddim_rate(16, 10.0, 8)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
-        ws_gb = proc._sampler("ddim", B).ws.bytes / 1e9
+        ws_gb = sum(w.bytes for w in proc._sampler("ddim", B).lane_ws) / 1e9
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -365,7 +368,7 @@ def run_ours(a):
             "config": {"workload": f"eval_fid-style DDIM-{T_STEPS} sampling, batch {B}/GPU, 64x64x3, InfoDiff a_dim {A_DIM} "
                                    f"(BASELINE configs[1]); random-init weights",
                        "global_batch": world * B, "parallelism": f"batch-sharded x{world}, final all_gather",
-                       "sample_chunk": a.chunk or B,
+                       "sample_chunk": a.chunk or B, "sample_lanes": a.lanes,
                        "l2": f"no explicit flush: {ws_gb:.1f} GB of activations are rewritten per UNet evaluation "
                              f"(>> 126 MB L2) and every step consumes the previous step's output"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": xT_h.numel() * 4 + a_h.numel() * 4,

@@ -91,10 +91,19 @@ class _FusedSampler:
         self.mod_z = torch.zeros(batch, self.pack.ncol, **f32)
         chunk = batch if chunk is None else min(chunk, batch)
         assert batch % chunk == 0, "chunk must divide the batch"
-        self.ws = Workspace(chunk, dev)
+        # lanes: micro-batches on different lanes run on different streams (own workspace each), so the small
+        # latency-bound layers of one micro-batch overlap with the other's work
+        n_lanes = max(1, min(int(getattr(proc, "lanes", 1)), batch // chunk))
+        self.lane_ws = [Workspace(chunk, dev) for _ in range(n_lanes)]
+        self.lane_plans: List[List[Plan]] = [[] for _ in range(n_lanes)]
+        self.lane_streams = [None] + [torch.cuda.Stream(dev) for _ in range(n_lanes - 1)]
+        self.ws = self.lane_ws[0]
         self.plans: List[Plan] = []
-        for c0 in range(0, batch, chunk):
+        for ci, c0 in enumerate(range(0, batch, chunk)):
             sl = slice(c0, c0 + chunk)
+            lane = ci % n_lanes
+            self.ws = self.lane_ws[lane]
+            n_before = len(self.plans)
             if with_encoder:
                 # bug-compatible reverse DDIM: re-encode the current x_t every step (sampling.py:84,
                 # models.py:709-710) and derive this chunk's z-modulation rows from the fresh latent
@@ -110,6 +119,8 @@ class _FusedSampler:
                               mod_t_table=self.tables.table, mod_z=self.mod_z[sl],
                               eps_out=None if self.eps is None else self.eps[sl], pack=self.pack)
             self.plans.append(bp)
+            self.lane_plans[lane] += self.plans[n_before:]
+        self.ws = self.lane_ws[0]
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.n_launch = sum(len(p.ops) for p in self.plans)
 
@@ -117,8 +128,19 @@ class _FusedSampler:
         self.tables.latent_rows(a.contiguous().float(), self.mod_z)
 
     def _enqueue(self) -> None:
-        for p in self.plans:
-            p.run()
+        if len(self.lane_plans) == 1:
+            for p in self.plans:
+                p.run()
+            return
+        cur = torch.cuda.current_stream(self.x.device)
+        for st in self.lane_streams[1:]:                 # fork (also valid inside a graph capture)
+            st.wait_stream(cur)
+        for plans, st in zip(self.lane_plans, self.lane_streams):
+            with torch.cuda.stream(st if st is not None else cur):
+                for p in plans:
+                    p.run()
+        for st in self.lane_streams[1:]:                 # join
+            cur.wait_stream(st)
 
     def capture(self) -> None:
         torch.cuda.synchronize(self.x.device)
@@ -161,6 +183,7 @@ class DiffusionProcess():
         self.diffusion_fn = diffusion_fn.to(device=device)
         self.device = device
         self.chunk = getattr(args, "sample_chunk", None)      # micro-batch per graph segment (None = whole batch)
+        self.lanes = int(getattr(args, "sample_lanes", 1))    # concurrent streams the micro-batches are spread over
         self.use_graph = getattr(args, "cuda_graph", True)
         self.honor_latent_in_reverse = getattr(args, "reverse_uses_given_latent", False)
         # noise_fn(idx, out) fills `out` with the step's N(0,1) noise; the default draws from torch's CUDA
