@@ -313,8 +313,9 @@ def q_sample(sch: Schedule, x: Tensor, idx: Tensor, eps: Tensor) -> Tensor:
 
 
 def infodiff_loss(sd: SD, sch: Schedule, x: Tensor, idx: Tensor, eps: Tensor, enc_noise: Tensor,
-                  prior: Tensor, mmd_weight: float, kld_weight: float, T: int) -> Dict[str, Tensor]:
-    """InfoDiff.loss_fn (prior='regular', use_C=False) with all random draws injected -- models.py:632-723."""
+                  prior: Tensor, mmd_weight: float, kld_weight: float, T: int, use_C: bool = False, C_max: float = 25.0,
+                  epochs: int = 1, curr_epoch: int = 0) -> Dict[str, Tensor]:
+    """InfoDiff.loss_fn (prior='regular') with all random draws injected -- models.py:632-723."""
     x_t = q_sample(sch, x, idx, eps)
     a, a_q, mu, log_var = encoder_forward(sd, x, noise=enc_noise)          # models.py:710, on CLEAN x
     use_q = (kld_weight != 0)                                              # models.py:714-721
@@ -330,7 +331,12 @@ def infodiff_loss(sd: SD, sch: Schedule, x: Tensor, idx: Tensor, eps: Tensor, en
         terms["mmd"] = mmd
     if kld_weight != 0:
         kld = torch.sum(-0.5 * torch.sum(1 + log_var - mu ** 2 - log_var.exp(), dim=1), dim=0)  # 663 / 687
-        loss = loss + kld_weight * kld
+        if use_C:                                                          # models.py:664-668 / 688-692
+            c_max = torch.tensor([C_max], dtype=torch.float32)
+            cc = torch.clamp(c_max / epochs * curr_epoch, torch.zeros(1), c_max)
+            loss = loss + kld_weight * (kld - cc.squeeze(dim=0)).abs()
+        else:
+            loss = loss + kld_weight * kld
         terms["kld"] = kld
     terms["loss"] = loss
     return terms

@@ -146,6 +146,34 @@ def main():
         out[f"{kind}_z0"] = z_ref.numpy()
     np.savez_compressed(OUT / "latent10_a32.npz", **out)
 
+    # ------------------------------------------------------------------ loss_fn with the KLD term and the control constant
+    argsk = make_args(a_dim=32, diffusion_steps=1000, kld_weight=0.5, mmd_weight=0.1, use_C=True, C_max=25.0, epochs=4)
+    torch.manual_seed(SEED)
+    mk = ref_models.InfoDiff(argsk, "cpu", (3, 64, 64))
+    sdk = perturb_state_dict(mk.state_dict())
+    mk.load_state_dict(sdk, strict=True)
+    mk.eval()
+    gl = torch.Generator().manual_seed(23)
+    xb = torch.rand(4, 3, 64, 64, generator=gl) * 2 - 1
+    idx = torch.randint(0, 1000, (4,), generator=gl)
+    eps = torch.randn(4, 3, 64, 64, generator=gl)
+    encn = torch.randn(4, 32, generator=gl)
+    prior = torch.randn(4, 32, generator=gl)
+    real_randint = torch.randint
+    torch.randint = lambda *a_, **k_: idx.clone()
+    try:
+        from oracle.make_golden import silenced
+        with torch.no_grad(), silenced(), patched_randn_like([eps.clone(), encn.clone(), prior.clone()]):
+            loss_ref = mk.loss_fn(argsk, xb, curr_epoch=2)
+    finally:
+        torch.randint = real_randint
+    sch = orc.Schedule.make(argsk.beta1, argsk.betaT, 1000)
+    with torch.no_grad():
+        terms = orc.infodiff_loss(sdk, sch, xb, idx, eps, encn, prior, 0.1, 0.5, 1000, use_C=True, C_max=25.0, epochs=4,
+                                  curr_epoch=2)
+    check("loss_fn kld + use_C", terms["loss"], loss_ref, 1e-6)
+    np.savez_compressed(OUT / "loss_kld_a32.npz", loss=loss_ref.numpy(), kld=terms["kld"].numpy(), mmd=terms["mmd"].numpy())
+
     meta_path.write_text(json.dumps(meta, indent=1))
     print("variant golden files written to", OUT)
 

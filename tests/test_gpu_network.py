@@ -417,3 +417,49 @@ def test_inference_follows_weight_updates(m10):
         w.grad = None
         with torch.no_grad():
             m.load_state_dict(sd)
+
+
+def test_kld_loss_value_and_gradients(golden_dir):
+    """kld_weight != 0 (+ control constant): the backbone is conditioned on the SAMPLED latent a_q and the KLD / MMD
+    terms act on (mu, log_var) (reference models.py:648-668, 714-721).  Loss value against the reference golden and
+    the oracle, gradients of every parameter against autograd through the oracle."""
+    kw = dict(kld_weight=0.5, mmd_weight=0.1, use_C=True, C_max=25.0, epochs=4)
+    args, m, sd = build(32, 1000, **kw)
+    gl = torch.Generator().manual_seed(23)
+    xb = torch.rand(4, 3, 64, 64, generator=gl) * 2 - 1
+    idx = torch.randint(0, 1000, (4,), generator=gl)
+    eps = torch.randn(4, 3, 64, 64, generator=gl)
+    encn = torch.randn(4, 32, generator=gl)
+    prior = torch.randn(4, 32, generator=gl)
+    gold = float(np.load(golden_dir / "loss_kld_a32.npz")["loss"])
+    with _patched_draws(idx.to(DEV), [eps.clone(), encn.clone(), prior.clone()]):
+        val = float(m.loss_fn(args, xb.to(DEV), curr_epoch=2))
+    print(f"\n[parity] kld loss_fn (eval forward): cuda {val:.6f} vs reference {gold:.6f}")
+    assert abs(val - gold) / abs(gold) < 2e-2
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point() and "timembedding.0" not in k) for k, v in sd.items()}
+    sch = orc.Schedule.make(args.beta1, args.betaT, args.diffusion_steps)
+    terms = orc.infodiff_loss(sdg, sch, xb, idx, eps, encn, prior, 0.1, 0.5, 1000, use_C=True, C_max=25.0, epochs=4, curr_epoch=2)
+    terms["loss"].backward()
+    m.train()
+    m.backbone.dropout_p = m.encoder.dropout_p = 0.0
+    m.zero_grad(set_to_none=True)
+    try:
+        with _patched_draws(idx.to(DEV), [eps.clone(), encn.clone(), prior.clone()]):
+            loss = m.loss_fn(args, xb.to(DEV), curr_epoch=2)
+        loss.backward()
+    finally:
+        m.eval()
+    assert abs(float(loss.detach()) - float(terms["loss"])) / abs(float(terms["loss"])) < 2e-2
+    rels = []
+    for name, p in m.named_parameters():
+        g_ref = sdg[name].grad
+        if g_ref is None or float(g_ref.abs().max()) == 0.0 or name.endswith("attn.proj_k.bias"):
+            continue
+        assert p.grad is not None, name
+        g, r = p.grad.cpu().double().flatten(), g_ref.double().flatten()
+        rels.append((float((g - r).norm() / r.norm()), float((g @ r) / (g.norm() * r.norm())), name))
+    rels.sort(reverse=True)
+    med = sorted(r[0] for r in rels)[len(rels) // 2]
+    print(f"[parity] kld gradients: {len(rels)} checked, median rel-L2 {med:.3e}, worst {rels[0]}")
+    assert len(rels) > 700 and med < 5e-2 and all(c > 0.98 for _, c, _ in rels)
+    assert any(n.startswith("encoder.fc_var") for _, _, n in rels)          # the log_var head trains in this configuration
