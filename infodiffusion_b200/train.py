@@ -78,6 +78,8 @@ class BwdState:
         self.keep: List = []
         self.wplans: List = []
         self.late: List[Callable[[], None]] = []        # pointer fix-ups once the fp32 arena exists
+        self.side: set = set()       # indices of ops that nothing later in the list depends on (weight / bias gradients)
+        self.side_stream: Optional[torch.cuda.Stream] = None
 
     # ---- fp32 arena (weight / bias gradients), zeroed once per step
     def arena(self, shape) -> Callable[[], torch.Tensor]:
@@ -154,6 +156,7 @@ def _wgrad(plan, st: BwdState, dout, x, x_rows: int, cin: int, cout: int, tap_of
     h = C.c_void_p()
     st.keep.append(d)
     st.wplans.append((d, h, get))           # created once the arena is allocated (needs the dw pointer)
+    st.side.add(len(st.ops))                 # leaf of the backward graph: runs on the side stream
     st.ops.append(lambda: (_lib.check(plan.lib.idf_wgrad_run(h, torch.cuda.current_stream(plan.device).cuda_stream)),
                            _lib.count_launch()))
     return get
@@ -161,6 +164,7 @@ def _wgrad(plan, st: BwdState, dout, x, x_rows: int, cin: int, cout: int, tap_of
 
 def _bias_grad(plan, st: BwdState, dout, cout: int):
     get = st.arena((cout,))
+    st.side.add(len(st.ops))
     st.ops.append(lambda: (_lib.check(plan.lib.idf_colsum_bf16(dout.t.data_ptr(), get().data_ptr(), dout.rows, cout,
                                                                torch.cuda.current_stream(plan.device).cuda_stream)),
                            _lib.count_launch()))
@@ -414,8 +418,26 @@ def _build_grad_maps(plan, st: BwdState) -> None:
 def run_backward(plan) -> None:
     st = finalize_backward(plan)
     st.flat.zero_()
-    for op in st.ops:
-        op()
+    # Weight and bias gradients are leaves: each needs only dY and the saved input of its layer, nothing on the
+    # data-gradient chain waits for them.  They are forked onto a second stream (inside the captured graph: parallel
+    # branches), where they fill the SMs that the small-batch chain kernels leave idle; joined before the gather.
+    main = torch.cuda.current_stream(plan.device)
+    if SIDE_STREAM and st.side:
+        if st.side_stream is None:
+            st.side_stream = torch.cuda.Stream(plan.device)
+        side = st.side_stream
+        side.wait_stream(main)
+        for i, op in enumerate(st.ops):
+            if i in st.side:
+                side.wait_stream(main)            # everything enqueued so far (dY of this layer) is a dependency
+                with torch.cuda.stream(side):
+                    op()
+            else:
+                op()
+        main.wait_stream(side)
+    else:
+        for op in st.ops:
+            op()
     stream = torch.cuda.current_stream(plan.device).cuda_stream
     for k, m in enumerate(st.grad_maps):         # parameter-shaped gradients, one gather launch per pass
         _lib.check(plan.lib.idf_gather_elems(st.flat.data_ptr(), m.data_ptr(), None, st.grad_flat.data_ptr(),
@@ -498,6 +520,7 @@ def collect_param_grads(plan) -> Dict[nn.Parameter, torch.Tensor]:
 # autograd bridge
 # ------------------------------------------------------------------------------------------------
 USE_GRAPHS = True
+SIDE_STREAM = True      # weight / bias gradient kernels on a second stream (parallel branches of the backward graph)
 
 
 def _replay(plan, slot: str, body: Callable[[], None]) -> None:
