@@ -98,7 +98,8 @@ def pad_cols(m: torch.Tensor, cols: int) -> torch.Tensor:
 # pad), so running one over "1 + flat index" tensors instead of values yields the gather map of the packing.
 # ------------------------------------------------------------------------------------------------
 class ParamIndex:
-    """Flat fp32 layout of a parameter list: parameter i occupies [offset[i], offset[i] + numel) (4-aligned)."""
+    """Flat fp32 layout of a parameter list: parameter i occupies [offset[i], offset[i] + numel), densely packed in
+    list order (what torch's flatten / unflatten helpers assume); `total` is rounded up to a multiple of 4."""
 
     def __init__(self, params: Sequence[torch.Tensor], device):
         self.params = list(params)
@@ -107,15 +108,17 @@ class ParamIndex:
         off = 0
         for p in self.params:
             self.offset[id(p)] = off
-            off += (p.numel() + 3) // 4 * 4
-        self.total = max(off, 4)
+            off += p.numel()
+        self.dense = off
+        self.total = max((off + 3) // 4 * 4, 4)
 
     def index_of(self, p) -> torch.Tensor:
         off = self.offset[id(p)]
         return torch.arange(off + 1, off + 1 + p.numel(), dtype=torch.int64, device=self.device).view(p.shape)
 
     def views(self, flat: torch.Tensor) -> List[torch.Tensor]:
-        return [flat[self.offset[id(p)]: self.offset[id(p)] + p.numel()].view(p.shape) for p in self.params]
+        """Parameter-shaped views of a flat buffer in this layout (one C++ call, not a Python loop over ~400 tensors)."""
+        return list(torch._utils._unflatten_dense_tensors(flat[: self.dense], self.params))
 
 
 _probe: List[ParamIndex] = []

@@ -32,6 +32,9 @@ class ClipAdamW(torch.optim.Optimizer):
         tb = self._tables.get(gi)
         if tb is not None and tb["key"] == key:
             return tb
+        if tb is not None and tb.get("uniform_step") is not None:       # the set changed: back to per-parameter counts
+            for p in tb["ps"]:
+                self.state[p]["step"] = tb["uniform_step"]
         dev = ps[0].device
         for p in ps:
             if p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous():
@@ -47,7 +50,7 @@ class ClipAdamW(torch.optim.Optimizer):
             co += list(range(n))
         i64 = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)
         i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
-        tb = dict(key=key, n=len(ct),
+        tb = dict(key=key, n=len(ct), ps=list(ps), uniform_step=None,
                   params=i64([p.data_ptr() for p in ps]),
                   m=i64([self.state[p]["exp_avg"].data_ptr() for p in ps]),
                   v=i64([self.state[p]["exp_avg_sq"].data_ptr() for p in ps]),
@@ -87,17 +90,26 @@ class ClipAdamW(torch.optim.Optimizer):
                 gh[i] = g.data_ptr()
             tb["grads"].copy_(gh, non_blocking=True)
             b1, b2 = group["betas"]
-            steps = []
-            for p in ps:                                   # one step count per parameter, like torch.optim.AdamW
-                st = self.state[p]
-                st["step"] = st.get("step", 0) + 1
-                steps.append(st["step"])
+            # one step count per parameter, like torch.optim.AdamW.  While the same set of parameters keeps receiving
+            # gradients (same table) and they all share one count, a single counter stands in for all of them.
             bch = tb["bc_host"]
-            if min(steps) == max(steps):
-                bch[:, 0] = 1.0 - b1 ** steps[0]
-                bch[:, 1] = 1.0 - b2 ** steps[0]
+            if tb.get("uniform_step") is not None:
+                tb["uniform_step"] += 1
+                k = tb["uniform_step"]
+                bch[:, 0] = 1.0 - b1 ** k
+                bch[:, 1] = 1.0 - b2 ** k
             else:
-                bch.copy_(torch.tensor([[1.0 - b1 ** k, 1.0 - b2 ** k] for k in steps], dtype=torch.float32))
+                steps = []
+                for p in ps:
+                    st = self.state[p]
+                    st["step"] = st.get("step", 0) + 1
+                    steps.append(st["step"])
+                if min(steps) == max(steps):
+                    tb["uniform_step"] = steps[0]
+                    bch[:, 0] = 1.0 - b1 ** steps[0]
+                    bch[:, 1] = 1.0 - b2 ** steps[0]
+                else:
+                    bch.copy_(torch.tensor([[1.0 - b1 ** k, 1.0 - b2 ** k] for k in steps], dtype=torch.float32))
             tb["bc"].copy_(bch, non_blocking=True)
             tb["staged"] = torch.cuda.Event()
             tb["staged"].record(torch.cuda.current_stream(dev))
