@@ -83,11 +83,13 @@ class ClipAdamW(torch.optim.Optimizer):
             if tb.get("staged") is not None:
                 tb["staged"].synchronize()                # the previous step's async copies read the pinned tables
             gh = tb["grads_host"]
-            for i, p in enumerate(ps):
+            ptrs = []
+            for p in ps:
                 g = p.grad
                 if g.dtype != torch.float32 or not g.is_contiguous():
                     g = p.grad = g.float().contiguous()
-                gh[i] = g.data_ptr()
+                ptrs.append(g.data_ptr())
+            gh.numpy()[:] = ptrs                           # one bulk conversion instead of a tensor store per parameter
             tb["grads"].copy_(gh, non_blocking=True)
             b1, b2 = group["betas"]
             # one step count per parameter, like torch.optim.AdamW.  While the same set of parameters keeps receiving
