@@ -381,6 +381,8 @@ def run_ours(a):
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: NCCL's version / debug banner (NCCL_DEBUG=VERSION|INFO) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     a = parse()
     if a.impl == "reference":
         run_reference(a)
