@@ -254,7 +254,20 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        # stdout carries exactly one JSON line: NCCL prints its version banner to fd 1 while the communicator is
+        # created, so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(dev))
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     B = a.batch
     args = make_args_ns(T_STEPS)
     args.sample_chunk = a.chunk
