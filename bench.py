@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("IDF_SAMPLE_LANES", "1")),
                     help="streams the micro-batches of a step are spread over (needs --chunk < batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pdl", type=int, default=int(os.environ.get("IDF_PDL", "0")),
+                    help="1: launch conv / AdaGN kernels with programmatic dependent launch")
     ap.add_argument("--fuse-adagn", action="store_true", help="fold every AdaGN into its consumer conv (A/B comparison)")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-throughput measurement")
     ap.add_argument("--train-batch", type=int, default=32)
@@ -403,4 +405,7 @@ if __name__ == "__main__":
         if a.fuse_adagn:
             from infodiffusion_b200 import engine
             engine.FUSE_ADAGN = True
+        if a.pdl:
+            from infodiffusion_b200 import _lib
+            _lib.check(_lib.load().idf_set_option(b"pdl", 1))
         run_ours(a)

@@ -26,6 +26,7 @@ namespace idf {
 // stages (five CTAs per SM) beat three or five -- the sweep is bound by resident warps, not by bytes in flight.
 int g_adagn_ring = 2;
 int g_adagn_ctas = 400;
+extern int g_pdl;
 
 constexpr int kAdaThreads = 256;
 constexpr int kMaxC = 256;
@@ -369,9 +370,13 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
     bulk_load(ring_raw + st * stage_bytes, p.src0 + (row_base + r0) * p.c0, b0, &s_full[st]);
     if (b1) bulk_load(ring_raw + st * stage_bytes + RB * p.c0 * 2, p.src1 + (row_base + r0) * p.c1, b1, &s_full[st]);
   };
+  griddep_launch();
   if (t == 0) {
     for (int i = 0; i < kRing; ++i) mbar_init(&s_full[i], 1);
     fence_mbar_init();
+  }
+  griddep_wait();                 // the sources, their statistics and the modulation rows come from earlier kernels
+  if (t == 0) {
     for (int b = 0; b < kRing && b < nblk; ++b) issue(b);
   }
 
@@ -543,8 +548,21 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    adagn_apply_kernel<<<dim3(slices, a.batch, 1), kAdaThreads, ring_bytes, stream>>>(p);
-    return cudaGetLastError();
+    if (!g_pdl) {
+      adagn_apply_kernel<<<dim3(slices, a.batch, 1), kAdaThreads, ring_bytes, stream>>>(p);
+      return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(slices, a.batch, 1);
+    cfg.blockDim = dim3(kAdaThreads, 1, 1);
+    cfg.dynamicSmemBytes = ring_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, adagn_apply_kernel, p);
   }
 
   // cluster size: slices of <= ~72 KB (3 CTAs per SM) when possible, at most 8 CTAs (portable limit)

@@ -11,7 +11,7 @@
 
 #include "kernels.cuh"
 
-namespace idf { extern int g_adagn_ring, g_adagn_ctas; }
+namespace idf { extern int g_adagn_ring, g_adagn_ctas, g_pdl; }
 using namespace idf;
 
 namespace {
@@ -102,6 +102,7 @@ int idf_set_option(const char* key, int32_t value) {
     g_skip_epilogue = value ? 1 : 0;
     return IDF_OK;
   }
+  if (key != nullptr && std::strcmp(key, "pdl") == 0) { g_pdl = value ? 1 : 0; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "adagn_ring") == 0 && value >= 1 && value <= 8) { g_adagn_ring = static_cast<int>(value); return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "adagn_ctas") == 0 && value >= 1) { g_adagn_ctas = static_cast<int>(value); return IDF_OK; }
   return fail(IDF_ERR_ARG, "unknown option or value");

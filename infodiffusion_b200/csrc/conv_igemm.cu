@@ -20,6 +20,8 @@
 
 namespace idf {
 
+int g_pdl = 0;     // idf_set_option("pdl", 1): launch conv / AdaGN with programmatic dependent launch
+
 __host__ __device__ constexpr int conv_b_stages(int bn) { return bn == 16 ? 8 : (bn == 64 ? 4 : 6); }
 // per-epilogue-warp staging tile: 32 rows x 64 B (+16 B pad per row: conflict-free for both the row-per-lane
 // and the 4-lanes-per-row access patterns)
@@ -230,6 +232,10 @@ __global__ void __launch_bounds__(XF ? 640 : 384, 1) conv_halo_kernel(const __gr
   const uint32_t tmem_base = lds32(smem_u32(tmem_slot));
 
   const int total = p.m_super * p.n_tiles;
+  // Programmatic dependent launch: everything above (barriers, TMEM, bias, tap table) touches only constants; the
+  // weight (B) producer may also run ahead.  Every other role waits for the producer of its inputs here.
+  griddep_launch();
+  if (warp != 3) griddep_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ A producer: one halo per group
@@ -531,8 +537,21 @@ static cudaError_t launch_cfg(const ConvKernelParams& p, int grid, cudaStream_t 
     if (e != cudaSuccess) return e;
     attr_smem = smem;
   }
-  conv_halo_kernel<BN, MT, XF><<<grid, XF ? 640 : 384, smem, stream>>>(p);
-  return cudaGetLastError();
+  if (!g_pdl) {
+    conv_halo_kernel<BN, MT, XF><<<grid, XF ? 640 : 384, smem, stream>>>(p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(XF ? 640 : 384, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, MT, XF>, p);
 }
 
 template <bool XF>

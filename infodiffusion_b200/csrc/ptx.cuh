@@ -247,6 +247,12 @@ constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1;
 // ---------------------------------------------------------------------------------------------
 // small numeric helpers
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor is still running; everything that reads or writes memory the predecessor (or, transitively,
+// anything before it) touches must come after griddep_wait().  griddep_launch() lets the successor start.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
