@@ -405,6 +405,9 @@ if __name__ == "__main__":
         if a.fuse_adagn:
             from infodiffusion_b200 import engine
             engine.FUSE_ADAGN = True
+        if os.environ.get("IDF_XF_DEBUG"):
+            from infodiffusion_b200 import _lib
+            _lib.check(_lib.load().idf_set_option(b"xf_debug", int(os.environ["IDF_XF_DEBUG"])))
         if a.pdl:
             from infodiffusion_b200 import _lib
             _lib.check(_lib.load().idf_set_option(b"pdl", 1))

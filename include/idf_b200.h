@@ -46,6 +46,7 @@ int idf_init(void);
  *   "conv_force_mt" = 0 (auto) | 1 | 2 | 4   128-row tiles per CTA work unit of the conv kernel
  *   "conv_debug_skip_epilogue" = 0 | 1       plans created while set drain no output (main-loop ceiling)
  *   "pdl" = 0 (default) | 1                   launch the conv / AdaGN kernels with programmatic dependent launch
+ *   "xf_debug" = 0 | 1 | 2                    measurement only: fused-AdaGN transform warps do nothing / skip the SiLU
  *   "adagn_ring" = 1..8 (default 2)          shared-memory stages per CTA of the streaming AdaGN kernel
  *   "adagn_ctas" >= 1 (default 400)          CTAs the streaming AdaGN kernel aims for (slices per image = ceil(v / batch)) */
 int idf_set_option(const char* key, int32_t value);

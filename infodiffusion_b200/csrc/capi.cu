@@ -11,7 +11,7 @@
 
 #include "kernels.cuh"
 
-namespace idf { extern int g_adagn_ring, g_adagn_ctas, g_pdl; }
+namespace idf { extern int g_adagn_ring, g_adagn_ctas, g_pdl, g_xf_debug; }
 using namespace idf;
 
 namespace {
@@ -103,6 +103,7 @@ int idf_set_option(const char* key, int32_t value) {
     return IDF_OK;
   }
   if (key != nullptr && std::strcmp(key, "pdl") == 0) { g_pdl = value ? 1 : 0; return IDF_OK; }
+  if (key != nullptr && std::strcmp(key, "xf_debug") == 0 && value >= 0 && value <= 2) { g_xf_debug = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "adagn_ring") == 0 && value >= 1 && value <= 8) { g_adagn_ring = static_cast<int>(value); return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "adagn_ctas") == 0 && value >= 1) { g_adagn_ctas = static_cast<int>(value); return IDF_OK; }
   return fail(IDF_ERR_ARG, "unknown option or value");
@@ -257,6 +258,7 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   p.xf_coef = reinterpret_cast<const float2*>(d->xf_coef);
   p.xf_ctot = d->xf_ctot;
   p.xf_silu = d->xf_silu;
+  p.xf_debug = g_xf_debug;
   pl->xform = false;
   for (int g = 0; g < p.n_groups; ++g) pl->xform = pl->xform || p.g_xf[g] >= 0;
   if (p.bias == nullptr) { delete pl; return fail(IDF_ERR_ARG, "bias is null"); }

@@ -21,6 +21,7 @@
 namespace idf {
 
 int g_pdl = 0;     // idf_set_option("pdl", 1): launch conv / AdaGN with programmatic dependent launch
+int g_xf_debug = 0;  // measurement only: 1 = transform warps forward the halo untouched, 2 = affine without the SiLU
 
 __host__ __device__ constexpr int conv_b_stages(int bn) { return bn == 16 ? 8 : (bn == 64 ? 4 : 6); }
 // per-epilogue-warp staging tile: 32 rows x 64 B (+16 B pad per row: conflict-free for both the row-per-lane
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(XF ? 640 : 384, 1) conv_halo_kernel(const __gr
     const unsigned grp_mask = 0xffu << (lane & 24);
     const int grp_lead = lane & 24;
     const float inv_wp = 1.0f / static_cast<float>(p.Wp), inv_hp = 1.0f / static_cast<float>(p.Hp);
-    const bool do_silu = p.xf_silu != 0;
+    const bool do_silu = p.xf_silu != 0 && p.xf_debug != 2;
     const float cs = do_silu ? 0.5f : 1.0f;          // SiLU(v) = h + h*tanh(h), h = v/2: fold the 1/2 into (A, B)
     const int rows32 = static_cast<int>(p.rows);
     int sa = 0;
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(XF ? 640 : 384, 1) conv_halo_kernel(const __gr
       for (int g = 0; g < p.n_groups; ++g) {
         const int cb = p.g_xf[g];
         mbar_wait(a_full + sa, pa);
-        if (cb >= 0) {
+        if (cb >= 0 && p.xf_debug != 1) {
           const int nrows = MT * kBM + p.extra_rows[p.g_src[g]];
           const int rbase = row0 + p.g_lo[g];
           const uint32_t base = smem_u32(smA + sa * p.a_stage_bytes) + static_cast<uint32_t>(gi * 16);

@@ -54,6 +54,7 @@ struct alignas(64) ConvKernelParams {
   int32_t xf_ctot;
   int32_t xf_silu;
   int32_t g_xf[kMaxGroups];             // channel base of the group's 64-channel slice in xf_coef, or -1
+  int32_t xf_debug;                     // measurement only (idf_set_option "xf_debug")
 };
 
 constexpr int kWgMaxUnits = 64;
