@@ -463,3 +463,29 @@ def test_kld_loss_value_and_gradients(golden_dir):
     print(f"[parity] kld gradients: {len(rels)} checked, median rel-L2 {med:.3e}, worst {rels[0]}")
     assert len(rels) > 700 and med < 5e-2 and all(c > 0.98 for _, c, _ in rels)
     assert any(n.startswith("encoder.fc_var") for _, _, n in rels)          # the log_var head trains in this configuration
+
+
+def test_programmatic_dependent_launch_is_bitwise_neutral(m10):
+    """idf_set_option("pdl", 1) only changes WHEN the conv / AdaGN kernels may start (programmatic dependent launch):
+    eps, a graph-replayed DDIM trajectory and the training gradients must be bit-identical / unchanged."""
+    from infodiffusion_b200 import _lib
+    lib = _lib.load()
+    args, m, sd = m10
+    x, t, a = rand_inputs(2, 32, 10)
+    xd, td, ad = x.to(DEV), t.to(DEV), a.to(DEV)
+    shape = tuple(x.shape)
+
+    def run():
+        m.backbone.invalidate_plans()
+        e = m.backbone(xd, td, ad)
+        p = _proc(args, m, True)
+        p.noise_fn = lambda idx, out: out.copy_(step_noise(idx, shape))
+        return e, p.sampling(2, xT=xd, a=ad)
+    e0, s0 = run()
+    _lib.check(lib.idf_set_option(b"pdl", 1))
+    try:
+        e1, s1 = run()
+    finally:
+        _lib.check(lib.idf_set_option(b"pdl", 0))
+        m.backbone.invalidate_plans()
+    assert torch.equal(e0, e1) and torch.equal(s0, s1)
