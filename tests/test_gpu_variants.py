@@ -296,3 +296,32 @@ def test_32x32_model_cifar_shape():
     want = orc.sample(sd, sch, xT, a, True, noise_fn=lambda i, like: step_noise(i, shape))
     x0 = p.sampling(3, xT=xT.to(DEV), a=a.to(DEV)).cpu()
     assert rel_l2(x0, want) < TOL_X
+
+
+def test_long_horizon_ddpm_and_latent_pipeline():
+    """BASELINE configs[4] in miniature: 1000-step DDPM through the graph-captured step (device-side step counter,
+    per-step coefficient table, noise drawn by torch's CUDA generator in the reference's order) is reproducible bit
+    for bit from the seed and stays finite; the eval_fid --is_latent pipeline (latent sampler -> image sampler,
+    run.py:283-285) composes."""
+    from infodiffusion_b200.models import Diff, InfoDiff
+    from infodiffusion_b200.sampling import DiffusionProcess, LatentDiffusionProcess
+    T, B, D = 1000, 4, 32
+    args = make_args(a_dim=D, diffusion_steps=T, deterministic=False)
+    torch.manual_seed(SEED)
+    m = _to_dev(InfoDiff(args, "cpu", (3, 64, 64)))
+    largs = make_args(a_dim=D, diffusion_steps=T, model="vanilla", is_latent=True, deterministic=False)
+    torch.manual_seed(SEED + 2)
+    lat = _to_dev(Diff(largs, "cpu", (1, D, D)))
+    p_lat = LatentDiffusionProcess(largs, lat, DEV)
+    p_img = DiffusionProcess(args, m, DEV, (3, 64, 64))
+
+    def run():
+        torch.manual_seed(123)
+        torch.cuda.manual_seed_all(123)
+        z = p_lat.sampling(sampling_number=B)
+        return z, p_img.sampling(sampling_number=B, a=z)
+    z0, x0 = run()
+    z1, x1 = run()
+    assert torch.equal(z0, z1) and torch.equal(x0, x1)
+    assert torch.isfinite(z0).all() and torch.isfinite(x0).all()
+    assert 0.05 < float(x0.std()) < 20.0 and z0.shape == (B, D) and x0.shape == (B, 3, 64, 64)
