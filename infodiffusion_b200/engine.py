@@ -83,6 +83,7 @@ FUSE_ADAGN = False
 # worse as well (332 vs 344 img/s with 16): the coefficient kernels and the slower convs cost more than the launches
 # saved.  0 disables.
 FUSE_ADAGN_MAX_H = 0
+TRAIN_PDL = True       # programmatic dependent launch once a training plan exists (library-wide switch)
 
 
 class Workspace:
@@ -164,6 +165,11 @@ class Plan:
         self.B = batch
         self.device = device
         self.training = training
+        if training and TRAIN_PDL:
+            # the training step is a chain of ~1000 small dependent kernels: let each conv / AdaGN kernel run its
+            # prologue (barriers, TMEM, bias, weight tiles) while its predecessor drains (+2.5 % step rate, bitwise
+            # neutral: tests/test_gpu_network.py::test_programmatic_dependent_launch_is_bitwise_neutral)
+            _lib.check(self.lib.idf_set_option(b"pdl", 1))
         self.fuse_adagn = FUSE_ADAGN and not training
         self.ws = ws if ws is not None else Workspace(batch, device, recycle=not training)
         self.tape: List = []         # training: backward emitters, one per forward composite, replayed in reverse
