@@ -13,6 +13,8 @@
 
 namespace idf {
 
+extern int g_pdl;
+
 constexpr int kBT = 256;       // threads
 constexpr int kBMaxC = 256;
 constexpr int kBSlices = 16;   // max row slices per sample (the launcher uses fewer for large batches / small maps)
@@ -146,6 +148,8 @@ __global__ void __launch_bounds__(kBT, 3) adagn_bwd_stats_kernel(const AdaGNBwdP
   __shared__ BwdShared sh;
   __shared__ float s_part[kBT][17];
   const int n = blockIdx.y, t = threadIdx.x, C = p.C, R = p.R;
+  griddep_launch();
+  griddep_wait();                 // programmatic dependent launch: all inputs come from earlier kernels
   bwd_prologue(p, n, sh);
   const int VPR = C >> 3, rpp = kBT / VPR;
   const bool active = t < rpp * VPR;
@@ -212,6 +216,8 @@ __global__ void __launch_bounds__(kBT, 3) adagn_bwd_apply_kernel(const AdaGNBwdP
   __shared__ float s_S[2 * kBMaxC];
   __shared__ float s_G[64];
   const int n = blockIdx.y, t = threadIdx.x, C = p.C, R = p.R;
+  griddep_launch();
+  griddep_wait();
   bwd_prologue(p, n, sh);
   const int cpg = C / 32;
   for (int i = t; i < 2 * C; i += kBT) {
@@ -351,11 +357,26 @@ cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, int num_sms, cudaStrea
   p.slice_rows = (p.R + ns - 1) / ns;
   p.n_slices = (p.R + p.slice_rows - 1) / p.slice_rows;
   const dim3 grid(p.n_slices, a.batch, 1);
-  adagn_bwd_stats_kernel<<<grid, kBT, 0, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
+  if (!g_pdl) {
+    adagn_bwd_stats_kernel<<<grid, kBT, 0, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    adagn_bwd_apply_kernel<<<grid, kBT, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kBT, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, adagn_bwd_stats_kernel, p);
   if (e != cudaSuccess) return e;
-  adagn_bwd_apply_kernel<<<grid, kBT, 0, stream>>>(p);
-  return cudaGetLastError();
+  return cudaLaunchKernelEx(&cfg, adagn_bwd_apply_kernel, p);
 }
 
 }  // namespace idf
