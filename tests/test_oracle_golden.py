@@ -133,3 +133,24 @@ def test_variant_goldens_and_constructor_digests(golden_dir):
     torch.manual_seed(SEED + 1)
     van.backbone = models.UNet(T=6, ch=64, ch_mult=[1, 2, 2, 2], shape=(3, 64, 64))
     assert state_digest(van.state_dict()) == meta["state_diff_unet_1222_T6_seed65"]["digest"]
+
+
+def test_kld_control_constant_loss_golden(golden_dir):
+    """InfoDiff.loss_fn with kld_weight != 0, use_C (reference models.py:648-668): oracle vs the reference's value."""
+    from infodiffusion_b200.models import InfoDiff
+    kw = dict(kld_weight=0.5, mmd_weight=0.1, use_C=True, C_max=25.0, epochs=4)
+    args = make_args(a_dim=32, diffusion_steps=1000, **kw)
+    torch.manual_seed(SEED)
+    sd = perturb_state_dict(InfoDiff(args, "cpu", (3, 64, 64)).state_dict())
+    gl = torch.Generator().manual_seed(23)
+    xb = torch.rand(4, 3, 64, 64, generator=gl) * 2 - 1
+    idx = torch.randint(0, 1000, (4,), generator=gl)
+    eps = torch.randn(4, 3, 64, 64, generator=gl)
+    encn = torch.randn(4, 32, generator=gl)
+    prior = torch.randn(4, 32, generator=gl)
+    sch = orc.Schedule.make(args.beta1, args.betaT, 1000)
+    with torch.no_grad():
+        terms = orc.infodiff_loss(sd, sch, xb, idx, eps, encn, prior, 0.1, 0.5, 1000, use_C=True, C_max=25.0, epochs=4, curr_epoch=2)
+    g = np.load(golden_dir / "loss_kld_a32.npz")
+    assert abs(float(terms["loss"]) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    assert abs(float(terms["kld"]) - float(g["kld"])) <= 1e-6 * abs(float(g["kld"]))
