@@ -489,3 +489,64 @@ def test_programmatic_dependent_launch_is_bitwise_neutral(m10):
         _lib.check(lib.idf_set_option(b"pdl", 0))
         m.backbone.invalidate_plans()
     assert torch.equal(e0, e1) and torch.equal(s0, s1)
+
+
+def test_three_training_steps_track_the_reference_recipe(m1000):
+    """run.py:195-200 for three steps -- loss_fn, backward, clip_grad_norm_(1.0), AdamW(lr, wd 1e-5) -- on the CUDA path
+    (fused ClipAdamW) and on the fp32 CPU oracle (torch autograd + torch.optim.AdamW) with identical draws: the loss
+    sequence agrees and the accumulated parameter update points the same way."""
+    from infodiffusion_b200.optim import ClipAdamW
+    args, m, sd = m1000
+    B, steps, lr = 2, 3, 1e-3
+    gl = torch.Generator().manual_seed(77)
+    draws = []
+    for _ in range(steps):
+        draws.append(dict(x=torch.rand(B, 3, 64, 64, generator=gl) * 2 - 1, idx=torch.randint(0, 1000, (B,), generator=gl),
+                          eps=torch.randn(B, 3, 64, 64, generator=gl), encn=torch.randn(B, 32, generator=gl),
+                          prior=torch.randn(B, 32, generator=gl)))
+    # oracle side
+    names = [k for k, v in sd.items() if v.is_floating_point() and "timembedding.0" not in k]
+    sdo = {k: (v.clone().requires_grad_(True) if k in names else v.clone()) for k, v in sd.items()}
+    opt_o = torch.optim.AdamW([sdo[k] for k in names], lr=lr, weight_decay=1e-5)
+    sch = orc.Schedule.make(args.beta1, args.betaT, args.diffusion_steps)
+    loss_o = []
+    for d in draws:
+        terms = orc.infodiff_loss(sdo, sch, d["x"], d["idx"], d["eps"], d["encn"], d["prior"], args.mmd_weight, args.kld_weight,
+                                  args.diffusion_steps)
+        opt_o.zero_grad(set_to_none=True)
+        terms["loss"].backward()
+        torch.nn.utils.clip_grad_norm_([sdo[k] for k in names if sdo[k].grad is not None], 1.0)
+        opt_o.step()
+        loss_o.append(float(terms["loss"]))
+    # CUDA side
+    m.train()
+    m.backbone.dropout_p = m.encoder.dropout_p = 0.0
+    opt = ClipAdamW(m.parameters(), lr=lr, weight_decay=1e-5, max_norm=1.0)
+    loss_g = []
+    try:
+        for d in draws:
+            with _patched_draws(d["idx"].to(DEV), [d["eps"].clone(), d["encn"].clone(), d["prior"].clone()]):
+                loss = m.loss_fn(args, d["x"].to(DEV))
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            loss_g.append(float(loss.detach()))
+        torch.cuda.synchronize()
+        print(f"\n[parity] 3 training steps: loss cuda {['%.5f' % v for v in loss_g]} vs oracle {['%.5f' % v for v in loss_o]}")
+        for a_, b_ in zip(loss_g, loss_o):
+            assert abs(a_ - b_) / abs(b_) < 2e-2
+        num = den_g = den_o = 0.0
+        for name, p in m.named_parameters():
+            if name not in names or sdo[name].grad is None:
+                continue
+            dg = (p.detach().cpu().double() - sd[name].double()).flatten()
+            do = (sdo[name].detach().double() - sd[name].double()).flatten()
+            num += float(dg @ do); den_g += float(dg @ dg); den_o += float(do @ do)
+        cos = num / (den_g ** 0.5 * den_o ** 0.5)
+        print(f"[parity] accumulated parameter update: cosine {cos:.4f}, norm ratio {(den_g / den_o) ** 0.5:.4f}")
+        assert cos > 0.9 and 0.8 < (den_g / den_o) ** 0.5 < 1.25
+    finally:
+        m.eval()
+        with torch.no_grad():
+            m.load_state_dict(sd)
+        m.zero_grad(set_to_none=True)
