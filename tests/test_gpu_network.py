@@ -494,10 +494,11 @@ def test_programmatic_dependent_launch_is_bitwise_neutral(m10):
 def test_three_training_steps_track_the_reference_recipe(m1000):
     """run.py:195-200 for three steps -- loss_fn, backward, clip_grad_norm_(1.0), AdamW(lr, wd 1e-5) -- on the CUDA path
     (fused ClipAdamW) and on the fp32 CPU oracle (torch autograd + torch.optim.AdamW) with identical draws: the loss
-    sequence agrees and the accumulated parameter update points the same way."""
+    sequence agrees (measured: 0.1 %) and the accumulated parameter update points the same way (measured cosine 0.996,
+    norm ratio 0.9999)."""
     from infodiffusion_b200.optim import ClipAdamW
     args, m, sd = m1000
-    B, steps, lr = 2, 3, 1e-3
+    B, steps, lr = 2, 3, 1e-4        # the reference's learning rate (run.py:60)
     gl = torch.Generator().manual_seed(77)
     draws = []
     for _ in range(steps):
@@ -544,7 +545,7 @@ def test_three_training_steps_track_the_reference_recipe(m1000):
             num += float(dg @ do); den_g += float(dg @ dg); den_o += float(do @ do)
         cos = num / (den_g ** 0.5 * den_o ** 0.5)
         print(f"[parity] accumulated parameter update: cosine {cos:.4f}, norm ratio {(den_g / den_o) ** 0.5:.4f}")
-        assert cos > 0.9 and 0.8 < (den_g / den_o) ** 0.5 < 1.25
+        assert cos > 0.97 and 0.95 < (den_g / den_o) ** 0.5 < 1.05
     finally:
         m.eval()
         with torch.no_grad():
