@@ -14,11 +14,16 @@
 // Roles (384 threads): warp 0 = A (halo) TMA producer     warp 3 = B (weights) TMA producer
 //                      warp 1 = UMMA issuer (1 thread)    warp 2 = TMEM allocator (+ second UMMA issuer when MT >= 2)
 //                      warps 4..11 = epilogue (two warps per TMEM lane quarter)
-//                      XF variant only: warps 12..19 = transform (fused AdaGN + SiLU on the halo, in place)
+//                      XF variant only: warps 12..23 = transform (fused AdaGN + SiLU on the halo, in place)
 // Pipelines: A halo stages x2, B ring x4-8 (full/empty mbarriers), TMEM accumulator sets x2.
 #include "kernels.cuh"
 
 namespace idf {
+
+// transform warps of the XF variant (4 rows per warp and pass).  Measured at batch 256 with bench.py --fuse-adagn:
+// 8 warps 327 img/s, 12 warps 344 img/s (= the unfused lowering), 16 warps 324 img/s (72 registers: the epilogue spills)
+constexpr int kXfWarps = 12;
+constexpr int kXfRows = 4 * kXfWarps;
 
 int g_pdl = 0;     // idf_set_option("pdl", 1): launch conv / AdaGN with programmatic dependent launch
 int g_xf_debug = 0;  // measurement only: 1 = transform warps forward the halo untouched, 2 = affine without the SiLU
@@ -176,11 +181,11 @@ __device__ __forceinline__ void epilogue_narrow(const ConvKernelParams& p, const
 }
 
 // ---------------------------------------------------------------------------------------------------
-// XF = true adds eight "transform" warps (threads 384..639) between the A producer and the UMMA issuers: they
+// XF = true adds kXfWarps "transform" warps (threads 384..) between the A producer and the UMMA issuers: they
 // apply the consumer-side AdaGN (y = act(A*x + B), coefficients per image and channel) to the halo in place, so
 // the normalised activation is never written to or read from HBM.
 template <int BN, int MT, bool XF>
-__global__ void __launch_bounds__(XF ? 640 : 384, 1) conv_halo_kernel(const __grid_constant__ ConvKernelParams p) {
+__global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = HaloCfg<BN, MT>;
   constexpr int AS = Cfg::A_STAGES, BS = Cfg::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(XF ? 640 : 384, 1) conv_halo_kernel(const __gr
     tma_prefetch_desc(&p.tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, Cfg::NI); mbar_init(a_ready + s, 8); }
+    for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, Cfg::NI); mbar_init(a_ready + s, kXfWarps); }
     for (int s = 0; s < BS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, Cfg::NI); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, Cfg::NI); mbar_init(tempty + a, 256); }
     fence_mbar_init();
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(XF ? 640 : 384, 1) conv_halo_kernel(const __gr
     }
   } else if (XF && warp >= 12) {
     // ------------------------------------------------------------------ transform warps (fused AdaGN + SiLU)
-    // 256 threads.  thread -> one physical 16-byte granule column gi and the rows rs, rs + 32, ...; all its rows
+    // 32 * kXfWarps threads.  thread -> one physical 16-byte granule column gi and the rows rs, rs + kXfRows, ...; all its rows
     // share (row & 7), so under the 128-byte swizzle it always holds the same logical 8 channels gl = gi ^ (rs & 7).
     // The 8 lanes of a row share the row bookkeeping: lane gi == 0 computes (valid, image) and broadcasts it.
     const int tt = threadIdx.x - 384;
@@ -380,12 +385,12 @@ __global__ void __launch_bounds__(XF ? 640 : 384, 1) conv_halo_kernel(const __gr
           };
           // four rows per trip: row bookkeeping and all four loads first, then branch-free arithmetic with predicated
           // stores when the rows share one image (the common case); rows of different images fall back to one by one
-          for (int i0 = rs; i0 < nrows; i0 += 128) {
+          for (int i0 = rs; i0 < nrows; i0 += 4 * kXfRows) {
             int info[4];
             uint4 u[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const int i = i0 + 32 * q;
+              const int i = i0 + kXfRows * q;
               int inf = -1;                                            // -1: leave the row alone
               if (gi == 0 && i < nrows) {
                 const int r = rbase + i;
@@ -412,14 +417,14 @@ __global__ void __launch_bounds__(XF ? 640 : 384, 1) conv_halo_kernel(const __gr
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const uint4 o = xform(u[q]);
-                if (info[q] >= 0) sts128(base + static_cast<uint32_t>(i0 + 32 * q) * 128u, o);
+                if (info[q] >= 0) sts128(base + static_cast<uint32_t>(i0 + kXfRows * q) * 128u, o);
               }
             } else {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 if (info[q] < 0) continue;
                 if (info[q] != cur) reload(info[q]);
-                sts128(base + static_cast<uint32_t>(i0 + 32 * q) * 128u, xform(u[q]));
+                sts128(base + static_cast<uint32_t>(i0 + kXfRows * q) * 128u, xform(u[q]));
               }
             }
           }
@@ -539,12 +544,12 @@ static cudaError_t launch_cfg(const ConvKernelParams& p, int grid, cudaStream_t 
     attr_smem = smem;
   }
   if (!g_pdl) {
-    conv_halo_kernel<BN, MT, XF><<<grid, XF ? 640 : 384, smem, stream>>>(p);
+    conv_halo_kernel<BN, MT, XF><<<grid, XF ? 384 + 32 * kXfWarps : 384, smem, stream>>>(p);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, 1, 1);
-  cfg.blockDim = dim3(XF ? 640 : 384, 1, 1);
+  cfg.blockDim = dim3(XF ? 384 + 32 * kXfWarps : 384, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -75,8 +75,8 @@ class VAct:
 
 # Inference plans can fold every AdaGN into its consumer conv (transform warps rewrite the A operand in shared
 # memory; the normalised activation never touches HBM, workspace 2.1 GB instead of 2.8 GB at batch 256).  Measured on
-# B200 at batch 256 it is a wash -- 327 img/s fused vs 319-331 unfused: the SiLU costs one MUFU op per element either
-# way and the transform competes with the epilogue warps for issue slots -- so the separate HBM-bound AdaGN kernels
+# B200 at batch 256 it is a wash -- 344 img/s either way at the same clocks: the transform's shared-memory
+# read-modify-write loop competes with the epilogue warps for issue slots -- so the separate HBM-bound AdaGN kernels
 # stay the default and this is an opt-in (bench.py --fuse-adagn).
 FUSE_ADAGN = False
 # Fusing only the small maps (H <= FUSE_ADAGN_MAX_H), whose stand-alone AdaGN launches are pure latency, measured
