@@ -163,7 +163,7 @@ def run_reference(a):
         return
     vals, sample, cores = [], "", 1
     for i in range(a.warmup + a.steps):
-        v, cores, sample = cpu_ddim_rate(16, 4.0, 4)
+        v, cores, sample = cpu_ddim_rate(32, 6.0, 12)      # one step = a bounded sample: <= 6 s or 12 UNet evaluations
         if i >= a.warmup:
             vals.append(v)
     v = statistics.mean(vals)
@@ -372,7 +372,7 @@ def run_ours(a):
         train = train_throughput(a, dev, world, rank)
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
-        v, cores, sample = cpu_ddim_rate(16, 10.0, 8)
+        v, cores, sample = cpu_ddim_rate(32, 15.0, 40)     # ~15 s of host work on all cores
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
         ws_gb = sum(w.bytes for w in proc._sampler("ddim", B).lane_ws) / 1e9
