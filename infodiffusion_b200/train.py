@@ -81,6 +81,14 @@ class BwdState:
         self.side: set = set()       # indices of ops that nothing later in the list depends on (weight / bias gradients)
         self.side_stream: Optional[torch.cuda.Stream] = None
 
+    def __del__(self):
+        try:
+            for _, h, _ in self.wplans:
+                if h:
+                    self.plan.lib.idf_wgrad_plan_destroy(h)
+        except Exception:
+            pass
+
     # ---- fp32 arena (weight / bias gradients), zeroed once per step
     def arena(self, shape) -> Callable[[], torch.Tensor]:
         n = 1

@@ -175,3 +175,30 @@ def test_product_never_imports_the_oracle_and_has_no_cpu_path():
         UNet(T=10, ch=64, ch_mult=[1, 2, 2, 2], shape=(3, 64, 64)).eval()(torch.zeros(1, 3, 64, 64), torch.zeros(1, dtype=torch.long))
     with pytest.raises(RuntimeError, match="CUDA"):
         LatentUNet(T=10, shape=(1, 8, 8)).eval()(torch.zeros(2, 8), torch.zeros(2, dtype=torch.long))
+
+
+def test_run_py_schedule_and_naming():
+    """run.py mirrors the reference's LR schedule (GradualWarmupScheduler over CosineAnnealingLR, run.py:182-185: the
+    sequence below was produced by the reference's own classes) and its experiment / folder naming (utils.py:49-61)."""
+    import warnings
+    import run as idf_run
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=1e-4)
+    cos = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer=opt, T_max=6, eta_min=0, last_epoch=-1)
+    warm = idf_run.GradualWarmupScheduler(optimizer=opt, multiplier=2., warm_epoch=1, after_scheduler=cos)
+    got = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(6):
+            got.append(opt.param_groups[0]["lr"])
+            opt.step()
+            warm.step()
+    want = [0.0001, 0.0002, 0.00021435935394489817, 0.0002, 0.00016076951545867363, 0.00010717967697244908]
+    assert all(abs(a - b) <= 1e-12 for a, b in zip(got, want)), got
+    args = idf_run.parse_args(["--model", "diff", "--mode", "train", "--prior", "regular", "--dataset", "celeba", "--a_dim", "32",
+                               "--kld_weight", "0.5", "--use_C", "--is_bottleneck"])
+    assert idf_run.generate_exp_string(args) == "celeba_32d_0.5kld_25C_0.1mmd_bottleneck"
+    assert idf_run.get_dataset_config(args) == (3, 64, 64) and args.unets_channels == 64
+    args.dataset = "mnist"
+    with pytest.raises(NotImplementedError):
+        idf_run.get_dataset_config(args)
