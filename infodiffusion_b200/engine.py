@@ -30,8 +30,8 @@ import torch.nn as nn
 from . import _lib
 from ._lib import EPI_BF16, EPI_F32_NCHW, EPI_SAMPLER, AdaGNArgs, ConvDesc
 from .layout import (ParamIndex, pack_conv1x1, pack_conv3x3, pad_cols as _pad_cols, pad_rows as _pad_rows, probing, pv,
-                     taps1x1, taps3x3, taps_stride2)
-from .modules import AttnBlock, AuxResBlock, DownSample, ResBlock, ResBlock_encoder, UpSample
+                     taps3x3, taps_stride2)
+from .modules import AttnBlock, AuxResBlock, DownSample, ResBlock, UpSample
 
 BF16 = torch.bfloat16
 

@@ -10,7 +10,7 @@ reference's order, so identical seeds give identical noise.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import List, Optional
 
 import torch
 
