@@ -25,7 +25,7 @@ def make(cin, cout, H, residual, stats, skip):
     b = torch.randn(cout, device=dev)
     out = torch.zeros(rows, cout, device=dev, dtype=BF)
     res = torch.randn(rows, cout, device=dev).to(BF) if residual else None
-    st = torch.zeros((rows + 127) // 128 * 3 * cout * 2, device=dev) if stats else None
+    st = torch.zeros(2 * ((rows + 127) // 128) * 4 * cout * 2, device=dev) if stats else None    # records A and B per 32-row window
     d = ConvDesc()
     d.n_src = 1
     d.src[0], d.src_rows[0], d.src_ld[0] = x.data_ptr(), rows, cin
@@ -73,4 +73,19 @@ for (cin, cout, H) in [(64, 64, 64), (128, 64, 64), (192, 64, 64), (128, 128, 64
         lib.idf_conv_plan_destroy(h)
         del keep
         line += f"{name} {us:7.1f} ({fl / us / 1e6:6.0f}, {fl / us / 1e6 / PEAK * 100:4.1f}%)  "
+    # planner's choice against every forced number of 128-row tiles per work unit
+    for mt in (1, 2, 4):
+        if mt == 4 and cout % 128 == 0:
+            continue
+        _lib.check(lib.idf_set_option(b"conv_force_mt", mt))
+        try:
+            h, keep = make(cin, cout, H, False, True, False)
+            us = timeit(h)
+            lib.idf_conv_plan_destroy(h)
+            del keep
+            line += f"MT={mt} {us:6.1f}  "
+        except Exception as e:       # configuration does not fit in shared memory
+            line += f"MT={mt}   n/a  "
+        finally:
+            _lib.check(lib.idf_set_option(b"conv_force_mt", 0))
     print(line)
