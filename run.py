@@ -269,14 +269,26 @@ def evaluate(args):
             root = os.path.join(args.img_folder, 'diff' if args.model == 'vanilla' else '', exp, 'eval')
         total = args.sampling_number
         for first in range(0, total, args.batch_size * world):
-            lo, hi = shard_range(min(args.batch_size * world, total - first), rank, world)
-            n_local = hi - lo
-            if n_local == 0:
-                continue
+            n_round = min(args.batch_size * world, total - first)
+            lo, hi = shard_range(n_round, rank, world)
+            # every rank draws the round's FULL batch from the same seed (x_T, then a, on the CPU generator like
+            # sampling.py:92-95; per-step noise on the CUDA generator) and keeps its slice: the images do not depend
+            # on the number of GPUs, and with one GPU the draws are the reference's
             if process_latent is not None:
-                batch = process.sampling(sampling_number=n_local, a=process_latent.sampling(sampling_number=n_local))
+                a_full = process_latent.sampling(sampling_number=n_round)
             else:
-                batch = process.sampling(sampling_number=n_local)
+                a_full = None
+            xT_full = torch.randn([n_round, *shape]).to(device=device)
+            if a_full is None:
+                a_full = torch.randn([n_round, args.a_dim]).to(device=device)
+            if hi == lo:
+                continue
+            if world > 1:
+                noise = lambda idx, out: out.copy_(torch.randn(n_round, *shape, device=device)[lo:hi])
+                for pr in (process, getattr(process, "p1", None), getattr(process, "p2", None)):
+                    if pr is not None:
+                        pr.noise_fn = noise
+            batch = process.sampling(sampling_number=hi - lo, xT=xT_full[lo:hi].contiguous(), a=a_full[lo:hi].contiguous())
             idf_io.save_eval_images(batch, root, first_index=first + lo, limit=total)     # every rank writes its own range
         if rank == 0:
             print("DONE", root)
