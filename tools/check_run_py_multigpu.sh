@@ -1,6 +1,7 @@
 #!/bin/bash
 # run.py under torchrun on 2 GPUs (data-parallel training, batch-sharded eval_fid) and the same eval_fid on 1 GPU:
-# the PNG folders must hold identical pixels (draws are independent of the number of GPUs).
+# the PNG folders must hold the same images (draws are independent of the number of GPUs; a sample's position in the
+# batch moves its fp32 GroupNorm summation order, i.e. single uint8 levels may differ).
 set -u
 R="${GRAFT_REPO_ROOT:-/root/repo}"
 W=$(mktemp -d)
@@ -17,6 +18,7 @@ import numpy as np
 from PIL import Image
 a = sorted(glob.glob("imgs/*/eval-fid-fast/*.png"))
 b = sorted(glob.glob("imgs1/*/eval-fid-fast/*.png"))
-same = all(np.array_equal(np.asarray(Image.open(x)), np.asarray(Image.open(y))) for x, y in zip(a, b))
-print("files", len(a), len(b), "identical pixels:", same)
+diff = [np.abs(np.asarray(Image.open(x)).astype(int) - np.asarray(Image.open(y)).astype(int)) for x, y in zip(a, b)]
+print("files", len(a), len(b), "max level difference:", max(int(d.max()) for d in diff),
+      "pixels equal: %.4f" % float(np.mean([np.mean(d == 0) for d in diff])))
 PY
