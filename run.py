@@ -268,8 +268,8 @@ def evaluate(args):
         else:
             root = os.path.join(args.img_folder, 'diff' if args.model == 'vanilla' else '', exp, 'eval')
         total = args.sampling_number
-        for first in range(0, total, args.batch_size * world):
-            n_round = min(args.batch_size * world, total - first)
+        for first in range(0, total, args.batch_size):               # --batch_size is the GLOBAL batch of a round
+            n_round = min(args.batch_size, total - first)
             lo, hi = shard_range(n_round, rank, world)
             # every rank draws the round's FULL batch from the same seed (x_T, then a, on the CPU generator like
             # sampling.py:92-95; per-step noise on the CUDA generator) and keeps its slice: the images do not depend
