@@ -8,7 +8,10 @@ What differs, on purpose:
     float in [-1, 1], optional `labels`) or are synthetic U[-1, 1] (--synthetic_size images);
   * shapes: the kernels cover the 64x64 / 64-channel configuration (celeba, ffhq, chairs-sized data with
     --unets_channels 64); other dataset names raise;
-  * torchrun: under WORLD_SIZE > 1 sampling / encoding are batch-sharded and training is data parallel.
+  * torchrun: under WORLD_SIZE > 1 training is data parallel (--batch_size per GPU, like BASELINE configs[2]);
+    sampling / encoding shard every round of --batch_size images over the ranks, all ranks drawing the round's full
+    batch from the same seed, so the written images do not depend on the number of GPUs (checked by
+    tools/check_run_py_multigpu.sh: 2 GPUs vs 1 GPU differ by at most one uint8 level in 0.01 % of the pixels).
 The VAE baseline and the analysis modes (disentangle, interpolate, latent_quality, plot_latent) are not built.
 """
 from __future__ import annotations
