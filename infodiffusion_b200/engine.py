@@ -1,4 +1,5 @@
-"""Network-level execution engine: lowers AuxiliaryUNet / Encoder onto the libidf_b200 kernels.
+"""Network-level execution engine: lowers the UNets (AuxiliaryUNet, BottleneckAuxUNet, UNet), the Encoder and the
+LatentUNet onto the libidf_b200 kernels.
 
 A *plan* is a static list of kernel launches over a preallocated workspace, built once per
 (network, batch).  It is CUDA-graph capturable: no allocation, no host sync, every per-step value
