@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from infodiffusion_b200 import layout
 from oracle import infodiff_oracle as orc
 from oracle.golden_util import SEED, make_args, state_digest
-from tests.helpers import emulate_igemm, from_padflat, space_to_depth, to_padflat
+from tests.helpers import emulate_igemm, from_padflat, interior_mask, space_to_depth, to_padflat
 
 ROOT = Path(__file__).resolve().parent.parent
 
@@ -202,3 +202,39 @@ def test_run_py_schedule_and_naming():
     args.dataset = "mnist"
     with pytest.raises(NotImplementedError):
         idf_run.get_dataset_config(args)
+
+
+def test_fused_adagn_operand_kblocks_match_conv_over_normalised_concat():
+    """engine.Plan._operand for a VAct (AdaGN of two channel-concatenated sources, applied inside the conv): the
+    k-block order it produces must match the (tap, concatenated channel) packing of the conv weight, and kb_xf must
+    point each k-block at its channels of the coefficient table -- checked by emulating the K loop on the CPU with
+    the transform applied per k-block."""
+    from infodiffusion_b200.engine import Act, Plan, VAct
+    g = torch.Generator().manual_seed(5)
+    B, H, c0, c1, cout = 2, 8, 128, 64, 64
+    x0 = torch.randn(B, c0, H, H, generator=g)
+    x1 = torch.randn(B, c1, H, H, generator=g)
+    A = torch.randn(B, c0 + c1, generator=g)
+    Bc = torch.randn(B, c0 + c1, generator=g)
+    w = torch.randn(cout, c0 + c1, 3, 3, generator=g) * 0.05
+    bias = torch.randn(cout, generator=g)
+    normed = F.silu(torch.cat([x0, x1], 1).double() * A.double()[:, :, None, None] + Bc.double()[:, :, None, None])
+    ref = F.conv2d(normed, w.double(), bias.double(), padding=1)
+    s0, s1 = Act(to_padflat(x0), H, c0, 1, 0), Act(to_padflat(x1), H, c1, 1, 0)
+    coef = torch.stack([A, Bc], dim=-1)                       # [B, C, 2] like idf_adagn_coef writes it
+    srcs, kb, xf = Plan._operand(VAct([s0, s1], coef, True, H, c0 + c1), layout.tap_offsets3x3(H, H))
+    assert [s.t.shape[1] for s in srcs] == [c0, c1] and len(kb) == 9 * (c0 + c1) // 64 == len(xf[2])
+    rows = B * (H + 1) * (H + 1)
+    img = torch.arange(rows) // ((H + 1) * (H + 1))
+    inside = interior_mask(B, H, H)
+    srcs_t = []
+    for si, c0s, off in kb:                                    # apply the transform per k-block, as the kernel does
+        cb = xf[2][len(srcs_t)]
+        raw = srcs[si].t[:, c0s:c0s + 64].double()
+        a_, b_ = coef[img, cb:cb + 64, 0].double(), coef[img, cb:cb + 64, 1].double()
+        t = F.silu(raw * a_ + b_)
+        t[~inside] = 0                                         # pad rows stay zero
+        srcs_t.append(t)
+    kb_t = [(k, 0, off) for k, (_, _, off) in enumerate(kb)]
+    out = emulate_igemm(srcs_t, kb_t, layout.pack_conv3x3(w), bias, B, H, H)
+    assert torch.allclose(from_padflat(out, B, H, H), ref, atol=1e-9)
