@@ -72,6 +72,22 @@ int encode_2d(CUtensorMap* tm, const void* base, int64_t rows, int32_t ld, int32
   return IDF_OK;
 }
 
+// 2-D bf16 row-major matrix [rows, ld] -> box {32 elements, 32 rows}, 64B swizzle: the epilogue's output tile
+// (one epilogue warp's 32 rows x 32 columns), written with a TMA store
+int encode_2d_out(CUtensorMap* tm, const void* base, int64_t rows, int32_t ld) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(IDF_ERR_ARG, "TMA base not 16-byte aligned");
+  if (ld % 8 != 0) return fail(IDF_ERR_ARG, "row pitch must be a multiple of 16 bytes");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(IDF_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed with CUresult %d", (int)r);
+  return IDF_OK;
+}
+
 }  // namespace
 
 struct idf_conv_plan {
@@ -243,6 +259,10 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   }
   rc = encode_2d(&p.tmB, d->weight, d->cout_pad, d->num_kb * kBK, d->block_n);
   if (rc != IDF_OK) { delete pl; return rc; }
+  if (d->epilogue == IDF_EPI_BF16) {
+    rc = encode_2d_out(&p.tmOut, d->out, p.rows, d->out_ld);
+    if (rc != IDF_OK) { delete pl; return rc; }
+  }
   p.cout = d->cout;
   p.epilogue = d->epilogue;
   p.bias = d->bias;

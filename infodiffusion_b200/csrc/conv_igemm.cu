@@ -29,11 +29,15 @@ int g_pdl = 0;     // idf_set_option("pdl", 1): launch conv / AdaGN with program
 int g_xf_debug = 0;  // measurement only: 1 = transform warps forward the halo untouched, 2 = affine without the SiLU
 
 __host__ __device__ constexpr int conv_b_stages(int bn) { return bn == 16 ? 8 : (bn == 64 ? 4 : 6); }
-// per-epilogue-warp staging tile: 32 rows x 64 B (+16 B pad per row: conflict-free for both the row-per-lane
-// and the 4-lanes-per-row access patterns)
-constexpr uint32_t kStageRowBytes = 80;
-constexpr uint32_t kStageBytes = 8 * 32 * kStageRowBytes;
+// per-epilogue-warp staging tile: 32 rows x 64 B in the TMA SWIZZLE_64B layout (16-byte chunk c of row r lives at
+// chunk c ^ ((r >> 1) & 3)): conflict-free for the row-per-lane 16-byte accesses, for the 4-lanes-per-row coalesced
+// residual deposit and for the column-pair reads of the GroupNorm partial sums; the tile leaves through ONE TMA store.
+constexpr uint32_t kStageTile = 32 * 64;
+constexpr uint32_t kStageBytes = 8 * kStageTile;
 constexpr uint32_t kBiasBytes = 512 * 4;   // bias vector of the whole conv (cout_pad <= 512), staged once per CTA
+__device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
+  return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
 
 template <int BN, int MT>
 struct HaloCfg {
@@ -49,8 +53,8 @@ struct HaloCfg {
 };
 
 __host__ __device__ inline uint32_t conv_smem_bytes(int a_stage_bytes, int a_stages, int b_stages, int b_bytes) {
-  return static_cast<uint32_t>(a_stages * a_stage_bytes + b_stages * b_bytes + 512 /*barriers*/ +
-                               256 /*tap table*/ + kStageBytes + kBiasBytes + 1024 /*align*/);
+  return static_cast<uint32_t>(a_stages * a_stage_bytes + b_stages * b_bytes + 1024 /*barriers + tap table*/ +
+                               kStageBytes + kBiasBytes + 1024 /*align*/);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -71,9 +75,9 @@ __device__ __forceinline__ void residual_fetch(const ConvKernelParams& p, int64_
 
 // One (accumulator, 32-column) work item of an epilogue warp; executed by all 32 lanes.
 //   out = bf16(acc + bias (+ residual)), pad rows forced to zero.
-// The warp's 32 rows x 64 B pass through a private shared-memory staging tile so that global traffic is
-// coalesced: 4 lanes cover one row's 64 B, 8 rows per instruction (8 LSU wavefronts instead of the 32 a
-// row-per-lane 16-byte store at 128-byte stride costs) -- for the residual read and for the output write.
+// The warp's 32 rows x 64 B pass through a private shared-memory staging tile (SWIZZLE_64B layout) and leave
+// with one TMA store (rows beyond the tensor are clipped by the tensor map); the residual, fetched coalesced one
+// item ahead (4 lanes per row), is deposited in the same tile first and read back row-per-lane.
 // Optional GroupNorm partials: column sums of the STAGED (bf16-rounded) tile, written per WARP (no
 // cross-warp exchange, no barriers, fixed summation order => deterministic):
 //   statsA[(tile*4 + q)][col] = (sum, sumsq) over the warp's rows in the image of its first row,
@@ -84,9 +88,12 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
                                                     int lane, uint32_t stage, uint32_t bias_sa,
                                                     const uint4 (&res)[4]) {
   const int sub_row = lane >> 2, sub_chunk = lane & 3;     // coalesced distribution: row = 8 i + sub_row
+  // the previous item's TMA store must have finished reading the staging tile
+  if (lane == 0) bulk_wait_read<0>();
+  __syncwarp();
   if (p.residual != nullptr) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) sts128(stage + (i * 8 + sub_row) * kStageRowBytes + sub_chunk * 16, res[i]);
+    for (int i = 0; i < 4; ++i) sts128(stage + stage_off(i * 8 + sub_row, sub_chunk), res[i]);
     __syncwarp();
   }
   float f[32];
@@ -98,16 +105,16 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
     f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + __uint_as_float(b.z);
     f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + __uint_as_float(b.w);
   }
-  const uint32_t my_row = stage + lane * kStageRowBytes;
-  if (p.residual != nullptr) {
+  const int sw = (lane >> 1) & 3;
+  const uint32_t my_row = stage + lane * 64;
+  if (p.residual != nullptr) {             // lane L reads row L, which only lane L overwrites below: no barrier needed
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint4 u = lds128(my_row + j * 16);
+      const uint4 u = lds128(my_row + ((j ^ sw) << 4));
       const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
       f[8 * j + 0] += a0.x; f[8 * j + 1] += a0.y; f[8 * j + 2] += a1.x; f[8 * j + 3] += a1.y;
       f[8 * j + 4] += a2.x; f[8 * j + 5] += a2.y; f[8 * j + 6] += a3.x; f[8 * j + 7] += a3.y;
     }
-    __syncwarp();
   }
   // ---- own row -> staging (zeros for pad / out-of-range rows)
 #pragma unroll
@@ -117,46 +124,59 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
     u.y = valid ? pack_bf16x2(f[8 * j + 2], f[8 * j + 3]) : 0u;
     u.z = valid ? pack_bf16x2(f[8 * j + 4], f[8 * j + 5]) : 0u;
     u.w = valid ? pack_bf16x2(f[8 * j + 6], f[8 * j + 7]) : 0u;
-    sts128(my_row + j * 16, u);
+    sts128(my_row + ((j ^ sw) << 4), u);
   }
+  fence_async_smem();                      // generic-proxy writes -> visible to the TMA store (async proxy)
   __syncwarp();
-  // ---- coalesced global write (pad rows receive zeros, which is what they already hold)
-  {
-    uint4 o[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = lds128(stage + (i * 8 + sub_row) * kStageRowBytes + sub_chunk * 16);
-    bf16* obase = p.out + (warp_row0 + sub_row) * p.out_ld + col0 + sub_chunk * 8;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (warp_row0 + i * 8 + sub_row < p.rows) *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(i) * 8 * p.out_ld) = o[i];
+  // ---- one TMA store for the warp's 32 x 32 tile (pad rows receive zeros, which is what they already hold)
+  if (lane == 0 && warp_row0 < p.rows) {
+    tma_store_2d(&p.tmOut, stage, col0, static_cast<int32_t>(warp_row0));
+    bulk_commit();
   }
   // ---- GroupNorm partial sums of the staged tile
   if (p.stats != nullptr && tile < p.m_tiles) {
-    // lane -> column pair (2 cp, 2 cp + 1), rows [16 hh, 16 hh + 16); rows < n_a belong to record A, the rest to B
+    // lane -> column pair (2 cp, 2 cp + 1) and row parity hh: rows hh, hh + 2, ..., hh + 30 (even rows occupy banks
+    // 0..15, odd rows banks 16..31: conflict-free).  rows < n_a belong to record A, the rest to record B.
     const int cp = lane & 15, hh = lane >> 4;
+    const uint32_t col_b = static_cast<uint32_t>((cp & 3) * 4);
+    const int cch = cp >> 2;
     uint32_t raw[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) raw[i] = lds32(stage + (hh * 16 + i) * kStageRowBytes + cp * 4);
-    float sa0 = 0.f, sa1 = 0.f, qa0 = 0.f, qa1 = 0.f, sb0 = 0.f, sb1 = 0.f, qb0 = 0.f, qb1 = 0.f;
-#pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const int row = hh * 16 + i;
-      const float2 w = unpack_bf16x2(raw[i]);
-      if (row < n_a) { sa0 += w.x; sa1 += w.y; qa0 = fmaf(w.x, w.x, qa0); qa1 = fmaf(w.y, w.y, qa1); }
-      else           { sb0 += w.x; sb1 += w.y; qb0 = fmaf(w.x, w.x, qb0); qb1 = fmaf(w.y, w.y, qb1); }
+      const int row = 2 * i + hh;       // (row >> 1) & 3 == i & 3
+      raw[i] = lds32(stage + static_cast<uint32_t>(row * 64 + ((cch ^ (i & 3)) << 4)) + col_b);
     }
-    // combine the two row halves (fixed order: lower half + upper half); lanes 0..15 write 16 B each = 256 B row
-    sa0 += __shfl_xor_sync(0xffffffffu, sa0, 16); sa1 += __shfl_xor_sync(0xffffffffu, sa1, 16);
-    qa0 += __shfl_xor_sync(0xffffffffu, qa0, 16); qa1 += __shfl_xor_sync(0xffffffffu, qa1, 16);
     const int64_t rec = (static_cast<int64_t>(tile) * 4 + q) * p.out_ld + col0 + 2 * cp;
-    if (hh == 0) *reinterpret_cast<float4*>(p.stats + 2 * rec) = make_float4(sa0, qa0, sa1, qa1);
-    if (n_a < 32) {                                  // warp-uniform: the window straddles an image boundary
+    if (n_a >= 32) {                                 // warp-uniform fast path: the window lies inside one image
+      float sa0 = 0.f, sa1 = 0.f, qa0 = 0.f, qa1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 w = unpack_bf16x2(raw[i]);
+        sa0 += w.x; sa1 += w.y; qa0 = fmaf(w.x, w.x, qa0); qa1 = fmaf(w.y, w.y, qa1);
+      }
+      sa0 += __shfl_xor_sync(0xffffffffu, sa0, 16); sa1 += __shfl_xor_sync(0xffffffffu, sa1, 16);
+      qa0 += __shfl_xor_sync(0xffffffffu, qa0, 16); qa1 += __shfl_xor_sync(0xffffffffu, qa1, 16);
+      if (hh == 0) *reinterpret_cast<float4*>(p.stats + 2 * rec) = make_float4(sa0, qa0, sa1, qa1);
+    } else {
+      float sa0 = 0.f, sa1 = 0.f, qa0 = 0.f, qa1 = 0.f, sb0 = 0.f, sb1 = 0.f, qb0 = 0.f, qb1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int row = 2 * i + hh;
+        const float2 w = unpack_bf16x2(raw[i]);
+        if (row < n_a) { sa0 += w.x; sa1 += w.y; qa0 = fmaf(w.x, w.x, qa0); qa1 = fmaf(w.y, w.y, qa1); }
+        else           { sb0 += w.x; sb1 += w.y; qb0 = fmaf(w.x, w.x, qb0); qb1 = fmaf(w.y, w.y, qb1); }
+      }
+      // combine the two row parities (fixed order: even + odd); lanes 0..15 write 16 B each = 256 B row
+      sa0 += __shfl_xor_sync(0xffffffffu, sa0, 16); sa1 += __shfl_xor_sync(0xffffffffu, sa1, 16);
+      qa0 += __shfl_xor_sync(0xffffffffu, qa0, 16); qa1 += __shfl_xor_sync(0xffffffffu, qa1, 16);
       sb0 += __shfl_xor_sync(0xffffffffu, sb0, 16); sb1 += __shfl_xor_sync(0xffffffffu, sb1, 16);
       qb0 += __shfl_xor_sync(0xffffffffu, qb0, 16); qb1 += __shfl_xor_sync(0xffffffffu, qb1, 16);
-      if (hh == 0) *reinterpret_cast<float4*>(p.stats + p.stats_b_off + 2 * rec) = make_float4(sb0, qb0, sb1, qb1);
+      if (hh == 0) {
+        *reinterpret_cast<float4*>(p.stats + 2 * rec) = make_float4(sa0, qa0, sa1, qa1);
+        *reinterpret_cast<float4*>(p.stats + p.stats_b_off + 2 * rec) = make_float4(sb0, qb0, sb1, qb1);
+      }
     }
   }
-  __syncwarp();   // staging is reused by the next item
 }
 
 __device__ __forceinline__ void epilogue_narrow(const ConvKernelParams& p, const uint32_t (&v)[16], int img, int y,
@@ -201,7 +221,7 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
   uint64_t* a_ready = tempty + 2;                                 // XF: halo transformed (one arrive per transform warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + AS);
   const uint32_t tap_sa = smem_u32(a_full) + 512;               // per-tap descriptor offsets
-  const uint32_t stage_sa = tap_sa + 256;                       // epilogue staging tiles
+  const uint32_t stage_sa = smem_u32(a_full) + 1024;            // epilogue staging tiles (1024-byte aligned: TMA swizzle)
   const uint32_t bias_sa = stage_sa + kStageBytes;              // bias vector
 
   const int warp = threadIdx.x >> 5;
@@ -213,6 +233,7 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
       if (p.extra_rows[i] > 0) tma_prefetch_desc(&p.tmAx[i]);
     }
     tma_prefetch_desc(&p.tmB);
+    if (p.epilogue == IDF_EPI_BF16) tma_prefetch_desc(&p.tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, Cfg::NI); mbar_init(a_ready + s, kXfWarps); }
@@ -506,7 +527,7 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
               mbar_arrive(tempty + as);
             }
             epilogue_bf16_chunk(p, v, wr0, valid, nt * BN + c * 32, n_a, tile, q, lane,
-                                stage_sa + e * (32 * kStageRowBytes), bias_sa, res_cur);
+                                stage_sa + e * kStageTile, bias_sa, res_cur);
           }
         } else {
           if ((m & 1) == half) {
@@ -522,6 +543,7 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
         mbar_arrive(tempty + as);
       }
     }
+    if (BN >= 32 && lane == 0) bulk_wait<0>();     // this warp's TMA stores have been performed
   }
 
   tc_fence_before();

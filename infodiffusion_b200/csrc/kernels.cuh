@@ -16,6 +16,7 @@ struct alignas(64) ConvKernelParams {
   CUtensorMap tmA[IDF_CONV_MAX_SRC];    // box {64, 128 rows}
   CUtensorMap tmAx[IDF_CONV_MAX_SRC];   // box {64, extra_rows[src]} -- tail of the halo
   CUtensorMap tmB;                      // box {64, BN}
+  CUtensorMap tmOut;                    // bf16 epilogue: output [rows, out_ld], box {32 cols, 32 rows}, SWIZZLE_64B (TMA store)
   int32_t n_src;
   int32_t extra_rows[IDF_CONV_MAX_SRC]; // halo rows beyond 128*MT (multiple of 8, 0 for 1x1 sources)
   // K loop = groups (one halo load each: source, 64-channel slice, cluster of taps) x taps

@@ -119,6 +119,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+// 2-D tiled store shared -> global (bulk async-group completion).  The shared-memory tile must have been written
+// with the tensor map's swizzle, followed by fence.proxy.async by every writing thread, before ONE thread issues this.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(smem_src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the issuing thread: all but the newest N bulk groups have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// ... have completed entirely (global writes performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, UMMA issue, commit, TMEM loads
 // ---------------------------------------------------------------------------------------------
