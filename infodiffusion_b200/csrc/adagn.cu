@@ -16,6 +16,8 @@
 // torch.cat([h, skip]) followed by GroupNorm behaves (models.py:321 -> modules.py:265).
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace cg = cooperative_groups;
@@ -26,6 +28,9 @@ namespace idf {
 // stages (five CTAs per SM) beat three or five -- the sweep is bound by resident warps, not by bytes in flight.
 int g_adagn_ring = 2;
 int g_adagn_ctas = 400;
+int g_adagn_ctas2 = 1184;    // streaming variant 2: CTAs aimed for (8 per SM)
+int g_adagn_impl = 1;      // 1 = shared-memory ring kernel (default: 4.6 TB/s on 64ch@64^2), 2 = direct-load kernel (4.1-4.25:
+                           // its per-CTA coefficient prologue is not overlapped with streaming)
 extern int g_pdl;
 
 constexpr int kAdaThreads = 256;
@@ -55,6 +60,7 @@ struct AdaGNParams {
   long long stats_b_windows;   // number of 32-row window records (offset of the B records, in records)
   int block_rows;              // rows per ring stage of the streaming variant
   int ring;                    // ring stages in use
+  int stream_threads;          // streaming variant 2: threads that stream (multiple of C/8)
   unsigned drop_thr16;         // dropout: drop iff 16 random bits < thr16 (0 = off)
   float drop_scale;            // 1 / (1 - p)
   const unsigned long long* drop_seed;
@@ -245,17 +251,20 @@ constexpr int kRingStageBytes = 16384;
 
 // Per-channel coefficients of image n: GroupNorm statistics from the producers' 32-row window records, folded with
 // gamma / beta and the two modulations into y = A*x + B.  All kAdaThreads threads of the block take part.
+template <int NT>
 struct CoefShared {
-  float2 sub[4][kMaxC];
+  float2 sub[NT];            // [sub-sequence][channel], NT / C sub-sequences of windows per channel
   float tot[2 * kMaxC];
   float mean[32], rstd[32];
   float2 ab[kMaxC];
 };
-__device__ __forceinline__ void fold_coefficients(const AdaGNParams& p, int n, CoefShared& sh, bool save) {
+template <int NT>
+__device__ __forceinline__ void fold_coefficients(const AdaGNParams& p, int n, CoefShared<NT>& sh, bool save) {
+  constexpr int kAdaThreads = NT;       // all NT threads of the block take part
   const int t = threadIdx.x;
   const int C = p.C;
   const int R = p.rows_per_img;
-  float2 (&s_sub)[4][kMaxC] = sh.sub;
+  float2* s_sub = sh.sub;
   float (&s_tot)[2 * kMaxC] = sh.tot;
   float (&s_mean)[32] = sh.mean;
   float (&s_rstd)[32] = sh.rstd;
@@ -290,12 +299,12 @@ __device__ __forceinline__ void fold_coefficients(const AdaGNParams& p, int n, C
       sx += v.x;
       sq += v.y;
     }
-    s_sub[sub][ch] = make_float2(sx, sq);
+    s_sub[sub * C + ch] = make_float2(sx, sq);
   }
   __syncthreads();
   for (int ch = t; ch < C; ch += kAdaThreads) {
     float sx = 0.f, sq = 0.f;
-    for (int sub = 0; sub < nsub; ++sub) { sx += s_sub[sub][ch].x; sq += s_sub[sub][ch].y; }
+    for (int sub = 0; sub < nsub; ++sub) { sx += s_sub[sub * C + ch].x; sq += s_sub[sub * C + ch].y; }
     s_tot[ch] = sx;
     s_tot[C + ch] = sq;
   }
@@ -336,19 +345,23 @@ __device__ __forceinline__ void fold_coefficients(const AdaGNParams& p, int n, C
 
 }
 
-// coefficients only (consumer convolution applies them to its A operand): one block per image
-__global__ void __launch_bounds__(kAdaThreads) adagn_coef_kernel(const AdaGNParams p, float2* __restrict__ coef_out) {
-  __shared__ CoefShared sh;
+// coefficients only (consumer convolution applies them to its A operand): one block per image, same thread count --
+// hence the same summation order, bit for bit -- as the apply kernels' prologue
+constexpr int kCoefThreads = kAdaThreads;
+__global__ void __launch_bounds__(kCoefThreads) adagn_coef_kernel(const AdaGNParams p, float2* __restrict__ coef_out) {
+  __shared__ CoefShared<kCoefThreads> sh;
   const int n = blockIdx.x;
-  fold_coefficients(p, n, sh, true);
-  for (int ch = threadIdx.x; ch < p.C; ch += kAdaThreads) coef_out[static_cast<long long>(n) * p.C + ch] = sh.ab[ch];
+  griddep_launch();
+  griddep_wait();
+  fold_coefficients<kCoefThreads>(p, n, sh, true);
+  for (int ch = threadIdx.x; ch < p.C; ch += kCoefThreads) coef_out[static_cast<long long>(n) * p.C + ch] = sh.ab[ch];
 }
 
 __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNParams p) {
   extern __shared__ __align__(128) uint8_t ring_raw[];
   __shared__ __align__(8) uint64_t s_full[kRingMax];
   const int kRing = p.ring;
-  __shared__ CoefShared sh;
+  __shared__ CoefShared<kAdaThreads> sh;
   const int n = blockIdx.y;
   const int t = threadIdx.x;
   const int C = p.C;
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
     for (int b = 0; b < kRing && b < nblk; ++b) issue(b);
   }
 
-  fold_coefficients(p, n, sh, blockIdx.x == 0);
+  fold_coefficients<kAdaThreads>(p, n, sh, blockIdx.x == 0);
   const float2 (&s_ab)[kMaxC] = sh.ab;
 
   // ---------------------------------------------------------------- streaming sweep
@@ -463,6 +476,103 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Streaming variant 2 (idf_set_option "adagn_impl" = 2; measured slower than the ring, kept for A/B): no ring.  A CTA owns the image rows [y0, y1) of image n and walks the
+// INTERIOR pixels only -- index i over (y, x, 16-byte channel granule) maps to the pad-flat address
+// (y*Wp)*VPR + i % (W*VPR), so there is no pad-row test, no division per element and the pad rows are never
+// touched.  Each thread keeps one channel granule (blockDim % VPR == 0), i.e. its 8 (A, B) pairs live in registers;
+// per 16 bytes: 1 LDG.128 (L1 no-allocate), 8 unpack, 8 FFMA, 8 MUFU.TANH, 8 FFMA, 4 pack, 1 STG.128 -- half the
+// instructions of the ring variant (ncu: that one issued ~100 instructions per 16 bytes at 54 % issue utilisation).
+// Four granules per thread are in flight; bytes in flight per SM = resident threads x 64 B.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+template <bool DROPOUT>
+__global__ void __launch_bounds__(kAdaThreads) adagn_stream_kernel(const AdaGNParams p) {
+  __shared__ CoefShared<kAdaThreads> sh;
+  const int n = blockIdx.y;
+  const int t = threadIdx.x;
+  const int C = p.C;
+  griddep_launch();
+  griddep_wait();                 // the sources, their statistics and the modulation rows come from earlier kernels
+  fold_coefficients<kAdaThreads>(p, n, sh, blockIdx.x == 0);
+
+  const int VPR = C >> 3;                       // 16-byte granules per pixel
+  const int NT = p.stream_threads;              // multiple of VPR (<= blockDim): the threads that stream
+  if (t >= NT) return;
+  const int vl = t % VPR;                       // this thread's channel granule, fixed for the whole kernel
+  const bool do_silu = p.apply_silu != 0;
+  const float cs = do_silu ? 0.5f : 1.0f;       // SiLU(v) = h + h*tanh(h) with h = v/2: the 1/2 is folded into (A, B)
+  float A[8], B[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float2 ab = sh.ab[vl * 8 + j]; A[j] = ab.x * cs; B[j] = ab.y * cs; }
+  const int v0 = p.c0 >> 3;
+  const bool from0 = vl < v0;
+  // source / destination columns of this thread; rows advance by whole pixels
+  const bf16* src = from0 ? p.src0 + vl * 8 : p.src1 + (vl - v0) * 8;
+  const int spitch = from0 ? p.c0 : p.c1;       // elements per pixel in the source
+  const long long img_row0 = static_cast<long long>(n) * p.rows_per_img;
+  const int tp = t / VPR;                       // this thread's pixel slot; PPI pixels per pass
+  const int PPI = NT / VPR;
+  const float inv_w = 1.0f / static_cast<float>(p.W);
+  const int y0 = blockIdx.x * p.slice_rows, y1 = min(p.H, y0 + p.slice_rows);     // slice_rows = IMAGE rows here
+  const int total = (y1 - y0) * p.W;            // interior pixels of the slice
+  const int row_y0 = static_cast<int>(img_row0) + y0 * p.Wp;         // pad-flat rows fit 22 bits (checked at launch)
+  const unsigned long long drop_seed = (DROPOUT && p.drop_seed != nullptr) ? *p.drop_seed : 0ull;
+
+  auto locate = [&](int q) -> int {              // interior pixel index in the slice -> pad-flat pixel row
+    const int yy = __float2int_rd((static_cast<float>(q) + 0.5f) * inv_w);      // exact: q < 2^23
+    return row_y0 + yy + q;                      // = row_y0 + yy*Wp + (q - yy*W) with Wp = W + 1
+  };
+  auto xform = [&](const uint4& u, int pix) -> uint4 {
+    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+    float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+    if (do_silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float h = fmaf(f[j], A[j], B[j]);
+        float th;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+        f[j] = fmaf(h, th, h);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], A[j], B[j]);
+    }
+    if (DROPOUT) {
+      const uint32_t keep = dropout_keep8(drop_seed, p.drop_layer, static_cast<uint64_t>(pix) * VPR + vl, p.drop_thr16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * p.drop_scale : 0.f;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+    return o;
+  };
+  bf16* const out = p.out + vl * 8;
+  int q = tp;
+  for (; q + 3 * PPI < total; q += 4 * PPI) {
+    int pix[4];
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      pix[k] = locate(q + k * PPI);
+      u[k] = ldg_stream(src + static_cast<uint32_t>(pix[k] * spitch));          // element offsets fit 31 bits
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(out + static_cast<uint32_t>(pix[k] * C)) = xform(u[k], pix[k]);
+  }
+  for (; q < total; q += PPI) {
+    const int pix = locate(q);
+    *reinterpret_cast<uint4*>(out + static_cast<uint32_t>(pix * C)) = xform(ldg_stream(src + static_cast<uint32_t>(pix * spitch)), pix);
+  }
+}
+
 static cudaError_t fill_params(const idf_adagn_args& a, AdaGNParams& p);
 
 cudaError_t launch_adagn_coef(const idf_adagn_args& a, float* coef_out, cudaStream_t stream) {
@@ -471,8 +581,21 @@ cudaError_t launch_adagn_coef(const idf_adagn_args& a, float* coef_out, cudaStre
   if (e != cudaSuccess) return e;
   if (p.stats0 == nullptr || (p.c1 != 0 && p.stats1 == nullptr) || a.dropout_p > 0.f) return cudaErrorInvalidValue;
   p.save_coef = nullptr;
-  adagn_coef_kernel<<<a.batch, kAdaThreads, 0, stream>>>(p, reinterpret_cast<float2*>(coef_out));
-  return cudaGetLastError();
+  if (!g_pdl) {
+    adagn_coef_kernel<<<a.batch, kCoefThreads, 0, stream>>>(p, reinterpret_cast<float2*>(coef_out));
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.batch, 1, 1);
+  cfg.blockDim = dim3(kCoefThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, adagn_coef_kernel, p, reinterpret_cast<float2*>(coef_out));
 }
 
 static cudaError_t fill_params(const idf_adagn_args& a, AdaGNParams& p) {
@@ -528,6 +651,33 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
     p.drop_scale = 65536.f / (65536.f - static_cast<float>(p.drop_thr16));
   }
   p.stats_b_windows = (static_cast<long long>(a.batch) * p.rows_per_img + kBM - 1) / kBM * 4;
+  if (g_adagn_impl == 2 && p.stats0 != nullptr && (p.c1 == 0 || p.stats1 != nullptr)) {
+    // streaming variant 2: a CTA owns whole image rows; enough CTAs for >= 4 per SM, each with >= 16 KB to stream
+    const int VPR = p.C / 8;
+    if (static_cast<long long>(a.batch) * p.rows_per_img * p.C >= (1ll << 31)) return cudaErrorInvalidValue;   // 32-bit element offsets
+    p.stream_threads = kAdaThreads / VPR * VPR;
+    const long long row_bytes = static_cast<long long>(p.W) * p.C * 2;
+    int slices = (g_adagn_ctas2 + a.batch - 1) / a.batch;
+    const int max_slices = static_cast<int>(std::max<long long>(1, static_cast<long long>(p.H) * row_bytes / 16384));
+    if (slices > max_slices) slices = max_slices;
+    if (slices > p.H) slices = p.H;
+    if (slices < 1) slices = 1;
+    p.slice_rows = (p.H + slices - 1) / slices;
+    slices = (p.H + p.slice_rows - 1) / p.slice_rows;
+    p.block_rows = 0; p.ring = 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(slices, a.batch, 1);
+    cfg.blockDim = dim3(kAdaThreads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    if (p.drop_thr16 != 0) return cudaLaunchKernelEx(&cfg, adagn_stream_kernel<true>, p);
+    return cudaLaunchKernelEx(&cfg, adagn_stream_kernel<false>, p);
+  }
   if (p.stats0 != nullptr && (p.c1 == 0 || p.stats1 != nullptr)) {
     // streaming variant: bytes in flight come from the per-CTA ring, not from occupancy, so a few hundred
     // CTAs suffice; large slices amortise the per-CTA coefficient prologue

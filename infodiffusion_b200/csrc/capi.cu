@@ -11,7 +11,7 @@
 
 #include "kernels.cuh"
 
-namespace idf { extern int g_adagn_ring, g_adagn_ctas, g_pdl, g_xf_debug; }
+namespace idf { extern int g_adagn_ring, g_adagn_ctas, g_adagn_ctas2, g_adagn_impl, g_pdl, g_xf_debug; }
 using namespace idf;
 
 namespace {
@@ -119,9 +119,11 @@ int idf_set_option(const char* key, int32_t value) {
     return IDF_OK;
   }
   if (key != nullptr && std::strcmp(key, "pdl") == 0) { g_pdl = value ? 1 : 0; return IDF_OK; }
-  if (key != nullptr && std::strcmp(key, "xf_debug") == 0 && value >= 0 && value <= 2) { g_xf_debug = value; return IDF_OK; }
+  if (key != nullptr && std::strcmp(key, "xf_debug") == 0 && value >= 0 && value <= 4) { g_xf_debug = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "adagn_ring") == 0 && value >= 1 && value <= 8) { g_adagn_ring = static_cast<int>(value); return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "adagn_ctas") == 0 && value >= 1) { g_adagn_ctas = static_cast<int>(value); return IDF_OK; }
+  if (key != nullptr && std::strcmp(key, "adagn_ctas2") == 0 && value >= 1) { g_adagn_ctas2 = static_cast<int>(value); return IDF_OK; }
+  if (key != nullptr && std::strcmp(key, "adagn_impl") == 0 && (value == 1 || value == 2)) { g_adagn_impl = static_cast<int>(value); return IDF_OK; }
   return fail(IDF_ERR_ARG, "unknown option or value");
 }
 

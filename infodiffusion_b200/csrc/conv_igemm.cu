@@ -11,10 +11,12 @@
 // (MT accumulators in TMEM), so each streamed weight tile B[BN x 64] feeds MT MMAs as well.
 // Operand bytes per MMA drop 3-7x (e.g. 64->64 @64^2: 221 KB -> 33 KB + weights per 128 rows).
 //
-// Roles (384 threads): warp 0 = A (halo) TMA producer     warp 3 = B (weights) TMA producer
-//                      warp 1 = UMMA issuer (1 thread)    warp 2 = TMEM allocator (+ second UMMA issuer when MT >= 2)
-//                      warps 4..11 = epilogue (two warps per TMEM lane quarter)
-//                      XF variant only: warps 12..23 = transform (fused AdaGN + SiLU on the halo, in place)
+// Roles (384 threads), LOW to HIGH warp id -- the SM sub-partition arbiter prefers the highest warp id among the
+// eligible warps, so the latency-critical single-thread roles sit on top and are never starved by the bulk warps:
+//                      XF variant only: warps 0..11 = transform (fused AdaGN + SiLU on the halo, in place)
+//                      next 8 warps = epilogue (two warps per TMEM lane quarter, quarter = warp % 4)
+//                      then: A (halo) TMA producer, B (weights) TMA producer,
+//                            TMEM allocator (+ second UMMA issuer when MT >= 2), UMMA issuer (1 thread)
 // Pipelines: A halo stages x2, B ring x4-8 (full/empty mbarriers), TMEM accumulator sets x2.
 #include "kernels.cuh"
 
@@ -226,8 +228,11 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int EPI0 = XF ? kXfWarps : 0;          // first of the 8 epilogue warps (multiple of 4: TMEM lane quarters)
+  constexpr int W_A = EPI0 + 8, W_B = EPI0 + 9, W_I2 = EPI0 + 10, W_I1 = EPI0 + 11;
+  static_assert(EPI0 % 4 == 0, "epilogue warps must start at a multiple of 4");
 
-  if (warp == 0 && lane == 0) {
+  if (warp == W_A && lane == 0) {
     for (int i = 0; i < p.n_src; ++i) {
       tma_prefetch_desc(&p.tmA[i]);
       if (p.extra_rows[i] > 0) tma_prefetch_desc(&p.tmAx[i]);
@@ -235,21 +240,21 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
     tma_prefetch_desc(&p.tmB);
     if (p.epilogue == IDF_EPI_BF16) tma_prefetch_desc(&p.tmOut);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == W_I1 && lane == 0) {
     for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, Cfg::NI); mbar_init(a_ready + s, kXfWarps); }
     for (int s = 0; s < BS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, Cfg::NI); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, Cfg::NI); mbar_init(tempty + a, 256); }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == W_I2) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
-  if (warp >= 4 && warp < 12) {   // bias -> shared memory
+  if (warp >= EPI0 && warp < EPI0 + 8) {   // bias -> shared memory
     const int nb = p.n_tiles * BN;
-    for (int i = threadIdx.x - 128; i < nb; i += 256) sts32(bias_sa + 4 * i, __float_as_uint(__ldg(p.bias + i)));
+    for (int i = threadIdx.x - EPI0 * 32; i < nb; i += 256) sts32(bias_sa + 4 * i, __float_as_uint(__ldg(p.bias + i)));
   }
-  if (warp == 3) {   // per-tap descriptor offsets (16-byte units) for the issuing threads
+  if (warp == W_B) {   // per-tap descriptor offsets (16-byte units) for the issuing threads
     for (int i = lane; i <= IDF_CONV_MAX_KB; i += 32)
       sts32(tap_sa + 4 * i, (i < p.n_taps) ? static_cast<uint32_t>(p.t_rel[i]) * 8u : 0u);
   }
@@ -262,9 +267,9 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
   // Programmatic dependent launch: everything above (barriers, TMEM, bias, tap table) touches only constants; the
   // weight (B) producer may also run ahead.  Every other role waits for the producer of its inputs here.
   griddep_launch();
-  if (warp != 3) griddep_wait();
+  if (warp != W_B) griddep_wait();
 
-  if (warp == 0) {
+  if (warp == W_A) {
     // ------------------------------------------------------------------ A producer: one halo per group
     if (lane == 0) {
       int sa = 0;
@@ -287,7 +292,7 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
         }
       }
     }
-  } else if (warp == 3) {
+  } else if (warp == W_B) {
     // ------------------------------------------------------------------ B producer: one weight tile per tap
     if (lane == 0) {
       int sb = 0;
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
         }
       }
     }
-  } else if (warp == 1 || (warp == 2 && Cfg::NI == 2)) {
+  } else if (warp == W_I1 || (warp == W_I2 && Cfg::NI == 2)) {
     // ------------------------------------------------------------------ UMMA issuers
     // One thread per issuer; with MT >= 2 the accumulators are split between two issuing threads so
     // that neither has to sustain more than one MMA per 64 cycles.  Both wait on the same full
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(kBM, BN, kFmtBF16);
       constexpr int M_PER = MT / Cfg::NI;
-      const int m_begin = (warp == 1) ? 0 : M_PER;
+      const int m_begin = (warp == W_I1) ? 0 : M_PER;
       int sa = 0, sb = 0, iter = 0;
       uint32_t pa = 0, pb = 0;
       const uint32_t b_lo0 = umma_desc_lo(smem_u32(smB));
@@ -346,12 +351,12 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
         umma_commit(tfull + as);
       }
     }
-  } else if (XF && warp >= 12) {
+  } else if (XF && warp < EPI0) {
     // ------------------------------------------------------------------ transform warps (fused AdaGN + SiLU)
     // 32 * kXfWarps threads.  thread -> one physical 16-byte granule column gi and the rows rs, rs + kXfRows, ...; all its rows
     // share (row & 7), so under the 128-byte swizzle it always holds the same logical 8 channels gl = gi ^ (rs & 7).
     // The 8 lanes of a row share the row bookkeeping: lane gi == 0 computes (valid, image) and broadcasts it.
-    const int tt = threadIdx.x - 384;
+    const int tt = threadIdx.x;
     const int gi = tt & 7, rs = tt >> 3;
     const int gl = gi ^ (rs & 7);
     const unsigned grp_mask = 0xffu << (lane & 24);
@@ -362,19 +367,20 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
     const int rows32 = static_cast<int>(p.rows);
     int sa = 0;
     uint32_t pa = 0;
+    int cur = -1, cur_cb = -1;           // (image, channel slice) of the coefficients held in A[], B[]
+    float A[8], B[8];
     for (int st = blockIdx.x; st < total; st += gridDim.x) {
       const int ms = st / p.n_tiles;
       const int row0 = ms * (MT * kBM);
       for (int g = 0; g < p.n_groups; ++g) {
         const int cb = p.g_xf[g];
+        if (cb != cur_cb) { cur = -1; cur_cb = cb; }
         mbar_wait(a_full + sa, pa);
         if (cb >= 0 && p.xf_debug != 1) {
           const int nrows = MT * kBM + p.extra_rows[p.g_src[g]];
           const int rbase = row0 + p.g_lo[g];
           const uint32_t base = smem_u32(smA + sa * p.a_stage_bytes) + static_cast<uint32_t>(gi * 16);
           const float2* ctab = p.xf_coef + cb + gl * 8;
-          int cur = -1;
-          float A[8], B[8];
           auto reload = [&](int img) {
             cur = img;
             const float4* c4 = reinterpret_cast<const float4*>(ctab + static_cast<int64_t>(img) * p.xf_ctot);
@@ -385,6 +391,7 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
             }
           };
           auto xform = [&](const uint4& u) -> uint4 {
+            if (p.xf_debug == 4) return u;          // measurement only: shared-memory round trip without arithmetic
             const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
             float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
             if (do_silu) {
@@ -406,7 +413,7 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
           };
           // four rows per trip: row bookkeeping and all four loads first, then branch-free arithmetic with predicated
           // stores when the rows share one image (the common case); rows of different images fall back to one by one
-          for (int i0 = rs; i0 < nrows; i0 += 4 * kXfRows) {
+          for (int i0 = rs; i0 < nrows && p.xf_debug != 3; i0 += 4 * kXfRows) {   // xf_debug 3: fence only
             int info[4];
             uint4 u[4];
 #pragma unroll
@@ -456,9 +463,9 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
         if (++sa == AS) { sa = 0; pa ^= 1u; }
       }
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= EPI0 && warp < EPI0 + 8) {
     // ------------------------------------------------------------------ epilogue (8 warps)
-    const int e = warp - 4;
+    const int e = warp - EPI0;
     const int q = e & 3;      // TMEM lane quarter (== warp % 4)
     const int half = e >> 2;  // which half of the (m, chunk) work items
     float cx = 0.f, ce = 0.f, cn = 0.f;
@@ -548,7 +555,7 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == W_I2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }

@@ -13,6 +13,9 @@ from infodiffusion_b200.sampling import DiffusionProcess  # noqa: E402
 
 B = int(os.environ.get("IDF_PROF_BATCH", "256"))
 dev = "cuda:0"
+if os.environ.get("IDF_FUSE"):
+    from infodiffusion_b200 import engine
+    engine.FUSE_ADAGN = True
 args = bench.make_args_ns(bench.T_STEPS)
 torch.manual_seed(64)
 model = InfoDiff(args, "cpu", (3, 64, 64)).to(dev).eval()
