@@ -84,6 +84,7 @@ FUSE_ADAGN = False
 # worse as well (332 vs 344 img/s with 16): the coefficient kernels and the slower convs cost more than the launches
 # saved.  0 disables.
 FUSE_ADAGN_MAX_H = 0
+MAX_GN_CHANNELS = 256  # widest GroupNorm the AdaGN kernels take (csrc/adagn.cu kMaxC)
 TRAIN_PDL = True       # programmatic dependent launch once a training plan exists (library-wide switch)
 
 

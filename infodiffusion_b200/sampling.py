@@ -273,7 +273,7 @@ class DiffusionProcess():
         """reference sampling.py:89-101: draws xT then a (in that order) when they are not given."""
         if xT is None:
             xT = torch.randn([sampling_number, *self.shape]).to(device=self.device)
-        if a is None:
+        if self.model != 'vanilla' and a is None:          # sampling.py:93-95: a vanilla model draws no latent
             a = torch.randn([sampling_number, self.a_dim]).to(device=self.device)
         return self._run("ddim" if self.deterministic else "ddpm", xT, a, trace)
 

@@ -461,7 +461,8 @@ def fused_param_grads(plan) -> List[Optional[torch.Tensor]]:
     flat = st.grad_flat.clone()
     views = plan.pindex.views(flat)
     if _grad_sync is not None:
-        _grad_sync.reduce(flat, [p for p, has in zip(plan.pindex.params, st.has_grad) if has])
+        _grad_sync.reduce(flat, [p for p, has in zip(plan.pindex.params, st.has_grad) if has],
+                          [v for v, has in zip(views, st.has_grad) if has])
     return [v if has else None for v, has in zip(views, st.has_grad)]
 
 
@@ -479,11 +480,16 @@ class GradSync:
         self.avg = dist.get_backend() == "nccl"            # gloo has no AVG: sum, then divide
         self.pending: List = []
         self.covered: set = set()
+        self.fixed_up = 0          # gradients that did not alias the reduced buffer and were copied from it (see finish)
 
-    def reduce(self, flat: torch.Tensor, params: Sequence[nn.Parameter]) -> None:
+    def reduce(self, flat: torch.Tensor, params: Sequence[nn.Parameter],
+               views: Optional[Sequence[torch.Tensor]] = None) -> None:
+        """Start the all-reduce of `flat`.  `views[i]` is the slice of `flat` that autograd receives as the gradient
+        of `params[i]`; `finish` uses it to make sure p.grad really holds the REDUCED values."""
         import torch.distributed as dist
         op = dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM
-        self.pending.append((dist.all_reduce(flat, op=op, async_op=True), flat))
+        self.pending.append((dist.all_reduce(flat, op=op, async_op=True), flat,
+                             list(zip(params, views)) if views is not None else []))
         self.covered.update(id(p) for p in params)
 
     def finish(self, params: Sequence[nn.Parameter]) -> None:
@@ -495,10 +501,22 @@ class GradSync:
             buf.div_(self.world)
             for g, f in zip(rest, torch._utils._unflatten_dense_tensors(buf, rest)):
                 g.copy_(f)
-        for work, flat in self.pending:
+        for work, flat, pv_pairs in self.pending:
             work.wait()
             if not self.avg:
                 flat.div_(self.world)
+            # The reduction happened in `flat`.  It reaches p.grad only if AccumulateGrad STOLE the view it was
+            # handed (p.grad aliases `flat`).  If p.grad already existed (zero_grad(set_to_none=False), gradient
+            # accumulation, a second loss term) or autograd cloned the incoming gradient, p.grad holds local values:
+            # overwrite it with the reduced slice so the ranks cannot drift apart silently.
+            lo = flat.data_ptr()
+            hi = lo + flat.numel() * flat.element_size()
+            for prm, view in pv_pairs:
+                g = prm.grad
+                if g is None or lo <= g.data_ptr() < hi:
+                    continue
+                self.fixed_up += 1
+                g.copy_(view.view_as(g))
         self.pending.clear()
         self.covered.clear()
 
@@ -558,6 +576,12 @@ class _ConvStackFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, plan, x, mod_t, mod_z, seed, *params):
+        # the plan's activations live in static buffers shared by every forward at this batch size: a second
+        # train-mode forward overwrites what a pending backward needs (gradient accumulation over two forwards, two
+        # loss terms each calling the model).  Every forward takes a generation number; backward() of a forward
+        # whose activations have since been overwritten raises instead of returning wrong gradients.
+        plan._fwd_gen = getattr(plan, "_fwd_gen", 0) + 1
+        ctx.gen = plan._fwd_gen
         plan.x_in.copy_(x)
         if mod_t is not None:
             plan.mod_t.copy_(mod_t)
@@ -574,6 +598,11 @@ class _ConvStackFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         plan = ctx.plan
+        if ctx.gen != plan._fwd_gen:
+            raise RuntimeError("infodiffusion_b200: backward of a stale forward -- the conv-stack plan keeps ONE set of "
+                               "saved activations per (network, batch size) and a later training forward has "
+                               "overwritten them.  Call backward() before the next forward (or run the extra forward "
+                               "under torch.no_grad() / eval()).")
         finalize_backward(plan)
         plan.d_out.copy_(d_out)
         _replay(plan, "_g_bwd", lambda: run_backward(plan))

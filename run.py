@@ -12,7 +12,9 @@ What differs, on purpose:
     sampling / encoding shard every round of --batch_size images over the ranks, all ranks drawing the round's full
     batch from the same seed, so the written images do not depend on the number of GPUs (checked by
     tools/check_run_py_multigpu.sh: 2 GPUs vs 1 GPU differ by at most one uint8 level in 0.01 % of the pixels).
-The VAE baseline and the analysis modes (disentangle, interpolate, latent_quality, plot_latent) are not built.
+The analysis modes latent_quality / disentangle / interpolate (run.py:310-341, 371-414, 444-481) are thin callers of
+the encoder, reverse DDIM and the sampler and are built; the VAE baseline, plot_latent (matplotlib) and save_original_img
+are not.
 """
 from __future__ import annotations
 
@@ -72,6 +74,10 @@ def parse_args(argv=None):
     # additions (see module docstring)
     p.add_argument('--data_npz', type=str, default=None, help='images (and labels) to train on / encode')
     p.add_argument('--synthetic_size', type=int, default=256, help='number of synthetic images when no --data_npz is given')
+    p.add_argument('--single_phase', action='store_true',
+                   help='eval_fid without --is_latent: skip the vanilla model / two-phase sampler (the reference requires it)')
+    p.add_argument('--allow_random_init', action='store_true',
+                   help='evaluate the seeded random initialisation when the checkpoint is missing (the reference raises)')
     return p.parse_args(argv)
 
 
@@ -201,7 +207,24 @@ def _fit(args, model, batches, device, rank, world, latent=False):
     model.eval()
 
 
+def _reseed_rank(r_seed: int, rank: int) -> None:
+    """After the model has been built from the COMMON seed (identical initial weights on every rank), give every rank
+    its own random stream: InfoDiff.forward draws the timesteps (CPU generator), eps, the dropout seeds, the encoder's
+    a_q noise and the MMD prior sample from torch's generators, and with one shared seed a global batch of B*world would
+    contain only B distinct (t, eps) draws."""
+    if rank > 0 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        torch.manual_seed(r_seed + 1000 * rank)
+        torch.cuda.manual_seed(r_seed + 1000 * rank)
+
+
 def _batches(x, batch_size, rank, world, seed):
+    usable = (x.shape[0] // (batch_size * world)) * batch_size * world
+    if usable == 0:
+        raise ValueError(f"{x.shape[0]} samples give no full batch of {batch_size} x {world} rank(s): lower --batch_size "
+                         "(plans are built per batch size, the tail batch is dropped)")
+    if usable < x.shape[0] and rank == 0:
+        print(f"[run.py] dropping the tail batch: {x.shape[0] - usable} of {x.shape[0]} samples per epoch are not used")
+
     def it(epoch):
         g = torch.Generator().manual_seed(seed * 1000 + epoch)
         perm = torch.randperm(x.shape[0], generator=g)
@@ -218,7 +241,9 @@ def train(args):
     device = torch.device("cuda", torch.cuda.current_device())
     shape = get_dataset_config(args)
     x, _ = load_images(args, shape)
+    _check_widths(args)
     model = InfoDiff(args, device, shape) if args.model == 'diff' else Diff(args, device, shape)
+    _reseed_rank(args.r_seed, rank)
     _fit(args, model, _batches(x, args.batch_size, rank, world, args.r_seed), device, rank, world)
 
 
@@ -228,16 +253,33 @@ def train_latent_ddim(args):
     device = torch.device("cuda", torch.cuda.current_device())
     z = torch.from_numpy(np.load("{}_{}_latent.npz".format(args.model, generate_exp_string(args).replace(".", "_")))["all_a"]).float()
     model = Diff(args, device, (1, args.a_dim, args.a_dim))
+    _reseed_rank(args.r_seed, rank)
     _fit(args, model, _batches(z, args.batch_size, rank, world, args.r_seed), device, rank, world, latent=True)
 
 
+def _check_widths(args, vanilla: bool = None) -> None:
+    """Fail EARLY and clearly for configurations the kernels do not cover (instead of deep inside plan creation)."""
+    from infodiffusion_b200.engine import MAX_GN_CHANNELS
+    vanilla = (args.model == 'vanilla') if vanilla is None else vanilla
+    if vanilla and not args.is_latent and args.mode != 'train_latent_ddim':
+        widest = 8 * args.unets_channels                      # Diff hard-wires ch_mult = [1, 2, 4, 8] (models.py:746)
+        if 2 * widest > MAX_GN_CHANNELS:
+            raise NotImplementedError(
+                f"the vanilla image model (Diff over UNet, ch_mult [1,2,4,8], {widest} channels, GroupNorm over "
+                f"{2 * widest}) exceeds the kernels' limit of {MAX_GN_CHANNELS} GroupNorm channels; see DESIGN.md section 7")
+
+
 def _load(args, device, shape):
+    _check_widths(args)
     model = InfoDiff(args, device, shape) if args.model == 'diff' else Diff(args, device, shape)
     path = os.path.join(_model_root(args), f'model-{args.epochs}.pth')
     if os.path.exists(path):
         model.load_state_dict(torch.load(path, map_location=device), strict=False)
+    elif not args.allow_random_init:
+        raise FileNotFoundError(f"no checkpoint at {path} (reference run.py:233 fails the same way); pass "
+                                "--allow_random_init to evaluate the seeded random initialisation")
     elif int(os.environ.get("RANK", "0")) == 0:
-        print(f"[run.py] no checkpoint at {path}: using the seeded random initialisation")
+        print(f"[run.py] no checkpoint at {path}: using the seeded random initialisation (--allow_random_init)")
     return model.eval()
 
 
@@ -262,9 +304,17 @@ def evaluate(args):
             else:                                                # run.py:244-252, 280: two-phase with the vanilla model
                 p2 = f'./models/diff/{args.dataset}_{args.a_dim}d/model-{args.epochs}.pth'
                 if os.path.exists(p2):
+                    _check_widths(args, vanilla=True)
                     model2 = Diff(args, device, shape)
                     model2.load_state_dict(torch.load(p2, map_location=device), strict=True)
                     process = TwoPhaseDiffusionProcess(args, model, model2.eval(), device, shape)
+                elif not getattr(args, "single_phase", False):
+                    raise FileNotFoundError(f"The file path {p2} does not exist, please train the vanilla diffusion model "
+                                            "first (reference run.py:249); pass --single_phase to sample with the "
+                                            "InfoDiff model alone instead of the two-phase sampler")
+                elif rank == 0:
+                    print("[run.py] --single_phase: sampling with the InfoDiff model alone (NOT the reference's two-phase "
+                          "procedure)")
         # run.py:265-274 (eval_fid: imgs/<exp>/eval-fid-latent|eval-fid-fast) and save_images (eval: imgs[/diff]/<exp>/eval)
         if args.mode == 'eval_fid':
             root = os.path.join(args.img_folder, exp, 'eval-fid-latent' if args.is_latent else 'eval-fid-fast')
@@ -307,14 +357,104 @@ def evaluate(args):
         if rank == 0:
             attr = labels if labels is not None else np.array(['No Attributes'] * x.shape[0])
             idf_io.save_latents_npz("{}_{}_latent".format(args.model, exp.replace(".", "_")), outs, [attr])
+    elif args.mode in ('latent_quality', 'disentangle', 'interpolate'):
+        _analysis_modes(args, model, device, shape, rank)
     else:
-        raise NotImplementedError(f"--mode {args.mode} is an analysis mode outside the hot path (SURVEY section 8f rank 4)")
+        raise NotImplementedError(f"--mode {args.mode}: plot_latent / save_original_img need matplotlib / the torchvision "
+                                  "datasets and are outside the hot path (SURVEY section 8f rank 4)")
+
+
+def _nth_batch(args, shape, n):
+    """The reference iterates its DataLoader (batch_size = args.batch_size, in order) and keeps batch `n` -- or the last
+    one when the data are shorter (run.py:316-321, 373-383, 446-451)."""
+    x, _ = load_images(args, shape)
+    nb = (x.shape[0] + args.batch_size - 1) // args.batch_size
+    i = min(n, nb - 1) * args.batch_size
+    return x[i:i + args.batch_size]
+
+
+def _encode(args, model, data, for_quality=False):
+    """run.py:322-329 / 386-392 / 452-461: the latent the analysis modes condition on."""
+    with torch.no_grad():
+        a, _, mu, log_var = model.encoder(data)
+    if args.kld_weight != 0:
+        return mu + torch.exp(0.5 * log_var) if for_quality else mu      # latent_quality adds the std (run.py:325)
+    return a
+
+
+def _save_grid(args, sample, name):
+    """reference save_images (run.py:103-143) for disentangle / interpolate: one row, normalised from [-1, 1]."""
+    from torchvision.utils import save_image
+    root = os.path.join(args.img_folder, 'diff' if args.model == 'vanilla' else '', generate_exp_string(args),
+                        f'{args.mode}-{args.img_id}')
+    os.makedirs(root, exist_ok=True)
+    path = os.path.join(root, name)
+    save_image(sample.float().cpu(), path, normalize=True, value_range=(-1, 1), nrow=sample.shape[0])
+    return path
+
+
+def _analysis_modes(args, model, device, shape, rank):
+    """latent_quality (run.py:310-341), disentangle (371-414), interpolate (444-481): thin callers of the encoder, the
+    reverse DDIM and the sampler.  Single process (the reference pins batch_size to 1 / 1 / 2, run.py:535-538)."""
+    if args.model != 'diff':
+        raise NotImplementedError("the analysis modes are built for --model diff (InfoDiff)")
+    process = DiffusionProcess(args, model, device, shape)
+    exp = generate_exp_string(args)
+    if args.mode == 'latent_quality':
+        data = _nth_batch(args, shape, 10).to(device)
+        a = _encode(args, model, data, for_quality=True)
+        xT = process.reverse_sampling(data, a)
+        xT_original = xT.repeat(args.sampling_number, 1, 1, 1)
+        a_original = a.repeat(args.sampling_number, 1)
+        xT = torch.randn_like(xT_original)
+        batch = process.sampling(xT=xT, a=a_original)
+        root = os.path.join(args.img_folder, exp, 'latent_quality')
+        # the reference joins the file name onto an undefined `path` here (run.py:340, NameError); the evident intent
+        # -- sample-%06d.png under <img_folder>/<exp>/latent_quality -- is what is written
+        idf_io.save_eval_images(batch, root)
+        if rank == 0:
+            print("DONE", root)
+    elif args.mode == 'disentangle':
+        data = _nth_batch(args, shape, args.img_id).to(device)
+        eta = [-1.5, -1.2, -0.9, -0.6, -0.3, 0.0, 0.3, 0.6, 0.9, 1.2, 1.5]
+        a = _encode(args, model, data)
+        xT = process.reverse_sampling(data, a).repeat(len(eta), 1, 1, 1)
+        for k in range(args.a_dim):
+            rows = []
+            for e in eta:
+                a_k = _encode(args, model, data).clone()
+                a_k[0][k] = e                                        # run.py:408: first image of the batch, dimension k
+                rows.append(a_k)
+            a_all = torch.stack(rows).squeeze(dim=1)
+            sample = process.sampling(xT=xT, a=a_all)
+            path = _save_grid(args, sample, f"sample{k}.png")
+        if rank == 0:
+            print("DONE", os.path.dirname(path))
+    else:                                                            # interpolate
+        data = _nth_batch(args, shape, args.img_id).to(device)
+        assert data.shape[0] >= 2, "interpolate needs two images (the reference sets batch_size = 2)"
+        a = _encode(args, model, data)
+        xT = process.reverse_sampling(data, a)
+        u, v = xT[0].reshape(-1), xT[1].reshape(-1)
+        theta = torch.arccos((torch.nn.functional.normalize(u, dim=0) * torch.nn.functional.normalize(v, dim=0)).sum())
+        etas = [0.0, 0.11, 0.22, 0.33, 0.44, 0.55, 0.66, 0.77, 0.88, 1.0]
+        intp_a = torch.stack([float(np.cos(e * np.pi / 2)) * a[0] + float(np.sin(e * np.pi / 2)) * a[1] for e in etas])
+        intp_x = torch.stack([(torch.sin((1 - e) * theta) * xT[0] + torch.sin(e * theta) * xT[1]) / torch.sin(theta)
+                              for e in etas])
+        sample = process.sampling(xT=intp_x, a=intp_a)
+        path = _save_grid(args, sample, "sample0.png")
+        if rank == 0:
+            print("DONE", path)
 
 
 if __name__ == '__main__':
     args = parse_args()
     if args.model == 'vae':
         raise NotImplementedError("the VAE baseline is out of scope (SURVEY section 2)")
+    if args.mode in ('disentangle', 'latent_quality'):               # reference run.py:535-538
+        args.batch_size = 1
+    elif args.mode == 'interpolate':
+        args.batch_size = 2
     if args.mode == 'train':
         train(args)
     elif args.mode == 'train_latent_ddim':

@@ -6,7 +6,7 @@ set -u
 R="${GRAFT_REPO_ROOT:-/root/repo}"
 W=$(mktemp -d)
 cd "$W"
-C="--model diff --prior regular --dataset synthetic --a_dim 32 --batch_size 4 --epochs 1 --save_epochs 1 --diffusion_steps 4 --synthetic_size 16 --r_seed 64"
+C="--model diff --prior regular --dataset synthetic --a_dim 32 --batch_size 4 --epochs 1 --save_epochs 1 --diffusion_steps 4 --synthetic_size 16 --r_seed 64 --single_phase"
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531"
 export PYTHONPATH="$R"
 $T "$R/run.py" $C --mode train 2>&1 | grep -E "Epoch|rror" | tail -3

@@ -3,7 +3,7 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 R=${ROUND_TAG:-r2a}
-run() { local name=$1; shift; timeout 300 python bench.py --steps 3 --warmup 3 --no-train --no-cpu-baseline "$@" > gpurun_out/sb_${R}_$name.json 2> gpurun_out/sb_${R}_$name.err; echo "$name rc=$? $(python -c "
+run() { local name=$1; shift; timeout 300 python bench.py --steps 3 --warmup 3 --no-train --no-cpu-baseline --no-extras "$@" > gpurun_out/sb_${R}_$name.json 2> gpurun_out/sb_${R}_$name.err; echo "$name rc=$? $(python -c "
 import json,sys
 try:
     d=json.loads(open('gpurun_out/sb_${R}_$name.json').read().strip().splitlines()[-1]); print(round(d['value'],1),'img/s', round(d['ms_per_step']/100,3),'ms/unet-step', {k: round(v['ms_per_unet_eval'],3) for k,v in (d.get('kernel_breakdown') or {}).items()})
