@@ -297,13 +297,6 @@ int idf_sampler_update(float* x, const float* eps, const float* noise, const flo
 int idf_mmd_fwd_bwd(const float* x, const float* y, float* loss, float* grad_y, int32_t B, int32_t D,
                     idf_stream_t stream);
 
-/* ------------------------------------------------------------------------------------------
- * Debug / hardware probe (not on the product path): UMMA with an A descriptor shifted by `shift`
- * 128-byte rows inside a TMA-written [256,64] bf16 tile; out[128,64] fp32 = A[shift:shift+128] . B^T.
- * mode 0: descriptor base_offset = 0; mode 1: base_offset = (start_address >> 7) & 7.
- * ------------------------------------------------------------------------------------------ */
-int idf_debug_shift_probe(const void* a, const void* b, float* out, int32_t shift, int32_t mode, idf_stream_t stream);
-
 #ifdef __cplusplus
 }
 #endif

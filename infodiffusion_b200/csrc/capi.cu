@@ -579,18 +579,4 @@ int idf_mmd_fwd_bwd(const float* x, const float* y, float* loss, float* grad_y, 
   return IDF_OK;
 }
 
-int idf_debug_shift_probe(const void* a, const void* b, float* out, int32_t shift, int32_t mode, idf_stream_t stream) {
-  int rc = ensure_init();
-  if (rc != IDF_OK) return rc;
-  if (shift < 0 || shift > 128) return fail(IDF_ERR_ARG, "shift must be in [0,128]");
-  CUtensorMap tmA, tmB;
-  rc = encode_2d(&tmA, a, 256, 64, 128);
-  if (rc != IDF_OK) return rc;
-  rc = encode_2d(&tmB, b, 64, 64, 64);
-  if (rc != IDF_OK) return rc;
-  cudaError_t e = launch_shift_probe(tmA, tmB, out, shift, mode, reinterpret_cast<cudaStream_t>(stream));
-  if (e != cudaSuccess) return cuda_fail(e, "shift probe launch");
-  return IDF_OK;
-}
-
 }  // extern "C"

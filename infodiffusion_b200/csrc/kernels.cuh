@@ -110,8 +110,6 @@ cudaError_t launch_colsum(const bf16* m, float* out, long long rows, int C, int 
 cudaError_t launch_padflat_to_nchw(const bf16* in, float* y, int batch, int C, int H, int W, cudaStream_t stream);
 cudaError_t launch_sampler_update(float* x, const float* eps, const float* noise, const float* coef,
                                   const int32_t* step_ptr, int64_t n, cudaStream_t stream);
-cudaError_t launch_shift_probe(const CUtensorMap& tmA, const CUtensorMap& tmB, float* out, int shift, int mode,
-                               cudaStream_t stream);
 cudaError_t launch_mmd(const float* x, const float* y, float* loss, float* grad_y, int B, int D, cudaStream_t stream);
 
 }  // namespace idf

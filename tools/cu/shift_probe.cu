@@ -1,7 +1,11 @@
-// Hardware probe (debug entry point, not on the product path): does a K-major SW128 UMMA descriptor
+// Hardware probe (STANDALONE program, not part of libidf_b200.so): does a K-major SW128 UMMA descriptor
 // whose start address is shifted by an arbitrary number of 128-byte rows read the rows TMA wrote?
 // Decides how the halo-reuse convolution addresses its 3x3 taps (base_offset semantics).
-#include "kernels.cuh"
+#include <cudaTypedefs.h>
+#include <cstdio>
+#include <vector>
+
+#include "../../infodiffusion_b200/csrc/ptx.cuh"
 
 namespace idf {
 
@@ -78,3 +82,47 @@ cudaError_t launch_shift_probe(const CUtensorMap& tmA, const CUtensorMap& tmB, f
 }
 
 }  // namespace idf
+
+// ---- host driver: A = 256 x 64 ramp, B = identity => D = A rows [shift, shift + 128)
+static int encode(PFN_cuTensorMapEncodeTiled_v12000 enc, CUtensorMap* tm, const void* base, int rows, int box_rows) {
+  cuuint64_t gdim[2] = {64, static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {128};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t es[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+int main() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return 2;
+  auto enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  std::vector<__nv_bfloat16> ha(256 * 64), hb(64 * 64);
+  for (int i = 0; i < 256 * 64; ++i) ha[i] = __float2bfloat16(((i % 509) - 254) / 4.0f);
+  for (int i = 0; i < 64 * 64; ++i) hb[i] = __float2bfloat16((i / 64 == i % 64) ? 1.0f : 0.0f);
+  __nv_bfloat16 *da, *db;
+  float* dout;
+  cudaMalloc(&da, ha.size() * 2); cudaMalloc(&db, hb.size() * 2); cudaMalloc(&dout, 128 * 64 * 4);
+  cudaMemcpy(da, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
+  CUtensorMap tmA, tmB;
+  if (encode(enc, &tmA, da, 256, 128) || encode(enc, &tmB, db, 64, 64)) return 3;
+  const int shifts[] = {0, 1, 2, 7, 8, 9, 16, 65, 66, 73, 127, 128};
+  std::vector<float> out(128 * 64);
+  for (int shift : shifts)
+    for (int mode = 0; mode < 2; ++mode) {
+      cudaMemset(dout, 0xff, 128 * 64 * 4);
+      if (idf::launch_shift_probe(tmA, tmB, dout, shift, mode, 0) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+        printf("shift %3d mode %d: CUDA error %s\n", shift, mode, cudaGetErrorString(cudaGetLastError()));
+        return 4;
+      }
+      cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost);
+      int bad = 0;
+      for (int r = 0; r < 128; ++r)
+        for (int c = 0; c < 64; ++c) bad += out[r * 64 + c] != __bfloat162float(ha[(r + shift) * 64 + c]);
+      printf("shift %3d mode %d: mismatches %d\n", shift, mode, bad);
+    }
+  return 0;
+}
