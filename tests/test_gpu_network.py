@@ -2,10 +2,13 @@
 against the fp32 CPU oracle on identical weights, inputs and injected noise, plus the committed
 golden vectors minted from the unmodified reference.
 
-Stated tolerance (bf16 path): rel-L2(eps) <= 3e-2, rel-L2(x_t) <= 1e-2 per step.  For calibration the
-reference itself under torch.autocast(bf16) sits at 2.3e-2 rel-L2 from fp64 (SURVEY.md section 6);
-BASELINE's 1e-3 figure is not reachable with 8-bit mantissas through 66 stacked convolutions and we
-report the measured error instead of assuming it (printed by each test, collected in DESIGN.md).
+Stated tolerance (bf16 path): rel-L2(eps) <= 2.1e-2, rel-L2(x_t) <= 4.3e-3 per step = 1.2 x the worst value
+measured on B200 (eps 1.75e-2 on the encoder's mu, x_t 3.5e-3 on reverse DDIM), so a regression shows.  For
+calibration the reference itself under torch.autocast(bf16) sits at 2.3e-2 rel-L2 from fp64 (SURVEY.md
+section 6).  BASELINE's 1e-3 figure is not reachable with bf16 STORAGE, whatever the kernels do: rounding only
+the conv weights to bf16 in the fp32 oracle already moves eps by 7.9e-3, only the conv operands by 8.9e-3, and all
+four storage roundings together by 1.48e-2 -- the measured error of the CUDA path (tools/error_budget.py,
+DESIGN.md section 5).  The measured errors are printed by each test.
 """
 import contextlib
 
@@ -18,8 +21,8 @@ from oracle.golden_util import SEED, make_args, perturb_state_dict, rand_inputs,
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-TOL_EPS = 3e-2
-TOL_X = 1e-2
+TOL_EPS = 2.1e-2
+TOL_X = 4.3e-3
 
 
 def build(a_dim, T, **kw):
@@ -178,6 +181,36 @@ def test_full_size_batch_independence_and_chunking():
     assert rel_l2(full[128:].cpu(), half.cpu()) < 2e-3
     chunked = run(slice(0, B), chunk=64)
     assert rel_l2(chunked.cpu(), full.cpu()) < 2e-3
+
+
+def test_full_size_two_ddim_steps_against_the_oracle():
+    """The BASELINE configuration itself -- batch 256, a_dim 256 -- against the fp32 CPU oracle: two DDIM steps with
+    per-step eps and x_t (about 30 s of CPU work for the oracle's two UNet evaluations at batch 256)."""
+    T, B = 2, 256
+    args, m, sd = build(256, T)
+    g = torch.Generator().manual_seed(21)
+    xT = torch.randn(B, 3, 64, 64, generator=g)
+    a = torch.randn(B, 256, generator=g)
+    shape = tuple(xT.shape)
+    sch = orc.Schedule.make(args.beta1, args.betaT, T)
+    rec = []
+    torch.set_num_threads(max(1, __import__("os").cpu_count() or 1))
+    orc.sample(sd, sch, xT, a, True, noise_fn=lambda i, like: step_noise(i, shape), record=rec)
+    p = _proc(args, m, True)
+    p.noise_fn = lambda idx, out: out.copy_(step_noise(idx, shape))
+    trace = []
+    x_fin = p.sampling(B, xT=xT.to(DEV), a=a.to(DEV), trace=trace)
+    worst_e = worst_x = worst_sample = 0.0
+    for (idx, eps_o, x_o), (idx_g, eps_g, x_g) in zip(rec, trace):
+        assert idx == idx_g
+        worst_e = max(worst_e, rel_l2(eps_g.cpu(), eps_o))
+        worst_x = max(worst_x, rel_l2(x_g.cpu(), x_o))
+        per = (eps_g.cpu() - eps_o).flatten(1).norm(dim=1) / eps_o.flatten(1).norm(dim=1)
+        worst_sample = max(worst_sample, float(per.max()))
+    print(f"\n[parity] batch 256 / a_dim 256, DDIM-2: worst per-step rel-L2 eps = {worst_e:.3e} "
+          f"(worst single sample {worst_sample:.3e}), x_t = {worst_x:.3e}")
+    assert torch.isfinite(x_fin).all()
+    assert worst_e < TOL_EPS and worst_x < TOL_X and worst_sample < 1.5 * TOL_EPS
 
 
 @contextlib.contextmanager

@@ -10,8 +10,8 @@ from oracle.golden_util import SEED, make_args, perturb_state_dict, rand_inputs,
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-TOL_EPS = 3e-2
-TOL_X = 1e-2
+TOL_EPS = 2.1e-2      # 1.2 x the worst measured value, see tests/test_gpu_network.py
+TOL_X = 4.3e-3
 
 
 def _to_dev(m):
@@ -263,6 +263,23 @@ def test_run_py_modes_end_to_end(tmp_path, monkeypatch):
     run("--mode", "eval_fid", "--is_latent", "--deterministic", "--sampling_number", "6")
     pngs = sorted((tmp_path / "imgs" / exp / "eval-fid-latent").glob("sample-*.png"))
     assert [p.name for p in pngs] == [f"sample-{i:06d}.png" for i in range(6)]
+    # the reference requires the vanilla model for eval_fid without --is_latent (run.py:249); so do we
+    r = subprocess.run([sys.executable, str(root / "run.py"), *common, "--mode", "eval_fid", "--sampling_number", "2"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=600,
+                       env={**__import__("os").environ, "PYTHONPATH": str(root)})
+    assert r.returncode != 0 and "FileNotFoundError" in r.stderr
+    # analysis modes (run.py:310-341, 371-414, 444-481): thin callers of encoder / reverse DDIM / sampler
+    run("--mode", "latent_quality", "--sampling_number", "3")
+    assert len(list((tmp_path / "imgs" / exp / "latent_quality").glob("sample-*.png"))) == 3
+    run("--mode", "interpolate", "--img_id", "1")
+    assert (tmp_path / "imgs" / exp / "interpolate-1" / "sample0.png").exists()
+    short = [c if c != "32" else "4" for c in common]            # a_dim 4: disentangle renders one grid per latent dim
+    exp4 = "synthetic_4d_0.1mmd"
+    subprocess.run([sys.executable, str(root / "run.py"), *short, "--mode", "train"], cwd=tmp_path, check=True,
+                   capture_output=True, timeout=600, env={**__import__("os").environ, "PYTHONPATH": str(root)})
+    subprocess.run([sys.executable, str(root / "run.py"), *short, "--mode", "disentangle", "--img_id", "0"], cwd=tmp_path,
+                   check=True, capture_output=True, timeout=600, env={**__import__("os").environ, "PYTHONPATH": str(root)})
+    assert sorted(p.name for p in (tmp_path / "imgs" / exp4 / "disentangle-0").glob("*.png")) == [f"sample{k}.png" for k in range(4)]
 
 
 def test_32x32_model_cifar_shape():
