@@ -11,6 +11,7 @@
 
 #include "kernels.cuh"
 
+namespace idf { extern int g_xf_ldg; }
 namespace idf { extern int g_adagn_ring, g_adagn_ctas, g_adagn_ctas2, g_adagn_impl, g_pdl, g_xf_debug; }
 using namespace idf;
 
@@ -118,6 +119,7 @@ int idf_set_option(const char* key, int32_t value) {
     g_skip_epilogue = value ? 1 : 0;
     return IDF_OK;
   }
+  if (key != nullptr && std::strcmp(key, "xf_ldg") == 0 && (value == 0 || value == 1)) { g_xf_ldg = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "pdl") == 0) { g_pdl = value ? 1 : 0; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "xf_debug") == 0 && value >= 0 && value <= 4) { g_xf_debug = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "adagn_ring") == 0 && value >= 1 && value <= 8) { g_adagn_ring = static_cast<int>(value); return IDF_OK; }
@@ -281,6 +283,8 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   p.xf_ctot = d->xf_ctot;
   p.xf_silu = d->xf_silu;
   p.xf_debug = g_xf_debug;
+  p.xf_ldg = g_xf_ldg;
+  for (int i = 0; i < d->n_src; ++i) { p.srcp[i] = static_cast<const bf16*>(d->src[i]); p.src_ld[i] = d->src_ld[i]; }
   pl->xform = false;
   for (int g = 0; g < p.n_groups; ++g) pl->xform = pl->xform || p.g_xf[g] >= 0;
   if (p.bias == nullptr) { delete pl; return fail(IDF_ERR_ARG, "bias is null"); }

@@ -28,6 +28,9 @@ constexpr int kXfWarps = 12;
 constexpr int kXfRows = 4 * kXfWarps;
 
 int g_pdl = 0;     // idf_set_option("pdl", 1): launch conv / AdaGN with programmatic dependent launch
+int g_xf_ldg = 0;     // fused AdaGN: 0 = rewrite the TMA-loaded halo in place (default), 1 = transform warps load the halo with
+                      // ld.global and store it once (idf_set_option "xf_ldg"; measured SLOWER at batch 256: conv 7.7 vs 6.7 ms,
+                      // the global latency is not hidden with the registers 768 threads leave)
 int g_xf_debug = 0;  // measurement only: 1 = transform warps forward the halo untouched, 2 = affine without the SiLU
 
 __host__ __device__ constexpr int conv_b_stages(int bn) { return bn == 16 ? 8 : (bn == 64 ? 4 : 6); }
@@ -280,6 +283,13 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
         for (int g = 0; g < p.n_groups; ++g) {
           const int src = p.g_src[g];
           const int ex = p.extra_rows[src];
+          if (XF && p.xf_ldg != 0 && p.g_xf[g] >= 0) {      // the transform warps load this halo themselves
+            // still observe this use's empty phase: a parity wait is only unambiguous for a waiter that has seen
+            // every earlier phase -- skipping one lets the NEXT wait on this stage alias to a phase two uses back
+            mbar_wait(a_empty + sa, pa ^ 1u);
+            if (++sa == AS) { sa = 0; pa ^= 1u; }
+            continue;
+          }
           mbar_wait(a_empty + sa, pa ^ 1u);
           mbar_arrive_expect_tx(a_full + sa, static_cast<uint32_t>((MT * kBM + ex) * 128));
           uint8_t* dst = smA + sa * p.a_stage_bytes;
@@ -369,6 +379,123 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
     uint32_t pa = 0;
     int cur = -1, cur_cb = -1;           // (image, channel slice) of the coefficients held in A[], B[]
     float A[8], B[8];
+    if (p.xf_ldg != 0) {
+      // ---- direct-load variant: global -> registers -> act(A*x + B) -> ONE st.shared into the swizzled operand tile.
+      // The MMAs saturate the shared-memory bandwidth, so the in-place variant's extra ld.shared + st.shared pass is
+      // paid in full (measured: +1.0 ms per UNet evaluation at batch 256); here the only shared-memory traffic is the
+      // write the TMA would have done anyway.  thread -> logical 16-byte channel granule gi (8 channels) and the halo
+      // rows rs, rs + kXfRows, ...; physical granule = gi ^ (row & 7) = gi ^ (rs & 7) (kXfRows % 8 == 0).
+      // Loads run one "quad" (4 rows) ahead of the arithmetic; a quad of the NEXT halo is requested before the last
+      // quad of this one is transformed, so the global latency overlaps the MMAs of the previous stage.
+      const uint32_t phys = static_cast<uint32_t>((gi ^ (rs & 7)) << 4);
+      struct Cur { int st, g, q, nq, nrows, rbase, cb; uint32_t sa, pa; const bf16* col; int ld; bool ok; };
+      auto setup = [&](Cur& c) {          // fill the derived fields for (st, g); c.ok = false past the end
+        c.ok = c.st < total;
+        if (!c.ok) return;
+        const int ms = c.st / p.n_tiles;
+        const int src = p.g_src[c.g];
+        c.cb = p.g_xf[c.g];
+        c.nrows = MT * kBM + p.extra_rows[src];
+        c.rbase = ms * (MT * kBM) + p.g_lo[c.g];
+        c.nq = c.cb >= 0 ? (c.nrows + 4 * kXfRows - 1) / (4 * kXfRows) : 1;
+        c.ld = p.src_ld[src];
+        c.col = p.srcp[src] + p.g_c0[c.g] + gi * 8;
+      };
+      auto advance = [&](Cur& c) {        // next quad; next group / item when the halo is complete
+        if (++c.q < c.nq) return;
+        c.q = 0;
+        if (++c.sa == AS) { c.sa = 0; c.pa ^= 1u; }
+        if (++c.g == p.n_groups) { c.g = 0; c.st += gridDim.x; }
+        setup(c);
+      };
+      auto load = [&](const Cur& c, uint4 (&u)[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = rs + kXfRows * (4 * c.q + k);
+          const int r = c.rbase + i;
+          u[k] = make_uint4(0, 0, 0, 0);
+          if (c.cb >= 0 && i < c.nrows && r >= 0 && r < rows32) {
+            const bf16* src = c.col + static_cast<int64_t>(r) * c.ld;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(u[k].x), "=r"(u[k].y), "=r"(u[k].z), "=r"(u[k].w) : "l"(src));
+          }
+        }
+      };
+      Cur c;
+      c.st = blockIdx.x; c.g = 0; c.q = 0; c.sa = 0; c.pa = 0;
+      setup(c);
+      uint32_t full_par = 0;      // bit s = phase parity of a_full[s]: that barrier only cycles for the TMA-loaded (raw) halos
+      uint4 u[4], un[4];
+      if (c.ok) load(c, u);
+      while (c.ok) {
+        Cur n = c;
+        advance(n);
+        if (n.ok) load(n, un);
+        if (c.cb < 0) {
+          mbar_wait(a_full + c.sa, (full_par >> c.sa) & 1u);      // raw halo: the A producer's TMA wrote it
+          full_par ^= 1u << c.sa;
+        } else {
+          if (c.cb != cur_cb) { cur = -1; cur_cb = c.cb; }
+          if (c.q == 0) mbar_wait(a_empty + c.sa, c.pa ^ 1u);     // the MMAs are done with this stage
+          const uint32_t base = smem_u32(smA + c.sa * p.a_stage_bytes) + phys;
+          const float2* ctab = p.xf_coef + c.cb + gi * 8;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = rs + kXfRows * (4 * c.q + k);
+            int inf = -1;                                            // -1: the row must hold zeros
+            if (gi == 0 && i < c.nrows) {
+              const int r = c.rbase + i;
+              if (r >= 0 && r < rows32) {
+                const int rq = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_wp);
+                const int x = r - rq * p.Wp;
+                const int img = __float2int_rd((static_cast<float>(rq) + 0.5f) * inv_hp);
+                const int y = rq - img * p.Hp;
+                if (x < p.W && y < p.H) inf = img;
+              }
+            }
+            inf = __shfl_sync(grp_mask, inf, grp_lead);
+            if (i >= c.nrows) continue;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (inf >= 0) {
+              if (inf != cur) {
+                cur = inf;
+                const float4* c4 = reinterpret_cast<const float4*>(ctab + static_cast<int64_t>(inf) * p.xf_ctot);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 cc = __ldg(c4 + j);
+                  A[2 * j] = cc.x * cs; B[2 * j] = cc.y * cs; A[2 * j + 1] = cc.z * cs; B[2 * j + 1] = cc.w * cs;
+                }
+              }
+              const float2 a0 = unpack_bf16x2(u[k].x), a1 = unpack_bf16x2(u[k].y), a2 = unpack_bf16x2(u[k].z), a3 = unpack_bf16x2(u[k].w);
+              float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+              if (do_silu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float h = fmaf(f[j], A[j], B[j]);
+                  float th;
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+                  f[j] = fmaf(h, th, h);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], A[j], B[j]);
+              }
+              o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+            }
+            sts128(base + static_cast<uint32_t>(i) * 128u, o);
+          }
+        }
+        if (c.q == c.nq - 1) {                        // halo complete: hand the stage to the UMMA issuers
+          if (c.cb >= 0) fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_ready + c.sa);
+        }
+        c = n;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = un[k];
+      }
+    } else
     for (int st = blockIdx.x; st < total; st += gridDim.x) {
       const int ms = st / p.n_tiles;
       const int row0 = ms * (MT * kBM);

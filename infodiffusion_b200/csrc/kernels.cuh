@@ -56,6 +56,11 @@ struct alignas(64) ConvKernelParams {
   int32_t xf_silu;
   int32_t g_xf[kMaxGroups];             // channel base of the group's 64-channel slice in xf_coef, or -1
   int32_t xf_debug;                     // measurement only (idf_set_option "xf_debug")
+  // direct-load transform (xf_ldg != 0): the transform warps read the halo of a fused-AdaGN group straight from global
+  // memory into registers and store act(A*x + B) ONCE into the swizzled operand tile -- no TMA write + read + rewrite
+  int32_t xf_ldg;
+  const bf16* srcp[IDF_CONV_MAX_SRC];   // raw source pointers / row pitches (elements) for those loads
+  int32_t src_ld[IDF_CONV_MAX_SRC];
 };
 
 constexpr int kWgMaxUnits = 64;

@@ -653,7 +653,9 @@ def test_clip_adamw_matches_torch():
 @pytest.mark.parametrize("c0,c1,cout,H,B,k,silu,mt,sc", [
     (64, 0, 64, 16, 3, 3, True, 0, False), (128, 0, 128, 8, 5, 3, True, 0, False), (128, 64, 64, 16, 2, 3, True, 0, True),
     (128, 128, 128, 8, 3, 3, True, 0, True), (128, 0, 384, 16, 2, 1, False, 0, False), (64, 0, 64, 32, 6, 3, True, 4, False),
-    (128, 0, 128, 16, 9, 3, True, 2, False), (64, 0, 3, 16, 3, 3, True, 0, False), (64, 0, 64, 64, 3, 3, True, 0, False)])
+    (128, 0, 128, 16, 9, 3, True, 2, False), (64, 0, 3, 16, 3, 3, True, 0, False), (64, 0, 64, 64, 3, 3, True, 0, False),
+    # several work items per CTA (persistent loop, both halo stages recycled), plain and with raw shortcut groups
+    (64, 0, 64, 32, 160, 3, True, 0, False), (128, 64, 64, 16, 300, 3, True, 0, True), (128, 0, 128, 32, 90, 3, True, 0, False)])
 def test_conv_with_fused_adagn_equals_adagn_then_conv(lib, c0, c1, cout, H, B, k, silu, mt, sc):
     """idf_conv with xf_coef (AdaGN + SiLU applied to the A operand in shared memory) against the two-kernel path
     idf_adagn_silu_fwd -> idf_conv on the same inputs.  Covers concatenated sources, an untransformed 1x1
