@@ -63,7 +63,7 @@ int idf_set_option(const char* key, int32_t value);
  * r runs over the pad-flat rows of the OUTPUT geometry and Wp is the packed bf16 weight matrix
  * [Cout_pad, 64*num_kb] (K contiguous).
  * ------------------------------------------------------------------------------------------ */
-#define IDF_CONV_MAX_KB 48
+#define IDF_CONV_MAX_KB 160   /* 9 taps x 1024 input channels / 64 + a 1x1 shortcut over 1024 channels */
 #define IDF_CONV_MAX_SRC 3
 
 typedef enum {
@@ -208,12 +208,27 @@ int idf_adagn_silu_bwd(const idf_adagn_bwd_args* args, idf_stream_t stream);
 int idf_attn_fwd(const void* qkv, void* out, int32_t batch, int32_t H, int32_t W, int32_t d, float scale,
                  idf_stream_t stream);
 
+/* Backward of idf_attn_fwd (autograd of modules.py:145-164): dqkv [rows, 3*d] (dq | dk | dv, interior rows only) from the
+ * saved qkv and dout = dL/dO [rows, d].  Two tcgen05 kernels per call (scores: P and dS rows -> workspace; gradients:
+ * dQ = dS K, dK = dS^T Q, dV = P^T dO); ws = idf_attn_bwd_ws_bytes(batch, H, W) bytes of device memory, 1024-aligned
+ * (unused for the small-map fallback H*W <= 64, H*W*d <= 8192). */
+int idf_attn_bwd(const void* qkv, const void* dout, void* dqkv, void* ws, int32_t batch, int32_t H, int32_t W, int32_t d,
+                 float scale, idf_stream_t stream);
+int64_t idf_attn_bwd_ws_bytes(int32_t batch, int32_t H, int32_t W);
+
+
 /* ------------------------------------------------------------------------------------------
  * Small fp32 linear:  y[m, n] = sum_k act(x[m, k]) * w[n, k] + b[n]   (act = SiLU if silu_in)
  * Replaces nn.Linear at modules.py:24,26,211,271,275 and models.py:244,470-472 (cuBLAS addmm).
  * ------------------------------------------------------------------------------------------ */
 int idf_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int32_t M,
                    int32_t N, int32_t K, int32_t silu_in, idf_stream_t stream);
+/* General small fp32 GEMM, C[M,N] (+)= op(A)[M,K] . op(B)[K,N] with op(X) = X or X^T (row-major, leading dimensions):
+ * the BACKWARD of those Linears under autograd (dX = dY.W, dW = dY^T.X, db = 1^T.dY) -- replaces cuBLAS gemm / addmm
+ * in the autograd graph of modules.py:24-27, 211, 271-275 and models.py:147-163, 223-234, 470-472. */
+int idf_gemm_f32(const float* A, int64_t lda, int32_t transA, const float* B, int64_t ldb, int32_t transB, float* C,
+                 int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t accumulate, idf_stream_t stream);
+
 /* y[m, :] = table[idx[m], :]  (nn.Embedding lookup, modules.py:23,37) */
 int idf_gather_rows_f32(const float* table, const int64_t* idx, float* y, int32_t M, int32_t N, idf_stream_t stream);
 /* LatentUNet layer tail, MLPLNAct.forward (models.py:147-163) after the Linear: out[m, :] = SiLU(LayerNorm(y[m, :] *

@@ -11,7 +11,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libidf_b200.so"
 
-IDF_CONV_MAX_KB = 48
+IDF_CONV_MAX_KB = 160
 IDF_CONV_MAX_SRC = 3
 EPI_BF16, EPI_F32_NCHW, EPI_SAMPLER = 0, 1, 2
 
@@ -117,8 +117,13 @@ SIGNATURES = {
     "idf_adagn_silu_bwd": (C.c_int, [C.POINTER(AdaGNBwdArgs), C.c_void_p]),
     "idf_attn_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                C.c_void_p]),
+    "idf_attn_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_float, C.c_void_p]),
+    "idf_attn_bwd_ws_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "idf_linear_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "idf_gemm_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
+                               C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "idf_scale_layernorm_silu": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_void_p]),

@@ -16,7 +16,7 @@ CSRC = PKG / "csrc"
 LIB = PKG / "libidf_b200.so"
 STAMP = PKG / "csrc" / ".build_stamp"
 
-SOURCES = ["capi.cu", "conv_igemm.cu", "adagn.cu", "attention.cu", "misc.cu", "wgrad.cu", "adagn_bwd.cu", "optim.cu"]
+SOURCES = ["capi.cu", "conv_igemm.cu", "adagn.cu", "attention.cu", "attention_bwd.cu", "misc.cu", "wgrad.cu", "adagn_bwd.cu", "optim.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -251,24 +251,27 @@ constexpr int kRingStageBytes = 16384;
 
 // Per-channel coefficients of image n: GroupNorm statistics from the producers' 32-row window records, folded with
 // gamma / beta and the two modulations into y = A*x + B.  All kAdaThreads threads of the block take part.
-template <int NT>
+// MAXC = 256 serves every layer of the InfoDiff networks; the 1024 instantiation exists for the vanilla Diff model
+// (ch_mult [1,2,4,8]: GroupNorm over 512 + 512 concatenated channels) and costs 18 KB more shared memory per CTA.
+constexpr int kMaxCWide = 1024;
+template <int NT, int MAXC = kMaxC>
 struct CoefShared {
-  float2 sub[NT];            // [sub-sequence][channel], NT / C sub-sequences of windows per channel
-  float tot[2 * kMaxC];
+  float2 sub[(NT > MAXC) ? NT : MAXC];   // [sub-sequence][channel], max(1, NT / C) sub-sequences of windows per channel
+  float tot[2 * MAXC];
   float mean[32], rstd[32];
-  float2 ab[kMaxC];
+  float2 ab[MAXC];
 };
-template <int NT>
-__device__ __forceinline__ void fold_coefficients(const AdaGNParams& p, int n, CoefShared<NT>& sh, bool save) {
+template <int NT, int MAXC>
+__device__ __forceinline__ void fold_coefficients(const AdaGNParams& p, int n, CoefShared<NT, MAXC>& sh, bool save) {
   constexpr int kAdaThreads = NT;       // all NT threads of the block take part
   const int t = threadIdx.x;
   const int C = p.C;
   const int R = p.rows_per_img;
   float2* s_sub = sh.sub;
-  float (&s_tot)[2 * kMaxC] = sh.tot;
+  float (&s_tot)[2 * MAXC] = sh.tot;
   float (&s_mean)[32] = sh.mean;
   float (&s_rstd)[32] = sh.rstd;
-  float2 (&s_ab)[kMaxC] = sh.ab;
+  float2 (&s_ab)[MAXC] = sh.ab;
   // per-channel totals over the 32-row window records that intersect image n.  All 256 threads take
   // part: thread -> (channel, sub-sequence of windows), loads issued four at a time; the order of every
   // addition is a function of (n, geometry) only, so the result is deterministic.
@@ -348,20 +351,22 @@ __device__ __forceinline__ void fold_coefficients(const AdaGNParams& p, int n, C
 // coefficients only (consumer convolution applies them to its A operand): one block per image, same thread count --
 // hence the same summation order, bit for bit -- as the apply kernels' prologue
 constexpr int kCoefThreads = kAdaThreads;
+template <int MAXC>
 __global__ void __launch_bounds__(kCoefThreads) adagn_coef_kernel(const AdaGNParams p, float2* __restrict__ coef_out) {
-  __shared__ CoefShared<kCoefThreads> sh;
+  __shared__ CoefShared<kCoefThreads, MAXC> sh;
   const int n = blockIdx.x;
   griddep_launch();
   griddep_wait();
-  fold_coefficients<kCoefThreads>(p, n, sh, true);
+  fold_coefficients<kCoefThreads, MAXC>(p, n, sh, true);
   for (int ch = threadIdx.x; ch < p.C; ch += kCoefThreads) coef_out[static_cast<long long>(n) * p.C + ch] = sh.ab[ch];
 }
 
+template <int MAXC>
 __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNParams p) {
   extern __shared__ __align__(128) uint8_t ring_raw[];
   __shared__ __align__(8) uint64_t s_full[kRingMax];
   const int kRing = p.ring;
-  __shared__ CoefShared<kAdaThreads> sh;
+  __shared__ CoefShared<kAdaThreads, MAXC> sh;
   const int n = blockIdx.y;
   const int t = threadIdx.x;
   const int C = p.C;
@@ -393,8 +398,8 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_apply_kernel(const AdaGNPar
     for (int b = 0; b < kRing && b < nblk; ++b) issue(b);
   }
 
-  fold_coefficients<kAdaThreads>(p, n, sh, blockIdx.x == 0);
-  const float2 (&s_ab)[kMaxC] = sh.ab;
+  fold_coefficients<kAdaThreads, MAXC>(p, n, sh, blockIdx.x == 0);
+  const float2 (&s_ab)[MAXC] = sh.ab;
 
   // ---------------------------------------------------------------- streaming sweep
   // The slice is pulled through a ring of kRing shared-memory stages by bulk-async copies (one per
@@ -500,7 +505,7 @@ __global__ void __launch_bounds__(kAdaThreads) adagn_stream_kernel(const AdaGNPa
   const int C = p.C;
   griddep_launch();
   griddep_wait();                 // the sources, their statistics and the modulation rows come from earlier kernels
-  fold_coefficients<kAdaThreads>(p, n, sh, blockIdx.x == 0);
+  fold_coefficients<kAdaThreads, kMaxC>(p, n, sh, blockIdx.x == 0);
 
   const int VPR = C >> 3;                       // 16-byte granules per pixel
   const int NT = p.stream_threads;              // multiple of VPR (<= blockDim): the threads that stream
@@ -582,7 +587,8 @@ cudaError_t launch_adagn_coef(const idf_adagn_args& a, float* coef_out, cudaStre
   if (p.stats0 == nullptr || (p.c1 != 0 && p.stats1 == nullptr) || a.dropout_p > 0.f) return cudaErrorInvalidValue;
   p.save_coef = nullptr;
   if (!g_pdl) {
-    adagn_coef_kernel<<<a.batch, kCoefThreads, 0, stream>>>(p, reinterpret_cast<float2*>(coef_out));
+    if (p.C <= kMaxC) adagn_coef_kernel<kMaxC><<<a.batch, kCoefThreads, 0, stream>>>(p, reinterpret_cast<float2*>(coef_out));
+    else              adagn_coef_kernel<kMaxCWide><<<a.batch, kCoefThreads, 0, stream>>>(p, reinterpret_cast<float2*>(coef_out));
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg = {};
@@ -595,7 +601,8 @@ cudaError_t launch_adagn_coef(const idf_adagn_args& a, float* coef_out, cudaStre
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, adagn_coef_kernel, p, reinterpret_cast<float2*>(coef_out));
+  if (p.C <= kMaxC) return cudaLaunchKernelEx(&cfg, adagn_coef_kernel<kMaxC>, p, reinterpret_cast<float2*>(coef_out));
+  return cudaLaunchKernelEx(&cfg, adagn_coef_kernel<kMaxCWide>, p, reinterpret_cast<float2*>(coef_out));
 }
 
 static cudaError_t fill_params(const idf_adagn_args& a, AdaGNParams& p) {
@@ -612,7 +619,7 @@ static cudaError_t fill_params(const idf_adagn_args& a, AdaGNParams& p) {
   p.mod_z = a.mod_z; p.mod_z_step_stride = a.mod_z_step_stride; p.mod_z_batch_stride = a.mod_z_batch_stride;
   p.step_ptr = a.step_ptr;
   p.apply_silu = a.apply_silu;
-  if (p.C > kMaxC || p.C % 32 != 0 || p.c0 % 8 != 0 || p.c1 % 8 != 0 || a.batch <= 0) return cudaErrorInvalidValue;
+  if (p.C > kMaxCWide || p.C % 32 != 0 || p.c0 % 8 != 0 || p.c1 % 8 != 0 || a.batch <= 0) return cudaErrorInvalidValue;
   p.stats0 = a.stats0;
   p.stats1 = a.stats1;
   p.slice_rows = 0;
@@ -638,7 +645,7 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
   p.mod_z = a.mod_z; p.mod_z_step_stride = a.mod_z_step_stride; p.mod_z_batch_stride = a.mod_z_batch_stride;
   p.step_ptr = a.step_ptr;
   p.apply_silu = a.apply_silu;
-  if (p.C > kMaxC || p.C % 32 != 0 || p.c0 % 8 != 0 || p.c1 % 8 != 0 || a.batch <= 0) return cudaErrorInvalidValue;
+  if (p.C > kMaxCWide || p.C % 32 != 0 || p.c0 % 8 != 0 || p.c1 % 8 != 0 || a.batch <= 0) return cudaErrorInvalidValue;
   p.stats0 = a.stats0;
   p.stats1 = a.stats1;
   p.slice_rows = 0;
@@ -651,7 +658,7 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
     p.drop_scale = 65536.f / (65536.f - static_cast<float>(p.drop_thr16));
   }
   p.stats_b_windows = (static_cast<long long>(a.batch) * p.rows_per_img + kBM - 1) / kBM * 4;
-  if (g_adagn_impl == 2 && p.stats0 != nullptr && (p.c1 == 0 || p.stats1 != nullptr)) {
+  if (g_adagn_impl == 2 && p.C <= kMaxC && p.stats0 != nullptr && (p.c1 == 0 || p.stats1 != nullptr)) {
     // streaming variant 2: a CTA owns whole image rows; enough CTAs for >= 4 per SM, each with >= 16 KB to stream
     const int VPR = p.C / 8;
     if (static_cast<long long>(a.batch) * p.rows_per_img * p.C >= (1ll << 31)) return cudaErrorInvalidValue;   // 32-bit element offsets
@@ -693,13 +700,18 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
     const size_t ring_bytes = static_cast<size_t>(p.ring) * p.block_rows * p.C * 2;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(adagn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(adagn_apply_kernel<kMaxC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kRingMax * kRingStageBytes);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(adagn_apply_kernel<kMaxCWide>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kRingMax * kRingStageBytes);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
+    const bool wide = p.C > kMaxC;
     if (!g_pdl) {
-      adagn_apply_kernel<<<dim3(slices, a.batch, 1), kAdaThreads, ring_bytes, stream>>>(p);
+      if (wide) adagn_apply_kernel<kMaxCWide><<<dim3(slices, a.batch, 1), kAdaThreads, ring_bytes, stream>>>(p);
+      else      adagn_apply_kernel<kMaxC><<<dim3(slices, a.batch, 1), kAdaThreads, ring_bytes, stream>>>(p);
       return cudaGetLastError();
     }
     cudaLaunchConfig_t cfg = {};
@@ -712,9 +724,11 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, adagn_apply_kernel, p);
+    if (wide) return cudaLaunchKernelEx(&cfg, adagn_apply_kernel<kMaxCWide>, p);
+    return cudaLaunchKernelEx(&cfg, adagn_apply_kernel<kMaxC>, p);
   }
 
+  if (p.C > kMaxC) return cudaErrorInvalidValue;       // the two-sweep fallback (no producer statistics) serves <= 256 channels
   // cluster size: slices of <= ~72 KB (3 CTAs per SM) when possible, at most 8 CTAs (portable limit)
   const long long bytes = static_cast<long long>(p.rows_per_img) * p.C * 2;
   int CL = 1;

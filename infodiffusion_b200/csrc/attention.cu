@@ -486,6 +486,93 @@ cudaError_t launch_attn_small(const bf16* qkv, bf16* out, int batch, int H, int 
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Wide heads (d = 256 / 512: the vanilla Diff model's UNet at ch_mult [1,2,4,8], models.py:746, attention at 256 and 512
+// channels).  K and V of one image do not fit next to Q in shared memory at these widths and the tensor-core kernel is
+// specialised for d = 128; this CUDA-core kernel keeps the model usable (two-phase sampler, --model vanilla): one CTA
+// per (image, 16 queries), scores in shared memory, K / V streamed from L2 with 16-byte loads.  Not on the measured
+// InfoDiff path (whose attention is always d = 128).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kGenQ = 16;
+__global__ void __launch_bounds__(256) attn_generic_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int H, int W,
+                                                           int d, float scale) {
+  extern __shared__ float sm[];
+  const int S = H * W, n = blockIdx.y, q0 = blockIdx.x * kGenQ, t = threadIdx.x;
+  float* q = sm;                       // [kGenQ][d]
+  float* sc = q + kGenQ * d;           // [kGenQ][S]
+  const long long img_row0 = static_cast<long long>(n) * (H + 1) * (W + 1);
+  auto prow = [&](int tok) -> long long { return img_row0 + (tok / W) * (W + 1) + (tok % W); };
+  const int ld = 3 * d;
+  for (int i = t; i < kGenQ * d; i += 256) {
+    const int a = i / d, c = i - a * d;
+    q[i] = (q0 + a < S) ? __bfloat162float(qkv[prow(q0 + a) * ld + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = t; j < S; j += 256) {                     // one key per thread
+    const uint4* kr = reinterpret_cast<const uint4*>(qkv + prow(j) * ld + d);
+    float acc[kGenQ];
+#pragma unroll
+    for (int a = 0; a < kGenQ; ++a) acc[a] = 0.f;
+    for (int c8 = 0; c8 < d / 8; ++c8) {
+      const uint4 u = __ldg(kr + c8);
+      const float2 k0 = unpack_bf16x2(u.x), k1 = unpack_bf16x2(u.y), k2 = unpack_bf16x2(u.z), k3 = unpack_bf16x2(u.w);
+      const float kv[8] = {k0.x, k0.y, k1.x, k1.y, k2.x, k2.y, k3.x, k3.y};
+#pragma unroll
+      for (int a = 0; a < kGenQ; ++a) {
+        const float* qa = q + a * d + c8 * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[a] = fmaf(qa[e], kv[e], acc[a]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < kGenQ; ++a) sc[a * S + j] = acc[a] * scale;
+  }
+  __syncthreads();
+  {                                                      // softmax: warp w owns query rows 2w, 2w + 1
+    const int warp = t >> 5, lane = t & 31;
+    for (int a = 2 * warp; a < 2 * warp + 2; ++a) {
+      float m = -INFINITY;
+      for (int j = lane; j < S; j += 32) m = fmaxf(m, sc[a * S + j]);
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sum = 0.f;
+      for (int j = lane; j < S; j += 32) { const float e = __expf(sc[a * S + j] - m); sc[a * S + j] = e; sum += e; }
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.0f / sum;
+      for (int j = lane; j < S; j += 32) sc[a * S + j] *= inv;
+    }
+  }
+  __syncthreads();
+  for (int c = t; c < d; c += 256) {                     // one output channel per thread and pass
+    float acc[kGenQ];
+#pragma unroll
+    for (int a = 0; a < kGenQ; ++a) acc[a] = 0.f;
+    const bf16* vc = qkv + 2 * d + c;
+    for (int j = 0; j < S; ++j) {
+      const float vv = __bfloat162float(vc[prow(j) * ld]);
+#pragma unroll
+      for (int a = 0; a < kGenQ; ++a) acc[a] = fmaf(sc[a * S + j], vv, acc[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < kGenQ; ++a)
+      if (q0 + a < S) out[prow(q0 + a) * d + c] = __float2bfloat16(acc[a]);
+  }
+}
+
+cudaError_t launch_attn_generic(const bf16* qkv, bf16* out, int batch, int H, int W, int d, float scale, cudaStream_t stream) {
+  const int S = H * W;
+  if (S <= 0 || S > 1024 || d % 8 != 0 || d > 1024) return cudaErrorInvalidValue;
+  const size_t smem = (static_cast<size_t>(kGenQ) * d + static_cast<size_t>(kGenQ) * S) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    attr = smem;
+  }
+  attn_generic_kernel<<<dim3((S + kGenQ - 1) / kGenQ, batch, 1), 256, smem, stream>>>(qkv, out, H, W, d, scale);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_attn(const bf16* qkv, bf16* out, int batch, int H, int W, int d, float scale,
                         cudaStream_t stream) {
   if (d != kD) return cudaErrorInvalidValue;

@@ -138,7 +138,7 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   if (d->block_n != 16 && d->block_n != 64 && d->block_n != 128) return fail(IDF_ERR_ARG, "block_n must be 16/64/128");
   if (d->cout_pad % d->block_n != 0) return fail(IDF_ERR_ARG, "cout_pad must be a multiple of block_n");
   if (d->batch < 1 || d->H < 1 || d->W < 1) return fail(IDF_ERR_ARG, "bad geometry");
-  if (d->cout_pad > 512) return fail(IDF_ERR_ARG, "cout_pad > 512 not supported (bias staging)");
+  if (d->cout_pad > 1536) return fail(IDF_ERR_ARG, "cout_pad > 1536 not supported (bias staging)");
   if (static_cast<int64_t>(d->batch) * (d->H + 1) * (d->W + 1) >= (1 << 22))
     return fail(IDF_ERR_ARG, "more than 2^22 pad-flat rows per launch: split the batch");
   if (d->epilogue == IDF_EPI_BF16) {
@@ -411,10 +411,14 @@ int idf_attn_fwd(const void* qkv, void* out, int32_t batch, int32_t H, int32_t W
   if (rc != IDF_OK) return rc;
   cudaError_t e;
   const int S_tok = H * W;
-  if (d != 128 || (S_tok != 64 && S_tok != 256)) {   // small maps (e.g. 4x4): plain-FMA kernel, one CTA per sample
-    e = launch_attn_small(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), batch, H, W, d, scale,
-                          reinterpret_cast<cudaStream_t>(stream));
-    if (e != cudaSuccess) return cuda_fail(e, "attention launch (supported: d=128 with H*W in {64,256}; or H*W <= 64 with H*W*d <= 8192)");
+  if (d != 128 || (S_tok != 64 && S_tok != 256)) {
+    if (S_tok <= 64 && S_tok * d <= 8192)      // small maps (e.g. 4x4): plain-FMA kernel, one CTA per sample
+      e = launch_attn_small(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), batch, H, W, d, scale,
+                            reinterpret_cast<cudaStream_t>(stream));
+    else                                       // wide heads (vanilla Diff model, d = 256 / 512): CUDA-core kernel
+      e = launch_attn_generic(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), batch, H, W, d, scale,
+                              reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "attention launch (tensor-core kernel: d=128 with H*W in {64,256}; otherwise d % 8 == 0, H*W <= 1024)");
     return IDF_OK;
   }
   if (g_attn_impl == 1) {   // v1: thread-gathered operands, V transposed in shared memory
@@ -430,11 +434,54 @@ int idf_attn_fwd(const void* qkv, void* out, int32_t batch, int32_t H, int32_t W
   return IDF_OK;
 }
 
+int idf_attn_bwd(const void* qkv, const void* dout, void* dqkv, void* ws, int32_t batch, int32_t H, int32_t W, int32_t d,
+                 float scale, idf_stream_t stream) {
+  if (qkv == nullptr || dout == nullptr || dqkv == nullptr) return fail(IDF_ERR_ARG, "null argument");
+  int rc = ensure_init();
+  if (rc != IDF_OK) return rc;
+  cudaError_t e;
+  const int S_tok = H * W;
+  if (d != 128 || (S_tok != 64 && S_tok != 256)) {
+    e = launch_attn_small_bwd(static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout), static_cast<bf16*>(dqkv), batch,
+                              H, W, d, scale, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "attention backward launch (supported: d=128 with H*W in {64,256}; or H*W <= 64 with H*W*d <= 8192)");
+    return IDF_OK;
+  }
+  if (ws == nullptr) return fail(IDF_ERR_ARG, "attention backward needs a workspace of idf_attn_bwd_ws_bytes()");
+  const int64_t rows = static_cast<int64_t>(batch) * (H + 1) * (W + 1);
+  const int64_t srows = static_cast<int64_t>(batch) * S_tok;
+  bf16* P = static_cast<bf16*>(ws);
+  bf16* dS = P + srows * S_tok;
+  CUtensorMap tmQKV, tmDO, tmPr, tmDSr, tmDSc;
+  rc = encode_2d(&tmQKV, qkv, rows, 3 * d, W);
+  if (rc == IDF_OK) rc = encode_2d(&tmDO, dout, rows, d, W);
+  if (rc == IDF_OK) rc = encode_2d(&tmPr, P, srows, S_tok, S_tok);
+  if (rc == IDF_OK) rc = encode_2d(&tmDSr, dS, srows, S_tok, 128);
+  if (rc == IDF_OK) rc = encode_2d(&tmDSc, dS, srows, S_tok, S_tok);
+  if (rc != IDF_OK) return rc;
+  e = launch_attn_bwd(tmQKV, tmDO, tmPr, tmDSr, tmDSc, P, dS, static_cast<bf16*>(dqkv), batch, H, W, d, scale,
+                      reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "attention backward launch");
+  return IDF_OK;
+}
+
+int64_t idf_attn_bwd_ws_bytes(int32_t batch, int32_t H, int32_t W) {
+  return 2ll * batch * H * W * H * W * 2ll + 1024;
+}
+
 int idf_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy, int32_t M,
                    int32_t N, int32_t K, int32_t silu_in, idf_stream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(IDF_ERR_ARG, "bad linear shape");
   cudaError_t e = launch_linear_f32(x, ldx, w, b, y, ldy, M, N, K, silu_in, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "linear launch");
+  return IDF_OK;
+}
+
+int idf_gemm_f32(const float* A, int64_t lda, int32_t transA, const float* B, int64_t ldb, int32_t transB, float* Cm,
+                 int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t accumulate, idf_stream_t stream) {
+  if (A == nullptr || B == nullptr || Cm == nullptr || M <= 0 || N <= 0 || K <= 0) return fail(IDF_ERR_ARG, "bad gemm arguments");
+  cudaError_t e = launch_gemm_f32(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, accumulate, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "gemm_f32 launch");
   return IDF_OK;
 }
 

@@ -39,7 +39,7 @@ __host__ __device__ constexpr int conv_b_stages(int bn) { return bn == 16 ? 8 : 
 // residual deposit and for the column-pair reads of the GroupNorm partial sums; the tile leaves through ONE TMA store.
 constexpr uint32_t kStageTile = 32 * 64;
 constexpr uint32_t kStageBytes = 8 * kStageTile;
-constexpr uint32_t kBiasBytes = 512 * 4;   // bias vector of the whole conv (cout_pad <= 512), staged once per CTA
+constexpr uint32_t kBiasBytes = 1536 * 4;  // bias vector of the whole conv (cout_pad <= 1536: q|k|v of a 512-wide head), staged once per CTA
 __device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
   return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
@@ -58,7 +58,7 @@ struct HaloCfg {
 };
 
 __host__ __device__ inline uint32_t conv_smem_bytes(int a_stage_bytes, int a_stages, int b_stages, int b_bytes) {
-  return static_cast<uint32_t>(a_stages * a_stage_bytes + b_stages * b_bytes + 1024 /*barriers + tap table*/ +
+  return static_cast<uint32_t>(a_stages * a_stage_bytes + b_stages * b_bytes + 2048 /*barriers 512 + tap table 1024 + pad*/ +
                                kStageBytes + kBiasBytes + 1024 /*align*/);
 }
 
@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
   uint64_t* a_ready = tempty + 2;                                 // XF: halo transformed (one arrive per transform warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + AS);
   const uint32_t tap_sa = smem_u32(a_full) + 512;               // per-tap descriptor offsets
-  const uint32_t stage_sa = smem_u32(a_full) + 1024;            // epilogue staging tiles (1024-byte aligned: TMA swizzle)
+  static_assert((IDF_CONV_MAX_KB + 1) * 4 <= 1024, "tap table region");
+  const uint32_t stage_sa = smem_u32(a_full) + 2048;            // epilogue staging tiles (1024-byte aligned: TMA swizzle)
   const uint32_t bias_sa = stage_sa + kStageBytes;              // bias vector
 
   const int warp = threadIdx.x >> 5;

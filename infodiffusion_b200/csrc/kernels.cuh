@@ -10,7 +10,7 @@ typedef __nv_bfloat16 bf16;
 constexpr int kBM = 128;  // output rows (pixels) per tile == UMMA M
 constexpr int kBK = 64;   // K elements per k-block == one 128-byte swizzle row
 
-constexpr int kMaxGroups = 16;
+constexpr int kMaxGroups = 40;   // halo loads per work item: (source, 64-channel slice, tap cluster); 1024 + 1024 channels = 32
 
 struct alignas(64) ConvKernelParams {
   CUtensorMap tmA[IDF_CONV_MAX_SRC];    // box {64, 128 rows}
@@ -76,6 +76,7 @@ struct alignas(64) WgradKernelParams {
 };
 cudaError_t launch_wgrad(const WgradKernelParams& p, int grid, cudaStream_t stream);
 
+static_assert(sizeof(ConvKernelParams) <= 4000, "kernel parameters are limited to 4 KB");
 cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, bool xform, int grid, cudaStream_t stream);
 cudaError_t launch_adagn_coef(const idf_adagn_args& a, float* coef_out, cudaStream_t stream);
 uint32_t conv_config_smem(int block_n, int a_stage_bytes);
@@ -84,10 +85,18 @@ cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, int num_sms, cudaStrea
 int64_t adagn_bwd_ws_floats(int batch, int C);
 cudaError_t launch_attn(const bf16* qkv, bf16* out, int batch, int H, int W, int d, float scale, cudaStream_t stream);
 cudaError_t launch_attn_small(const bf16* qkv, bf16* out, int batch, int H, int W, int d, float scale, cudaStream_t stream);
+cudaError_t launch_attn_generic(const bf16* qkv, bf16* out, int batch, int H, int W, int d, float scale, cudaStream_t stream);
 cudaError_t launch_attn_v2(const CUtensorMap& tm, bf16* out, int batch, int H, int W, int d, float scale,
                            cudaStream_t stream);
+cudaError_t launch_attn_bwd(const CUtensorMap& tmQKV, const CUtensorMap& tmDO, const CUtensorMap& tmPr,
+                            const CUtensorMap& tmDSr, const CUtensorMap& tmDSc, bf16* P, bf16* dS, bf16* dqkv, int batch,
+                            int H, int W, int d, float scale, cudaStream_t stream);
+cudaError_t launch_attn_small_bwd(const bf16* qkv, const bf16* dout, bf16* dqkv, int batch, int H, int W, int d, float scale,
+                                  cudaStream_t stream);
 cudaError_t launch_linear_f32(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy,
                               int M, int N, int K, int silu_in, cudaStream_t stream);
+cudaError_t launch_gemm_f32(const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB, float* Cm,
+                            int64_t ldc, int M, int N, int K, int accumulate, cudaStream_t stream);
 struct ClipAdamWParams {
   void* const* params; const void* const* grads; void* const* exp_avg; void* const* exp_avg_sq;
   const long long* numel; const int* chunk_tensor; const int* chunk_offset;

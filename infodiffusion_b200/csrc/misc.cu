@@ -442,6 +442,71 @@ cudaError_t launch_linear_f32(const float* x, int64_t ldx, const float* w, const
   return cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------------------------
+// general small fp32 GEMM for the BACKWARD of the fp32 Linears (time / latent MLPs, fc heads, LatentUNet layers):
+//   C[M,N] (+)= op(A)[M,K] . op(B)[K,N]     op(X) = X or X^T, all row-major with leading dimensions
+// dX = dY . W (A = dY, B = W), dW = dY^T . X (A = dY transposed, B = X), db = 1^T . dY.  64x64 output tile, 4x4
+// accumulators per thread, K in chunks of 16 staged k-major; fixed fp32 FMA order over k (deterministic).  These GEMMs
+// are tiny (M = batch <= 1024, N, K <= 8192) and weight-bandwidth bound: tensor cores would not help (fp32 operands).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, long long lda, int transA,
+                                                       const float* __restrict__ B, long long ldb, int transB,
+                                                       float* __restrict__ Cm, long long ldc, int M, int N, int K,
+                                                       int accumulate) {
+  __shared__ __align__(16) float as[16][68];
+  __shared__ __align__(16) float bs[16][68];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int t = threadIdx.x;
+  const int tm = (t >> 4) * 4, tn = (t & 15) * 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = t; i < 64 * 16; i += 256) {
+      // pick the index order that walks the operand's contiguous dimension with consecutive threads
+      int r, c;
+      if (transA) { r = i & 63; c = i >> 6; } else { r = i >> 4; c = i & 15; }
+      float v = 0.f;
+      if (m0 + r < M && k0 + c < K) v = transA ? A[static_cast<long long>(k0 + c) * lda + m0 + r] : A[static_cast<long long>(m0 + r) * lda + k0 + c];
+      as[c][r] = v;
+      if (transB) { r = i >> 4; c = i & 15; } else { r = i & 63; c = i >> 6; }
+      v = 0.f;
+      if (n0 + r < N && k0 + c < K) v = transB ? B[static_cast<long long>(n0 + r) * ldb + k0 + c] : B[static_cast<long long>(k0 + c) * ldb + n0 + r];
+      bs[c][r] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 av = *reinterpret_cast<const float4*>(&as[c][tm]);
+      const float4 bv = *reinterpret_cast<const float4*>(&bs[c][tn]);
+      const float aa[4] = {av.x, av.y, av.z, av.w}, ba[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], ba[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + tm + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tn + j;
+      if (n < N) {
+        float* dst = Cm + static_cast<long long>(m) * ldc + n;
+        *dst = accumulate ? *dst + acc[i][j] : acc[i][j];
+      }
+    }
+  }
+}
+
+cudaError_t launch_gemm_f32(const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB, float* Cm,
+                            int64_t ldc, int M, int N, int K, int accumulate, cudaStream_t stream) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64, 1);
+  gemm_f32_kernel<<<grid, 256, 0, stream>>>(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, accumulate);
+  return cudaGetLastError();
+}
+
 __global__ void gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx,
                                    float* __restrict__ y, int N) {
   const int m = blockIdx.x;

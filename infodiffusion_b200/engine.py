@@ -84,7 +84,8 @@ FUSE_ADAGN = False
 # worse as well (332 vs 344 img/s with 16): the coefficient kernels and the slower convs cost more than the launches
 # saved.  0 disables.
 FUSE_ADAGN_MAX_H = 0
-MAX_GN_CHANNELS = 256  # widest GroupNorm the AdaGN kernels take (csrc/adagn.cu kMaxC)
+MAX_GN_CHANNELS = 1024       # widest GroupNorm the AdaGN forward kernels take (csrc/adagn.cu kMaxCWide)
+MAX_TRAIN_GN_CHANNELS = 256  # ... and their backward kernels (csrc/adagn_bwd.cu); wgrad plans stop at 64 work units
 TRAIN_PDL = True       # programmatic dependent launch once a training plan exists (library-wide switch)
 
 
@@ -984,17 +985,22 @@ def latent_forward(net, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
 
 
 def latent_forward_autograd(net, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
-    """Training-mode LatentUNet forward (reference models.py:223-234, 147-163) as a torch autograd composite on
-    the GPU: train_latent_ddim is not on the measured hot path and has no backward kernels of its own."""
+    """Training-mode LatentUNet forward (reference models.py:223-234, 147-163) inside torch's autograd graph.  Every
+    Linear -- the time MLP, the ten layers, their condition projections -- runs forward AND backward on the library's
+    own fp32 kernels (infodiffusion_b200.linear: idf_linear_f32 / idf_gemm_f32); the elementwise glue (SiLU, the
+    (1 + cond) scale, LayerNorm, dropout, cat) is ordinary torch."""
+    from . import linear as L
     from .modules import timestep_embedding
     _require_cuda(x, "x")
-    temb = net.time_embed(timestep_embedding(t, net.num_time_emb_channels))
+    temb = timestep_embedding(t, net.num_time_emb_channels)
+    for m in net.time_embed:
+        temb = L.apply(m, temb) if isinstance(m, nn.Linear) else m(temb)
     h = x
     for i, layer in enumerate(net.layers):
         if i in net.skip_layers:
             h = torch.cat([h, x], dim=1)
-        h = layer.linear(h)
+        h = L.apply(layer.linear, h)
         if layer.use_cond:
-            h = h * (layer.condition_bias + layer.cond_layers(temb))
+            h = h * (layer.condition_bias + L.apply(layer.linear_emb, layer.act(temb)))
         h = layer.dropout(layer.act(layer.norm(h)))
     return h

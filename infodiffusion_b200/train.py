@@ -351,29 +351,19 @@ def bwd_adagn(plan, a, src0, src1, out, gn: nn.GroupNorm, gamma: torch.Tensor, b
 
 
 def bwd_attention(plan, qkv, out, d: int) -> None:
-    """Softmax attention backward, recomputed from the saved q, k, v with torch matmuls (fp32)."""
+    """Softmax attention backward (reference modules.py:145-164 under autograd) on the tcgen05 kernels of
+    csrc/attention_bwd.cu: P and dS are recomputed from the saved q | k | v, then dQ = dS K, dK = dS^T Q, dV = P^T dO."""
     st = _state(plan)
     dout = st.grad(out)
     gq = st.grad(qkv)
     H = qkv.H
-    B, S = plan.B, H * H
-    scale = float(d) ** -0.5
-
-    def dense(t, Cc):       # pad-flat [rows, C] -> [B, S, C] fp32
-        return t.view(B, H + 1, H + 1, Cc)[:, :H, :H, :].reshape(B, S, Cc).float()
+    ws = torch.empty(int(plan.lib.idf_attn_bwd_ws_bytes(plan.B, H, H)), dtype=torch.uint8, device=plan.device)
+    plan.keep.append(ws)
+    args = (qkv.t.data_ptr(), dout.t.data_ptr(), gq.t.data_ptr(), ws.data_ptr(), plan.B, H, H, d, float(d) ** -0.5)
 
     def run():
-        x = dense(qkv.t, 3 * d)
-        q, k, v = x[..., :d], x[..., d:2 * d], x[..., 2 * d:]
-        do = dense(dout.t, d)
-        p = torch.softmax(torch.bmm(q, k.transpose(1, 2)) * scale, dim=-1)
-        dv = torch.bmm(p.transpose(1, 2), do)
-        dp = torch.bmm(do, v.transpose(1, 2))
-        ds = p * (dp - (dp * p).sum(-1, keepdim=True))
-        dq = torch.bmm(ds, k) * scale
-        dk = torch.bmm(ds.transpose(1, 2), q) * scale
-        full = torch.cat([dq, dk, dv], dim=-1).to(BF16).view(B, H, H, 3 * d)
-        gq.t.view(B, H + 1, H + 1, 3 * d)[:, :H, :H, :] = full
+        _lib.check(plan.lib.idf_attn_bwd(*args, torch.cuda.current_stream(plan.device).cuda_stream))
+        _lib.count_launch(2)
     st.ops.append(run)
     st.mark(qkv)
 
@@ -633,19 +623,22 @@ def backbone_train_forward(net, x_t: torch.Tensor, t: torch.Tensor, a: torch.Ten
         plans[key] = BackbonePlan(net, B, x_t.device, mode="train", dropout_p=dropout_p)
     plan = plans[key]
     # modulation rows through torch autograd (tiny GEMMs): temb -> all blocks' temb_proj, a -> fc_a -> aemb_proj
+    from . import linear as L                    # fp32 Linears with autograd on the library's own kernels (no cuBLAS)
+    silu = torch.nn.functional.silu
     te = net.time_embedding.timembedding
-    temb = te[3](torch.nn.functional.silu(te[1](te[0].weight[t])))
+    temb = L.apply(te[3], silu(L.apply(te[1], te[0].weight[t])))
     blocks = conditioned_blocks(net)
     w_t = torch.cat([b.temb_proj[1].weight for b in blocks], 0)
     b_t = torch.cat([b.temb_proj[1].bias for b in blocks], 0)
-    mod_t = torch.nn.functional.linear(torch.nn.functional.silu(temb), w_t, b_t)
+    mod_t = L.linear(silu(temb), w_t, b_t)
     if hasattr(net, "fc_a"):
-        aemb = net.fc_a(a)                       # Linear (AuxiliaryUNet) or SiLU -> Linear (BottleneckAuxUNet)
+        # Linear (AuxiliaryUNet) or SiLU -> Linear (BottleneckAuxUNet)
+        aemb = L.apply(net.fc_a[1], silu(a)) if isinstance(net.fc_a, nn.Sequential) else L.apply(net.fc_a, a)
         w_z = torch.cat([b.aemb_proj[1].weight if hasattr(b, "aemb_proj") else torch.zeros_like(b.temb_proj[1].weight)
                          for b in blocks], 0)
         b_z = torch.cat([b.aemb_proj[1].bias if hasattr(b, "aemb_proj") else torch.zeros_like(b.temb_proj[1].bias)
                          for b in blocks], 0)
-        mod_z = torch.nn.functional.linear(torch.nn.functional.silu(aemb), w_z, b_z)
+        mod_z = L.linear(silu(aemb), w_z, b_z)
     else:
         mod_z = torch.zeros_like(mod_t)          # UNet: no block reads it
     params = stack_params(net)
@@ -663,10 +656,11 @@ def encoder_train_forward(net, x: torch.Tensor, seed: int, dropout_p: float):
     plan = plans[key]
     params = stack_params(net)
     fmap = _ConvStackFn.apply(plan, x, None, None, seed, *params)
+    from . import linear as L
     h = torch.flatten(fmap, start_dim=1)
-    a = net.fc_a(h)
-    mu = net.fc_mu(a)
-    log_var = net.fc_var(a)
+    a = L.apply(net.fc_a, h)
+    mu = L.apply(net.fc_mu, a)
+    log_var = L.apply(net.fc_var, a)
     a_q = mu + torch.randn_like(mu) * torch.exp(0.5 * log_var)
     return a, a_q, mu, log_var
 

@@ -259,14 +259,16 @@ def train_latent_ddim(args):
 
 def _check_widths(args, vanilla: bool = None) -> None:
     """Fail EARLY and clearly for configurations the kernels do not cover (instead of deep inside plan creation)."""
-    from infodiffusion_b200.engine import MAX_GN_CHANNELS
+    from infodiffusion_b200.engine import MAX_GN_CHANNELS, MAX_TRAIN_GN_CHANNELS
     vanilla = (args.model == 'vanilla') if vanilla is None else vanilla
     if vanilla and not args.is_latent and args.mode != 'train_latent_ddim':
         widest = 8 * args.unets_channels                      # Diff hard-wires ch_mult = [1, 2, 4, 8] (models.py:746)
-        if 2 * widest > MAX_GN_CHANNELS:
+        limit = MAX_TRAIN_GN_CHANNELS if args.mode == 'train' else MAX_GN_CHANNELS
+        if 2 * widest > limit:
             raise NotImplementedError(
                 f"the vanilla image model (Diff over UNet, ch_mult [1,2,4,8], {widest} channels, GroupNorm over "
-                f"{2 * widest}) exceeds the kernels' limit of {MAX_GN_CHANNELS} GroupNorm channels; see DESIGN.md section 7")
+                f"{2 * widest}) exceeds the kernels' limit of {limit} GroupNorm channels for --mode {args.mode} "
+                "(inference covers 1024, the backward kernels 256); see DESIGN.md section 7")
 
 
 def _load(args, device, shape):

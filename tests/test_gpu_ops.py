@@ -761,3 +761,57 @@ def test_attention_small_maps(lib, H, B, d):
     ref = torch.bmm(torch.softmax(torch.bmm(qq, kk) * d ** -0.5, dim=-1), vv).reshape(B, H, H, d).permute(0, 3, 1, 2)
     assert pad_is_zero(out, B, H, H)
     assert_close(unpf(out, B, H, H), ref, rel_l2=3e-3, max_rel=1e-2, what=f"small attention S={S} d={d}")
+
+
+@pytest.mark.parametrize("M,K,N,bias", [(2, 64, 256, True), (32, 256, 4992, True), (5, 4096, 32, True), (70, 1280, 1024, False),
+                                         (1, 33, 7, True)])
+def test_linear_autograd_on_own_kernels(lib, M, K, N, bias):
+    """infodiffusion_b200.linear (idf_linear_f32 forward, idf_gemm_f32 for dX / dW / db) against torch's F.linear in
+    fp64: the Linears of the time / latent MLPs and fc heads under autograd (modules.py:24-27, models.py:147-163, 470-472)."""
+    from infodiffusion_b200 import linear as L
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + K + N)
+    x = torch.randn(M, K, device=DEV, generator=g, requires_grad=True)
+    w = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).requires_grad_()
+    b = torch.randn(N, device=DEV, generator=g).requires_grad_() if bias else None
+    dy = torch.randn(M, N, device=DEV, generator=g)
+    y = L.linear(x, w, b)
+    y.backward(dy)
+    xr, wr = x.detach().double().requires_grad_(), w.detach().double().requires_grad_()
+    br = b.detach().double().requires_grad_() if bias else None
+    yr = torch.nn.functional.linear(xr, wr, br)
+    yr.backward(dy.double())
+    # fp32 accumulation over up to 4992 terms in a fixed order
+    assert_close(y.detach(), yr.detach(), rel_l2=3e-6, max_rel=1e-4, what="linear y")
+    assert_close(x.grad, xr.grad, rel_l2=3e-6, max_rel=1e-4, what="linear dx")
+    assert_close(w.grad, wr.grad, rel_l2=3e-6, max_rel=1e-4, what="linear dw")
+    if bias:
+        assert_close(b.grad, br.grad, rel_l2=3e-6, max_rel=1e-4, what="linear db")
+
+
+@pytest.mark.parametrize("H,B,d", [(16, 3, 128), (8, 5, 128), (16, 33, 128), (4, 3, 128), (2, 2, 128)])
+def test_attention_backward(lib, H, B, d):
+    """idf_attn_bwd (tcgen05: S and dP recomputed, P / dS rows through a workspace, then dQ = dS K, dK = dS^T Q,
+    dV = P^T dO; plain-FMA kernel for the small maps) against torch autograd of the reference's attention
+    (modules.py:152-161) in fp64."""
+    g = torch.Generator(device=DEV).manual_seed(41 + H + B)
+    S = H * H
+    q, k, v = (rbf(torch.randn(B, d, H, H, device=DEV, generator=g) * s) for s in (1.2, 1.2, 1.0))
+    do = rbf(torch.randn(B, d, H, H, device=DEV, generator=g))
+    qkv = pf(torch.cat([q, k, v], 1))
+    dout = pf(do)
+    dqkv = torch.zeros(B * (H + 1) * (H + 1), 3 * d, device=DEV, dtype=BF)
+    ws = torch.empty(int(lib.idf_attn_bwd_ws_bytes(B, H, H)), dtype=torch.uint8, device=DEV)
+    check(lib.idf_attn_bwd(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), ws.data_ptr(), B, H, H, d, d ** -0.5, stream()))
+    torch.cuda.synchronize()
+    qq = q.double().permute(0, 2, 3, 1).reshape(B, S, d).requires_grad_()
+    kk = k.double().permute(0, 2, 3, 1).reshape(B, S, d).requires_grad_()
+    vv = v.double().permute(0, 2, 3, 1).reshape(B, S, d).requires_grad_()
+    w = torch.softmax(torch.bmm(qq, kk.transpose(1, 2)) * d ** -0.5, dim=-1)
+    o = torch.bmm(w, vv)
+    o.backward(do.double().permute(0, 2, 3, 1).reshape(B, S, d))
+    got = unpf(dqkv, B, H, H)                                   # [B, 3d, H, W]
+    assert pad_is_zero(dqkv, B, H, H)
+    for name, ref, sl in (("dq", qq.grad, slice(0, d)), ("dk", kk.grad, slice(d, 2 * d)), ("dv", vv.grad, slice(2 * d, 3 * d))):
+        ref = ref.reshape(B, H, H, d).permute(0, 3, 1, 2)
+        # P and dS pass through bf16 (2^-9 relative per entry) before the second set of GEMMs
+        assert_close(got[:, sl], ref, rel_l2=8e-3, max_rel=3e-2, what=f"attention backward {name} S={S}")
