@@ -73,6 +73,21 @@ def main():
     check("unet eps", eps_or, eps_ref, 1e-6)
     np.savez_compressed(OUT / "unet_1222_T1000.npz", eps=eps_ref.numpy())
 
+    # ------------------------------------------------------------------ vanilla UNet at the widths Diff hard-wires
+    # (models.py:746, ch_mult [1,2,4,8]: 512 channels, GroupNorm over 1024, attention heads of 256 and 512)
+    torch.manual_seed(SEED)
+    uw = ref_models.UNet(T=1000, ch=64, ch_mult=[1, 2, 4, 8], shape=(3, 64, 64))
+    meta["state_unet_1248_T1000"] = dict(digest=state_digest(uw.state_dict()), nkeys=len(uw.state_dict()))
+    sdw = perturb_state_dict({"backbone." + k: v for k, v in uw.state_dict().items()})
+    uw.load_state_dict({k[len("backbone."):]: v for k, v in sdw.items()}, strict=True)
+    uw.eval()
+    with torch.no_grad():
+        eps_ref = uw(x, t)
+        eps_or = orc.unet_forward(sdw, x, t)
+    check("unet [1,2,4,8] eps", eps_or, eps_ref, 1e-6)
+    np.savez_compressed(OUT / "unet_1248_T1000.npz", eps=eps_ref.numpy())
+    del uw, sdw
+
     # ------------------------------------------------------------------ Diff wrapper (a16) + two-phase sampler (a22)
     T = 6
     args6 = make_args(a_dim=32, diffusion_steps=T, model="vanilla", split_step=2)

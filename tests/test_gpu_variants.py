@@ -81,6 +81,50 @@ def test_vanilla_unet_eps_and_training_gradients(golden_dir):
     assert len(rels) > 300 and med < 5e-2 and all(c > 0.98 for _, c, _ in rels)
 
 
+def test_vanilla_unet_at_the_widths_diff_hard_wires(golden_dir):
+    """Diff(model='vanilla') builds its UNet with ch_mult [1,2,4,8] (models.py:746): 512 channels, GroupNorm over up to
+    1024 concatenated channels, convolutions with up to 160 k-blocks, attention heads of 256 (16x16) and 512 (8x8)
+    channels.  eps through the public constructor against the oracle and the golden minted from the reference (which
+    needs the crossattn= patch to construct at all), plus a short DDIM trajectory through Diff + DiffusionProcess."""
+    from infodiffusion_b200.models import Diff
+    from infodiffusion_b200.sampling import DiffusionProcess
+    T = 1000
+    args = make_args(a_dim=32, diffusion_steps=T, model="vanilla")
+    torch.manual_seed(SEED)
+    m = Diff(args, "cpu", (3, 64, 64))
+    assert m.backbone.ch_mult == [1, 2, 4, 8]
+    sd = perturb_state_dict(m.state_dict())
+    m.load_state_dict(sd)
+    m = _to_dev(m)
+    x, t, _ = rand_inputs(2, 32, T)
+    with torch.no_grad():
+        ref = orc.unet_forward(sd, x, t)
+    got = m.backbone(x.to(DEV), t.to(DEV)).cpu()
+    gold = torch.from_numpy(np.load(golden_dir / "unet_1248_T1000.npz")["eps"])
+    print(f"\n[parity] unet [1,2,4,8] eps rel-L2 vs oracle {rel_l2(got, ref):.3e}, vs reference golden {rel_l2(got, gold):.3e}")
+    assert torch.isfinite(got).all()
+    assert rel_l2(got, ref) < TOL_EPS and rel_l2(got, gold) < TOL_EPS
+    # three DDIM steps of the vanilla sampler (diffusion_fn(x, idx), sampling.py:31-32)
+    T3 = 3
+    args3 = make_args(a_dim=32, diffusion_steps=T3, model="vanilla", deterministic=True)
+    torch.manual_seed(SEED)
+    m3 = Diff(args3, "cpu", (3, 64, 64))
+    sd3 = perturb_state_dict(m3.state_dict())
+    m3.load_state_dict(sd3)
+    m3 = _to_dev(m3)
+    shape = (2, 3, 64, 64)
+    xT = torch.randn(*shape, generator=torch.Generator().manual_seed(12))
+    p = DiffusionProcess(args3, m3, DEV, (3, 64, 64))
+    p.noise_fn = lambda idx, out: out.copy_(step_noise(idx, shape))
+    x0 = p.sampling(2, xT=xT.to(DEV)).cpu()
+    sch = orc.Schedule.make(args3.beta1, args3.betaT, T3)
+    want = None
+    for _, _, want in orc.ddim_steps(sch, orc.vanilla_eps_fn(sd3), xT, lambda i, like: step_noise(i, shape)):
+        pass
+    print(f"[parity] vanilla [1,2,4,8] DDIM-3 x0 rel-L2 {rel_l2(x0, want):.3e}")
+    assert rel_l2(x0, want) < TOL_X
+
+
 @pytest.fixture(scope="module")
 def two_models():
     from infodiffusion_b200.models import Diff, InfoDiff, UNet
