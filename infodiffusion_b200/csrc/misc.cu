@@ -459,17 +459,21 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
   const int t = threadIdx.x;
   const int tm = (t >> 4) * 4, tn = (t & 15) * 4;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  // split-K: blockIdx.z owns the k range [kb, ke); partial tiles are combined with atomicAdd (C pre-zeroed by the
+  // launcher).  Used when M x N alone gives too few CTAs (dX of a [batch, 4992] x [4992, 256] Linear: 4 tiles, K = 4992).
+  const int kchunk = ((K + gridDim.z - 1) / gridDim.z + 15) / 16 * 16;
+  const int kb = blockIdx.z * kchunk, ke = min(K, kb + kchunk);
+  for (int k0 = kb; k0 < ke; k0 += 16) {
     for (int i = t; i < 64 * 16; i += 256) {
       // pick the index order that walks the operand's contiguous dimension with consecutive threads
       int r, c;
       if (transA) { r = i & 63; c = i >> 6; } else { r = i >> 4; c = i & 15; }
       float v = 0.f;
-      if (m0 + r < M && k0 + c < K) v = transA ? A[static_cast<long long>(k0 + c) * lda + m0 + r] : A[static_cast<long long>(m0 + r) * lda + k0 + c];
+      if (m0 + r < M && k0 + c < ke) v = transA ? A[static_cast<long long>(k0 + c) * lda + m0 + r] : A[static_cast<long long>(m0 + r) * lda + k0 + c];
       as[c][r] = v;
       if (transB) { r = i >> 4; c = i & 15; } else { r = i & 63; c = i >> 6; }
       v = 0.f;
-      if (n0 + r < N && k0 + c < K) v = transB ? B[static_cast<long long>(n0 + r) * ldb + k0 + c] : B[static_cast<long long>(k0 + c) * ldb + n0 + r];
+      if (n0 + r < N && k0 + c < ke) v = transB ? B[static_cast<long long>(n0 + r) * ldb + k0 + c] : B[static_cast<long long>(k0 + c) * ldb + n0 + r];
       bs[c][r] = v;
     }
     __syncthreads();
@@ -494,7 +498,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
       const int n = n0 + tn + j;
       if (n < N) {
         float* dst = Cm + static_cast<long long>(m) * ldc + n;
-        *dst = accumulate ? *dst + acc[i][j] : acc[i][j];
+        if (gridDim.z > 1) atomicAdd(dst, acc[i][j]);
+        else *dst = accumulate ? *dst + acc[i][j] : acc[i][j];
       }
     }
   }
@@ -503,6 +508,25 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 cudaError_t launch_gemm_f32(const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB, float* Cm,
                             int64_t ldc, int M, int N, int K, int accumulate, cudaStream_t stream) {
   dim3 grid((N + 63) / 64, (M + 63) / 64, 1);
+  const int tiles = static_cast<int>(grid.x * grid.y);
+  int splits = 1;
+  if (tiles < 64 && K >= 512) {                       // too few tiles to fill the machine and a long K loop
+    splits = 148 / tiles;
+    if (splits > K / 128) splits = K / 128;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > 1) {
+    grid.z = splits;
+    if (!accumulate) {                                // the partial tiles are added atomically
+      if (ldc == N) {
+        cudaError_t e = cudaMemsetAsync(Cm, 0, static_cast<size_t>(M) * N * sizeof(float), stream);
+        if (e != cudaSuccess) return e;
+      } else {
+        cudaError_t e = cudaMemset2DAsync(Cm, static_cast<size_t>(ldc) * sizeof(float), 0, static_cast<size_t>(N) * sizeof(float), M, stream);
+        if (e != cudaSuccess) return e;
+      }
+    }
+  }
   gemm_f32_kernel<<<grid, 256, 0, stream>>>(A, lda, transA, B, ldb, transB, Cm, ldc, M, N, K, accumulate);
   return cudaGetLastError();
 }

@@ -29,10 +29,16 @@ class _LinearFn(torch.autograd.Function):
         x2 = x.reshape(-1, K).contiguous().float()
         w = w.contiguous().float()
         M = x2.shape[0]
-        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
         bb = None if b is None else b.contiguous().float()
-        _lib.check(lib.idf_linear_f32(x2.data_ptr(), K, w.data_ptr(), None if bb is None else bb.data_ptr(), y.data_ptr(), N,
-                                      M, N, K, 0, _stream(x)))
+        if K >= 1024 and ((N + 63) // 64) * ((M + 63) // 64) < 32:
+            # few output tiles and a long reduction (the encoder's fc_a: [B, 4096] -> a_dim): split-K GEMM accumulated on
+            # top of the bias (atomic partial sums -- training only; the inference plans keep the deterministic kernel)
+            y = (bb if bb is not None else torch.zeros(N, device=x.device)).expand(M, N).contiguous()
+            _lib.check(lib.idf_gemm_f32(x2.data_ptr(), K, 0, w.data_ptr(), K, 1, y.data_ptr(), N, M, N, K, 1, _stream(x)))
+        else:
+            y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+            _lib.check(lib.idf_linear_f32(x2.data_ptr(), K, w.data_ptr(), None if bb is None else bb.data_ptr(), y.data_ptr(), N,
+                                          M, N, K, 0, _stream(x)))
         _lib.count_launch()
         ctx.save_for_backward(x2, w)
         ctx.has_bias = b is not None

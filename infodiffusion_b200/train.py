@@ -478,8 +478,10 @@ class GradSync:
         of `params[i]`; `finish` uses it to make sure p.grad really holds the REDUCED values."""
         import torch.distributed as dist
         op = dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM
-        self.pending.append((dist.all_reduce(flat, op=op, async_op=True), flat,
-                             list(zip(params, views)) if views is not None else []))
+        # keep (offset, numel), NOT the view tensors: a second reference to a view stops AccumulateGrad from stealing
+        # it (use_count check), and every gradient would then be cloned before the reduction has finished
+        spans = [(p, v.storage_offset() - flat.storage_offset(), v.numel()) for p, v in zip(params, views)] if views is not None else []
+        self.pending.append((dist.all_reduce(flat, op=op, async_op=True), flat, spans))
         self.covered.update(id(p) for p in params)
 
     def finish(self, params: Sequence[nn.Parameter]) -> None:
@@ -501,12 +503,12 @@ class GradSync:
             # overwrite it with the reduced slice so the ranks cannot drift apart silently.
             lo = flat.data_ptr()
             hi = lo + flat.numel() * flat.element_size()
-            for prm, view in pv_pairs:
+            for prm, off, numel in pv_pairs:
                 g = prm.grad
                 if g is None or lo <= g.data_ptr() < hi:
                     continue
                 self.fixed_up += 1
-                g.copy_(view.view_as(g))
+                g.copy_(flat[off:off + numel].view_as(g))
         self.pending.clear()
         self.covered.clear()
 

@@ -72,6 +72,19 @@ def _worker(rank: int, world: int, port: int, total: int, tmp: str):
         assert torch.allclose(qs[1].grad, (torch.arange(4.0) + 4).view(2, 2) * mean)
         assert torch.allclose(qs[2].grad, torch.full((3,), 10.0 * mean))
         assert not sync.pending and not sync.covered
+        # a gradient that does NOT alias the reduced buffer (autograd cloned it, or it existed before backward: gradient
+        # accumulation, zero_grad(set_to_none=False)) must still end up holding the REDUCED values
+        rs = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(2, 2))]
+        flat2 = torch.arange(8.0) * (rank + 1)
+        views = [flat2[:4], flat2[4:].view(2, 2)]
+        rs[0].grad = views[0]                              # stolen view: aliases flat2
+        rs[1].grad = views[1].clone()                      # local copy: would stay un-reduced without the check
+        sync.reduce(flat2, rs, views)
+        del views
+        sync.finish(rs)
+        assert torch.allclose(rs[0].grad, torch.arange(4.0) * mean)
+        assert torch.allclose(rs[1].grad, (torch.arange(4.0) + 4).view(2, 2) * mean)
+        assert sync.fixed_up == 1
         with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:
