@@ -171,14 +171,15 @@ def load(build_if_missing: bool = True):
             raise IdfError(f"{LIB_PATH} is missing; run `python -m infodiffusion_b200.build`")
         from . import build as _build
         _build.build()
-    lib = C.CDLL(str(LIB_PATH))
+    import os
+    # kernel development only: A/B an alternative build of the SAME C-ABI (e.g. the previous commit's kernels)
+    lib = C.CDLL(os.environ.get("IDF_LIB_AB") or str(LIB_PATH))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
     _lib = lib
     # tuning / measurement switches without code changes: IDF_OPTS="adagn_impl=1,pdl=1" -> idf_set_option per pair
-    import os
     for kv in filter(None, os.environ.get("IDF_OPTS", "").split(",")):
         k, v = kv.split("=")
         if lib.idf_set_option(k.strip().encode(), int(v)) != 0:

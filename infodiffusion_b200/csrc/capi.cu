@@ -36,6 +36,8 @@ int g_num_sms = 0;
 int g_attn_impl = 2;
 int g_force_mt = 0;   // 0 = choose automatically
 int g_skip_epilogue = 0;
+int g_conv_l2_prefetch = 0;  // idf_set_option "conv_l2_prefetch"
+int g_conv_pair = 1;  // conv kernels with N >= 64 run as CTA pairs (idf_set_option "conv_pair", 0 = single CTAs)
 
 int ensure_init() {
   if (g_encode != nullptr) return IDF_OK;
@@ -97,6 +99,7 @@ struct idf_conv_plan {
   int mt;      // 128-row tiles per CTA work unit
   int grid;
   bool xform;  // some halo group carries a fused AdaGN: launch the variant with transform warps
+  bool pair;   // launched as clusters of two CTAs (tcgen05 cta_group::2)
   int64_t tiles;
 };
 
@@ -119,6 +122,8 @@ int idf_set_option(const char* key, int32_t value) {
     g_skip_epilogue = value ? 1 : 0;
     return IDF_OK;
   }
+  if (key != nullptr && std::strcmp(key, "conv_l2_prefetch") == 0 && (value == 0 || value == 1)) { g_conv_l2_prefetch = value; return IDF_OK; }
+  if (key != nullptr && std::strcmp(key, "conv_pair") == 0 && (value == 0 || value == 1)) { g_conv_pair = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "xf_ldg") == 0 && (value == 0 || value == 1)) { g_xf_ldg = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "pdl") == 0) { g_pdl = value ? 1 : 0; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "xf_debug") == 0 && value >= 0 && value <= 4) { g_xf_debug = value; return IDF_OK; }
@@ -224,15 +229,19 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   // MT 128-row tiles per CTA work unit: the largest (best weight-tile reuse: MT = 1 streams 16 KB of
   // weights per 256 MMA cycles and is L2-bound) that still fills the machine with <= 15 % quantisation
   // loss in the number of rounds over the SMs.
+  // CTA pairs (cta_group::2, see conv_igemm.cu): a worker is two CTAs and its work unit 2*MT tiles.
+  const bool pair = g_conv_pair != 0 && d->block_n >= 64 && g_num_sms % 2 == 0;
+  const int pw = pair ? 2 : 1;
+  const int workers = g_num_sms / pw;
   const int mt_max = (d->block_n == 128) ? 2 : 4;
   int mt = 1;
   for (int cand = mt_max; cand > 1; cand >>= 1) {
     if (d->block_n == 16 && cand == 2) continue;   // instantiated: 16x{1,4}
-    const int64_t units = (m_tiles + cand - 1) / cand * p.n_tiles;
-    const int64_t rounds = (units + g_num_sms - 1) / g_num_sms;
+    const int64_t units = (m_tiles + cand * pw - 1) / (cand * pw) * p.n_tiles;
+    const int64_t rounds = (units + workers - 1) / workers;
     const int stage = ((cand * kBM + extra_max) * 128 + 1023) / 1024 * 1024;
-    if (units >= g_num_sms && rounds * g_num_sms * 100 <= units * 115 &&
-        conv_config_smem(d->block_n, stage) <= 227 * 1024) {
+    if (units >= workers && rounds * workers * 100 <= units * 115 &&
+        conv_config_smem(d->block_n, stage, pair) <= 227 * 1024) {
       mt = cand;
       break;
     }
@@ -242,13 +251,14 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
     if (mt > mt_max || (d->block_n == 16 && mt == 2)) { delete pl; return fail(IDF_ERR_ARG, "forced MT not available"); }
   }
   p.a_stage_bytes = ((mt * kBM + extra_max) * 128 + 1023) / 1024 * 1024;
-  if (conv_config_smem(d->block_n, p.a_stage_bytes) > 227 * 1024) {
+  if (conv_config_smem(d->block_n, p.a_stage_bytes, pair) > 227 * 1024) {
     delete pl;
     return fail(IDF_ERR_ARG, "halo does not fit in shared memory (extra rows %d)", extra_max);
   }
-  p.m_super = static_cast<int32_t>((m_tiles + mt - 1) / mt);
+  p.m_super = static_cast<int32_t>((m_tiles + mt * pw - 1) / (mt * pw));
   p.m_tiles = static_cast<int32_t>(m_tiles);
   p.debug_skip_epilogue = g_skip_epilogue;
+  p.l2_prefetch = g_conv_l2_prefetch;
   p.stats = (d->epilogue == IDF_EPI_BF16) ? d->stats_out : nullptr;
   p.stats_b_off = static_cast<int64_t>(m_tiles) * 4 * d->cout * 2;
   if (p.stats != nullptr && d->out_ld != d->cout) { delete pl; return fail(IDF_ERR_ARG, "stats_out needs out_ld == cout"); }
@@ -261,7 +271,7 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
       if (rc != IDF_OK) { delete pl; return rc; }
     }
   }
-  rc = encode_2d(&p.tmB, d->weight, d->cout_pad, d->num_kb * kBK, d->block_n);
+  rc = encode_2d(&p.tmB, d->weight, d->cout_pad, d->num_kb * kBK, d->block_n / pw);
   if (rc != IDF_OK) { delete pl; return rc; }
   if (d->epilogue == IDF_EPI_BF16) {
     rc = encode_2d_out(&p.tmOut, d->out, p.rows, d->out_ld);
@@ -290,9 +300,10 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   if (p.bias == nullptr) { delete pl; return fail(IDF_ERR_ARG, "bias is null"); }
   pl->block_n = d->block_n;
   pl->mt = mt;
+  pl->pair = pair;
   pl->tiles = m_tiles * p.n_tiles;
   const long long units = static_cast<long long>(p.m_super) * p.n_tiles;
-  pl->grid = static_cast<int>(units < g_num_sms ? units : g_num_sms);
+  pl->grid = pw * static_cast<int>(units < workers ? units : workers);
   *out_plan = pl;
   return IDF_OK;
 }
@@ -308,7 +319,7 @@ int64_t idf_conv_plan_tiles(const idf_conv_plan* plan) {
 
 int idf_conv_run(const idf_conv_plan* plan, idf_stream_t stream) {
   if (plan == nullptr) return fail(IDF_ERR_ARG, "null plan");
-  cudaError_t e = launch_conv_igemm(plan->params, plan->block_n, plan->mt, plan->xform, plan->grid, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_conv_igemm(plan->params, plan->block_n, plan->mt, plan->xform, plan->pair, plan->grid, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "conv_igemm launch");
   return IDF_OK;
 }

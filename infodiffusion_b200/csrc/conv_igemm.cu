@@ -38,22 +38,24 @@ __host__ __device__ constexpr int conv_b_stages(int bn) { return bn == 16 ? 8 : 
 // chunk c ^ ((r >> 1) & 3)): conflict-free for the row-per-lane 16-byte accesses, for the 4-lanes-per-row coalesced
 // residual deposit and for the column-pair reads of the GroupNorm partial sums; the tile leaves through ONE TMA store.
 constexpr uint32_t kStageTile = 32 * 64;
-constexpr uint32_t kStageBytes = 8 * kStageTile;
+// two staging tiles per drain warp: a warp only waits for the TMA store it issued two work items ago (the TMA engine
+// also serves the operand loads and drains the staging tiles late) and the statistics warps get a full item of slack
+constexpr uint32_t kStageBytes = 16 * kStageTile;
 constexpr uint32_t kBiasBytes = 1536 * 4;  // bias vector of the whole conv (cout_pad <= 1536: q|k|v of a 512-wide head), staged once per CTA
 __device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
   return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
 
-template <int BN, int MT>
+template <int BN, int MT, bool PAIR = false>
 struct HaloCfg {
   static constexpr int A_STAGES = 2;
   static constexpr int B_STAGES = conv_b_stages(BN);
-  static constexpr uint32_t B_BYTES = BN * kBK * 2;
+  static constexpr uint32_t B_BYTES = BN * kBK * 2 / (PAIR ? 2 : 1);   // per CTA: a pair splits the weight tile along N
   static constexpr uint32_t ACC_COLS = MT * BN;                       // one accumulator set
   static constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64
                                         : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
   static_assert(2 * ACC_COLS <= 512, "accumulators do not fit in TMEM");
-  static constexpr int NBARS = 3 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int NBARS = 3 * A_STAGES + 2 * B_STAGES + 4 + 32;   // + staged / stats-done per drain warp and tile
   static constexpr int NI = (MT >= 2) ? 2 : 1;                        // UMMA issuing threads (accumulators split)
 };
 
@@ -78,23 +80,21 @@ __device__ __forceinline__ void residual_fetch(const ConvKernelParams& p, int64_
   }
 }
 
-// One (accumulator, 32-column) work item of an epilogue warp; executed by all 32 lanes.
+// One (accumulator, 32-column) work item of a drain warp; executed by all 32 lanes.
 //   out = bf16(acc + bias (+ residual)), pad rows forced to zero.
-// The warp's 32 rows x 64 B pass through a private shared-memory staging tile (SWIZZLE_64B layout) and leave
-// with one TMA store (rows beyond the tensor are clipped by the tensor map); the residual, fetched coalesced one
-// item ahead (4 lanes per row), is deposited in the same tile first and read back row-per-lane.
-// Optional GroupNorm partials: column sums of the STAGED (bf16-rounded) tile, written per WARP (no
-// cross-warp exchange, no barriers, fixed summation order => deterministic):
-//   statsA[(tile*4 + q)][col] = (sum, sumsq) over the warp's rows in the image of its first row,
-//   statsB[(tile*4 + q)][col] = the same over the rows that already belong to the next image
-//                               (written only when the 32-row window straddles an image boundary).
-__device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, const uint32_t (&v)[32],
-                                                    int64_t warp_row0, bool valid, int col0, int n_a, int tile, int q,
-                                                    int lane, uint32_t stage, uint32_t bias_sa,
-                                                    const uint4 (&res)[4]) {
+// The warp's 32 rows x 64 B pass through one of its two private shared-memory staging tiles (SWIZZLE_64B layout) and
+// leave with one TMA store (rows beyond the tensor are clipped by the tensor map); the residual, fetched coalesced one
+// item ahead (4 lanes per row), is deposited in the same tile first and read back row-per-lane.  Before the tile is
+// rewritten, the TMA store issued from it two items ago must have read it and the statistics warp must be done with it.
+__device__ __forceinline__ void epilogue_drain_chunk(const ConvKernelParams& p, const uint32_t (&v)[32],
+                                                     int64_t warp_row0, bool valid, int col0, int lane, uint32_t stage,
+                                                     uint32_t bias_sa, const uint4 (&res)[4], uint64_t* staged,
+                                                     uint64_t* sdone, uint32_t use) {
   const int sub_row = lane >> 2, sub_chunk = lane & 3;     // coalesced distribution: row = 8 i + sub_row
-  // the previous item's TMA store must have finished reading the staging tile
-  if (lane == 0) bulk_wait_read<0>();
+  if (lane == 0) {
+    bulk_wait_read<1>();                     // all but the newest store (which reads the OTHER tile) are done reading
+    mbar_wait(sdone, (use & 1u) ^ 1u);       // the statistics of this tile's previous contents have been taken
+  }
   __syncwarp();
   if (p.residual != nullptr) {
 #pragma unroll
@@ -133,12 +133,24 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
   }
   fence_async_smem();                      // generic-proxy writes -> visible to the TMA store (async proxy)
   __syncwarp();
-  // ---- one TMA store for the warp's 32 x 32 tile (pad rows receive zeros, which is what they already hold)
-  if (lane == 0 && warp_row0 < p.rows) {
-    tma_store_2d(&p.tmOut, stage, col0, static_cast<int32_t>(warp_row0));
+  // ---- one TMA store for the warp's 32 x 32 tile (pad rows receive zeros, which is what they already hold), and the
+  //      hand-over to the statistics warp (release: the tile written by all lanes is ordered before by __syncwarp)
+  if (lane == 0) {
+    if (warp_row0 < p.rows) tma_store_2d(&p.tmOut, stage, col0, static_cast<int32_t>(warp_row0));
     bulk_commit();
+    mbar_arrive(staged);
   }
-  // ---- GroupNorm partial sums of the staged tile
+}
+
+// GroupNorm partial sums of one staged (bf16-rounded) 32 x 32 tile, taken by a statistics warp (all 32 lanes), so the
+// drain warps only move data: column sums written per tile and lane quarter (no cross-warp exchange, fixed summation
+// order => deterministic):
+//   statsA[(tile*4 + q)][col] = (sum, sumsq) over the window's rows in the image of its first row,
+//   statsB[(tile*4 + q)][col] = the same over the rows that already belong to the next image
+//                               (written only when the 32-row window straddles an image boundary).
+__device__ __forceinline__ void epilogue_stats_chunk(const ConvKernelParams& p, uint32_t stage, int col0, int n_a, int tile,
+                                                     int q, int lane, uint64_t* staged, uint64_t* sdone, uint32_t use) {
+  mbar_wait(staged, use & 1u);
   if (p.stats != nullptr && tile < p.m_tiles) {
     // lane -> column pair (2 cp, 2 cp + 1) and row parity hh: rows hh, hh + 2, ..., hh + 30 (even rows occupy banks
     // 0..15, odd rows banks 16..31: conflict-free).  rows < n_a belong to record A, the rest to record B.
@@ -182,6 +194,9 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const ConvKernelParams& p, c
       }
     }
   }
+  // the sums above consumed every shared-memory load (the global stores precede this asm with its memory clobber)
+  __syncwarp();
+  if (lane == 0) mbar_arrive(sdone);
 }
 
 __device__ __forceinline__ void epilogue_narrow(const ConvKernelParams& p, const uint32_t (&v)[16], int img, int y,
@@ -209,9 +224,22 @@ __device__ __forceinline__ void epilogue_narrow(const ConvKernelParams& p, const
 // XF = true adds kXfWarps "transform" warps (threads 384..) between the A producer and the UMMA issuers: they
 // apply the consumer-side AdaGN (y = act(A*x + B), coefficients per image and channel) to the halo in place, so
 // the normalised activation is never written to or read from HBM.
-template <int BN, int MT, bool XF>
-__global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = HaloCfg<BN, MT>;
+//
+// PAIR = true: the kernel runs as clusters of two CTAs (tcgen05 cta_group::2).  A pair owns 2*MT consecutive 128-row
+// tiles -- rank r the r-th half, each CTA with its own halo, accumulators and epilogue exactly as in the single-CTA
+// kernel -- but every UMMA is one M = 256 instruction issued by the leader (rank 0) over both CTAs' A tiles and a
+// weight tile of which each CTA holds HALF (BN/2 rows).  An N = 128 MMA block then reads 16 + 8 KB instead of 16 + 16 KB
+// of shared memory per CTA and 256 cycles (N = 64: 16 + 4 instead of 16 + 8 KB per 128 cycles): the operand fetch no
+// longer saturates the 128 B/clk shared-memory port, which leaves room for the epilogue staging and the fused-AdaGN
+// transform traffic.  Barriers the leader's issuing threads wait on (A ready, B full, accumulator empty) live in the
+// leader's shared memory and are signalled by both CTAs; "empty" / "accumulator full" barriers are signalled in both
+// CTAs by multicast tcgen05.commit.
+// threads per CTA: [transform warps (XF)] + 8 drain + 4 statistics + A producer, B producer, 2 UMMA issuers / TMEM allocator
+__host__ __device__ constexpr int conv_threads(bool xf) { return 32 * ((xf ? kXfWarps : 0) + 8 + 4 + 4); }
+
+template <int BN, int MT, bool XF, bool PAIR>
+__global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __grid_constant__ ConvKernelParams p) {
+  using Cfg = HaloCfg<BN, MT, PAIR>;
   constexpr int AS = Cfg::A_STAGES, BS = Cfg::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -224,17 +252,28 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
   uint64_t* tfull = b_empty + BS;
   uint64_t* tempty = tfull + 2;
   uint64_t* a_ready = tempty + 2;                                 // XF: halo transformed (one arrive per transform warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + AS);
+  uint64_t* staged = a_ready + AS;                                // [drain warp][tile]: tile written, TMA store issued
+  uint64_t* sdone = staged + 16;                                  // [drain warp][tile]: statistics taken
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdone + 16);
+  static_assert(Cfg::NBARS * 8 + 4 <= 512, "barrier region");
   const uint32_t tap_sa = smem_u32(a_full) + 512;               // per-tap descriptor offsets
   static_assert((IDF_CONV_MAX_KB + 1) * 4 <= 1024, "tap table region");
   const uint32_t stage_sa = smem_u32(a_full) + 2048;            // epilogue staging tiles (1024-byte aligned: TMA swizzle)
-  const uint32_t bias_sa = stage_sa + kStageBytes;              // bias vector
+  const uint32_t bias_sa = stage_sa + kStageBytes;        // bias vector
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int EPI0 = XF ? kXfWarps : 0;          // first of the 8 epilogue warps (multiple of 4: TMEM lane quarters)
-  constexpr int W_A = EPI0 + 8, W_B = EPI0 + 9, W_I2 = EPI0 + 10, W_I1 = EPI0 + 11;
+  constexpr int STAT0 = EPI0 + 8;                  // four statistics warps, one per lane quarter
+  constexpr int W_A = EPI0 + 12, W_B = EPI0 + 13, W_I2 = EPI0 + 14, W_I1 = EPI0 + 15;
   static_assert(EPI0 % 4 == 0, "epilogue warps must start at a multiple of 4");
+  // work distribution: `unit0`-th of `n_units` workers (CTAs, or CTA pairs); a pair's super tile is 2 * MT tiles and
+  // this CTA owns the `rank`-th half of it
+  constexpr int PW = PAIR ? 2 : 1;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int unit0 = static_cast<int>(blockIdx.x) / PW;
+  const int n_units = static_cast<int>(gridDim.x) / PW;
 
   if (warp == W_A && lane == 0) {
     for (int i = 0; i < p.n_src; ++i) {
@@ -245,14 +284,20 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
     if (p.epilogue == IDF_EPI_BF16) tma_prefetch_desc(&p.tmOut);
   }
   if (warp == W_I1 && lane == 0) {
-    for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, Cfg::NI); mbar_init(a_ready + s, kXfWarps); }
+    for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, Cfg::NI); mbar_init(a_ready + s, PW * kXfWarps); }
     for (int s = 0; s < BS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, Cfg::NI); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, Cfg::NI); mbar_init(tempty + a, 256); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, Cfg::NI); mbar_init(tempty + a, PW * 8); }   // one arrive per drain warp
+    for (int i = 0; i < 16; ++i) { mbar_init(staged + i, 1); mbar_init(sdone + i, 1); }
     fence_mbar_init();
   }
   if (warp == W_I2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   if (warp >= EPI0 && warp < EPI0 + 8) {   // bias -> shared memory
     const int nb = p.n_tiles * BN;
@@ -263,11 +308,12 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
       sts32(tap_sa + 4 * i, (i < p.n_taps) ? static_cast<uint32_t>(p.t_rel[i]) * 8u : 0u);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = lds32(smem_u32(tmem_slot));
 
-  const int total = p.m_super * p.n_tiles;
+  const int total = p.m_super * p.n_tiles;    // m_super counts super tiles of PW * MT tiles
   // Programmatic dependent launch: everything above (barriers, TMEM, bias, tap table) touches only constants; the
   // weight (B) producer may also run ahead.  Every other role waits for the producer of its inputs here.
   griddep_launch();
@@ -278,9 +324,9 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
     if (lane == 0) {
       int sa = 0;
       uint32_t pa = 0;
-      for (int st = blockIdx.x; st < total; st += gridDim.x) {
+      for (int st = unit0; st < total; st += n_units) {
         const int ms = st / p.n_tiles;
-        const int row0 = ms * (MT * kBM);
+        const int row0 = (ms * PW + static_cast<int>(rank)) * (MT * kBM);
         for (int g = 0; g < p.n_groups; ++g) {
           const int src = p.g_src[g];
           const int ex = p.extra_rows[src];
@@ -292,14 +338,38 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
             continue;
           }
           mbar_wait(a_empty + sa, pa ^ 1u);
-          mbar_arrive_expect_tx(a_full + sa, static_cast<uint32_t>((MT * kBM + ex) * 128));
           uint8_t* dst = smA + sa * p.a_stage_bytes;
           const int r = row0 + p.g_lo[g];
+          const uint32_t bytes = static_cast<uint32_t>((MT * kBM + ex) * 128);
+          if constexpr (PAIR && !XF) {
+            // the leader's issuing threads wait for BOTH halves: one barrier (the leader's) counts both CTAs' bytes
+            const uint32_t bar = mapa_u32(smem_u32(a_full + sa), 0);
+            if (leader) mbar_arrive_expect_tx(a_full + sa, 2 * bytes);
 #pragma unroll
-          for (int m = 0; m < MT; ++m)
-            tma_load_2d(dst + m * (kBM * 128), &p.tmA[src], a_full + sa, p.g_c0[g], r + m * kBM);
-          if (ex > 0) tma_load_2d(dst + MT * (kBM * 128), &p.tmAx[src], a_full + sa, p.g_c0[g], r + MT * kBM);
+            for (int m = 0; m < MT; ++m)
+              tma_load_2d_pair(dst + m * (kBM * 128), &p.tmA[src], bar, p.g_c0[g], r + m * kBM);
+            if (ex > 0) tma_load_2d_pair(dst + MT * (kBM * 128), &p.tmAx[src], bar, p.g_c0[g], r + MT * kBM);
+          } else {
+            mbar_arrive_expect_tx(a_full + sa, bytes);      // XF: consumed by this CTA's own transform warps
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              tma_load_2d(dst + m * (kBM * 128), &p.tmA[src], a_full + sa, p.g_c0[g], r + m * kBM);
+            if (ex > 0) tma_load_2d(dst + MT * (kBM * 128), &p.tmAx[src], a_full + sa, p.g_c0[g], r + MT * kBM);
+          }
           if (++sa == AS) { sa = 0; pa ^= 1u; }
+          // the halo this producer will request AS groups from now: start moving it from HBM into L2 already (the
+          // 64x64 layers run close to the HBM roofline and two shared-memory stages do not cover the DRAM latency)
+          if (p.l2_prefetch != 0) {
+            int g2 = g + AS, st2 = st;
+            while (g2 >= p.n_groups) { g2 -= p.n_groups; st2 += n_units; }
+            if (st2 < total && !(XF && p.xf_ldg != 0 && p.g_xf[g2] >= 0)) {
+              const int src2 = p.g_src[g2];
+              const int r2 = ((st2 / p.n_tiles) * PW + static_cast<int>(rank)) * (MT * kBM) + p.g_lo[g2];
+#pragma unroll
+              for (int m = 0; m < MT; ++m) tma_prefetch_l2_2d(&p.tmA[src2], p.g_c0[g2], r2 + m * kBM);
+              if (p.extra_rows[src2] > 0) tma_prefetch_l2_2d(&p.tmAx[src2], p.g_c0[g2], r2 + MT * kBM);
+            }
+          }
         }
       }
     }
@@ -308,37 +378,51 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
     if (lane == 0) {
       int sb = 0;
       uint32_t pb = 0;
-      for (int st = blockIdx.x; st < total; st += gridDim.x) {
+      for (int st = unit0; st < total; st += n_units) {
         const int nt = st % p.n_tiles;
         for (int t = 0; t < p.n_taps; ++t) {
           mbar_wait(b_empty + sb, pb ^ 1u);
-          mbar_arrive_expect_tx(b_full + sb, Cfg::B_BYTES);
-          tma_load_2d(smB + sb * Cfg::B_BYTES, &p.tmB, b_full + sb, p.t_kb[t] * kBK, nt * BN);
+          if constexpr (PAIR) {     // this CTA's half of the weight tile (p.tmB has a box of BN/2 rows); bytes counted by the leader
+            if (leader) mbar_arrive_expect_tx(b_full + sb, 2 * Cfg::B_BYTES);
+            tma_load_2d_pair(smB + sb * Cfg::B_BYTES, &p.tmB, mapa_u32(smem_u32(b_full + sb), 0), p.t_kb[t] * kBK,
+                             nt * BN + static_cast<int>(rank) * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(b_full + sb, Cfg::B_BYTES);
+            tma_load_2d(smB + sb * Cfg::B_BYTES, &p.tmB, b_full + sb, p.t_kb[t] * kBK, nt * BN);
+          }
           if (++sb == BS) { sb = 0; pb ^= 1u; }
         }
       }
     }
   } else if (warp == W_I1 || (warp == W_I2 && Cfg::NI == 2)) {
     // ------------------------------------------------------------------ UMMA issuers
-    // One thread per issuer; with MT >= 2 the accumulators are split between two issuing threads so
-    // that neither has to sustain more than one MMA per 64 cycles.  Both wait on the same full
-    // barriers; every empty / accumulator-full barrier counts one tcgen05.commit per issuer.
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN, kFmtBF16);
+    // One warp per issuer; with MT >= 2 the accumulators are split between two issuing warps so that neither has to
+    // sustain more than one MMA per 64 cycles.  Both wait on the same full barriers; every empty / accumulator-full
+    // barrier counts one tcgen05.commit per issuer.  The loop runs warp-convergent on warp-uniform values and only
+    // the tcgen05 instructions sit under elect.sync: the compiler then keeps descriptors and addresses in uniform
+    // registers (3 instructions per MMA).  Inside `if (lane == 0)` every operand went through an ELECT / R2UR.BROADCAST
+    // waterfall loop, ~13 instructions per MMA -- the ncu samples showed the issuing thread, not the tensor pipe or the
+    // barriers, as the limit of the N = 64 layers.
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_f16(PW * kBM, BN, kFmtBF16);
       constexpr int M_PER = MT / Cfg::NI;
-      const int m_begin = (warp == W_I1) ? 0 : M_PER;
+      const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const int m_begin = (warp_u == W_I1) ? 0 : M_PER;
       int sa = 0, sb = 0, iter = 0;
       uint32_t pa = 0, pb = 0;
       const uint32_t b_lo0 = umma_desc_lo(smem_u32(smB));
-      for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
+      for (int st = unit0; st < total; st += n_units, ++iter) {
         const int as = iter & 1;
-        mbar_wait(tempty + as, ((iter >> 1) & 1u) ^ 1u);
+        if constexpr (PAIR) mbar_wait_cluster(tempty + as, ((iter >> 1) & 1u) ^ 1u);
+        else mbar_wait(tempty + as, ((iter >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + static_cast<uint32_t>(as * Cfg::ACC_COLS + m_begin * BN);
+        const uint32_t d0 = tmem_u + static_cast<uint32_t>(as * Cfg::ACC_COLS + m_begin * BN);
         int t = 0;
-        uint32_t rel = lds32(tap_sa);
+        uint32_t rel = static_cast<uint32_t>(p.t_rel[0]) * 8u;     // tap view offset in 16-byte units
         for (int g = 0; g < p.n_groups; ++g) {
-          mbar_wait((XF ? a_ready : a_full) + sa, pa);
+          if constexpr (PAIR && XF) mbar_wait_cluster(a_ready + sa, pa);   // the peer's transform warps arrive remotely
+          else mbar_wait((XF ? a_ready : a_full) + sa, pa);
           if constexpr (XF) tc_fence_after();
           const uint32_t a_lo0 = umma_desc_lo(smem_u32(smA + sa * p.a_stage_bytes)) +
                                  static_cast<uint32_t>(m_begin * (kBM * 128 / 16));
@@ -348,18 +432,30 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + rel;           // tap view: any 128-byte row start is legal
             const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(sb) * (Cfg::B_BYTES / 16);
-            rel = lds32(tap_sa + 4 * (t + 1));           // prefetch next tap's offset
+            rel = static_cast<uint32_t>(p.t_rel[t + 1 < IDF_CONV_MAX_KB ? t + 1 : t]) * 8u;   // next tap's offset
+            if (elect_one()) {
 #pragma unroll
-            for (int m = 0; m < M_PER; ++m)
-              umma_f16_x4(d0 + static_cast<uint32_t>(m * BN), a_lo + static_cast<uint32_t>(m * (kBM * 128 / 16)), b_lo,
-                          idesc, t != 0 ? 1u : 0u);
-            umma_commit(b_empty + sb);
+              for (int m = 0; m < M_PER; ++m) {
+                if constexpr (PAIR)
+                  umma_f16_x4_pair(d0 + static_cast<uint32_t>(m * BN), a_lo + static_cast<uint32_t>(m * (kBM * 128 / 16)), b_lo,
+                                   idesc, t != 0 ? 1u : 0u);
+                else
+                  umma_f16_x4(d0 + static_cast<uint32_t>(m * BN), a_lo + static_cast<uint32_t>(m * (kBM * 128 / 16)), b_lo,
+                              idesc, t != 0 ? 1u : 0u);
+              }
+              if constexpr (PAIR) umma_commit_pair(b_empty + sb); else umma_commit(b_empty + sb);
+              if (t + 1 == t_end) {
+                if constexpr (PAIR) umma_commit_pair(a_empty + sa); else umma_commit(a_empty + sa);
+                if (g + 1 == p.n_groups) {
+                  if constexpr (PAIR) umma_commit_pair(tfull + as); else umma_commit(tfull + as);
+                }
+              }
+            }
+            __syncwarp();
             if (++sb == BS) { sb = 0; pb ^= 1u; }
           }
-          umma_commit(a_empty + sa);
           if (++sa == AS) { sa = 0; pa ^= 1u; }
         }
-        umma_commit(tfull + as);
       }
     }
   } else if (XF && warp < EPI0) {
@@ -397,7 +493,7 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
         const int src = p.g_src[c.g];
         c.cb = p.g_xf[c.g];
         c.nrows = MT * kBM + p.extra_rows[src];
-        c.rbase = ms * (MT * kBM) + p.g_lo[c.g];
+        c.rbase = (ms * PW + static_cast<int>(rank)) * (MT * kBM) + p.g_lo[c.g];
         c.nq = c.cb >= 0 ? (c.nrows + 4 * kXfRows - 1) / (4 * kXfRows) : 1;
         c.ld = p.src_ld[src];
         c.col = p.srcp[src] + p.g_c0[c.g] + gi * 8;
@@ -406,7 +502,7 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
         if (++c.q < c.nq) return;
         c.q = 0;
         if (++c.sa == AS) { c.sa = 0; c.pa ^= 1u; }
-        if (++c.g == p.n_groups) { c.g = 0; c.st += gridDim.x; }
+        if (++c.g == p.n_groups) { c.g = 0; c.st += n_units; }
         setup(c);
       };
       auto load = [&](const Cur& c, uint4 (&u)[4]) {
@@ -423,7 +519,7 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
         }
       };
       Cur c;
-      c.st = blockIdx.x; c.g = 0; c.q = 0; c.sa = 0; c.pa = 0;
+      c.st = unit0; c.g = 0; c.q = 0; c.sa = 0; c.pa = 0;
       setup(c);
       uint32_t full_par = 0;      // bit s = phase parity of a_full[s]: that barrier only cycles for the TMA-loaded (raw) halos
       uint4 u[4], un[4];
@@ -490,16 +586,19 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
         if (c.q == c.nq - 1) {                        // halo complete: hand the stage to the UMMA issuers
           if (c.cb >= 0) fence_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(a_ready + c.sa);
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(a_ready + c.sa), 0));
+            else mbar_arrive(a_ready + c.sa);
+          }
         }
         c = n;
 #pragma unroll
         for (int k = 0; k < 4; ++k) u[k] = un[k];
       }
     } else
-    for (int st = blockIdx.x; st < total; st += gridDim.x) {
+    for (int st = unit0; st < total; st += n_units) {
       const int ms = st / p.n_tiles;
-      const int row0 = ms * (MT * kBM);
+      const int row0 = (ms * PW + static_cast<int>(rank)) * (MT * kBM);
       for (int g = 0; g < p.n_groups; ++g) {
         const int cb = p.g_xf[g];
         if (cb != cur_cb) { cur = -1; cur_cb = cb; }
@@ -587,7 +686,10 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
           fence_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready + sa);
+        if (lane == 0) {     // hand the stage to the (leader's) UMMA issuers
+          if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(a_ready + sa), 0));
+          else mbar_arrive(a_ready + sa);
+        }
         if (++sa == AS) { sa = 0; pa ^= 1u; }
       }
     }
@@ -605,26 +707,34 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
     }
     constexpr int CHUNKS = (BN >= 32) ? BN / 32 : 1;
     uint4 res_next[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-    if (BN >= 32 && p.residual != nullptr && static_cast<int>(blockIdx.x) < total) {   // first item of the first super tile
-      const int ms0 = blockIdx.x / p.n_tiles, nt0 = blockIdx.x - ms0 * p.n_tiles;
-      residual_fetch(p, static_cast<int64_t>(ms0) * MT * kBM + q * 32, nt0 * BN + half * 32, lane, res_next);
+    if (BN >= 32 && p.residual != nullptr && unit0 < total) {   // first item of the first super tile
+      const int ms0 = unit0 / p.n_tiles, nt0 = unit0 - ms0 * p.n_tiles;
+      residual_fetch(p, static_cast<int64_t>(ms0 * PW + static_cast<int>(rank)) * MT * kBM + q * 32, nt0 * BN + half * 32, lane,
+                     res_next);
     }
+    const uint32_t tempty_bar = PAIR ? mapa_u32(smem_u32(tempty), 0) : smem_u32(tempty);   // the leader's barriers
+    auto release_acc = [&](int as) {       // all TMEM reads of this warp are complete: one arrive per warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster_relaxed(tempty_bar + 8u * static_cast<uint32_t>(as));
+        else mbar_arrive(tempty + as);
+      }
+    };
     int iter = 0;
-    for (int st = blockIdx.x; st < total; st += gridDim.x, ++iter) {
-      const int ms = st / p.n_tiles;
-      const int nt = st - ms * p.n_tiles;
+    uint32_t k = 0;         // work items staged so far: tile k & 1, its (k >> 1)-th use
+    for (int st = unit0; st < total; st += n_units, ++iter) {
+      const int ms = (st / p.n_tiles) * PW + static_cast<int>(rank);     // this CTA's super tile of MT tiles
+      const int nt = st % p.n_tiles;
       const int as = iter & 1;
       mbar_wait(tfull + as, (iter >> 1) & 1u);
       tc_fence_after();
       const uint32_t t0 = tmem_base + static_cast<uint32_t>(as * Cfg::ACC_COLS) + (static_cast<uint32_t>(q * 32) << 16);
       if (p.debug_skip_epilogue) {     // measurement only
-        tc_fence_before();
-        mbar_arrive(tempty + as);
+        release_acc(as);
         continue;
       }
-      const int R = p.Hp * p.Wp;
-      const float inv_wp = 1.0f / static_cast<float>(p.Wp), inv_hp = 1.0f / static_cast<float>(p.Hp),
-                  inv_R = 1.0f / static_cast<float>(R);
+      const float inv_wp = 1.0f / static_cast<float>(p.Wp), inv_hp = 1.0f / static_cast<float>(p.Hp);
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
         // row bookkeeping once per 128-row tile (exact float reciprocals: all quotients < 2^23)
@@ -636,12 +746,9 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
         const int img = __float2int_rd((static_cast<float>(rq) + 0.5f) * inv_hp);
         const int y = rq - img * p.Hp;
         const bool valid = (r < p.rows) && (x < p.W) && (y < p.H);
-        const int img_w = __float2int_rd((static_cast<float>(wr0) + 0.5f) * inv_R);
-        const int64_t next_img_row = static_cast<int64_t>(img_w + 1) * R;
-        const int n_a = static_cast<int>((next_img_row - wr0 < 32) ? (next_img_row - wr0) : 32);
         if constexpr (BN >= 32) {
 #pragma unroll 1
-          for (int c = ((m * CHUNKS) & 1) ^ half; c < CHUNKS; c += 2) {   // items (m, c) alternate between the halves
+          for (int c = half; c < CHUNKS; c += 2) {   // items (m, c) alternate between the halves (CHUNKS is even)
             uint32_t v[32];
             tmem_ld_32x32(t0 + static_cast<uint32_t>(m * BN + c * 32), v);
             uint4 res_cur[4];
@@ -649,20 +756,19 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
             for (int i = 0; i < 4; ++i) res_cur[i] = res_next[i];
             if (p.residual != nullptr) {             // prefetch the NEXT item's residual (this or the next super tile)
               int nm = m, nc = c + 2, nms = ms, nnt = nt;
-              if (nc >= CHUNKS) { nm = m + 1; nc = (((m + 1) * CHUNKS) & 1) ^ half; }
+              if (nc >= CHUNKS) { nm = m + 1; nc = half; }
               if (nm >= MT) {
-                const int nst = st + static_cast<int>(gridDim.x);
-                nms = nst / p.n_tiles; nnt = nst - nms * p.n_tiles; nm = 0; nc = half;
+                const int nst = st + n_units;
+                nms = (nst / p.n_tiles) * PW + static_cast<int>(rank); nnt = nst % p.n_tiles; nm = 0; nc = half;
               }
               residual_fetch(p, (static_cast<int64_t>(nms) * MT + nm) * kBM + q * 32, nnt * BN + nc * 32, lane, res_next);
             }
             tmem_ld_wait();
-            if (m == MT - 1 && c + 2 >= CHUNKS) {       // last TMEM read of this warp: release the accumulators early
-              tc_fence_before();
-              mbar_arrive(tempty + as);
-            }
-            epilogue_bf16_chunk(p, v, wr0, valid, nt * BN + c * 32, n_a, tile, q, lane,
-                                stage_sa + e * kStageTile, bias_sa, res_cur);
+            if (m == MT - 1 && c + 2 >= CHUNKS) release_acc(as);   // last TMEM read of this warp: release the accumulators early
+            const uint32_t sl = 2u * e + (k & 1u);
+            epilogue_drain_chunk(p, v, wr0, valid, nt * BN + c * 32, lane, stage_sa + sl * kStageTile, bias_sa, res_cur,
+                                 staged + sl, sdone + sl, k >> 1);
+            ++k;
           }
         } else {
           if ((m & 1) == half) {
@@ -673,72 +779,119 @@ __global__ void __launch_bounds__(XF ? 384 + 32 * kXfWarps : 384, 1) conv_halo_k
           }
         }
       }
-      if constexpr (BN < 32) {
-        tc_fence_before();
-        mbar_arrive(tempty + as);
-      }
+      if constexpr (BN < 32) release_acc(as);
     }
     if (BN >= 32 && lane == 0) bulk_wait<0>();     // this warp's TMA stores have been performed
+  } else if (BN >= 32 && warp >= STAT0 && warp < STAT0 + 4) {
+    // ------------------------------------------------------------------ statistics (4 warps, one per lane quarter)
+    // follows the two drain warps of its quarter through the same item sequence and takes the GroupNorm partial sums
+    // of every tile they stage; it runs even when no statistics are wanted so that the tile hand-shake stays in step
+    const int q = warp - STAT0;
+    constexpr int CHUNKS = BN / 32;
+    const int R = p.Hp * p.Wp;
+    const float inv_R = 1.0f / static_cast<float>(R);
+    uint32_t k = 0;          // items per drain warp so far (both drain warps of a quarter advance in lock step)
+    if (!p.debug_skip_epilogue) {
+      for (int st = unit0; st < total; st += n_units) {
+        const int ms = (st / p.n_tiles) * PW + static_cast<int>(rank);
+        const int nt = st % p.n_tiles;
+#pragma unroll 1
+        for (int m = 0; m < MT; ++m) {
+          const int tile = ms * MT + m;
+          const int64_t wr0 = static_cast<int64_t>(tile) * kBM + q * 32;
+          const int img_w = __float2int_rd((static_cast<float>(wr0) + 0.5f) * inv_R);
+          const int64_t next_img_row = static_cast<int64_t>(img_w + 1) * R;
+          const int n_a = static_cast<int>((next_img_row - wr0 < 32) ? (next_img_row - wr0) : 32);
+#pragma unroll 1
+          for (int c = 0; c < CHUNKS; ++c, k += (c & 1) ? 0u : 1u) {     // chunk c belongs to drain warp (c & 1) * 4 + q
+            const uint32_t sl = 2u * ((c & 1) * 4 + q) + (k & 1u);
+            epilogue_stats_chunk(p, stage_sa + sl * kStageTile, nt * BN + c * 32, n_a, tile, q, lane, staged + sl, sdone + sl,
+                                 k >> 1);
+          }
+        }
+      }
+    }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();    // neither CTA may exit (or free TMEM) while the other still uses its memory
+  else __syncthreads();
   if (warp == W_I2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN, int MT, bool XF>
+template <int BN, int MT, bool XF, bool PAIR>
 static cudaError_t launch_cfg(const ConvKernelParams& p, int grid, cudaStream_t stream) {
-  using Cfg = HaloCfg<BN, MT>;
+  using Cfg = HaloCfg<BN, MT, PAIR>;
   const uint32_t smem = conv_smem_bytes(p.a_stage_bytes, Cfg::A_STAGES, Cfg::B_STAGES, Cfg::B_BYTES);
   static uint32_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, MT, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, MT, XF, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     attr_smem = smem;
   }
-  if (!g_pdl) {
-    conv_halo_kernel<BN, MT, XF><<<grid, XF ? 384 + 32 * kXfWarps : 384, smem, stream>>>(p);
+  if (!g_pdl && !PAIR) {
+    conv_halo_kernel<BN, MT, XF, PAIR><<<grid, conv_threads(XF), smem, stream>>>(p);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, 1, 1);
-  cfg.blockDim = dim3(XF ? 384 + 32 * kXfWarps : 384, 1, 1);
+  cfg.blockDim = dim3(conv_threads(XF), 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, MT, XF>, p);
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, MT, XF, PAIR>, p);
 }
 
-template <bool XF>
+template <bool XF, bool PAIR>
 static cudaError_t launch_sel(const ConvKernelParams& p, int block_n, int mt, int grid, cudaStream_t stream) {
   const int key = block_n * 10 + mt;
   switch (key) {
-    case 1281: return launch_cfg<128, 1, XF>(p, grid, stream);
-    case 1282: return launch_cfg<128, 2, XF>(p, grid, stream);
-    case 641: return launch_cfg<64, 1, XF>(p, grid, stream);
-    case 642: return launch_cfg<64, 2, XF>(p, grid, stream);
-    case 644: return launch_cfg<64, 4, XF>(p, grid, stream);
-    case 161: return launch_cfg<16, 1, XF>(p, grid, stream);
-    case 164: return launch_cfg<16, 4, XF>(p, grid, stream);
-    default: return cudaErrorInvalidValue;
+    case 1281: return launch_cfg<128, 1, XF, PAIR>(p, grid, stream);
+    case 1282: return launch_cfg<128, 2, XF, PAIR>(p, grid, stream);
+    case 641: return launch_cfg<64, 1, XF, PAIR>(p, grid, stream);
+    case 642: return launch_cfg<64, 2, XF, PAIR>(p, grid, stream);
+    case 644: return launch_cfg<64, 4, XF, PAIR>(p, grid, stream);
+    default: break;
   }
+  if constexpr (!PAIR) {
+    switch (key) {
+      case 161: return launch_cfg<16, 1, XF, false>(p, grid, stream);
+      case 164: return launch_cfg<16, 4, XF, false>(p, grid, stream);
+      default: break;
+    }
+  }
+  return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, bool xform, int grid, cudaStream_t stream) {
-  return xform ? launch_sel<true>(p, block_n, mt, grid, stream) : launch_sel<false>(p, block_n, mt, grid, stream);
+cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, bool xform, bool pair, int grid,
+                              cudaStream_t stream) {
+  if (pair) return xform ? launch_sel<true, true>(p, block_n, mt, grid, stream) : launch_sel<false, true>(p, block_n, mt, grid, stream);
+  return xform ? launch_sel<true, false>(p, block_n, mt, grid, stream) : launch_sel<false, false>(p, block_n, mt, grid, stream);
 }
 
 // shared-memory need of a configuration (host side, for plan validation)
-uint32_t conv_config_smem(int block_n, int a_stage_bytes) {
-  return conv_smem_bytes(a_stage_bytes, 2, conv_b_stages(block_n), block_n * kBK * 2);
+uint32_t conv_config_smem(int block_n, int a_stage_bytes, bool pair) {
+  return conv_smem_bytes(a_stage_bytes, 2, conv_b_stages(block_n), block_n * kBK * 2 / (pair ? 2 : 1));
 }
 
 }  // namespace idf

@@ -15,7 +15,7 @@ constexpr int kMaxGroups = 40;   // halo loads per work item: (source, 64-channe
 struct alignas(64) ConvKernelParams {
   CUtensorMap tmA[IDF_CONV_MAX_SRC];    // box {64, 128 rows}
   CUtensorMap tmAx[IDF_CONV_MAX_SRC];   // box {64, extra_rows[src]} -- tail of the halo
-  CUtensorMap tmB;                      // box {64, BN}
+  CUtensorMap tmB;                      // box {64, BN} (CTA pairs: {64, BN/2}, each CTA loads its half)
   CUtensorMap tmOut;                    // bf16 epilogue: output [rows, out_ld], box {32 cols, 32 rows}, SWIZZLE_64B (TMA store)
   int32_t n_src;
   int32_t extra_rows[IDF_CONV_MAX_SRC]; // halo rows beyond 128*MT (multiple of 8, 0 for 1x1 sources)
@@ -29,12 +29,13 @@ struct alignas(64) ConvKernelParams {
   int32_t t_rel[IDF_CONV_MAX_KB];       // tap row offset relative to its group's halo start (>= 0)
   int32_t t_kb[IDF_CONV_MAX_KB];        // k-block index of the tap in the packed weight matrix
   int32_t a_stage_bytes;                // bytes of one halo stage (multiple of 1024)
-  int32_t m_super, n_tiles;             // super tiles of MT*128 rows; N tiles
+  int32_t m_super, n_tiles;             // super tiles of MT*128 rows (CTA pairs: 2*MT*128 rows); N tiles
   int32_t m_tiles;                      // 128-row tiles
   float* stats;                         // optional GroupNorm partial sums: records A then records B, each
                                         // [m_tiles*4 (32-row windows)][out_ld][2] fp32 (sum, sumsq)
   int64_t stats_b_off;                  // float offset of the B records
   int32_t debug_skip_epilogue;          // measurement only: epilogue warps drain nothing (main-loop ceiling)
+  int32_t l2_prefetch;                  // A producer issues L2 prefetches two halo loads ahead
   int64_t rows;
   int32_t Hp, Wp, H, W;
   int32_t cout;
@@ -77,9 +78,9 @@ struct alignas(64) WgradKernelParams {
 cudaError_t launch_wgrad(const WgradKernelParams& p, int grid, cudaStream_t stream);
 
 static_assert(sizeof(ConvKernelParams) <= 4000, "kernel parameters are limited to 4 KB");
-cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, bool xform, int grid, cudaStream_t stream);
+cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, bool xform, bool pair, int grid, cudaStream_t stream);
 cudaError_t launch_adagn_coef(const idf_adagn_args& a, float* coef_out, cudaStream_t stream);
-uint32_t conv_config_smem(int block_n, int a_stage_bytes);
+uint32_t conv_config_smem(int block_n, int a_stage_bytes, bool pair = false);
 cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream);
 cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, int num_sms, cudaStream_t stream);
 int64_t adagn_bwd_ws_floats(int batch, int C);

@@ -119,6 +119,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+// Warm L2 with the box a later tma_load_2d will fetch (no shared-memory destination, no completion signal)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
+
 // 2-D tiled store shared -> global (bulk async-group completion).  The shared-memory tile must have been written
 // with the tensor map's swizzle, followed by fence.proxy.async by every writing thread, before ONE thread issues this.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t smem_src, int32_t c0, int32_t c1) {
@@ -229,6 +234,124 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA pairs (cluster of 2, tcgen05 cta_group::2): one UMMA of M = 256 spans both CTAs -- each supplies its own 128
+// rows of A and HALF of the B tile, so the shared-memory operand traffic per CTA drops from A + B to A + B/2.
+// The leader (cluster rank 0) issues the MMAs; barriers the leader waits on live in ITS shared memory and the peer
+// signals them through shared::cluster addresses (mapa).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// arrive without release semantics: for signals that publish no memory writes (e.g. "accumulator drained": the TMEM
+// reads completed with tcgen05.wait::ld and the data lives in registers).  The .release.cluster form costs a
+// MEMBAR.ALL.GPU + ERRBAR per arrive (13 % of the epilogue warps' time in the ncu samples).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+               : "memory");
+}
+// wait that also acquires writes released by the peer CTA (remote arrives)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0 && (clock64() - t0) > 4000000000LL) __trap();
+  }
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are counted on an mbarrier given as a shared::cluster
+// address (the leader's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr,
+                                                 int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {  // one full warp in EACH CTA
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// umma_f16_x4 for a CTA pair (M = 256); issued by one thread of the leader CTA only
+__device__ __forceinline__ void umma_f16_x4_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                 uint32_t accumulate_first) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 da, db;\n"
+      ".reg .b32 al, bl;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 q, %4, %4;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n"
+      "add.u32 al, %1, 2;\n"
+      "add.u32 bl, %2, 2;\n"
+      "mov.b64 da, {al, %5};\n"
+      "mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, q;\n"
+      "add.u32 al, %1, 4;\n"
+      "add.u32 bl, %2, 4;\n"
+      "mov.b64 da, {al, %5};\n"
+      "mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, q;\n"
+      "add.u32 al, %1, 6;\n"
+      "add.u32 bl, %2, 6;\n"
+      "mov.b64 da, {al, %5};\n"
+      "mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, q;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "r"(kDescHiKSw128)
+      : "memory");
+}
+// Arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair when the issued UMMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b16 m;\n"
+      "mov.b16 m, 3;\n"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
+      "}\n" ::"r"(smem_u32(bar))
       : "memory");
 }
 

@@ -1,6 +1,7 @@
 """Per-shape timing of the conv kernel at the benchmark batch (CUDA events), with the epilogue and the
 GroupNorm partials switched off in turn: separates main-loop (TMA + UMMA) time from epilogue time."""
 import ctypes as C
+import os
 import sys
 from pathlib import Path
 
@@ -14,8 +15,10 @@ lib = _lib.load()
 _lib.check(lib.idf_init())
 dev = "cuda:0"
 BF = torch.bfloat16
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+B = int(os.environ.get("IDF_MB_BATCH", "256"))
 PEAK = 1406.4
+PAIR_DEFAULT = int(os.environ.get("IDF_CONV_PAIR", "1"))
+_lib.check(lib.idf_set_option(b"conv_pair", PAIR_DEFAULT))
 
 
 def make(cin, cout, H, residual, stats, skip):
@@ -61,31 +64,40 @@ def timeit(h, n=20):
     return e0.elapsed_time(e1) / n * 1e3   # us
 
 
-print(f"batch {B}; us per launch (TFLOP/s, % of {PEAK} sustained)")
-for (cin, cout, H) in [(64, 64, 64), (128, 64, 64), (192, 64, 64), (128, 128, 64), (128, 128, 32), (256, 128, 32),
-                       (128, 128, 16), (256, 128, 16), (128, 128, 8)]:
-    fl = 2.0 * B * H * H * 9 * cin * cout
-    line = f"{cin:3d}->{cout:3d} @{H:2d}: "
-    for name, (res, stats, skip) in {"full": (False, True, False), "+res": (True, True, False),
-                                     "nostats": (False, False, False), "mainloop": (False, False, True)}.items():
-        h, keep = make(cin, cout, H, res, stats, skip)
-        us = timeit(h)
-        lib.idf_conv_plan_destroy(h)
-        del keep
-        line += f"{name} {us:7.1f} ({fl / us / 1e6:6.0f}, {fl / us / 1e6 / PEAK * 100:4.1f}%)  "
-    # planner's choice against every forced number of 128-row tiles per work unit
-    for mt in (1, 2, 4):
-        if mt == 4 and cout % 128 == 0:
-            continue
-        _lib.check(lib.idf_set_option(b"conv_force_mt", mt))
-        try:
-            h, keep = make(cin, cout, H, False, True, False)
+def main():
+    print(f"batch {B}; us per launch (TFLOP/s, % of {PEAK} sustained)")
+    for (cin, cout, H) in [(64, 64, 64), (128, 64, 64), (192, 64, 64), (128, 128, 64), (128, 128, 32), (256, 128, 32),
+                           (128, 128, 16), (256, 128, 16), (128, 128, 8)]:
+        fl = 2.0 * B * H * H * 9 * cin * cout
+        line = f"{cin:3d}->{cout:3d} @{H:2d}: "
+        for name, (res, stats, skip) in {"full": (False, True, False), "+res": (True, True, False),
+                                         "nostats": (False, False, False), "mainloop": (False, False, True)}.items():
+            h, keep = make(cin, cout, H, res, stats, skip)
             us = timeit(h)
             lib.idf_conv_plan_destroy(h)
             del keep
-            line += f"MT={mt} {us:6.1f}  "
-        except Exception as e:       # configuration does not fit in shared memory
-            line += f"MT={mt}   n/a  "
-        finally:
-            _lib.check(lib.idf_set_option(b"conv_force_mt", 0))
-    print(line)
+            line += f"{name} {us:7.1f} ({fl / us / 1e6:6.0f}, {fl / us / 1e6 / PEAK * 100:4.1f}%)  "
+        # planner's choice against every forced number of 128-row tiles per work unit, as single CTAs and as CTA pairs
+        for pair in (() if os.environ.get("IDF_MB_QUICK") else (0, 1)):
+            _lib.check(lib.idf_set_option(b"conv_pair", pair))
+            line += "| pair " if pair else "| single "
+            for mt in (1, 2, 4):
+                if mt == 4 and cout % 128 == 0:
+                    continue
+                _lib.check(lib.idf_set_option(b"conv_force_mt", mt))
+                try:
+                    h, keep = make(cin, cout, H, False, True, False)
+                    us = timeit(h)
+                    lib.idf_conv_plan_destroy(h)
+                    del keep
+                    line += f"MT={mt} {us:6.1f}  "
+                except Exception as e:       # configuration does not fit in shared memory
+                    line += f"MT={mt}   n/a  "
+                finally:
+                    _lib.check(lib.idf_set_option(b"conv_force_mt", 0))
+        _lib.check(lib.idf_set_option(b"conv_pair", PAIR_DEFAULT))
+        print(line, flush=True)
+
+
+if __name__ == "__main__":
+    main()
