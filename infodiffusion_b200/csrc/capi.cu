@@ -11,7 +11,6 @@
 
 #include "kernels.cuh"
 
-namespace idf { extern int g_xf_ldg; }
 namespace idf { extern int g_adagn_ring, g_adagn_ctas, g_adagn_ctas2, g_adagn_impl, g_pdl, g_xf_debug; }
 using namespace idf;
 
@@ -36,7 +35,6 @@ int g_num_sms = 0;
 int g_attn_impl = 2;
 int g_force_mt = 0;   // 0 = choose automatically
 int g_skip_epilogue = 0;
-int g_conv_l2_prefetch = 0;  // idf_set_option "conv_l2_prefetch"
 int g_conv_pair = 1;  // conv kernels with N >= 64 run as CTA pairs (idf_set_option "conv_pair", 0 = single CTAs)
 
 int ensure_init() {
@@ -122,9 +120,7 @@ int idf_set_option(const char* key, int32_t value) {
     g_skip_epilogue = value ? 1 : 0;
     return IDF_OK;
   }
-  if (key != nullptr && std::strcmp(key, "conv_l2_prefetch") == 0 && (value == 0 || value == 1)) { g_conv_l2_prefetch = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "conv_pair") == 0 && (value == 0 || value == 1)) { g_conv_pair = value; return IDF_OK; }
-  if (key != nullptr && std::strcmp(key, "xf_ldg") == 0 && (value == 0 || value == 1)) { g_xf_ldg = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "pdl") == 0) { g_pdl = value ? 1 : 0; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "xf_debug") == 0 && value >= 0 && value <= 4) { g_xf_debug = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "adagn_ring") == 0 && value >= 1 && value <= 8) { g_adagn_ring = static_cast<int>(value); return IDF_OK; }
@@ -241,7 +237,7 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
     const int64_t rounds = (units + workers - 1) / workers;
     const int stage = ((cand * kBM + extra_max) * 128 + 1023) / 1024 * 1024;
     if (units >= workers && rounds * workers * 100 <= units * 115 &&
-        conv_config_smem(d->block_n, stage, pair) <= 227 * 1024) {
+        conv_config_smem(d->block_n, stage, pair, use_xf) <= 227 * 1024) {
       mt = cand;
       break;
     }
@@ -251,14 +247,13 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
     if (mt > mt_max || (d->block_n == 16 && mt == 2)) { delete pl; return fail(IDF_ERR_ARG, "forced MT not available"); }
   }
   p.a_stage_bytes = ((mt * kBM + extra_max) * 128 + 1023) / 1024 * 1024;
-  if (conv_config_smem(d->block_n, p.a_stage_bytes, pair) > 227 * 1024) {
+  if (conv_config_smem(d->block_n, p.a_stage_bytes, pair, use_xf) > 227 * 1024) {
     delete pl;
     return fail(IDF_ERR_ARG, "halo does not fit in shared memory (extra rows %d)", extra_max);
   }
   p.m_super = static_cast<int32_t>((m_tiles + mt * pw - 1) / (mt * pw));
   p.m_tiles = static_cast<int32_t>(m_tiles);
   p.debug_skip_epilogue = g_skip_epilogue;
-  p.l2_prefetch = g_conv_l2_prefetch;
   p.stats = (d->epilogue == IDF_EPI_BF16) ? d->stats_out : nullptr;
   p.stats_b_off = static_cast<int64_t>(m_tiles) * 4 * d->cout * 2;
   if (p.stats != nullptr && d->out_ld != d->cout) { delete pl; return fail(IDF_ERR_ARG, "stats_out needs out_ld == cout"); }
@@ -293,8 +288,6 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   p.xf_ctot = d->xf_ctot;
   p.xf_silu = d->xf_silu;
   p.xf_debug = g_xf_debug;
-  p.xf_ldg = g_xf_ldg;
-  for (int i = 0; i < d->n_src; ++i) { p.srcp[i] = static_cast<const bf16*>(d->src[i]); p.src_ld[i] = d->src_ld[i]; }
   pl->xform = false;
   for (int g = 0; g < p.n_groups; ++g) pl->xform = pl->xform || p.g_xf[g] >= 0;
   if (p.bias == nullptr) { delete pl; return fail(IDF_ERR_ARG, "bias is null"); }

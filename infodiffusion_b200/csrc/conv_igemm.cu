@@ -11,27 +11,27 @@
 // (MT accumulators in TMEM), so each streamed weight tile B[BN x 64] feeds MT MMAs as well.
 // Operand bytes per MMA drop 3-7x (e.g. 64->64 @64^2: 221 KB -> 33 KB + weights per 128 rows).
 //
-// Roles (384 threads), LOW to HIGH warp id -- the SM sub-partition arbiter prefers the highest warp id among the
-// eligible warps, so the latency-critical single-thread roles sit on top and are never starved by the bulk warps:
-//                      XF variant only: warps 0..11 = transform (fused AdaGN + SiLU on the halo, in place)
-//                      next 8 warps = epilogue (two warps per TMEM lane quarter, quarter = warp % 4)
+// Roles (512 threads; 768 in the XF variant), LOW to HIGH warp id -- the SM sub-partition arbiter prefers the highest
+// warp id among the eligible warps, so the latency-critical single-warp roles sit on top and are never starved:
+//                      XF variant only: warps 0..7 = transform (fused AdaGN + SiLU on the halo, in place)
+//                      next 8 warps = drain (TMEM -> bf16 staging tile -> TMA store; two warps per TMEM lane quarter)
+//                      next 4 warps = GroupNorm statistics of the staged tiles (one warp per lane quarter)
 //                      then: A (halo) TMA producer, B (weights) TMA producer,
-//                            TMEM allocator (+ second UMMA issuer when MT >= 2), UMMA issuer (1 thread)
-// Pipelines: A halo stages x2, B ring x4-8 (full/empty mbarriers), TMEM accumulator sets x2.
+//                            TMEM allocator (+ second UMMA issuer when MT >= 2), UMMA issuer
+// Pipelines: A halo stages x2, B ring x4-8 (full/empty mbarriers), TMEM accumulator sets x2, staging tiles x2 per warp.
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace idf {
 
-// transform warps of the XF variant (4 rows per warp and pass).  Measured at batch 256 with bench.py --fuse-adagn:
-// 8 warps 327 img/s, 12 warps 344 img/s (= the unfused lowering), 16 warps 324 img/s (72 registers: the epilogue spills)
-constexpr int kXfWarps = 12;
+// transform warps of the XF variant (4 rows per warp and pass).  With the row table (see the transform branch) 8 and 12
+// warps measure the same at batch 256 (bench.py --fuse-adagn: 376-382 img/s); 8 leave 80 registers per thread at launch.
+constexpr int kXfWarps = 8;
 constexpr int kXfRows = 4 * kXfWarps;
 
 int g_pdl = 0;     // idf_set_option("pdl", 1): launch conv / AdaGN with programmatic dependent launch
-int g_xf_ldg = 0;     // fused AdaGN: 0 = rewrite the TMA-loaded halo in place (default), 1 = transform warps load the halo with
-                      // ld.global and store it once (idf_set_option "xf_ldg"; measured SLOWER at batch 256: conv 7.7 vs 6.7 ms,
-                      // the global latency is not hidden with the registers 768 threads leave)
-int g_xf_debug = 0;  // measurement only: 1 = transform warps forward the halo untouched, 2 = affine without the SiLU
+int g_xf_debug = 0;  // measurement only: 1 = transform warps forward the halo untouched, 2 = affine without the SiLU (others: ignored)
 
 __host__ __device__ constexpr int conv_b_stages(int bn) { return bn == 16 ? 8 : (bn == 64 ? 4 : 6); }
 // per-epilogue-warp staging tile: 32 rows x 64 B in the TMA SWIZZLE_64B layout (16-byte chunk c of row r lives at
@@ -41,6 +41,8 @@ constexpr uint32_t kStageTile = 32 * 64;
 // two staging tiles per drain warp: a warp only waits for the TMA store it issued two work items ago (the TMA engine
 // also serves the operand loads and drains the staging tiles late) and the statistics warps get a full item of slack
 constexpr uint32_t kStageBytes = 16 * kStageTile;
+constexpr int kXfMaxRows = 4 * 128 + 256;   // rows of the largest halo (MT = 4 tiles + the widest tap spread)
+constexpr uint32_t kRowTabBytes = 2 * 2 * kXfMaxRows;   // XF variant: int16 row table per halo stage
 constexpr uint32_t kBiasBytes = 1536 * 4;  // bias vector of the whole conv (cout_pad <= 1536: q|k|v of a 512-wide head), staged once per CTA
 __device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
   return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
@@ -59,9 +61,9 @@ struct HaloCfg {
   static constexpr int NI = (MT >= 2) ? 2 : 1;                        // UMMA issuing threads (accumulators split)
 };
 
-__host__ __device__ inline uint32_t conv_smem_bytes(int a_stage_bytes, int a_stages, int b_stages, int b_bytes) {
+__host__ __device__ inline uint32_t conv_smem_bytes(int a_stage_bytes, int a_stages, int b_stages, int b_bytes, bool xf) {
   return static_cast<uint32_t>(a_stages * a_stage_bytes + b_stages * b_bytes + 2048 /*barriers 512 + tap table 1024 + pad*/ +
-                               kStageBytes + kBiasBytes + 1024 /*align*/);
+                               kStageBytes + kBiasBytes + (xf ? kRowTabBytes : 0u) + 1024 /*align*/);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -234,6 +236,28 @@ __device__ __forceinline__ void epilogue_narrow(const ConvKernelParams& p, const
 // transform traffic.  Barriers the leader's issuing threads wait on (A ready, B full, accumulator empty) live in the
 // leader's shared memory and are signalled by both CTAs; "empty" / "accumulator full" barriers are signalled in both
 // CTAs by multicast tcgen05.commit.
+// bf16(act(A * x + B)) of one 16-byte granule (8 channels); SiLU(v) = h + h * tanh(h) with h = v / 2 folded into (A, B)
+template <bool SILU>
+__device__ __forceinline__ uint4 xf_apply(const uint4& u, const float (&A)[8], const float (&B)[8]) {
+  const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+  float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float h = fmaf(f[j], A[j], B[j]);
+    if constexpr (SILU) {
+      float th;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+      f[j] = fmaf(h, th, h);
+    } else {
+      f[j] = h;
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
 // threads per CTA: [transform warps (XF)] + 8 drain + 4 statistics + A producer, B producer, 2 UMMA issuers / TMEM allocator
 __host__ __device__ constexpr int conv_threads(bool xf) { return 32 * ((xf ? kXfWarps : 0) + 8 + 4 + 4); }
 
@@ -255,11 +279,10 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
   uint64_t* staged = a_ready + AS;                                // [drain warp][tile]: tile written, TMA store issued
   uint64_t* sdone = staged + 16;                                  // [drain warp][tile]: statistics taken
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdone + 16);
-  static_assert(Cfg::NBARS * 8 + 4 <= 512, "barrier region");
-  const uint32_t tap_sa = smem_u32(a_full) + 512;               // per-tap descriptor offsets
-  static_assert((IDF_CONV_MAX_KB + 1) * 4 <= 1024, "tap table region");
+  static_assert(Cfg::NBARS * 8 + 4 <= 2048, "barrier region");
   const uint32_t stage_sa = smem_u32(a_full) + 2048;            // epilogue staging tiles (1024-byte aligned: TMA swizzle)
-  const uint32_t bias_sa = stage_sa + kStageBytes;        // bias vector
+  const uint32_t bias_sa = stage_sa + kStageBytes;              // bias vector
+  const uint32_t rowtab_sa = bias_sa + kBiasBytes;              // XF: row tables
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -303,10 +326,6 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
     const int nb = p.n_tiles * BN;
     for (int i = threadIdx.x - EPI0 * 32; i < nb; i += 256) sts32(bias_sa + 4 * i, __float_as_uint(__ldg(p.bias + i)));
   }
-  if (warp == W_B) {   // per-tap descriptor offsets (16-byte units) for the issuing threads
-    for (int i = lane; i <= IDF_CONV_MAX_KB; i += 32)
-      sts32(tap_sa + 4 * i, (i < p.n_taps) ? static_cast<uint32_t>(p.t_rel[i]) * 8u : 0u);
-  }
   tc_fence_before();
   if constexpr (PAIR) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   else __syncthreads();
@@ -319,6 +338,12 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
   griddep_launch();
   if (warp != W_B) griddep_wait();
 
+  // Register budget of the XF variant (768 threads: 80 registers each at launch).  The drain warps need ~120 to hold a
+  // 32 x 32 fp32 tile plus the prefetched residual without spilling; the single-thread roles and the statistics warps
+  // need few.  setmaxnreg (per warpgroup of 4 warps) moves the surplus within the CTA's 6 x 80: 2 x 80 (transform) +
+  // 2 x 112 (drain) + 56 (statistics) + 40 (producers, issuers).
+  if (warp >= W_A) {
+    if constexpr (XF) reg_dec<40>();
   if (warp == W_A) {
     // ------------------------------------------------------------------ A producer: one halo per group
     if (lane == 0) {
@@ -330,13 +355,6 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
         for (int g = 0; g < p.n_groups; ++g) {
           const int src = p.g_src[g];
           const int ex = p.extra_rows[src];
-          if (XF && p.xf_ldg != 0 && p.g_xf[g] >= 0) {      // the transform warps load this halo themselves
-            // still observe this use's empty phase: a parity wait is only unambiguous for a waiter that has seen
-            // every earlier phase -- skipping one lets the NEXT wait on this stage alias to a phase two uses back
-            mbar_wait(a_empty + sa, pa ^ 1u);
-            if (++sa == AS) { sa = 0; pa ^= 1u; }
-            continue;
-          }
           mbar_wait(a_empty + sa, pa ^ 1u);
           uint8_t* dst = smA + sa * p.a_stage_bytes;
           const int r = row0 + p.g_lo[g];
@@ -357,19 +375,6 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
             if (ex > 0) tma_load_2d(dst + MT * (kBM * 128), &p.tmAx[src], a_full + sa, p.g_c0[g], r + MT * kBM);
           }
           if (++sa == AS) { sa = 0; pa ^= 1u; }
-          // the halo this producer will request AS groups from now: start moving it from HBM into L2 already (the
-          // 64x64 layers run close to the HBM roofline and two shared-memory stages do not cover the DRAM latency)
-          if (p.l2_prefetch != 0) {
-            int g2 = g + AS, st2 = st;
-            while (g2 >= p.n_groups) { g2 -= p.n_groups; st2 += n_units; }
-            if (st2 < total && !(XF && p.xf_ldg != 0 && p.g_xf[g2] >= 0)) {
-              const int src2 = p.g_src[g2];
-              const int r2 = ((st2 / p.n_tiles) * PW + static_cast<int>(rank)) * (MT * kBM) + p.g_lo[g2];
-#pragma unroll
-              for (int m = 0; m < MT; ++m) tma_prefetch_l2_2d(&p.tmA[src2], p.g_c0[g2], r2 + m * kBM);
-              if (p.extra_rows[src2] > 0) tma_prefetch_l2_2d(&p.tmAx[src2], p.g_c0[g2], r2 + MT * kBM);
-            }
-          }
         }
       }
     }
@@ -422,7 +427,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
         uint32_t rel = static_cast<uint32_t>(p.t_rel[0]) * 8u;     // tap view offset in 16-byte units
         for (int g = 0; g < p.n_groups; ++g) {
           if constexpr (PAIR && XF) mbar_wait_cluster(a_ready + sa, pa);   // the peer's transform warps arrive remotely
-          else mbar_wait((XF ? a_ready : a_full) + sa, pa);
+          else mbar_wait(XF ? a_ready + sa : a_full + sa, pa);
           if constexpr (XF) tc_fence_after();
           const uint32_t a_lo0 = umma_desc_lo(smem_u32(smA + sa * p.a_stage_bytes)) +
                                  static_cast<uint32_t>(m_begin * (kBM * 128 / 16));
@@ -458,17 +463,22 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
         }
       }
     }
+  }
   } else if (XF && warp < EPI0) {
     // ------------------------------------------------------------------ transform warps (fused AdaGN + SiLU)
-    // 32 * kXfWarps threads.  thread -> one physical 16-byte granule column gi and the rows rs, rs + kXfRows, ...; all its rows
-    // share (row & 7), so under the 128-byte swizzle it always holds the same logical 8 channels gl = gi ^ (rs & 7).
-    // The 8 lanes of a row share the row bookkeeping: lane gi == 0 computes (valid, image) and broadcasts it.
+    // 32 * kXfWarps threads.  thread -> one physical 16-byte granule column gi and the rows rs, rs + kXfRows, ...; all
+    // its rows share (row & 7), so under the 128-byte swizzle it always holds the same logical 8 channels
+    // gl = gi ^ (rs & 7).  Per halo the warps first fill a small row table (image of the row relative to the halo's
+    // first image, -1 for pad / out-of-range rows) -- each row classified once instead of by every granule's thread --
+    // and then stream the halo: one table read, one 16-byte load, 8 x (FMA, tanh, FMA), one 16-byte store per granule.
+    // (The first version classified rows inside the streaming loop with float divisions and group shuffles:
+    // 114 instructions per granule, and the ncu samples showed the UMMA issuers waiting for these warps 63 % of the time.)
+    constexpr int NXT = 32 * kXfWarps;
     const int tt = threadIdx.x;
     const int gi = tt & 7, rs = tt >> 3;
     const int gl = gi ^ (rs & 7);
-    const unsigned grp_mask = 0xffu << (lane & 24);
-    const int grp_lead = lane & 24;
-    const float inv_wp = 1.0f / static_cast<float>(p.Wp), inv_hp = 1.0f / static_cast<float>(p.Hp);
+    const float inv_wp = 1.0f / static_cast<float>(p.Wp), inv_R = 1.0f / static_cast<float>(p.Hp * p.Wp);
+    const int R = p.Hp * p.Wp;
     const bool do_silu = p.xf_silu != 0 && p.xf_debug != 2;
     const float cs = do_silu ? 0.5f : 1.0f;          // SiLU(v) = h + h*tanh(h), h = v/2: fold the 1/2 into (A, B)
     const int rows32 = static_cast<int>(p.rows);
@@ -476,136 +486,35 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
     uint32_t pa = 0;
     int cur = -1, cur_cb = -1;           // (image, channel slice) of the coefficients held in A[], B[]
     float A[8], B[8];
-    if (p.xf_ldg != 0) {
-      // ---- direct-load variant: global -> registers -> act(A*x + B) -> ONE st.shared into the swizzled operand tile.
-      // The MMAs saturate the shared-memory bandwidth, so the in-place variant's extra ld.shared + st.shared pass is
-      // paid in full (measured: +1.0 ms per UNet evaluation at batch 256); here the only shared-memory traffic is the
-      // write the TMA would have done anyway.  thread -> logical 16-byte channel granule gi (8 channels) and the halo
-      // rows rs, rs + kXfRows, ...; physical granule = gi ^ (row & 7) = gi ^ (rs & 7) (kXfRows % 8 == 0).
-      // Loads run one "quad" (4 rows) ahead of the arithmetic; a quad of the NEXT halo is requested before the last
-      // quad of this one is transformed, so the global latency overlaps the MMAs of the previous stage.
-      const uint32_t phys = static_cast<uint32_t>((gi ^ (rs & 7)) << 4);
-      struct Cur { int st, g, q, nq, nrows, rbase, cb; uint32_t sa, pa; const bf16* col; int ld; bool ok; };
-      auto setup = [&](Cur& c) {          // fill the derived fields for (st, g); c.ok = false past the end
-        c.ok = c.st < total;
-        if (!c.ok) return;
-        const int ms = c.st / p.n_tiles;
-        const int src = p.g_src[c.g];
-        c.cb = p.g_xf[c.g];
-        c.nrows = MT * kBM + p.extra_rows[src];
-        c.rbase = (ms * PW + static_cast<int>(rank)) * (MT * kBM) + p.g_lo[c.g];
-        c.nq = c.cb >= 0 ? (c.nrows + 4 * kXfRows - 1) / (4 * kXfRows) : 1;
-        c.ld = p.src_ld[src];
-        c.col = p.srcp[src] + p.g_c0[c.g] + gi * 8;
-      };
-      auto advance = [&](Cur& c) {        // next quad; next group / item when the halo is complete
-        if (++c.q < c.nq) return;
-        c.q = 0;
-        if (++c.sa == AS) { c.sa = 0; c.pa ^= 1u; }
-        if (++c.g == p.n_groups) { c.g = 0; c.st += n_units; }
-        setup(c);
-      };
-      auto load = [&](const Cur& c, uint4 (&u)[4]) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int i = rs + kXfRows * (4 * c.q + k);
-          const int r = c.rbase + i;
-          u[k] = make_uint4(0, 0, 0, 0);
-          if (c.cb >= 0 && i < c.nrows && r >= 0 && r < rows32) {
-            const bf16* src = c.col + static_cast<int64_t>(r) * c.ld;
-            asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(u[k].x), "=r"(u[k].y), "=r"(u[k].z), "=r"(u[k].w) : "l"(src));
-          }
-        }
-      };
-      Cur c;
-      c.st = unit0; c.g = 0; c.q = 0; c.sa = 0; c.pa = 0;
-      setup(c);
-      uint32_t full_par = 0;      // bit s = phase parity of a_full[s]: that barrier only cycles for the TMA-loaded (raw) halos
-      uint4 u[4], un[4];
-      if (c.ok) load(c, u);
-      while (c.ok) {
-        Cur n = c;
-        advance(n);
-        if (n.ok) load(n, un);
-        if (c.cb < 0) {
-          mbar_wait(a_full + c.sa, (full_par >> c.sa) & 1u);      // raw halo: the A producer's TMA wrote it
-          full_par ^= 1u << c.sa;
-        } else {
-          if (c.cb != cur_cb) { cur = -1; cur_cb = c.cb; }
-          if (c.q == 0) mbar_wait(a_empty + c.sa, c.pa ^ 1u);     // the MMAs are done with this stage
-          const uint32_t base = smem_u32(smA + c.sa * p.a_stage_bytes) + phys;
-          const float2* ctab = p.xf_coef + c.cb + gi * 8;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int i = rs + kXfRows * (4 * c.q + k);
-            int inf = -1;                                            // -1: the row must hold zeros
-            if (gi == 0 && i < c.nrows) {
-              const int r = c.rbase + i;
-              if (r >= 0 && r < rows32) {
-                const int rq = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_wp);
-                const int x = r - rq * p.Wp;
-                const int img = __float2int_rd((static_cast<float>(rq) + 0.5f) * inv_hp);
-                const int y = rq - img * p.Hp;
-                if (x < p.W && y < p.H) inf = img;
-              }
-            }
-            inf = __shfl_sync(grp_mask, inf, grp_lead);
-            if (i >= c.nrows) continue;
-            uint4 o = make_uint4(0, 0, 0, 0);
-            if (inf >= 0) {
-              if (inf != cur) {
-                cur = inf;
-                const float4* c4 = reinterpret_cast<const float4*>(ctab + static_cast<int64_t>(inf) * p.xf_ctot);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float4 cc = __ldg(c4 + j);
-                  A[2 * j] = cc.x * cs; B[2 * j] = cc.y * cs; A[2 * j + 1] = cc.z * cs; B[2 * j + 1] = cc.w * cs;
-                }
-              }
-              const float2 a0 = unpack_bf16x2(u[k].x), a1 = unpack_bf16x2(u[k].y), a2 = unpack_bf16x2(u[k].z), a3 = unpack_bf16x2(u[k].w);
-              float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-              if (do_silu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float h = fmaf(f[j], A[j], B[j]);
-                  float th;
-                  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-                  f[j] = fmaf(h, th, h);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], A[j], B[j]);
-              }
-              o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-            }
-            sts128(base + static_cast<uint32_t>(i) * 128u, o);
-          }
-        }
-        if (c.q == c.nq - 1) {                        // halo complete: hand the stage to the UMMA issuers
-          if (c.cb >= 0) fence_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(a_ready + c.sa), 0));
-            else mbar_arrive(a_ready + c.sa);
-          }
-        }
-        c = n;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) u[k] = un[k];
-      }
-    } else
     for (int st = unit0; st < total; st += n_units) {
       const int ms = st / p.n_tiles;
       const int row0 = (ms * PW + static_cast<int>(rank)) * (MT * kBM);
       for (int g = 0; g < p.n_groups; ++g) {
         const int cb = p.g_xf[g];
         if (cb != cur_cb) { cur = -1; cur_cb = cb; }
+        const int nrows = MT * kBM + p.extra_rows[p.g_src[g]];
+        const int rbase = row0 + p.g_lo[g];
+        const uint32_t tab = rowtab_sa + static_cast<uint32_t>(sa) * (2u * kXfMaxRows);
+        const int rfirst = rbase < 0 ? 0 : rbase;
+        const int img0 = __float2int_rd((static_cast<float>(rfirst) + 0.5f) * inv_R);     // image of the halo's first row
+        if (cb >= 0 && p.xf_debug != 1) {
+          // ---- row table (exact float reciprocals: all quotients < 2^22), while the TMA load is still in flight
+          for (int i = tt; i < nrows; i += NXT) {
+            const int r = rbase + i;
+            int inf = -1;
+            if (r >= 0 && r < rows32) {                              // outside the tensor: TMA wrote zeros
+              const int img = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_R);
+              const int rr = r - img * R;
+              const int y = __float2int_rd((static_cast<float>(rr) + 0.5f) * inv_wp);
+              const int x = rr - y * p.Wp;
+              if (x < p.W && y < p.H) inf = img - img0;               // pad rows hold zeros and must keep them
+            }
+            sts16(tab + 2u * static_cast<uint32_t>(i), static_cast<uint16_t>(inf));
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(NXT) : "memory");      // the transform warps only
+        }
         mbar_wait(a_full + sa, pa);
         if (cb >= 0 && p.xf_debug != 1) {
-          const int nrows = MT * kBM + p.extra_rows[p.g_src[g]];
-          const int rbase = row0 + p.g_lo[g];
           const uint32_t base = smem_u32(smA + sa * p.a_stage_bytes) + static_cast<uint32_t>(gi * 16);
           const float2* ctab = p.xf_coef + cb + gl * 8;
           auto reload = [&](int img) {
@@ -617,72 +526,33 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
               A[2 * j] = c.x * cs; B[2 * j] = c.y * cs; A[2 * j + 1] = c.z * cs; B[2 * j + 1] = c.w * cs;
             }
           };
-          auto xform = [&](const uint4& u) -> uint4 {
-            if (p.xf_debug == 4) return u;          // measurement only: shared-memory round trip without arithmetic
-            const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-            float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-            if (do_silu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float h = fmaf(f[j], A[j], B[j]);
-                float th;
-                asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-                f[j] = fmaf(h, th, h);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], A[j], B[j]);
-            }
-            uint4 o;
-            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-            return o;
-          };
-          // four rows per trip: row bookkeeping and all four loads first, then branch-free arithmetic with predicated
-          // stores when the rows share one image (the common case); rows of different images fall back to one by one
-          for (int i0 = rs; i0 < nrows && p.xf_debug != 3; i0 += 4 * kXfRows) {   // xf_debug 3: fence only
-            int info[4];
-            uint4 u[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int i = i0 + kXfRows * q;
-              int inf = -1;                                            // -1: leave the row alone
-              if (gi == 0 && i < nrows) {
-                const int r = rbase + i;
-                if (r >= 0 && r < rows32) {                            // outside the tensor: TMA wrote zeros
-                  const int rq = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_wp);
-                  const int x = r - rq * p.Wp;
-                  const int img = __float2int_rd((static_cast<float>(rq) + 0.5f) * inv_hp);
-                  const int y = rq - img * p.Hp;
-                  if (x < p.W && y < p.H) inf = img;                   // pad rows hold zeros and must keep them
-                }
-              }
-              info[q] = __shfl_sync(grp_mask, inf, grp_lead);
-              u[q] = lds128(base + static_cast<uint32_t>(min(i, nrows - 1)) * 128u);
-            }
-            int want = -1;
-#pragma unroll
-            for (int q = 3; q >= 0; --q) want = info[q] >= 0 ? info[q] : want;
-            if (want < 0) continue;
-            if (want != cur) reload(want);
-            bool uniform = true;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) uniform = uniform && (info[q] < 0 || info[q] == cur);
-            if (uniform) {
+          // four rows per trip: table entries and the four loads first, then the arithmetic row by row; the loop exists
+          // twice so that the activation is not a per-element branch.  (A variant that ran the four rows as 32
+          // independent chains in straight-line code with predicated stores measured the same at 64^2 and worse on
+          // the small maps, whose trips often cross an image boundary; 12 instead of 8 warps measured the same too:
+          // the transform is bound by the shared-memory port it shares with the tensor core, not by issue slots.)
+          auto stream = [&](auto silu_tag) {
+            constexpr bool SILU = decltype(silu_tag)::value;
+#pragma unroll 1
+            for (int i0 = rs; i0 < nrows; i0 += 4 * kXfRows) {
+              int info[4];
+              uint4 u[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const uint4 o = xform(u[q]);
-                if (info[q] >= 0) sts128(base + static_cast<uint32_t>(i0 + kXfRows * q) * 128u, o);
+                const int i = i0 + kXfRows * q;
+                const int ic = i < nrows ? i : i0;                    // clamp: the duplicate is never stored
+                info[q] = i < nrows ? lds_s16(tab + 2u * static_cast<uint32_t>(ic)) : -1;
+                u[q] = lds128(base + static_cast<uint32_t>(ic) * 128u);
               }
-            } else {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 if (info[q] < 0) continue;
-                if (info[q] != cur) reload(info[q]);
-                sts128(base + static_cast<uint32_t>(i0 + kXfRows * q) * 128u, xform(u[q]));
+                if (info[q] + img0 != cur) reload(info[q] + img0);
+                sts128(base + static_cast<uint32_t>(i0 + kXfRows * q) * 128u, xf_apply<SILU>(u[q], A, B));
               }
             }
-          }
+          };
+          if (do_silu) stream(std::true_type{}); else stream(std::false_type{});
           fence_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
         }
         __syncwarp();
@@ -694,7 +564,8 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
       }
     }
   } else if (warp >= EPI0 && warp < EPI0 + 8) {
-    // ------------------------------------------------------------------ epilogue (8 warps)
+    // ------------------------------------------------------------------ epilogue: 8 drain warps
+    if constexpr (XF) reg_inc<112>();
     const int e = warp - EPI0;
     const int q = e & 3;      // TMEM lane quarter (== warp % 4)
     const int half = e >> 2;  // which half of the (m, chunk) work items
@@ -782,7 +653,9 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
       if constexpr (BN < 32) release_acc(as);
     }
     if (BN >= 32 && lane == 0) bulk_wait<0>();     // this warp's TMA stores have been performed
-  } else if (BN >= 32 && warp >= STAT0 && warp < STAT0 + 4) {
+  } else if (warp >= STAT0 && warp < STAT0 + 4) {
+    if constexpr (XF) reg_dec<56>();
+    if constexpr (BN >= 32) {
     // ------------------------------------------------------------------ statistics (4 warps, one per lane quarter)
     // follows the two drain warps of its quarter through the same item sequence and takes the GroupNorm partial sums
     // of every tile they stage; it runs even when no statistics are wanted so that the tile hand-shake stays in step
@@ -811,6 +684,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
         }
       }
     }
+    }
   }
 
   tc_fence_before();
@@ -826,7 +700,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
 template <int BN, int MT, bool XF, bool PAIR>
 static cudaError_t launch_cfg(const ConvKernelParams& p, int grid, cudaStream_t stream) {
   using Cfg = HaloCfg<BN, MT, PAIR>;
-  const uint32_t smem = conv_smem_bytes(p.a_stage_bytes, Cfg::A_STAGES, Cfg::B_STAGES, Cfg::B_BYTES);
+  const uint32_t smem = conv_smem_bytes(p.a_stage_bytes, Cfg::A_STAGES, Cfg::B_STAGES, Cfg::B_BYTES, XF);
   static uint32_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, MT, XF, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -890,8 +764,8 @@ cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, bo
 }
 
 // shared-memory need of a configuration (host side, for plan validation)
-uint32_t conv_config_smem(int block_n, int a_stage_bytes, bool pair) {
-  return conv_smem_bytes(a_stage_bytes, 2, conv_b_stages(block_n), block_n * kBK * 2 / (pair ? 2 : 1));
+uint32_t conv_config_smem(int block_n, int a_stage_bytes, bool pair, bool xf) {
+  return conv_smem_bytes(a_stage_bytes, 2, conv_b_stages(block_n), block_n * kBK * 2 / (pair ? 2 : 1), xf);
 }
 
 }  // namespace idf

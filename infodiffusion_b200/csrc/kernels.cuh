@@ -35,7 +35,6 @@ struct alignas(64) ConvKernelParams {
                                         // [m_tiles*4 (32-row windows)][out_ld][2] fp32 (sum, sumsq)
   int64_t stats_b_off;                  // float offset of the B records
   int32_t debug_skip_epilogue;          // measurement only: epilogue warps drain nothing (main-loop ceiling)
-  int32_t l2_prefetch;                  // A producer issues L2 prefetches two halo loads ahead
   int64_t rows;
   int32_t Hp, Wp, H, W;
   int32_t cout;
@@ -57,11 +56,6 @@ struct alignas(64) ConvKernelParams {
   int32_t xf_silu;
   int32_t g_xf[kMaxGroups];             // channel base of the group's 64-channel slice in xf_coef, or -1
   int32_t xf_debug;                     // measurement only (idf_set_option "xf_debug")
-  // direct-load transform (xf_ldg != 0): the transform warps read the halo of a fused-AdaGN group straight from global
-  // memory into registers and store act(A*x + B) ONCE into the swizzled operand tile -- no TMA write + read + rewrite
-  int32_t xf_ldg;
-  const bf16* srcp[IDF_CONV_MAX_SRC];   // raw source pointers / row pitches (elements) for those loads
-  int32_t src_ld[IDF_CONV_MAX_SRC];
 };
 
 constexpr int kWgMaxUnits = 64;
@@ -80,7 +74,7 @@ cudaError_t launch_wgrad(const WgradKernelParams& p, int grid, cudaStream_t stre
 static_assert(sizeof(ConvKernelParams) <= 4000, "kernel parameters are limited to 4 KB");
 cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, bool xform, bool pair, int grid, cudaStream_t stream);
 cudaError_t launch_adagn_coef(const idf_adagn_args& a, float* coef_out, cudaStream_t stream);
-uint32_t conv_config_smem(int block_n, int a_stage_bytes, bool pair = false);
+uint32_t conv_config_smem(int block_n, int a_stage_bytes, bool pair, bool xf);
 cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream);
 cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, int num_sms, cudaStream_t stream);
 int64_t adagn_bwd_ws_floats(int batch, int C);

@@ -46,6 +46,11 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ int lds_s16(uint32_t a) {      // sign-extended 16-bit load
+  int v;
+  asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ float2 lds_f2(uint32_t a) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
@@ -257,8 +262,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Remote arrive with the default (.release.cta) semantics, as CUTLASS's ClusterBarrier::arrive does for its 2-SM
+// transform pipelines: what it publishes are shared-memory writes of THIS CTA made visible to the async proxy by
+// fence.proxy.async beforehand and read by the pair's tensor core, not by the waiting thread.  (The .release.cluster
+// form compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR, several hundred cycles per arrive.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // arrive without release semantics: for signals that publish no memory writes (e.g. "accumulator drained": the TMEM
 // reads completed with tcgen05.wait::ld and the data lives in registers).  The .release.cluster form costs a
@@ -270,13 +279,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_a
   asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
                : "memory");
 }
-// wait that also acquires writes released by the peer CTA (remote arrives)
+// wait on a barrier of this CTA that the peer CTA signals with remote arrives
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
@@ -381,6 +390,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N, ui
   return (1u << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1;
+
+// Per-warpgroup register reallocation (all 4 warps of the warpgroup execute it): dec releases registers to the CTA's
+// pool, inc blocks until the pool can supply them.
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---------------------------------------------------------------------------------------------
 // small numeric helpers

@@ -21,7 +21,7 @@ PAIR_DEFAULT = int(os.environ.get("IDF_CONV_PAIR", "1"))
 _lib.check(lib.idf_set_option(b"conv_pair", PAIR_DEFAULT))
 
 
-def make(cin, cout, H, residual, stats, skip):
+def make(cin, cout, H, residual, stats, skip, xf=False):
     rows = B * (H + 1) * (H + 1)
     x = torch.randn(rows, cin, device=dev).to(BF)
     w = (torch.randn(cout, 9 * cin, device=dev) * 0.02).to(BF)
@@ -44,11 +44,17 @@ def make(cin, cout, H, residual, stats, skip):
         d.residual, d.res_ld = res.data_ptr(), cout
     if st is not None:
         d.stats_out = st.data_ptr()
+    coef = None
+    if xf:      # fused AdaGN on the A operand: per-image (A, B) coefficients, SiLU on
+        coef = torch.stack([1.0 + 0.1 * torch.randn(B, cin, device=dev), 0.1 * torch.randn(B, cin, device=dev)], dim=-1).contiguous()
+        d.xf_coef, d.xf_ctot, d.xf_silu = coef.data_ptr(), cin, 1
+        for k, (si, c0, off) in enumerate(kb):
+            d.kb_xf[k] = c0
     _lib.check(lib.idf_set_option(b"conv_debug_skip_epilogue", int(skip)))
     h = C.c_void_p()
     _lib.check(lib.idf_conv_plan_create(C.byref(d), C.byref(h)))
     _lib.check(lib.idf_set_option(b"conv_debug_skip_epilogue", 0))
-    return h, (x, w, b, out, res, st, d)
+    return h, (x, w, b, out, res, st, d, coef)
 
 
 def timeit(h, n=20):
@@ -77,6 +83,15 @@ def main():
             lib.idf_conv_plan_destroy(h)
             del keep
             line += f"{name} {us:7.1f} ({fl / us / 1e6:6.0f}, {fl / us / 1e6 / PEAK * 100:4.1f}%)  "
+        if os.environ.get("IDF_MB_XF"):
+            for dbg in (0, 4, 1):
+                _lib.check(lib.idf_set_option(b"xf_debug", dbg))
+                h, keep = make(cin, cout, H, False, True, False, xf=True)
+                us = timeit(h)
+                lib.idf_conv_plan_destroy(h)
+                del keep
+                line += f"xf{dbg} {us:7.1f}  "
+            _lib.check(lib.idf_set_option(b"xf_debug", 0))
         # planner's choice against every forced number of 128-row tiles per work unit, as single CTAs and as CTA pairs
         for pair in (() if os.environ.get("IDF_MB_QUICK") else (0, 1)):
             _lib.check(lib.idf_set_option(b"conv_pair", pair))
