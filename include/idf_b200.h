@@ -102,11 +102,15 @@ typedef struct {
   const float* noise;                 /* NCHW fp32 (mode 2; may be NULL => cn ignored)           */
   const float* coef;                  /* [n_steps, 3] fp32 (mode 2)                              */
   const int32_t* step_ptr;            /* device scalar (mode 2)                                  */
-  /* optional (IDF_EPI_BF16): GroupNorm partial sums of the stored (bf16-rounded) output, one record per
-   * 32-row window k = row/32 (windows never span 128-row tiles): fp32 [2][ceil(rows/128)*4][cout][2].
-   *   A[k][c] = (sum, sumsq) over the window's rows in the image of its first row,
-   *   B[k][c] = the same over its rows in the following image (only written if the window straddles).
-   * Consumed by idf_adagn_silu_fwd (stats0 / stats1).                                             */
+  /* optional (IDF_EPI_BF16): GroupNorm partial sums of the stored (bf16-rounded) output, fp32
+   * [2][ceil(rows/128)*4][cout][2] (capacity; the item form below fills a prefix).  Records cover UNITS of
+   * idf_conv_plan_stats_unit(plan) rows:
+   *   unit = 32   one record per 32-row window k = row/32 (windows never span 128-row tiles);
+   *   unit = 128*MT (chosen when an image has at least that many pad-flat rows): 4 records per work item of MT
+   *                 tiles, k = item*4 + q, q = lane quarter (rows 32q..32q+31 of each of the item's tiles).
+   *   A[k][c] = (sum, sumsq) over the record's rows in the image the UNIT starts in,
+   *   B[k][c] = the same over its rows in the following image (only written if the unit straddles).
+   * Consumed by idf_adagn_silu_fwd / idf_adagn_coef (stats0 / stats1 with stats_unit0 / stats_unit1).   */
   float* stats_out;
   /* optional: AdaGN (+SiLU) of the CONSUMED activation fused into the A-operand path (inference): k-blocks with
    * kb_xf[k] >= 0 are read as bf16(act(A*x + B)), (A, B) = xf_coef[image][kb_xf[k] + channel - kb_c0[k]], act = SiLU
@@ -125,6 +129,8 @@ int idf_conv_plan_destroy(idf_conv_plan* plan);
 int idf_conv_run(const idf_conv_plan* plan, idf_stream_t stream);
 /* number of 128-row x block_n tiles a run processes (for roofline accounting) */
 int64_t idf_conv_plan_tiles(const idf_conv_plan* plan);
+/* rows per GroupNorm statistics unit of the records this plan writes to stats_out (32, or 128 * tiles per work item) */
+int32_t idf_conv_plan_stats_unit(const idf_conv_plan* plan);
 
 /* ------------------------------------------------------------------------------------------
  * Convolution weight gradient (autograd of nn.Conv2d w.r.t. weight), tcgen05, split-K with atomics:
@@ -173,6 +179,8 @@ typedef struct {
   /* training only, optional: fp32 [batch, C, 4] = (A, B, group mean, group rstd) per sample and channel with
    * v = A*x + B, written by the forward (streaming variant) and read back by idf_adagn_silu_bwd. */
   float* save_coef;
+  /* rows per statistics unit of stats0 / stats1 (idf_conv_plan_stats_unit of the producing plan); 0 = 32 */
+  int32_t stats_unit0, stats_unit1;
 } idf_adagn_args;
 int idf_adagn_silu_fwd(const idf_adagn_args* args, idf_stream_t stream);
 /* Coefficients only: coef_out[n][c] = (A, B) with AdaGN(x)[n, c, :, :] = A*x + B (before the activation), from the

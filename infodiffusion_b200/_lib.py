@@ -71,6 +71,7 @@ class AdaGNArgs(C.Structure):
         ("stats0", C.c_void_p), ("stats1", C.c_void_p),
         ("dropout_p", C.c_float), ("dropout_seed", C.c_void_p), ("dropout_layer", C.c_uint32),
         ("save_coef", C.c_void_p),
+        ("stats_unit0", C.c_int32), ("stats_unit1", C.c_int32),
     ]
 
 
@@ -108,6 +109,7 @@ SIGNATURES = {
     "idf_conv_plan_destroy": (C.c_int, [C.c_void_p]),
     "idf_conv_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "idf_conv_plan_tiles": (C.c_int64, [C.c_void_p]),
+    "idf_conv_plan_stats_unit": (C.c_int32, [C.c_void_p]),
     "idf_wgrad_plan_create": (C.c_int, [C.POINTER(WgradDesc), C.POINTER(C.c_void_p)]),
     "idf_wgrad_plan_destroy": (C.c_int, [C.c_void_p]),
     "idf_wgrad_run": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -57,7 +57,8 @@ struct AdaGNParams {
   const float* stats0;   // per-tile partial sums from the producing conv (streaming variant)
   const float* stats1;
   int slice_rows;        // rows per CTA of the streaming variant
-  long long stats_b_windows;   // number of 32-row window records (offset of the B records, in records)
+  long long stats_b_windows;   // capacity in records of the A part (offset of the B records, in records)
+  int unit0, unit1;            // rows per statistics unit of stats0 / stats1: 32 (1 record per unit) or 128*MT (4 records)
   int block_rows;              // rows per ring stage of the streaming variant
   int ring;                    // ring stages in use
   int stream_threads;          // streaming variant 2: threads that stream (multiple of C/8)
@@ -272,21 +273,26 @@ __device__ __forceinline__ void fold_coefficients(const AdaGNParams& p, int n, C
   float (&s_mean)[32] = sh.mean;
   float (&s_rstd)[32] = sh.rstd;
   float2 (&s_ab)[MAXC] = sh.ab;
-  // per-channel totals over the 32-row window records that intersect image n.  All 256 threads take
-  // part: thread -> (channel, sub-sequence of windows), loads issued four at a time; the order of every
-  // addition is a function of (n, geometry) only, so the result is deterministic.
-  const int w_first = (n * R) / 32;
-  const int w_last = ((n + 1) * R - 1) / 32;
-  const bool first_straddles = (w_first * 32) < n * R;     // window starts in image n-1: take its B record
+  // per-channel totals over the statistics records that intersect image n (units of 32 rows with one record each, or
+  // of a producer work item with four; see idf_conv_desc.stats_out).  All 256 threads take part: thread -> (channel,
+  // sub-sequence of records), loads issued eight at a time; the order of every addition is a function of
+  // (n, geometry) only, so the result is deterministic.
   const int nsub = (kAdaThreads / C) > 0 ? (kAdaThreads / C) : 1;     // 4, 2, 1, 1 for C = 64, 128, 192, 256
   for (int idx = t; idx < C * nsub; idx += kAdaThreads) {
     const int ch = idx % C, sub = idx / C;
     const bool first = ch < p.c0;
     const int cs = first ? p.c0 : p.c1;
+    const int U = first ? p.unit0 : p.unit1;
+    const int S = U > 32 ? 4 : 1;                           // records per unit
+    const int u_first = (n * R) / U;
+    const int u_last = ((n + 1) * R - 1) / U;
+    const bool first_straddles = (u_first * U) < n * R;     // unit starts in image n-1: take its B records
+    const int w_first = u_first * S, w_last = u_last * S + S - 1;
+    const int w_bend = w_first + S;                         // records below belong to the first unit
     const float2* stA = reinterpret_cast<const float2*>(first ? p.stats0 : p.stats1) + (first ? ch : ch - p.c0);
     const float2* stB = stA + p.stats_b_windows * cs;
     auto part = [&](int w) -> float2 {
-      const float2* st = (w == w_first && first_straddles) ? stB : stA;
+      const float2* st = (w < w_bend && first_straddles) ? stB : stA;
       return __ldg(st + static_cast<long long>(w) * cs);
     };
     float sx = 0.f, sq = 0.f;
@@ -627,6 +633,10 @@ static cudaError_t fill_params(const idf_adagn_args& a, AdaGNParams& p) {
   p.drop_layer = a.dropout_layer;
   p.save_coef = a.save_coef;
   p.stats_b_windows = (static_cast<long long>(a.batch) * p.rows_per_img + kBM - 1) / kBM * 4;
+  p.unit0 = a.stats_unit0 > 0 ? a.stats_unit0 : 32;
+  p.unit1 = a.stats_unit1 > 0 ? a.stats_unit1 : 32;
+  if (p.unit0 > p.rows_per_img && p.unit0 > 32) return cudaErrorInvalidValue;    // a unit may span at most two images
+  if (p.unit1 > p.rows_per_img && p.unit1 > 32) return cudaErrorInvalidValue;
   return cudaSuccess;
 }
 
@@ -658,6 +668,9 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
     p.drop_scale = 65536.f / (65536.f - static_cast<float>(p.drop_thr16));
   }
   p.stats_b_windows = (static_cast<long long>(a.batch) * p.rows_per_img + kBM - 1) / kBM * 4;
+  p.unit0 = a.stats_unit0 > 0 ? a.stats_unit0 : 32;
+  p.unit1 = a.stats_unit1 > 0 ? a.stats_unit1 : 32;
+  if ((p.unit0 > 32 && p.unit0 > p.rows_per_img) || (p.unit1 > 32 && p.unit1 > p.rows_per_img)) return cudaErrorInvalidValue;
   if (g_adagn_impl == 2 && p.C <= kMaxC && p.stats0 != nullptr && (p.c1 == 0 || p.stats1 != nullptr)) {
     // streaming variant 2: a CTA owns whole image rows; enough CTAs for >= 4 per SM, each with >= 16 KB to stream
     const int VPR = p.C / 8;

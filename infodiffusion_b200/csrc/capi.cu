@@ -35,6 +35,7 @@ int g_num_sms = 0;
 int g_attn_impl = 2;
 int g_force_mt = 0;   // 0 = choose automatically
 int g_skip_epilogue = 0;
+int g_stats_item = 1;  // GroupNorm partials per work item instead of per 32-row window (idf_set_option "stats_item")
 int g_conv_pair = 1;  // conv kernels with N >= 64 run as CTA pairs (idf_set_option "conv_pair", 0 = single CTAs)
 
 int ensure_init() {
@@ -98,6 +99,7 @@ struct idf_conv_plan {
   int grid;
   bool xform;  // some halo group carries a fused AdaGN: launch the variant with transform warps
   bool pair;   // launched as clusters of two CTAs (tcgen05 cta_group::2)
+  int stats_unit;  // rows per GroupNorm statistics unit of the records written to stats_out
   int64_t tiles;
 };
 
@@ -120,6 +122,7 @@ int idf_set_option(const char* key, int32_t value) {
     g_skip_epilogue = value ? 1 : 0;
     return IDF_OK;
   }
+  if (key != nullptr && std::strcmp(key, "stats_item") == 0 && (value == 0 || value == 1)) { g_stats_item = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "conv_pair") == 0 && (value == 0 || value == 1)) { g_conv_pair = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "pdl") == 0) { g_pdl = value ? 1 : 0; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "xf_debug") == 0 && value >= 0 && value <= 4) { g_xf_debug = value; return IDF_OK; }
@@ -256,6 +259,10 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   p.debug_skip_epilogue = g_skip_epilogue;
   p.stats = (d->epilogue == IDF_EPI_BF16) ? d->stats_out : nullptr;
   p.stats_b_off = static_cast<int64_t>(m_tiles) * 4 * d->cout * 2;
+  // item-level records when a work item spans at most two images
+  p.stats_item = (p.stats != nullptr && g_stats_item != 0 && d->block_n >= 64 &&
+                  static_cast<int64_t>(p.Hp) * p.Wp >= static_cast<int64_t>(mt) * kBM) ? 1 : 0;
+  pl->stats_unit = p.stats_item ? mt * kBM : 32;
   if (p.stats != nullptr && d->out_ld != d->cout) { delete pl; return fail(IDF_ERR_ARG, "stats_out needs out_ld == cout"); }
   for (int i = 0; i < d->n_src; ++i) {
     rc = encode_2d(&p.tmA[i], d->src[i], d->src_rows[i], d->src_ld[i], kBM);
@@ -308,6 +315,10 @@ int idf_conv_plan_destroy(idf_conv_plan* plan) {
 
 int64_t idf_conv_plan_tiles(const idf_conv_plan* plan) {
   return plan ? plan->tiles : 0;
+}
+
+int32_t idf_conv_plan_stats_unit(const idf_conv_plan* plan) {
+  return plan ? plan->stats_unit : 0;
 }
 
 int idf_conv_run(const idf_conv_plan* plan, idf_stream_t stream) {

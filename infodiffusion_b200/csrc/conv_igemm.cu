@@ -201,6 +201,40 @@ __device__ __forceinline__ void epilogue_stats_chunk(const ConvKernelParams& p, 
   if (lane == 0) mbar_arrive(sdone);
 }
 
+// Item-level statistics: the same column sums accumulated over ALL tiles of a work item (lane -> column pair and row
+// parity as above); a[0..3] = (sum0, sumsq0, sum1, sumsq1) of the rows before `n_a` (record A), a[4..7] of the rest.
+__device__ __forceinline__ void epilogue_stats_accum(uint32_t stage, int n_a, int lane, uint64_t* staged, uint64_t* sdone,
+                                                     uint32_t use, bool active, float (&a)[8]) {
+  mbar_wait(staged, use & 1u);
+  if (active) {
+    const int cp = lane & 15, hh = lane >> 4;
+    const uint32_t col_b = static_cast<uint32_t>((cp & 3) * 4);
+    const int cch = cp >> 2;
+    uint32_t raw[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      raw[i] = lds32(stage + static_cast<uint32_t>((2 * i + hh) * 64 + ((cch ^ (i & 3)) << 4)) + col_b);
+    if (n_a >= 32) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 w = unpack_bf16x2(raw[i]);
+        a[0] += w.x; a[2] += w.y; a[1] = fmaf(w.x, w.x, a[1]); a[3] = fmaf(w.y, w.y, a[3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 w = unpack_bf16x2(raw[i]);
+        if (2 * i + hh < n_a) { a[0] += w.x; a[2] += w.y; a[1] = fmaf(w.x, w.x, a[1]); a[3] = fmaf(w.y, w.y, a[3]); }
+        else                  { a[4] += w.x; a[6] += w.y; a[5] = fmaf(w.x, w.x, a[5]); a[7] = fmaf(w.y, w.y, a[7]); }
+      }
+    }
+  }
+  // all shared-memory loads above have been consumed by the additions: the tile may be rewritten
+  asm volatile("" ::"f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]) : "memory");
+  __syncwarp();
+  if (lane == 0) mbar_arrive(sdone);
+}
+
 __device__ __forceinline__ void epilogue_narrow(const ConvKernelParams& p, const uint32_t (&v)[16], int img, int y,
                                                 int x, float cx, float ce, float cn) {
   const int64_t plane = static_cast<int64_t>(p.H) * p.W;
@@ -664,7 +698,52 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
     const int R = p.Hp * p.Wp;
     const float inv_R = 1.0f / static_cast<float>(R);
     uint32_t k = 0;          // items per drain warp so far (both drain warps of a quarter advance in lock step)
-    if (!p.debug_skip_epilogue) {
+    if (!p.debug_skip_epilogue && p.stats_item != 0) {
+      // one record per (work item, lane quarter) instead of one per 32-row window: MT times fewer records to write
+      // here and to reduce in the consumer's prologue.  Used when an item spans at most two images (rows per image
+      // >= rows per item); record index = item * 4 + q, A / B split at the end of the image the ITEM starts in.
+      for (int st = unit0; st < total; st += n_units) {
+        const int ms = (st / p.n_tiles) * PW + static_cast<int>(rank);
+        const int nt = st % p.n_tiles;
+        const int64_t item_row0 = static_cast<int64_t>(ms) * (MT * kBM);
+        const int img_i = __float2int_rd((static_cast<float>(item_row0) + 0.5f) * inv_R);
+        const int64_t boundary = static_cast<int64_t>(img_i + 1) * R;
+        const bool active = p.stats != nullptr && item_row0 < p.rows;
+        float acc[CHUNKS][8];
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+#pragma unroll 1
+        for (int m = 0; m < MT; ++m) {
+          const int64_t wr0 = item_row0 + m * kBM + q * 32;
+          const int64_t left = boundary - wr0;
+          const int n_a = left >= 32 ? 32 : (left <= 0 ? 0 : static_cast<int>(left));
+#pragma unroll
+          for (int c = 0; c < CHUNKS; ++c) {
+            const uint32_t kk = k + static_cast<uint32_t>(c >> 1);
+            const uint32_t sl = 2u * ((c & 1) * 4 + q) + (kk & 1u);
+            epilogue_stats_accum(stage_sa + sl * kStageTile, n_a, lane, staged + sl, sdone + sl, kk >> 1, active, acc[c]);
+          }
+          k += CHUNKS / 2;
+        }
+        if (active) {
+          const int cp = lane & 15, hh = lane >> 4;
+          const bool straddles = boundary < item_row0 + MT * kBM;
+#pragma unroll
+          for (int c = 0; c < CHUNKS; ++c) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[c][j] += __shfl_xor_sync(0xffffffffu, acc[c][j], 16);   // even + odd rows
+            if (hh == 0) {
+              const int64_t rec = (static_cast<int64_t>(ms) * 4 + q) * p.out_ld + nt * BN + c * 32 + 2 * cp;
+              *reinterpret_cast<float4*>(p.stats + 2 * rec) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+              if (straddles)
+                *reinterpret_cast<float4*>(p.stats + p.stats_b_off + 2 * rec) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+            }
+          }
+        }
+      }
+    } else if (!p.debug_skip_epilogue) {
       for (int st = unit0; st < total; st += n_units) {
         const int ms = (st / p.n_tiles) * PW + static_cast<int>(rank);
         const int nt = st % p.n_tiles;

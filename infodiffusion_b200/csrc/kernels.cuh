@@ -34,6 +34,7 @@ struct alignas(64) ConvKernelParams {
   float* stats;                         // optional GroupNorm partial sums: records A then records B, each
                                         // [m_tiles*4 (32-row windows)][out_ld][2] fp32 (sum, sumsq)
   int64_t stats_b_off;                  // float offset of the B records
+  int32_t stats_item;                   // 1: one record per (work item of MT tiles, lane quarter) instead of per window
   int32_t debug_skip_epilogue;          // measurement only: epilogue warps drain nothing (main-loop ceiling)
   int64_t rows;
   int32_t Hp, Wp, H, W;

@@ -51,12 +51,13 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 # ------------------------------------------------------------------------------------------------
 class Act:
     """A pad-flat bf16 activation buffer [phases * B*(H+1)*(W+1), C]."""
-    __slots__ = ("t", "H", "C", "phases", "rows", "stats", "has_stats")
+    __slots__ = ("t", "H", "C", "phases", "rows", "stats", "has_stats", "stats_unit")
 
     def __init__(self, t, H, C, phases, rows):
         self.t, self.H, self.C, self.phases, self.rows = t, H, C, phases, rows
-        self.stats = None          # fp32 [2, ceil(rows/128)*4, C, 2] GroupNorm window partial sums (conv epilogues)
+        self.stats = None          # fp32 [2, ceil(rows/128)*4, C, 2] GroupNorm partial sums (conv epilogues)
         self.has_stats = False     # True while `stats` describes the current contents of `t`
+        self.stats_unit = 32       # rows per statistics unit of the records in `stats` (idf_conv_plan_stats_unit)
 
     def stats_buffer(self) -> torch.Tensor:
         if self.stats is None:
@@ -328,6 +329,8 @@ class Plan:
         self.conv_plans.append(h)
         self.keep.append(d)
         self.conv_tiles += int(self.lib.idf_conv_plan_tiles(h))
+        if out is not None and want_stats:
+            out.stats_unit = int(self.lib.idf_conv_plan_stats_unit(h))
         macs = real_macs_per_row if real_macs_per_row is not None else 64 * len(kblocks) * cout
         self._emit("conv_igemm", self.lib.idf_conv_run, (h,), flops=2 * self.B * H * H * macs)
 
@@ -340,9 +343,9 @@ class Plan:
             Cc = src0.C + (src1.C if src1 is not None else 0)
             a = AdaGNArgs()
             a.c0 = src0.C
-            a.stats0 = src0.stats.data_ptr()
+            a.stats0, a.stats_unit0 = src0.stats.data_ptr(), src0.stats_unit
             if src1 is not None:
-                a.c1, a.stats1 = src1.C, src1.stats.data_ptr()
+                a.c1, a.stats1, a.stats_unit1 = src1.C, src1.stats.data_ptr(), src1.stats_unit
             a.batch, a.H, a.W = self.B, src0.H, src0.H
             gamma, beta = self.f32(lambda: pv(gn.weight)), self.f32(lambda: pv(gn.bias))
             a.gamma, a.beta, a.eps = gamma.data_ptr(), beta.data_ptr(), float(gn.eps)
@@ -401,9 +404,9 @@ class Plan:
         a.step_ptr = _ptr(step)
         a.apply_silu = 1 if silu else 0
         if src0.has_stats and (src1 is None or src1.has_stats):
-            a.stats0 = src0.stats.data_ptr()
+            a.stats0, a.stats_unit0 = src0.stats.data_ptr(), src0.stats_unit
             if src1 is not None:
-                a.stats1 = src1.stats.data_ptr()
+                a.stats1, a.stats_unit1 = src1.stats.data_ptr(), src1.stats_unit
         if dropout and self.training and self.dropout_p > 0:
             self._drop_layers += 1
             a.dropout_p, a.dropout_seed, a.dropout_layer = self.dropout_p, self.dropout_seed.data_ptr(), self._drop_layers

@@ -83,7 +83,24 @@ def tile_partials(m, B, H, W):
     return out.reshape(2, nwin, Cc, 2).contiguous()
 
 
-def run_conv(lib, srcs, kblocks, wp, bias, B, H, cout, block_n, residual=None, epilogue=0, **extra):
+def unit_partials(m, B, H, W, unit):
+    """The same for work-item units (idf_conv_desc.stats_out, unit = 128 * MT rows): record k = item * 4 + q sums the
+    rows 32q..32q+31 of each of the item's 128-row tiles, A = rows in the image the ITEM starts in, B = the rest."""
+    rows, Cc = m.shape
+    R = (H + 1) * (W + 1)
+    nwin = (rows + 127) // 128 * 4
+    r = torch.arange(rows, device=m.device)
+    item = r // unit
+    k = item * 4 + (r % 128) // 32
+    which = (r // R) - ((item * unit) // R)
+    v = m.float()
+    out = torch.zeros(2 * nwin, Cc, 2, device=m.device)
+    out[:, :, 0].index_add_(0, which * nwin + k, v)
+    out[:, :, 1].index_add_(0, which * nwin + k, v * v)
+    return out.reshape(2, nwin, Cc, 2).contiguous()
+
+
+def run_conv(lib, srcs, kblocks, wp, bias, B, H, cout, block_n, residual=None, epilogue=0, info=None, **extra):
     from infodiffusion_b200._lib import ConvDesc
     d = ConvDesc()
     d.n_src = len(srcs)
@@ -107,6 +124,8 @@ def run_conv(lib, srcs, kblocks, wp, bias, B, H, cout, block_n, residual=None, e
     check(lib.idf_conv_plan_create(C.byref(d), C.byref(h)))
     check(lib.idf_conv_run(h, stream()))
     torch.cuda.synchronize()
+    if info is not None:
+        info["stats_unit"] = int(lib.idf_conv_plan_stats_unit(h))
     lib.idf_conv_plan_destroy(h)
     return out
 
@@ -177,9 +196,12 @@ def test_conv3x3_large_auto_tiles(lib):
         assert_close(unpf(out, B, H, H), ref, what=f"conv3x3 {cin}->{cout}@{H} B={B}")
 
 
-@pytest.mark.parametrize("cin,cout,H,B,mt", [(64, 64, 16, 3, 0), (128, 128, 8, 7, 0), (64, 128, 8, 5, 2), (64, 64, 32, 2, 4)])
-def test_conv_epilogue_groupnorm_partials(lib, cin, cout, H, B, mt):
-    """stats_out of the conv epilogue == per-tile (sum, sumsq) of the bf16 output it stored."""
+@pytest.mark.parametrize("item", [0, 1])
+@pytest.mark.parametrize("cin,cout,H,B,mt", [(64, 64, 16, 3, 0), (128, 128, 8, 7, 0), (64, 128, 8, 5, 2), (64, 64, 32, 2, 4),
+                                             (64, 64, 16, 5, 2), (128, 128, 32, 3, 2), (64, 64, 64, 2, 4), (128, 128, 16, 9, 1)])
+def test_conv_epilogue_groupnorm_partials(lib, cin, cout, H, B, mt, item):
+    """stats_out of the conv epilogue == (sum, sumsq) of the bf16 output it stored, per 32-row window or -- when an
+    image has at least as many rows as a work item -- per (work item, lane quarter)."""
     from infodiffusion_b200 import layout
     g = torch.Generator(device=DEV).manual_seed(300 + cin + cout + H)
     x = rbf(torch.randn(B, cin, H, H, device=DEV, generator=g))
@@ -189,15 +211,26 @@ def test_conv_epilogue_groupnorm_partials(lib, cin, cout, H, B, mt):
     nwin = (rows + 127) // 128 * 4
     stats = torch.zeros(2, nwin, cout, 2, device=DEV)
     stats[0] = float("nan")                        # every A record must be written; B records only when straddling
+    info = {}
     check(lib.idf_set_option(b"conv_force_mt", mt))
+    check(lib.idf_set_option(b"stats_item", item))
     try:
         out = run_conv(lib, [pf(x)], layout.taps3x3(cin, H, H), layout.pack_conv3x3(w).to(BF).contiguous(), b, B, H,
-                       cout, 128 if cout % 128 == 0 else 64, stats_out=stats)
+                       cout, 128 if cout % 128 == 0 else 64, stats_out=stats, info=info)
     finally:
         check(lib.idf_set_option(b"conv_force_mt", 0))
-    ref = tile_partials(out, B, H, H)
-    assert torch.isfinite(stats).all(), "a window record was not written"
-    assert_close(stats, ref, rel_l2=1e-5, max_rel=1e-5, what="conv epilogue GroupNorm partials")
+        check(lib.idf_set_option(b"stats_item", 1))
+    unit = info["stats_unit"]
+    assert unit == 32 or (item == 1 and unit % 128 == 0 and unit <= (H + 1) * (H + 1))
+    if unit == 32:
+        ref = tile_partials(out, B, H, H)
+        assert torch.isfinite(stats).all(), "a window record was not written"
+    else:
+        ref = unit_partials(out, B, H, H, unit)
+        n_rec = (rows + unit - 1) // unit * 4
+        assert torch.isfinite(stats[0, :n_rec]).all(), "an item record was not written"
+        stats[0, n_rec:] = 0.0                     # capacity beyond the item records is not touched
+    assert_close(stats, ref, rel_l2=1e-5, max_rel=1e-5, what=f"conv epilogue GroupNorm partials (unit {unit})")
 
 
 @pytest.mark.parametrize("cin,cout,H,B", [(64, 64, 16, 3), (128, 128, 8, 5), (64, 128, 16, 2), (256, 128, 8, 3),
@@ -394,6 +427,21 @@ def test_adagn(lib, c0, c1, H, B, mod, silu):
     torch.cuda.synchronize()
     assert pad_is_zero(out2, B, H, H)
     assert_close(unpf(out2, B, H, H), ref, rel_l2=3e-3, max_rel=8e-3, what=f"adagn (streaming) C={c0}+{c1}@{H}")
+    # the same with work-item statistics units (128 * MT rows, four records each); the two sources of a concatenation
+    # may come from producers with different units
+    R = (H + 1) * (H + 1)
+    units = [u for u in (512, 256, 128) if u <= R]
+    if units:
+        out3 = torch.zeros_like(out)
+        u0, u1 = units[0], units[-1]
+        st0u = unit_partials(s0, B, H, H, u0)
+        a.stats0, a.stats_unit0, a.out = st0u.data_ptr(), u0, out3.data_ptr()
+        if c1:
+            st1u = unit_partials(s1, B, H, H, u1)
+            a.stats1, a.stats_unit1 = st1u.data_ptr(), u1
+        check(lib.idf_adagn_silu_fwd(C.byref(a), stream()))
+        torch.cuda.synchronize()
+        assert_close(out3.float(), out2.float(), rel_l2=1e-3, max_rel=2e-2, what=f"adagn (item units {u0}/{u1}) vs window units")
 
 
 @pytest.mark.parametrize("save", [False, True])
