@@ -59,9 +59,11 @@ def parse():
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("IDF_SAMPLE_LANES", "1")),
                     help="streams the micro-batches of a step are spread over (needs --chunk < batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pdl", type=int, default=int(os.environ.get("IDF_PDL", "0")),
+    ap.add_argument("--pdl", type=int, default=int(os.environ.get("IDF_PDL", "1")),
                     help="1: launch conv / AdaGN kernels with programmatic dependent launch")
-    ap.add_argument("--fuse-adagn", action="store_true", help="fold every AdaGN into its consumer conv (A/B comparison)")
+    ap.add_argument("--fuse-adagn", action="store_true", help="fold EVERY AdaGN into its consumer conv (A/B comparison; "
+                    "the default folds the 64x64 maps only, engine.FUSE_ADAGN_MIN_H)")
+    ap.add_argument("--no-fuse-adagn", action="store_true", help="stand-alone AdaGN kernels everywhere (A/B comparison)")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-throughput measurement")
     ap.add_argument("--train-batch", type=int, default=32)
     return ap.parse_args()
@@ -672,7 +674,7 @@ def run_ours(a):
         tot = sum(d["ms"] for d in acc.values())
         c = acc["conv_igemm"]
         tfs = c["flops"] / (c["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM)", "achieved": tfs,
+        roof = {"bound": "tensor", "kernel": "conv_halo_kernel (tcgen05 implicit GEMM, CTA pairs)", "achieved": tfs,
                 "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": tfs / pk["tf_sus"], "traffic": ncu_traffic("conv")[0],
                 "traffic_source": ncu_traffic("conv")[1],
                 "peak_source": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
@@ -684,10 +686,15 @@ def run_ours(a):
             gbs = g_["bytes"] / (g_["ms"] * 1e-3) / 1e9
             breakdown["adagn"].update({"bound": "hbm", "achieved_GBps": gbs, "peak_GBps": pk["hbm"], "frac": gbs / pk["hbm"],
                                        "traffic": ncu_traffic("adagn")[0], "traffic_source": ncu_traffic("adagn")[1]})
-        else:
-            roof["note"] = ("AdaGN+SiLU is applied to the conv's A operand in shared memory (transform warps): the 73 "
-                            "normalised activations are never written to or read from HBM; only the per-image "
-                            "coefficient kernels (adagn_coef) remain")
+        if "conv_igemm_xf" in acc:   # convs that also apply a fused AdaGN+SiLU to their A operand: tensor work AND the HBM pass they replace
+            x_ = acc["conv_igemm_xf"]
+            breakdown["conv_igemm_xf"].update({"bound": "tensor + shared memory", "achieved_TFLOPs": x_["flops"] / (x_["ms"] * 1e-3) / 1e12,
+                                               "frac_of_tensor_peak": x_["flops"] / (x_["ms"] * 1e-3) / 1e12 / pk["tf_sus"],
+                                               "adagn_hbm_bytes_replaced_per_unet_eval": x_["bytes"] // reps})
+        if "adagn_coef" in acc:
+            roof["note"] = (f"{acc['adagn_coef']['n'] // reps} of the 73 AdaGN+SiLU are applied to the consumer conv's A operand "
+                            "in shared memory (transform warps): those normalised activations are never written to or read "
+                            "from HBM, only their per-image coefficient kernels (adagn_coef) remain")
     ws_gb = sum(w.bytes for w in proc._sampler("ddim", B).lane_ws) / 1e9
     del proc
     model.backbone.invalidate_plans()
@@ -742,10 +749,12 @@ if __name__ == "__main__":
         if a.fuse_adagn:
             from infodiffusion_b200 import engine
             engine.FUSE_ADAGN = True
+        if a.no_fuse_adagn:
+            from infodiffusion_b200 import engine
+            engine.FUSE_ADAGN_MIN_H = 0
         if os.environ.get("IDF_XF_DEBUG"):
             from infodiffusion_b200 import _lib
             _lib.check(_lib.load().idf_set_option(b"xf_debug", int(os.environ["IDF_XF_DEBUG"])))
-        if a.pdl:
-            from infodiffusion_b200 import _lib
-            _lib.check(_lib.load().idf_set_option(b"pdl", 1))
+        from infodiffusion_b200 import _lib
+        _lib.check(_lib.load().idf_set_option(b"pdl", 1 if a.pdl else 0))
         run_ours(a)

@@ -232,18 +232,21 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   const bool pair = g_conv_pair != 0 && d->block_n >= 64 && g_num_sms % 2 == 0;
   const int pw = pair ? 2 : 1;
   const int workers = g_num_sms / pw;
+  // MT 128-row tiles per work item: larger items reuse every streamed weight tile MT times and have relatively less
+  // halo, but quantise the work more coarsely.  Cost model: rounds over the workers x (MT tiles + 0.4 of a tile for the
+  // per-item pipeline fill and weight stream), e.g. 162 tiles on 74 pairs: MT = 2 -> 41 items, one round of 2.4, beats
+  // MT = 1 -> 81 items, two rounds of 1.4.  Ties go to the larger MT.
   const int mt_max = (d->block_n == 128) ? 2 : 4;
   int mt = 1;
-  for (int cand = mt_max; cand > 1; cand >>= 1) {
+  double best = 1e30;
+  for (int cand = 1; cand <= mt_max; cand <<= 1) {
     if (d->block_n == 16 && cand == 2) continue;   // instantiated: 16x{1,4}
+    const int stage = ((cand * kBM + extra_max) * 128 + 1023) / 1024 * 1024;
+    if (conv_config_smem(d->block_n, stage, pair, use_xf) > 227 * 1024) continue;
     const int64_t units = (m_tiles + cand * pw - 1) / (cand * pw) * p.n_tiles;
     const int64_t rounds = (units + workers - 1) / workers;
-    const int stage = ((cand * kBM + extra_max) * 128 + 1023) / 1024 * 1024;
-    if (units >= workers && rounds * workers * 100 <= units * 115 &&
-        conv_config_smem(d->block_n, stage, pair, use_xf) <= 227 * 1024) {
-      mt = cand;
-      break;
-    }
+    const double cost = static_cast<double>(rounds) * (cand + 0.4);
+    if (cost <= best) { best = cost; mt = cand; }
   }
   if (g_force_mt != 0) {
     mt = g_force_mt;

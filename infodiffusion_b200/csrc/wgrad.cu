@@ -83,27 +83,38 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {                       // ---- UMMA issuer
-        const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(ci_n), kFmtBF16) | (1u << 15) | (1u << 16);
-        int st = 0; uint32_t ph = 0;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(full + st, ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + st * STAGE);
-          const uint32_t b_addr = a_addr + A_BYTES;
-          for (int t = 0; t < ntap; ++t) {
-            const uint32_t brow = b_addr + static_cast<uint32_t>(p.u_rel[unit * 3 + t]) * 128u;
+      // ---- UMMA issuer: the whole warp runs the loop on warp-uniform values, only the tcgen05 instructions sit under
+      // elect.sync, so descriptors stay in uniform registers (see the issuer of conv_halo_kernel)
+      const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(ci_n), kFmtBF16) | (1u << 15) | (1u << 16);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint32_t idesc_u = __shfl_sync(0xffffffffu, idesc, 0);
+      int st = 0; uint32_t ph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(full + st, ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + st * STAGE);
+        const uint32_t b_addr = a_addr + A_BYTES;
+        for (int t = 0; t < ntap; ++t) {
+          // (shuffles from lane 0 tell the compiler these are warp-uniform)
+          const uint32_t brow = __shfl_sync(0xffffffffu, b_addr + static_cast<uint32_t>(p.u_rel[unit * 3 + t]) * 128u, 0);
+          const uint32_t a_u = __shfl_sync(0xffffffffu, a_addr, 0);
+          const uint32_t d = __shfl_sync(0xffffffffu, tmem_u + static_cast<uint32_t>(t * ci_n), 0);
+          const uint32_t acc0 = kb > kb_begin ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kWgKB / 16; ++k) {
-              const uint64_t da = umma_desc_mn(a_addr + k * 2048, kWgKB * 128);
+              const uint64_t da = umma_desc_mn(a_u + k * 2048, kWgKB * 128);
               const uint64_t db = umma_desc_mn(brow + k * 2048, B_ATOM);
-              umma_f16(tmem + static_cast<uint32_t>(t * ci_n), da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+              umma_f16(d, da, db, idesc_u, k > 0 ? 1u : acc0);
+            }
+            if (t + 1 == ntap) {
+              umma_commit(empty + st);
+              if (kb + 1 == kb_end) umma_commit(done);
             }
           }
-          umma_commit(empty + st);
-          if (++st == kWgStages) { st = 0; ph ^= 1u; }
+          __syncwarp();
         }
-        umma_commit(done);
+        if (++st == kWgStages) { st = 0; ph ^= 1u; }
       }
     } else {
       // ---- epilogue (warps 2..5): TMEM lane quarter = warp % 4

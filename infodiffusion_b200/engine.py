@@ -75,16 +75,16 @@ class VAct:
         self.srcs, self.coef, self.silu, self.H, self.C = srcs, coef, silu, H, C
 
 
-# Inference plans can fold every AdaGN into its consumer conv (transform warps rewrite the A operand in shared
-# memory; the normalised activation never touches HBM, workspace 2.1 GB instead of 2.8 GB at batch 256).  Measured on
-# B200 at batch 256 it is a wash -- 344 img/s either way at the same clocks: the transform's shared-memory
-# read-modify-write loop competes with the epilogue warps for issue slots -- so the separate HBM-bound AdaGN kernels
-# stay the default and this is an opt-in (bench.py --fuse-adagn).
+# Inference plans can fold an AdaGN into its consumer conv (transform warps rewrite the A operand in shared memory; the
+# normalised activation never touches HBM).  The transform shares the shared-memory port with the tensor core's operand
+# fetch, so it is not free: measured per layer at batch 256 (tools/conv_microbench.py, IDF_MB_XF=1) the fused conv
+# beats conv + stand-alone AdaGN on the 64x64 maps (125 vs 80 + 55 us for 64->64, 208 vs 135 + 120 us for the 128-channel
+# concatenations), ties on 32x32 and loses on the 16x16 / 8x8 maps, where the extra coefficient kernel costs as much as
+# the AdaGN launch it replaces.  FUSE_ADAGN = True fuses every layer (bench.py --fuse-adagn all); FUSE_ADAGN_MIN_H fuses
+# the maps of at least that size when the batch is large enough to fill the machine (the default: 64x64 maps).
 FUSE_ADAGN = False
-# Fusing only the small maps (H <= FUSE_ADAGN_MAX_H), whose stand-alone AdaGN launches are pure latency, measured
-# worse as well (332 vs 344 img/s with 16): the coefficient kernels and the slower convs cost more than the launches
-# saved.  0 disables.
-FUSE_ADAGN_MAX_H = 0
+FUSE_ADAGN_MIN_H = 64
+FUSE_ADAGN_MIN_ROWS = 128 * 65 * 65      # ... and only from this many pad-flat rows (batch 128 at 64x64)
 MAX_GN_CHANNELS = 1024       # widest GroupNorm the AdaGN forward kernels take (csrc/adagn.cu kMaxCWide)
 MAX_TRAIN_GN_CHANNELS = 256  # ... and their backward kernels (csrc/adagn_bwd.cu); wgrad plans stop at 64 work units
 TRAIN_PDL = True       # programmatic dependent launch once a training plan exists (library-wide switch)
@@ -332,13 +332,19 @@ class Plan:
         if out is not None and want_stats:
             out.stats_unit = int(self.lib.idf_conv_plan_stats_unit(h))
         macs = real_macs_per_row if real_macs_per_row is not None else 64 * len(kblocks) * cout
-        self._emit("conv_igemm", self.lib.idf_conv_run, (h,), flops=2 * self.B * H * H * macs)
+        # conv_igemm_xf: the launches that also apply a fused AdaGN (+SiLU) to their A operand -- they replace a
+        # stand-alone AdaGN pass and are accounted separately from the plain implicit GEMMs
+        self._emit("conv_igemm_xf" if xf is not None else "conv_igemm", self.lib.idf_conv_run, (h,),
+                   flops=2 * self.B * H * H * macs,
+                   nbytes=(2 * 2 * self.B * H * H * 64 * len({(si, c0) for (si, c0, _), v in zip(kblocks, xf[2]) if v >= 0})
+                           if xf is not None else 0))       # HBM bytes of the AdaGN pass this launch replaces
 
     def norm(self, src0: Act, src1: Optional[Act], gn: nn.GroupNorm, silu: bool, mod_t=None, mod_z=None, step=None,
              dropout: bool = False, mod_cols: Optional[int] = None):
         """AdaGN of one or two (channel-concatenated) activations for a following conv.  Inference plans return a
         VAct (coefficients only, applied inside the conv); otherwise the activation is materialised."""
-        fuse = self.fuse_adagn or (not self.training and src0.H <= FUSE_ADAGN_MAX_H)
+        fuse = self.fuse_adagn or (not self.training and FUSE_ADAGN_MIN_H > 0 and src0.H >= FUSE_ADAGN_MIN_H
+                                   and src0.rows >= FUSE_ADAGN_MIN_ROWS)
         if fuse and src0.has_stats and (src1 is None or src1.has_stats):
             Cc = src0.C + (src1.C if src1 is not None else 0)
             a = AdaGNArgs()

@@ -23,7 +23,7 @@ convs = [d for d in plan.keep if isinstance(d, _lib.ConvDesc)]
 ci = 0
 for i, ((fn, a), m) in enumerate(zip(plan.ops, plan.meta)):
     desc = None
-    if m["tag"] == "conv_igemm":
+    if m["tag"].startswith("conv_igemm"):
         desc = convs[ci]; ci += 1
     try:
         _lib.check(fn(*a, st))
