@@ -277,6 +277,22 @@ __device__ __forceinline__ void fold_coefficients(const AdaGNParams& p, int n, C
   // of a producer work item with four; see idf_conv_desc.stats_out).  All 256 threads take part: thread -> (channel,
   // sub-sequence of records), loads issued eight at a time; the order of every addition is a function of
   // (n, geometry) only, so the result is deterministic.
+  // the affine / modulation values of this thread's (first) channel do not depend on the statistics: request them
+  // first, so that their global-memory latency (step counter -> modulation row: two dependent loads) hides behind the
+  // record loads instead of following the three block barriers below
+  const int step = p.step_ptr ? *p.step_ptr : 0;
+  float pg = 0.f, pb = 0.f, pts = 0.f, pth = 0.f, pzs = 0.f, pzh = 0.f;
+  if (t < C) {
+    pg = __ldg(p.gamma + t); pb = __ldg(p.beta + t);
+    if (p.mod_t != nullptr) {
+      const float* m = p.mod_t + step * p.mod_t_step_stride + n * p.mod_t_batch_stride;
+      pts = __ldg(m + t); pth = __ldg(m + C + t);
+    }
+    if (p.mod_z != nullptr) {
+      const float* m = p.mod_z + step * p.mod_z_step_stride + n * p.mod_z_batch_stride;
+      pzs = __ldg(m + t); pzh = __ldg(m + C + t);
+    }
+  }
   const int nsub = (kAdaThreads / C) > 0 ? (kAdaThreads / C) : 1;     // 4, 2, 1, 1 for C = 64, 128, 192, 256
   for (int idx = t; idx < C * nsub; idx += kAdaThreads) {
     const int ch = idx % C, sub = idx / C;
@@ -329,20 +345,20 @@ __device__ __forceinline__ void fold_coefficients(const AdaGNParams& p, int n, C
     s_rstd[t] = rsqrtf(var + p.eps);
   }
   __syncthreads();
-  const int step = p.step_ptr ? *p.step_ptr : 0;
   for (int ch = t; ch < C; ch += kAdaThreads) {
     const int g = ch / cpg;
-    float A = s_rstd[g] * p.gamma[ch];
-    float B = p.beta[ch] - s_mean[g] * A;
+    const bool pre = ch == t;                       // first channel of the thread: values prefetched above
+    float A = s_rstd[g] * (pre ? pg : p.gamma[ch]);
+    float B = (pre ? pb : p.beta[ch]) - s_mean[g] * A;
     if (p.mod_t != nullptr) {
       const float* m = p.mod_t + step * p.mod_t_step_stride + n * p.mod_t_batch_stride;
-      const float sc = 1.0f + m[ch], sh = m[C + ch];
+      const float sc = 1.0f + (pre ? pts : m[ch]), sh = pre ? pth : m[C + ch];
       A *= sc;
       B = B * sc + sh;
     }
     if (p.mod_z != nullptr) {
       const float* m = p.mod_z + step * p.mod_z_step_stride + n * p.mod_z_batch_stride;
-      const float sc = 1.0f + m[ch], sh = m[C + ch];
+      const float sc = 1.0f + (pre ? pzs : m[ch]), sh = pre ? pzh : m[C + ch];
       A *= sc;
       B = B * sc + sh;
     }
