@@ -125,7 +125,7 @@ int idf_set_option(const char* key, int32_t value) {
   if (key != nullptr && std::strcmp(key, "stats_item") == 0 && (value == 0 || value == 1)) { g_stats_item = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "conv_pair") == 0 && (value == 0 || value == 1)) { g_conv_pair = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "pdl") == 0) { g_pdl = value ? 1 : 0; return IDF_OK; }
-  if (key != nullptr && std::strcmp(key, "xf_debug") == 0 && value >= 0 && value <= 4) { g_xf_debug = value; return IDF_OK; }
+  if (key != nullptr && std::strcmp(key, "xf_debug") == 0 && value >= 0 && value <= 5) { g_xf_debug = value; return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "adagn_ring") == 0 && value >= 1 && value <= 8) { g_adagn_ring = static_cast<int>(value); return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "adagn_ctas") == 0 && value >= 1) { g_adagn_ctas = static_cast<int>(value); return IDF_OK; }
   if (key != nullptr && std::strcmp(key, "adagn_ctas2") == 0 && value >= 1) { g_adagn_ctas2 = static_cast<int>(value); return IDF_OK; }

@@ -25,6 +25,21 @@
 
 namespace idf {
 
+// Pipeline trace (development builds only, -DIDF_CONV_TRACE; tools/conv_trace.py): CTA 0 records globaltimer stamps of
+// every work item's phases into the buffer passed as out_f32 (unused by the bf16 epilogue): [item][8] int64.
+#ifdef IDF_CONV_TRACE
+#define IDF_TRACE(slot, item)                                                                                     \
+  do {                                                                                                            \
+    if (blockIdx.x == 0 && p.out_f32 != nullptr && (item) < 64) {                                                 \
+      unsigned long long t_;                                                                                      \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                      \
+      reinterpret_cast<unsigned long long*>(p.out_f32)[(item) * 8 + (slot)] = t_;                                 \
+    }                                                                                                             \
+  } while (0)
+#else
+#define IDF_TRACE(slot, item) do { } while (0)
+#endif
+
 // transform warps of the XF variant (4 rows per warp and pass).  With the row table (see the transform branch) 8 and 12
 // warps measure the same at batch 256 (bench.py --fuse-adagn: 376-382 img/s); 8 leave 80 registers per thread at launch.
 constexpr int kXfWarps = 8;
@@ -392,6 +407,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
           const int src = p.g_src[g];
           const int ex = p.extra_rows[src];
           mbar_wait(a_empty + sa, pa ^ 1u);
+          if (g == 0) IDF_TRACE(0, (st - unit0) / n_units);
           uint8_t* dst = smA + sa * p.a_stage_bytes;
           const int r = row0 + p.g_lo[g];
           const uint32_t bytes = static_cast<uint32_t>((MT * kBM + ex) * 128);
@@ -465,6 +481,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
           if constexpr (PAIR && XF) mbar_wait_cluster(a_ready + sa, pa);   // the peer's transform warps arrive remotely
           else mbar_wait(XF ? a_ready + sa : a_full + sa, pa);
           if constexpr (XF) tc_fence_after();
+          if (lane == 0 && g == 0 && warp_u == W_I1) IDF_TRACE(3, iter);
           const uint32_t a_lo0 = umma_desc_lo(smem_u32(smA + sa * p.a_stage_bytes)) +
                                  static_cast<uint32_t>(m_begin * (kBM * 128 / 16));
           const int t_end = t + p.g_ntaps[g];
@@ -477,6 +494,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
             if (elect_one()) {
 #pragma unroll
               for (int m = 0; m < M_PER; ++m) {
+                if (XF && p.xf_debug == 5) break;      // measurement only: no MMAs (what does the transform cost alone?)
                 if constexpr (PAIR)
                   umma_f16_x4_pair(d0 + static_cast<uint32_t>(m * BN), a_lo + static_cast<uint32_t>(m * (kBM * 128 / 16)), b_lo,
                                    idesc, t != 0 ? 1u : 0u);
@@ -497,6 +515,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
           }
           if (++sa == AS) { sa = 0; pa ^= 1u; }
         }
+        if (lane == 0 && warp_u == W_I1) IDF_TRACE(4, iter);
       }
     }
   }
@@ -550,6 +569,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
           asm volatile("bar.sync 1, %0;" ::"n"(NXT) : "memory");      // the transform warps only
         }
         mbar_wait(a_full + sa, pa);
+        if (tt == 0 && g == 0) IDF_TRACE(1, (st - unit0) / n_units);
         if (cb >= 0 && p.xf_debug != 1) {
           const uint32_t base = smem_u32(smA + sa * p.a_stage_bytes) + static_cast<uint32_t>(gi * 16);
           const float2* ctab = p.xf_coef + cb + gl * 8;
@@ -592,6 +612,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
           fence_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
         }
         __syncwarp();
+        if (tt == 0 && g == 0) IDF_TRACE(2, (st - unit0) / n_units);
         if (lane == 0) {     // hand the stage to the (leader's) UMMA issuers
           if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(a_ready + sa), 0));
           else mbar_arrive(a_ready + sa);
@@ -636,6 +657,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
       const int as = iter & 1;
       mbar_wait(tfull + as, (iter >> 1) & 1u);
       tc_fence_after();
+      if (e == 0 && lane == 0) IDF_TRACE(5, iter);
       const uint32_t t0 = tmem_base + static_cast<uint32_t>(as * Cfg::ACC_COLS) + (static_cast<uint32_t>(q * 32) << 16);
       if (p.debug_skip_epilogue) {     // measurement only
         release_acc(as);
