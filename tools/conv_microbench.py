@@ -84,7 +84,7 @@ def main():
             del keep
             line += f"{name} {us:7.1f} ({fl / us / 1e6:6.0f}, {fl / us / 1e6 / PEAK * 100:4.1f}%)  "
         if os.environ.get("IDF_MB_XF"):
-            for dbg in (0, 5, 1):
+            for dbg in (0, 2, 5, 1):
                 _lib.check(lib.idf_set_option(b"xf_debug", dbg))
                 h, keep = make(cin, cout, H, False, True, False, xf=True)
                 us = timeit(h)
