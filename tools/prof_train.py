@@ -1,4 +1,5 @@
 """Kernel-time breakdown of one training step (torch profiler, CUDA activities)."""
+import os
 import sys
 from pathlib import Path
 
@@ -18,6 +19,8 @@ model.device = dev
 for n in ("alpha_bars", "betas", "alphas", "alpha_prev_bars"):
     setattr(model, n, getattr(model, n).to(dev))
 model.train()
+if os.environ.get("IDF_TRAIN_DROPOUT") is not None:      # what does the mask generator cost?
+    model.backbone.dropout_p = model.encoder.dropout_p = float(os.environ["IDF_TRAIN_DROPOUT"])
 params = [p for p in model.parameters() if p.requires_grad]
 from infodiffusion_b200.optim import ClipAdamW  # noqa: E402
 opt = ClipAdamW(params, lr=1e-4, weight_decay=1e-5, max_norm=1.0)      # fused clip_grad_norm_(1.0) + AdamW (run.py:199-200)
@@ -45,4 +48,5 @@ from torch.profiler import ProfilerActivity, profile
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+if not os.environ.get("IDF_NO_TABLE"):
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
