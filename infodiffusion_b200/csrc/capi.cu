@@ -242,7 +242,7 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   for (int cand = 1; cand <= mt_max; cand <<= 1) {
     if (d->block_n == 16 && cand == 2) continue;   // instantiated: 16x{1,4}
     const int stage = ((cand * kBM + extra_max) * 128 + 1023) / 1024 * 1024;
-    if (conv_config_smem(d->block_n, stage, pair, use_xf) > 227 * 1024) continue;
+    if (conv_config_smem(d->block_n, cand, stage, pair, use_xf) > 227 * 1024) continue;
     const int64_t units = (m_tiles + cand * pw - 1) / (cand * pw) * p.n_tiles;
     const int64_t rounds = (units + workers - 1) / workers;
     const double cost = static_cast<double>(rounds) * (cand + 0.4);
@@ -253,7 +253,7 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
     if (mt > mt_max || (d->block_n == 16 && mt == 2)) { delete pl; return fail(IDF_ERR_ARG, "forced MT not available"); }
   }
   p.a_stage_bytes = ((mt * kBM + extra_max) * 128 + 1023) / 1024 * 1024;
-  if (conv_config_smem(d->block_n, p.a_stage_bytes, pair, use_xf) > 227 * 1024) {
+  if (conv_config_smem(d->block_n, mt, p.a_stage_bytes, pair, use_xf) > 227 * 1024) {
     delete pl;
     return fail(IDF_ERR_ARG, "halo does not fit in shared memory (extra rows %d)", extra_max);
   }

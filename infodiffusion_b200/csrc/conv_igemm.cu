@@ -59,15 +59,21 @@ constexpr uint32_t kStageTile = 32 * 64;
 // also serves the operand loads and drains the staging tiles late) and the statistics warps get a full item of slack
 constexpr uint32_t kStageBytes = 16 * kStageTile;
 constexpr int kXfMaxRows = 4 * 128 + 256;   // rows of the largest halo (MT = 4 tiles + the widest tap spread)
-constexpr uint32_t kRowTabBytes = 2 * 2 * kXfMaxRows;   // XF variant: int16 row table per halo stage
+constexpr uint32_t kRowTabBytes = 3 * 2 * kXfMaxRows;   // XF variant: int16 row table per halo stage
 constexpr uint32_t kBiasBytes = 1536 * 4;  // bias vector of the whole conv (cout_pad <= 1536: q|k|v of a 512-wide head), staged once per CTA
 __device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
   return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
 
-template <int BN, int MT, bool PAIR = false>
+// Halo stages.  The plain kernel is MMA-bound with two (the next halo lands while the MMAs of this one run).  In the
+// fused-AdaGN variant load -> transform -> MMAs are serial per stage, so two stages bound the item period by half that
+// chain (tools/conv_trace.py: 3.9 + 5.9 + 4.0 us per 512-row item, 7.2 us period); items of at most two tiles leave room
+// for a third stage, which lets the load of item i+2 and the transform of item i+1 run under the MMAs of item i.
+__host__ __device__ constexpr int conv_a_stages(int mt, bool xf) { return (xf && mt <= 2) ? 3 : 2; }
+
+template <int BN, int MT, bool PAIR = false, bool XF = false>
 struct HaloCfg {
-  static constexpr int A_STAGES = 2;
+  static constexpr int A_STAGES = conv_a_stages(MT, XF);
   static constexpr int B_STAGES = conv_b_stages(BN);
   static constexpr uint32_t B_BYTES = BN * kBK * 2 / (PAIR ? 2 : 1);   // per CTA: a pair splits the weight tile along N
   static constexpr uint32_t ACC_COLS = MT * BN;                       // one accumulator set
@@ -314,7 +320,7 @@ __host__ __device__ constexpr int conv_threads(bool xf) { return 32 * ((xf ? kXf
 
 template <int BN, int MT, bool XF, bool PAIR>
 __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = HaloCfg<BN, MT, PAIR>;
+  using Cfg = HaloCfg<BN, MT, PAIR, XF>;
   constexpr int AS = Cfg::A_STAGES, BS = Cfg::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -802,7 +808,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
 
 template <int BN, int MT, bool XF, bool PAIR>
 static cudaError_t launch_cfg(const ConvKernelParams& p, int grid, cudaStream_t stream) {
-  using Cfg = HaloCfg<BN, MT, PAIR>;
+  using Cfg = HaloCfg<BN, MT, PAIR, XF>;
   const uint32_t smem = conv_smem_bytes(p.a_stage_bytes, Cfg::A_STAGES, Cfg::B_STAGES, Cfg::B_BYTES, XF);
   static uint32_t attr_smem = 0;
   if (smem > attr_smem) {
@@ -867,8 +873,8 @@ cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, bo
 }
 
 // shared-memory need of a configuration (host side, for plan validation)
-uint32_t conv_config_smem(int block_n, int a_stage_bytes, bool pair, bool xf) {
-  return conv_smem_bytes(a_stage_bytes, 2, conv_b_stages(block_n), block_n * kBK * 2 / (pair ? 2 : 1), xf);
+uint32_t conv_config_smem(int block_n, int mt, int a_stage_bytes, bool pair, bool xf) {
+  return conv_smem_bytes(a_stage_bytes, conv_a_stages(mt, xf), conv_b_stages(block_n), block_n * kBK * 2 / (pair ? 2 : 1), xf);
 }
 
 }  // namespace idf

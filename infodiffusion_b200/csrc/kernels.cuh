@@ -75,7 +75,7 @@ cudaError_t launch_wgrad(const WgradKernelParams& p, int grid, cudaStream_t stre
 static_assert(sizeof(ConvKernelParams) <= 4000, "kernel parameters are limited to 4 KB");
 cudaError_t launch_conv_igemm(const ConvKernelParams& p, int block_n, int mt, bool xform, bool pair, int grid, cudaStream_t stream);
 cudaError_t launch_adagn_coef(const idf_adagn_args& a, float* coef_out, cudaStream_t stream);
-uint32_t conv_config_smem(int block_n, int a_stage_bytes, bool pair, bool xf);
+uint32_t conv_config_smem(int block_n, int mt, int a_stage_bytes, bool pair, bool xf);
 cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream);
 cudaError_t launch_adagn_bwd(const idf_adagn_bwd_args& b, int num_sms, cudaStream_t stream);
 int64_t adagn_bwd_ws_floats(int batch, int C);
