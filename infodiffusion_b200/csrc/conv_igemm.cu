@@ -588,11 +588,13 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
               A[2 * j] = c.x * cs; B[2 * j] = c.y * cs; A[2 * j + 1] = c.z * cs; B[2 * j + 1] = c.w * cs;
             }
           };
-          // four rows per trip: table entries and the four loads first, then the arithmetic row by row; the loop exists
-          // twice so that the activation is not a per-element branch.  (A variant that ran the four rows as 32
-          // independent chains in straight-line code with predicated stores measured the same at 64^2 and worse on
-          // the small maps, whose trips often cross an image boundary; 12 instead of 8 warps measured the same too:
-          // the transform is bound by the shared-memory port it shares with the tensor core, not by issue slots.)
+          // four rows per trip: table entries and the four loads first; then -- when the valid rows share one image,
+          // i.e. in every trip that does not cross an image boundary -- the arithmetic in three phases over 16
+          // elements at a time (affines, tanh, second FMA + pack) with predicated stores.  The phases keep 32 independent
+          // chains in flight, so that one warp's MUFU phase overlaps the other warps' FMA phases: tools/cu/xf_bench.cu
+          // measures 2.09 instead of 2.70 us per 648-row halo for 8 warps (row-by-row code leaves the 8 MUFU results
+          // of a granule on the critical path of its store).  The loop exists twice so that the activation is not a
+          // per-element branch.
           auto stream = [&](auto silu_tag) {
             constexpr bool SILU = decltype(silu_tag)::value;
 #pragma unroll 1
@@ -606,11 +608,52 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
                 info[q] = i < nrows ? lds_s16(tab + 2u * static_cast<uint32_t>(ic)) : -1;
                 u[q] = lds128(base + static_cast<uint32_t>(ic) * 128u);
               }
+              int want = -1;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (info[q] < 0) continue;
-                if (info[q] + img0 != cur) reload(info[q] + img0);
-                sts128(base + static_cast<uint32_t>(i0 + kXfRows * q) * 128u, xf_apply<SILU>(u[q], A, B));
+              for (int q = 0; q < 4; ++q) want = info[q] >= 0 ? info[q] : want;      // the last valid row's image
+              if (want < 0) continue;
+              bool uniform = true;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) uniform = uniform && (info[q] < 0 || info[q] == want);
+              if (uniform) {
+                if (want + img0 != cur) reload(want + img0);
+#pragma unroll
+                for (int q0 = 0; q0 < 4; q0 += 2) {          // two granules (16 independent chains) per phase group
+                  float h[2][8];
+#pragma unroll
+                  for (int q = 0; q < 2; ++q) {
+                    const uint4& uu = u[q0 + q];
+                    const float2 a0 = unpack_bf16x2(uu.x), a1 = unpack_bf16x2(uu.y), a2 = unpack_bf16x2(uu.z), a3 = unpack_bf16x2(uu.w);
+                    const float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) h[q][j] = fmaf(f[j], A[j], B[j]);
+                  }
+                  if constexpr (SILU) {
+                    float th[2][8];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) asm volatile("tanh.approx.f32 %0, %1;" : "=f"(th[q][j]) : "f"(h[q][j]));
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) h[q][j] = fmaf(h[q][j], th[q][j], h[q][j]);
+                  }
+#pragma unroll
+                  for (int q = 0; q < 2; ++q) {
+                    uint4 o;
+                    o.x = pack_bf16x2(h[q][0], h[q][1]); o.y = pack_bf16x2(h[q][2], h[q][3]);
+                    o.z = pack_bf16x2(h[q][4], h[q][5]); o.w = pack_bf16x2(h[q][6], h[q][7]);
+                    if (info[q0 + q] >= 0) sts128(base + static_cast<uint32_t>(i0 + kXfRows * (q0 + q)) * 128u, o);
+                  }
+                }
+              } else {
+#pragma unroll           // (a rolled loop would index u[] / info[] dynamically and push them into local memory)
+                for (int q = 0; q < 4; ++q) {
+                  if (info[q] < 0) continue;
+                  if (info[q] + img0 != cur) reload(info[q] + img0);
+                  sts128(base + static_cast<uint32_t>(i0 + kXfRows * q) * 128u, xf_apply<SILU>(u[q], A, B));
+                }
               }
             }
           };
