@@ -558,6 +558,16 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
         const uint32_t tab = rowtab_sa + static_cast<uint32_t>(sa) * (2u * kXfMaxRows);
         const int rfirst = rbase < 0 ? 0 : rbase;
         const int img0 = __float2int_rd((static_cast<float>(rfirst) + 0.5f) * inv_R);     // image of the halo's first row
+        // coefficients of the halo's first image (consecutive items of a CTA lie in different images, so every halo
+        // starts with a reload): requested here, consumed after the wait for the halo -- their L2 latency hides behind
+        // the row table and the TMA load
+        const float2* ctab = p.xf_coef + (cb >= 0 ? cb : 0) + gl * 8;
+        const bool pre = cb >= 0 && p.xf_debug != 1 && img0 != cur && rfirst < rows32;
+        float4 pc0, pc1, pc2, pc3;
+        if (pre) {
+          const float4* c4 = reinterpret_cast<const float4*>(ctab + static_cast<int64_t>(img0) * p.xf_ctot);
+          pc0 = __ldg(c4); pc1 = __ldg(c4 + 1); pc2 = __ldg(c4 + 2); pc3 = __ldg(c4 + 3);
+        }
         if (cb >= 0 && p.xf_debug != 1) {
           // ---- row table (exact float reciprocals: all quotients < 2^22), while the TMA load is still in flight
           for (int i = tt; i < nrows; i += NXT) {
@@ -576,9 +586,15 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
         }
         mbar_wait(a_full + sa, pa);
         if (tt == 0 && g == 0) IDF_TRACE(1, (st - unit0) / n_units);
+        if (pre) {
+          cur = img0;
+          A[0] = pc0.x * cs; B[0] = pc0.y * cs; A[1] = pc0.z * cs; B[1] = pc0.w * cs;
+          A[2] = pc1.x * cs; B[2] = pc1.y * cs; A[3] = pc1.z * cs; B[3] = pc1.w * cs;
+          A[4] = pc2.x * cs; B[4] = pc2.y * cs; A[5] = pc2.z * cs; B[5] = pc2.w * cs;
+          A[6] = pc3.x * cs; B[6] = pc3.y * cs; A[7] = pc3.z * cs; B[7] = pc3.w * cs;
+        }
         if (cb >= 0 && p.xf_debug != 1) {
           const uint32_t base = smem_u32(smA + sa * p.a_stage_bytes) + static_cast<uint32_t>(gi * 16);
-          const float2* ctab = p.xf_coef + cb + gl * 8;
           auto reload = [&](int img) {
             cur = img;
             const float4* c4 = reinterpret_cast<const float4*>(ctab + static_cast<int64_t>(img) * p.xf_ctot);
