@@ -83,7 +83,7 @@ class VAct:
 # the AdaGN launch it replaces.  FUSE_ADAGN = True fuses every layer (bench.py --fuse-adagn all); FUSE_ADAGN_MIN_H fuses
 # the maps of at least that size when the batch is large enough to fill the machine (the default: 64x64 maps).
 FUSE_ADAGN = False
-FUSE_ADAGN_MIN_H = 64
+FUSE_ADAGN_MIN_H = int(__import__("os").environ.get("IDF_FUSE_MIN_H", "64"))
 FUSE_ADAGN_MIN_ROWS = 128 * 65 * 65      # ... and only from this many pad-flat rows (batch 128 at 64x64)
 MAX_GN_CHANNELS = 1024       # widest GroupNorm the AdaGN forward kernels take (csrc/adagn.cu kMaxCWide)
 MAX_TRAIN_GN_CHANNELS = 256  # ... and their backward kernels (csrc/adagn_bwd.cu); wgrad plans stop at 64 work units
