@@ -162,10 +162,12 @@ def test_conv3x3(lib, cin, cout, H, B, res):
     assert_close(unpf(out, B, H, H), ref, what=f"conv3x3 {cin}->{cout}@{H} B={B} res={res}")
 
 
+@pytest.mark.parametrize("pair", [1, 0])
 @pytest.mark.parametrize("cin,cout,H,B,mt", [(64, 64, 16, 3, 2), (64, 64, 16, 3, 4), (128, 128, 16, 3, 2),
-                                              (128, 64, 8, 5, 4), (256, 128, 8, 4, 2)])
-def test_conv3x3_forced_tiles_per_cta(lib, cin, cout, H, B, mt):
-    """Every (BN, MT) instantiation of the halo kernel, including partially filled work units."""
+                                              (128, 64, 8, 5, 4), (256, 128, 8, 4, 2), (128, 128, 8, 37, 1)])
+def test_conv3x3_forced_tiles_per_cta(lib, cin, cout, H, B, mt, pair):
+    """Every (BN, MT) instantiation of the halo kernel, as CTA pairs (cta_group::2, odd numbers of super tiles leave the
+    peer CTA's rows out of range) and as single CTAs, including partially filled work units; both give the same bits."""
     from infodiffusion_b200 import layout
     g = torch.Generator(device=DEV).manual_seed(100 + cin + cout + H + mt)
     x = rbf(torch.randn(B, cin, H, H, device=DEV, generator=g))
@@ -173,13 +175,19 @@ def test_conv3x3_forced_tiles_per_cta(lib, cin, cout, H, B, mt):
     b = torch.randn(cout, device=DEV, generator=g)
     ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
     check(lib.idf_set_option(b"conv_force_mt", mt))
+    check(lib.idf_set_option(b"conv_pair", pair))
     try:
         out = run_conv(lib, [pf(x)], layout.taps3x3(cin, H, H), layout.pack_conv3x3(w).to(BF).contiguous(), b, B, H,
                        cout, 128 if cout % 128 == 0 else 64)
+        check(lib.idf_set_option(b"conv_pair", 1 - pair))
+        out2 = run_conv(lib, [pf(x)], layout.taps3x3(cin, H, H), layout.pack_conv3x3(w).to(BF).contiguous(), b, B, H,
+                        cout, 128 if cout % 128 == 0 else 64)
     finally:
         check(lib.idf_set_option(b"conv_force_mt", 0))
+        check(lib.idf_set_option(b"conv_pair", 1))
     assert pad_is_zero(out, B, H, H)
-    assert_close(unpf(out, B, H, H), ref, what=f"conv3x3 {cin}->{cout}@{H} MT={mt}")
+    assert_close(unpf(out, B, H, H), ref, what=f"conv3x3 {cin}->{cout}@{H} MT={mt} pair={pair}")
+    assert torch.equal(out, out2), "CTA pairs and single CTAs must produce identical bits"
 
 
 def test_conv3x3_large_auto_tiles(lib):
