@@ -18,7 +18,8 @@
 //                      next 4 warps = GroupNorm statistics of the staged tiles (one warp per lane quarter)
 //                      then: A (halo) TMA producer, B (weights) TMA producer,
 //                            TMEM allocator (+ second UMMA issuer when MT >= 2), UMMA issuer
-// Pipelines: A halo stages x2, B ring x4-8 (full/empty mbarriers), TMEM accumulator sets x2, staging tiles x2 per warp.
+// Pipelines: A halo stages x2 (x3: XF with MT <= 2), B ring x4-8 (full/empty mbarriers), TMEM accumulator sets x2,
+// staging tiles x2 per drain warp.  With PAIR the kernel runs as clusters of two CTAs (tcgen05 cta_group::2), see below.
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -40,15 +41,17 @@ namespace idf {
 #define IDF_TRACE(slot, item) do { } while (0)
 #endif
 
-// transform warps of the XF variant (4 rows per warp and pass).  With the row table (see the transform branch) 8 and 12
-// warps measure the same at batch 256 (bench.py --fuse-adagn: 376-382 img/s); 8 leave 80 registers per thread at launch.
+// transform warps of the XF variant (4 rows per warp and pass).  In isolation 12 warps beat 8 (tools/cu/xf_bench.cu: 1.8 vs
+// 2.2 us per 648-row halo), inside the kernel they do not: 896 threads leave 72 registers per thread at launch and the
+// drain / statistics / producer warps pay for it (64->64 @64^2 fused: 120 vs 105 us).
 constexpr int kXfWarps = 8;
 constexpr int kXfRows = 4 * kXfWarps;
 
 int g_pdl = 1;     // conv / AdaGN kernels are launched with programmatic dependent launch: their prologue (barriers, TMEM,
                    // bias, weight tiles) overlaps the predecessor's tail.  +6 % sampling rate at 32 images per GPU, neutral
                    // at 256, bitwise neutral; idf_set_option("pdl", 0) disables
-int g_xf_debug = 0;  // measurement only: 1 = transform warps forward the halo untouched, 2 = affine without the SiLU (others: ignored)
+int g_xf_debug = 0;  // measurement only: 1 = transform warps forward the halo untouched, 2 = affine without the SiLU,
+                     // 5 = full transform but no MMAs are issued
 
 __host__ __device__ constexpr int conv_b_stages(int bn) { return bn == 16 ? 8 : (bn == 64 ? 4 : 6); }
 // per-epilogue-warp staging tile: 32 rows x 64 B in the TMA SWIZZLE_64B layout (16-byte chunk c of row r lives at
