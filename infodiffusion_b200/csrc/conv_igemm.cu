@@ -366,11 +366,18 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
     tma_prefetch_desc(&p.tmB);
     if (p.epilogue == IDF_EPI_BF16) tma_prefetch_desc(&p.tmOut);
   }
-  if (warp == W_I1 && lane == 0) {
-    for (int s = 0; s < AS; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, Cfg::NI); mbar_init(a_ready + s, PW * kXfWarps); }
-    for (int s = 0; s < BS; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, Cfg::NI); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, Cfg::NI); mbar_init(tempty + a, PW * 8); }   // one arrive per drain warp
-    for (int i = 0; i < 16; ++i) { mbar_init(staged + i, 1); mbar_init(sdone + i, 1); }
+  if (warp == W_I1) {
+    // ~55 barriers: one per lane and pass instead of a serial loop of one thread (the prologue is on the critical path of
+    // every single-round launch, i.e. of every layer at small per-GPU batches).  Layout: a_full[AS] a_empty[AS] b_full[BS]
+    // b_empty[BS] tfull[2] tempty[2] a_ready[AS] staged[16] sdone[16]
+    for (int i = lane; i < Cfg::NBARS; i += 32) {
+      uint32_t cnt = 1;                                               // a_full, b_full, staged, sdone
+      if (i >= AS && i < 2 * AS) cnt = Cfg::NI;                        // a_empty
+      else if (i >= 2 * AS + BS && i < 2 * AS + 2 * BS + 2) cnt = Cfg::NI;           // b_empty, tfull
+      else if (i >= 2 * AS + 2 * BS + 2 && i < 2 * AS + 2 * BS + 4) cnt = PW * 8;    // tempty: one arrive per drain warp
+      else if (i >= 2 * AS + 2 * BS + 4 && i < 3 * AS + 2 * BS + 4) cnt = PW * kXfWarps;   // a_ready
+      mbar_init(a_full + i, cnt);
+    }
     fence_mbar_init();
   }
   if (warp == W_I2) {
