@@ -125,6 +125,16 @@ typedef struct {
   int32_t xf_ctot;
   int32_t xf_silu;
   int32_t kb_xf[IDF_CONV_MAX_KB];
+  /* optional (IDF_EPI_BF16): nearest-neighbour x2 upsampling folded into a 3x3 conv (UpSample, modules.py:89-92:
+   * F.interpolate(scale 2, nearest) then Conv2d 3x3).  Output pixel (2y+py, 2x+px) only sees the 2x2 input
+   * neighbourhood rows {y-1+py, y+py} x columns {x-1+px, x+px}, with the 3x3 weights that fall on the same input
+   * pixel pre-summed: 4 taps instead of 9 and no upsampled tensor.  With up2 = 1 the GEMM runs over the INPUT grid
+   * (batch, H, W = input geometry); the k-blocks are the 4 taps of parity (0, 0) (row offsets -(W+1)-1, -(W+1), -1, 0);
+   * weight is [4*cout, 4*cin]: row block p = 2*py+px holds parity p's pre-summed taps; block_n == cout, cout_pad ==
+   * 4*cout (column tile = parity, whose taps are shifted by py*(W+1)+px); `out` is the (2H) x (2W) pad-flat map
+   * [batch*(2H+1)*(2W+1), out_ld]; stats_out records are 4*cout wide (one plane per parity, see idf_adagn_args
+   * stats_planes / stats_rows).  residual must be NULL. */
+  int32_t up2;
 } idf_conv_desc;
 
 typedef struct idf_conv_plan idf_conv_plan;
@@ -185,6 +195,10 @@ typedef struct {
   float* save_coef;
   /* rows per statistics unit of stats0 / stats1 (idf_conv_plan_stats_unit of the producing plan); 0 = 32 */
   int32_t stats_unit0, stats_unit1;
+  /* statistics written by an up2 conv plan: records are stats_planes * c columns wide (the planes are summed) and
+   * indexed over the PRODUCER's grid of stats_rows pad-flat rows per image ((H/2+1)*(W/2+1)); 0 = 1 plane, this map's rows */
+  int32_t stats_planes0, stats_planes1;
+  int32_t stats_rows0, stats_rows1;
 } idf_adagn_args;
 int idf_adagn_silu_fwd(const idf_adagn_args* args, idf_stream_t stream);
 /* Coefficients only: coef_out[n][c] = (A, B) with AdaGN(x)[n, c, :, :] = A*x + B (before the activation), from the

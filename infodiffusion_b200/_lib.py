@@ -44,6 +44,7 @@ class ConvDesc(C.Structure):
         ("step_ptr", C.c_void_p),
         ("stats_out", C.c_void_p),
         ("xf_coef", C.c_void_p), ("xf_ctot", C.c_int32), ("xf_silu", C.c_int32), ("kb_xf", C.c_int32 * IDF_CONV_MAX_KB),
+        ("up2", C.c_int32),
     ]
 
 
@@ -72,6 +73,7 @@ class AdaGNArgs(C.Structure):
         ("dropout_p", C.c_float), ("dropout_seed", C.c_void_p), ("dropout_layer", C.c_uint32),
         ("save_coef", C.c_void_p),
         ("stats_unit0", C.c_int32), ("stats_unit1", C.c_int32),
+        ("stats_planes0", C.c_int32), ("stats_planes1", C.c_int32), ("stats_rows0", C.c_int32), ("stats_rows1", C.c_int32),
     ]
 
 

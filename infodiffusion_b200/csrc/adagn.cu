@@ -59,6 +59,9 @@ struct AdaGNParams {
   int slice_rows;        // rows per CTA of the streaming variant
   long long stats_b_windows;   // capacity in records of the A part (offset of the B records, in records)
   int unit0, unit1;            // rows per statistics unit of stats0 / stats1: 32 (1 record per unit) or 128*MT (4 records)
+  int planes0, planes1;        // record rows are planes * c columns wide (up2 producers: 4 parity planes, summed here)
+  int rsrc0, rsrc1;            // pad-flat rows per image of the PRODUCER's grid (up2: the half-resolution grid)
+  long long bwin0, bwin1;      // records before the B part of stats0 / stats1
   int block_rows;              // rows per ring stage of the streaming variant
   int ring;                    // ring stages in use
   int stream_threads;          // streaming variant 2: threads that stream (multiple of C/8)
@@ -299,17 +302,25 @@ __device__ __forceinline__ void fold_coefficients(const AdaGNParams& p, int n, C
     const bool first = ch < p.c0;
     const int cs = first ? p.c0 : p.c1;
     const int U = first ? p.unit0 : p.unit1;
+    const int P = first ? p.planes0 : p.planes1;
+    const int Rs = first ? p.rsrc0 : p.rsrc1;               // rows per image on the producer's grid
     const int S = U > 32 ? 4 : 1;                           // records per unit
-    const int u_first = (n * R) / U;
-    const int u_last = ((n + 1) * R - 1) / U;
-    const bool first_straddles = (u_first * U) < n * R;     // unit starts in image n-1: take its B records
+    const int u_first = (n * Rs) / U;
+    const int u_last = ((n + 1) * Rs - 1) / U;
+    const bool first_straddles = (u_first * U) < n * Rs;    // unit starts in image n-1: take its B records
     const int w_first = u_first * S, w_last = u_last * S + S - 1;
     const int w_bend = w_first + S;                         // records below belong to the first unit
+    const long long rw = static_cast<long long>(P) * cs;    // record row width
     const float2* stA = reinterpret_cast<const float2*>(first ? p.stats0 : p.stats1) + (first ? ch : ch - p.c0);
-    const float2* stB = stA + p.stats_b_windows * cs;
+    const float2* stB = stA + (first ? p.bwin0 : p.bwin1) * rw;
     auto part = [&](int w) -> float2 {
-      const float2* st = (w < w_bend && first_straddles) ? stB : stA;
-      return __ldg(st + static_cast<long long>(w) * cs);
+      const float2* st = ((w < w_bend && first_straddles) ? stB : stA) + static_cast<long long>(w) * rw;
+      float2 v = __ldg(st);
+      for (int pl = 1; pl < P; ++pl) {                      // parity planes of an up2 producer (fixed order)
+        const float2 o = __ldg(st + static_cast<long long>(pl) * cs);
+        v.x += o.x; v.y += o.y;
+      }
+      return v;
     };
     float sx = 0.f, sq = 0.f;
     int w = w_first + sub;
@@ -651,8 +662,13 @@ static cudaError_t fill_params(const idf_adagn_args& a, AdaGNParams& p) {
   p.stats_b_windows = (static_cast<long long>(a.batch) * p.rows_per_img + kBM - 1) / kBM * 4;
   p.unit0 = a.stats_unit0 > 0 ? a.stats_unit0 : 32;
   p.unit1 = a.stats_unit1 > 0 ? a.stats_unit1 : 32;
-  if (p.unit0 > p.rows_per_img && p.unit0 > 32) return cudaErrorInvalidValue;    // a unit may span at most two images
-  if (p.unit1 > p.rows_per_img && p.unit1 > 32) return cudaErrorInvalidValue;
+  p.planes0 = a.stats_planes0 > 0 ? a.stats_planes0 : 1;
+  p.planes1 = a.stats_planes1 > 0 ? a.stats_planes1 : 1;
+  p.rsrc0 = a.stats_rows0 > 0 ? a.stats_rows0 : p.rows_per_img;
+  p.rsrc1 = a.stats_rows1 > 0 ? a.stats_rows1 : p.rows_per_img;
+  p.bwin0 = (static_cast<long long>(a.batch) * p.rsrc0 + kBM - 1) / kBM * 4;
+  p.bwin1 = (static_cast<long long>(a.batch) * p.rsrc1 + kBM - 1) / kBM * 4;
+  if ((p.unit0 > 32 && p.unit0 > p.rsrc0) || (p.unit1 > 32 && p.unit1 > p.rsrc1)) return cudaErrorInvalidValue;   // a unit spans <= 2 images
   return cudaSuccess;
 }
 
@@ -686,7 +702,13 @@ cudaError_t launch_adagn(const idf_adagn_args& a, cudaStream_t stream) {
   p.stats_b_windows = (static_cast<long long>(a.batch) * p.rows_per_img + kBM - 1) / kBM * 4;
   p.unit0 = a.stats_unit0 > 0 ? a.stats_unit0 : 32;
   p.unit1 = a.stats_unit1 > 0 ? a.stats_unit1 : 32;
-  if ((p.unit0 > 32 && p.unit0 > p.rows_per_img) || (p.unit1 > 32 && p.unit1 > p.rows_per_img)) return cudaErrorInvalidValue;
+  p.planes0 = a.stats_planes0 > 0 ? a.stats_planes0 : 1;
+  p.planes1 = a.stats_planes1 > 0 ? a.stats_planes1 : 1;
+  p.rsrc0 = a.stats_rows0 > 0 ? a.stats_rows0 : p.rows_per_img;
+  p.rsrc1 = a.stats_rows1 > 0 ? a.stats_rows1 : p.rows_per_img;
+  p.bwin0 = (static_cast<long long>(a.batch) * p.rsrc0 + kBM - 1) / kBM * 4;
+  p.bwin1 = (static_cast<long long>(a.batch) * p.rsrc1 + kBM - 1) / kBM * 4;
+  if ((p.unit0 > 32 && p.unit0 > p.rsrc0) || (p.unit1 > 32 && p.unit1 > p.rsrc1)) return cudaErrorInvalidValue;   // a unit spans <= 2 images
   if (g_adagn_impl == 2 && p.C <= kMaxC && p.stats0 != nullptr && (p.c1 == 0 || p.stats1 != nullptr)) {
     // streaming variant 2: a CTA owns whole image rows; enough CTAs for >= 4 per SM, each with >= 16 KB to stream
     const int VPR = p.C / 8;

@@ -147,9 +147,13 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
     return fail(IDF_ERR_ARG, "more than 2^22 pad-flat rows per launch: split the batch");
   if (d->epilogue == IDF_EPI_BF16) {
     if (d->block_n < 64) return fail(IDF_ERR_ARG, "bf16 epilogue needs block_n >= 64");
-    if (d->out == nullptr || d->out_ld % 8 != 0 || d->cout != d->cout_pad)
+    if (d->out == nullptr || d->out_ld % 8 != 0 || (d->up2 == 0 && d->cout != d->cout_pad))
       return fail(IDF_ERR_ARG, "bf16 epilogue: out/out_ld/cout invalid");
+    if (d->up2 != 0 && (d->block_n != d->cout || d->cout_pad != 4 * d->cout || d->residual != nullptr || d->xf_coef != nullptr))
+      return fail(IDF_ERR_ARG, "up2: needs block_n == cout, cout_pad == 4*cout, no residual, no fused AdaGN");
     if (d->residual != nullptr && d->res_ld % 8 != 0) return fail(IDF_ERR_ARG, "res_ld must be a multiple of 8");
+  } else if (d->up2 != 0) {
+    return fail(IDF_ERR_ARG, "up2 needs the bf16 epilogue");
   } else if (d->epilogue == IDF_EPI_F32_NCHW || d->epilogue == IDF_EPI_SAMPLER) {
     if (d->block_n != 16 || d->cout > 16) return fail(IDF_ERR_ARG, "fp32/sampler epilogue needs block_n == 16");
     if (d->epilogue == IDF_EPI_F32_NCHW && d->out_f32 == nullptr) return fail(IDF_ERR_ARG, "out_f32 is null");
@@ -210,6 +214,8 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
     p.g_ntaps[g]++;
     group_hi[g] = t.off;
   }
+  if (d->up2 != 0)      // the parity column tiles shift the taps by up to one row and one pixel
+    for (int g = 0; g < p.n_groups; ++g) group_hi[g] += (d->W + 1) + 1;
   int extra_max = 0;
   for (int i = 0; i < d->n_src; ++i) p.extra_rows[i] = 0;
   for (int g = 0; g < p.n_groups; ++g) {
@@ -261,7 +267,9 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   p.m_tiles = static_cast<int32_t>(m_tiles);
   p.debug_skip_epilogue = g_skip_epilogue;
   p.stats = (d->epilogue == IDF_EPI_BF16) ? d->stats_out : nullptr;
-  p.stats_b_off = static_cast<int64_t>(m_tiles) * 4 * d->cout * 2;
+  p.up2 = d->up2 != 0 ? 1 : 0;
+  p.stats_ld = d->up2 != 0 ? d->cout_pad : d->out_ld;
+  p.stats_b_off = static_cast<int64_t>(m_tiles) * 4 * p.stats_ld * 2;
   // item-level records when a work item spans at most two images
   p.stats_item = (p.stats != nullptr && g_stats_item != 0 && d->block_n >= 64 &&
                   static_cast<int64_t>(p.Hp) * p.Wp >= static_cast<int64_t>(mt) * kBM) ? 1 : 0;
@@ -278,7 +286,7 @@ int idf_conv_plan_create(const idf_conv_desc* d, idf_conv_plan** out_plan) {
   }
   rc = encode_2d(&p.tmB, d->weight, d->cout_pad, d->num_kb * kBK, d->block_n / pw);
   if (rc != IDF_OK) { delete pl; return rc; }
-  if (d->epilogue == IDF_EPI_BF16) {
+  if (d->epilogue == IDF_EPI_BF16 && d->up2 == 0) {
     rc = encode_2d_out(&p.tmOut, d->out, p.rows, d->out_ld);
     if (rc != IDF_OK) { delete pl; return rc; }
   }

@@ -114,10 +114,12 @@ __device__ __forceinline__ void residual_fetch(const ConvKernelParams& p, int64_
 // leave with one TMA store (rows beyond the tensor are clipped by the tensor map); the residual, fetched coalesced one
 // item ahead (4 lanes per row), is deposited in the same tile first and read back row-per-lane.  Before the tile is
 // rewritten, the TMA store issued from it two items ago must have read it and the statistics warp must be done with it.
+// up_row >= 0 (up2 plans): the lane's row goes to row `up_row` of the twice as large output map, columns col0 - up_col0
+// (the column tile is the output parity); the staging tile is still written for the statistics warp.
 __device__ __forceinline__ void epilogue_drain_chunk(const ConvKernelParams& p, const uint32_t (&v)[32],
                                                      int64_t warp_row0, bool valid, int col0, int lane, uint32_t stage,
                                                      uint32_t bias_sa, const uint4 (&res)[4], uint64_t* staged,
-                                                     uint64_t* sdone, uint32_t use) {
+                                                     uint64_t* sdone, uint32_t use, int64_t up_row = -1, int up_col0 = 0) {
   const int sub_row = lane >> 2, sub_chunk = lane & 3;     // coalesced distribution: row = 8 i + sub_row
   if (lane == 0) {
     bulk_wait_read<1>();                     // all but the newest store (which reads the OTHER tile) are done reading
@@ -158,13 +160,15 @@ __device__ __forceinline__ void epilogue_drain_chunk(const ConvKernelParams& p, 
     u.z = valid ? pack_bf16x2(f[8 * j + 4], f[8 * j + 5]) : 0u;
     u.w = valid ? pack_bf16x2(f[8 * j + 6], f[8 * j + 7]) : 0u;
     sts128(my_row + ((j ^ sw) << 4), u);
+    if (up_row >= 0 && valid)       // scatter: 64 bytes of this pixel's parity copy (pad rows of the output stay zero)
+      *reinterpret_cast<uint4*>(p.out + up_row * p.out_ld + (col0 - up_col0) + 8 * j) = u;
   }
   fence_async_smem();                      // generic-proxy writes -> visible to the TMA store (async proxy)
   __syncwarp();
   // ---- one TMA store for the warp's 32 x 32 tile (pad rows receive zeros, which is what they already hold), and the
   //      hand-over to the statistics warp (release: the tile written by all lanes is ordered before by __syncwarp)
   if (lane == 0) {
-    if (warp_row0 < p.rows) tma_store_2d(&p.tmOut, stage, col0, static_cast<int32_t>(warp_row0));
+    if (warp_row0 < p.rows && p.up2 == 0) tma_store_2d(&p.tmOut, stage, col0, static_cast<int32_t>(warp_row0));
     bulk_commit();
     mbar_arrive(staged);
   }
@@ -191,7 +195,7 @@ __device__ __forceinline__ void epilogue_stats_chunk(const ConvKernelParams& p, 
       const int row = 2 * i + hh;       // (row >> 1) & 3 == i & 3
       raw[i] = lds32(stage + static_cast<uint32_t>(row * 64 + ((cch ^ (i & 3)) << 4)) + col_b);
     }
-    const int64_t rec = (static_cast<int64_t>(tile) * 4 + q) * p.out_ld + col0 + 2 * cp;
+    const int64_t rec = (static_cast<int64_t>(tile) * 4 + q) * p.stats_ld + col0 + 2 * cp;
     if (n_a >= 32) {                                 // warp-uniform fast path: the window lies inside one image
       float sa0 = 0.f, sa1 = 0.f, qa0 = 0.f, qa1 = 0.f;
 #pragma unroll
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
       if (p.extra_rows[i] > 0) tma_prefetch_desc(&p.tmAx[i]);
     }
     tma_prefetch_desc(&p.tmB);
-    if (p.epilogue == IDF_EPI_BF16) tma_prefetch_desc(&p.tmOut);
+    if (p.epilogue == IDF_EPI_BF16 && p.up2 == 0) tma_prefetch_desc(&p.tmOut);
   }
   if (warp == W_I1) {
     // ~55 barriers: one per lane and pass instead of a serial loop of one thread (the prologue is on the critical path of
@@ -492,7 +496,11 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
         tc_fence_after();
         const uint32_t d0 = tmem_u + static_cast<uint32_t>(as * Cfg::ACC_COLS + m_begin * BN);
         int t = 0;
-        uint32_t rel = static_cast<uint32_t>(p.t_rel[0]) * 8u;     // tap view offset in 16-byte units
+        // up2 (nearest x2 folded into the conv): column tile nt = output parity (py, px); its taps are the base taps
+        // shifted by py rows and px pixels of the input grid
+        const int nt_i = st % p.n_tiles;
+        const uint32_t nt_shift = p.up2 != 0 ? static_cast<uint32_t>((nt_i >> 1) * p.Wp + (nt_i & 1)) * 8u : 0u;
+        uint32_t rel = static_cast<uint32_t>(p.t_rel[0]) * 8u + nt_shift;     // tap view offset in 16-byte units
         for (int g = 0; g < p.n_groups; ++g) {
           if constexpr (PAIR && XF) mbar_wait_cluster(a_ready + sa, pa);   // the peer's transform warps arrive remotely
           else mbar_wait(XF ? a_ready + sa : a_full + sa, pa);
@@ -506,7 +514,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + rel;           // tap view: any 128-byte row start is legal
             const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(sb) * (Cfg::B_BYTES / 16);
-            rel = static_cast<uint32_t>(p.t_rel[t + 1 < IDF_CONV_MAX_KB ? t + 1 : t]) * 8u;   // next tap's offset
+            rel = static_cast<uint32_t>(p.t_rel[t + 1 < IDF_CONV_MAX_KB ? t + 1 : t]) * 8u + nt_shift;   // next tap's offset
             if (elect_one()) {
 #pragma unroll
               for (int m = 0; m < M_PER; ++m) {
@@ -770,8 +778,11 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
             tmem_ld_wait();
             if (m == MT - 1 && c + 2 >= CHUNKS) release_acc(as);   // last TMEM read of this warp: release the accumulators early
             const uint32_t sl = 2u * e + (k & 1u);
+            int64_t up_row = -1;
+            if (p.up2 != 0)        // (n, y, x) of the input grid -> parity (nt >> 1, nt & 1) of the (2H) x (2W) output map
+              up_row = (static_cast<int64_t>(img) * (2 * p.H + 1) + 2 * y + (nt >> 1)) * (2 * p.W + 1) + 2 * x + (nt & 1);
             epilogue_drain_chunk(p, v, wr0, valid, nt * BN + c * 32, lane, stage_sa + sl * kStageTile, bias_sa, res_cur,
-                                 staged + sl, sdone + sl, k >> 1);
+                                 staged + sl, sdone + sl, k >> 1, up_row, nt * BN);
             ++k;
           }
         } else {
@@ -834,7 +845,7 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[c][j] += __shfl_xor_sync(0xffffffffu, acc[c][j], 16);   // even + odd rows
             if (hh == 0) {
-              const int64_t rec = (static_cast<int64_t>(ms) * 4 + q) * p.out_ld + nt * BN + c * 32 + 2 * cp;
+              const int64_t rec = (static_cast<int64_t>(ms) * 4 + q) * p.stats_ld + nt * BN + c * 32 + 2 * cp;
               *reinterpret_cast<float4*>(p.stats + 2 * rec) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
               if (straddles)
                 *reinterpret_cast<float4*>(p.stats + p.stats_b_off + 2 * rec) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);

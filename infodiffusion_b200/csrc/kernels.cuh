@@ -34,6 +34,8 @@ struct alignas(64) ConvKernelParams {
   float* stats;                         // optional GroupNorm partial sums: records A then records B, each
                                         // [m_tiles*4 (32-row windows)][out_ld][2] fp32 (sum, sumsq)
   int64_t stats_b_off;                  // float offset of the B records
+  int32_t stats_ld;                     // columns of a statistics record row (out_ld; up2: cout_pad = 4 parity planes)
+  int32_t up2;                          // nearest x2 upsampling folded in: column tile = output parity, scatter epilogue
   int32_t stats_item;                   // 1: one record per (work item of MT tiles, lane quarter) instead of per window
   int32_t debug_skip_epilogue;          // measurement only: epilogue warps drain nothing (main-loop ceiling)
   int64_t rows;

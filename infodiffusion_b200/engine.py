@@ -30,8 +30,8 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import EPI_BF16, EPI_F32_NCHW, EPI_SAMPLER, AdaGNArgs, ConvDesc
-from .layout import (ParamIndex, pack_conv1x1, pack_conv3x3, pad_cols as _pad_cols, pad_rows as _pad_rows, probing, pv,
-                     taps3x3, taps_stride2)
+from .layout import (ParamIndex, pack_conv1x1, pack_conv3x3, pack_conv3x3_up2, pad_cols as _pad_cols, pad_rows as _pad_rows,
+                     probing, pv, taps3x3, taps_stride2, taps_up2)
 from .modules import AttnBlock, AuxResBlock, DownSample, ResBlock, UpSample
 
 BF16 = torch.bfloat16
@@ -51,18 +51,23 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 # ------------------------------------------------------------------------------------------------
 class Act:
     """A pad-flat bf16 activation buffer [phases * B*(H+1)*(W+1), C]."""
-    __slots__ = ("t", "H", "C", "phases", "rows", "stats", "has_stats", "stats_unit")
+    __slots__ = ("t", "H", "C", "phases", "rows", "stats", "has_stats", "stats_unit", "stats_planes", "stats_rows")
 
     def __init__(self, t, H, C, phases, rows):
         self.t, self.H, self.C, self.phases, self.rows = t, H, C, phases, rows
         self.stats = None          # fp32 [2, ceil(rows/128)*4, C, 2] GroupNorm partial sums (conv epilogues)
         self.has_stats = False     # True while `stats` describes the current contents of `t`
         self.stats_unit = 32       # rows per statistics unit of the records in `stats` (idf_conv_plan_stats_unit)
+        self.stats_planes = 0      # > 0: records written by an up2 conv (parity planes, producer grid of stats_rows rows / image)
+        self.stats_rows = 0
 
-    def stats_buffer(self) -> torch.Tensor:
+    def stats_buffer(self, min_floats: int = 0) -> torch.Tensor:
+        """Allocated once per buffer (plans keep raw pointers to it): sized for the map's own tiles plus the slack an
+        up2 producer needs (its records cover the input grid's tiles, 4 parity planes wide: <= 1.13x for H >= 16)."""
         if self.stats is None:
             tiles = (self.rows + 127) // 128
-            self.stats = torch.zeros(2 * tiles * 4 * self.C * 2, dtype=torch.float32, device=self.t.device)
+            self.stats = torch.zeros(2 * (tiles + tiles // 4 + 8) * 4 * self.C * 2, dtype=torch.float32, device=self.t.device)
+        assert self.stats.numel() >= min_floats, "statistics buffer too small for this producer"
         return self.stats
 
 
@@ -87,6 +92,7 @@ FUSE_ADAGN_MIN_H = int(__import__("os").environ.get("IDF_FUSE_MIN_H", "64"))
 FUSE_ADAGN_MIN_ROWS = 128 * 65 * 65      # ... and only from this many pad-flat rows (batch 128 at 64x64)
 MAX_GN_CHANNELS = 1024       # widest GroupNorm the AdaGN forward kernels take (csrc/adagn.cu kMaxCWide)
 MAX_TRAIN_GN_CHANNELS = 256  # ... and their backward kernels (csrc/adagn_bwd.cu); wgrad plans stop at 64 work units
+UPSAMPLE_FOLD = __import__("os").environ.get("IDF_UPSAMPLE_FOLD", "1") != "0"   # inference: nearest x2 folded into the following conv (see Plan.upsample)
 TRAIN_PDL = True       # programmatic dependent launch once a training plan exists (library-wide switch)
 
 
@@ -107,6 +113,7 @@ class Workspace:
         if fl:
             a = fl.pop()
             a.has_stats = False
+            a.stats_planes = a.stats_rows = 0
             return a
         rows = self.batch * (H + 1) * (H + 1)
         t = torch.zeros(phases * rows, C_, dtype=BF16, device=self.device)
@@ -288,7 +295,7 @@ class Plan:
              bias: torch.Tensor, H: int, cout: int, block_n: int, out: Optional[Act] = None,
              residual: Optional[Act] = None, epilogue: int = EPI_BF16, out_f32=None, x_io=None, noise=None,
              coef=None, step=None, real_macs_per_row: Optional[int] = None, want_stats: bool = True,
-             xf: Optional[Tuple[torch.Tensor, bool, Sequence[int]]] = None) -> None:
+             xf: Optional[Tuple[torch.Tensor, bool, Sequence[int]]] = None, up2: bool = False) -> None:
         """`xf` = (coefficients [B, Ctot, 2], silu?, per-k-block channel base or -1): fused AdaGN on the A operand."""
         d = ConvDesc()
         d.n_src = len(srcs)
@@ -308,11 +315,14 @@ class Plan:
         d.bias = bias.data_ptr()
         d.batch, d.H, d.W = self.B, H, H
         d.epilogue = epilogue
+        d.up2 = 1 if up2 else 0
         if out is not None:
-            assert out.H == H and out.C == cout
+            assert out.H == (2 * H if up2 else H) and out.C == cout
             d.out, d.out_ld = out.t.data_ptr(), out.C
             if want_stats:
-                d.stats_out = out.stats_buffer().data_ptr()
+                # (an up2 plan writes records over the input grid's tiles, 4 parity planes wide)
+                tiles_in = (self.B * (H + 1) * (H + 1) + 127) // 128
+                d.stats_out = out.stats_buffer(2 * tiles_in * 4 * 4 * cout * 2 if up2 else 0).data_ptr()
                 out.has_stats = True
         if residual is not None:
             assert residual.H == H and residual.C == cout
@@ -331,6 +341,7 @@ class Plan:
         self.conv_tiles += int(self.lib.idf_conv_plan_tiles(h))
         if out is not None and want_stats:
             out.stats_unit = int(self.lib.idf_conv_plan_stats_unit(h))
+            out.stats_planes, out.stats_rows = (4, (H + 1) * (H + 1)) if up2 else (0, 0)
         macs = real_macs_per_row if real_macs_per_row is not None else 64 * len(kblocks) * cout
         # conv_igemm_xf: the launches that also apply a fused AdaGN (+SiLU) to their A operand -- they replace a
         # stand-alone AdaGN pass and are accounted separately from the plain implicit GEMMs
@@ -350,8 +361,10 @@ class Plan:
             a = AdaGNArgs()
             a.c0 = src0.C
             a.stats0, a.stats_unit0 = src0.stats.data_ptr(), src0.stats_unit
+            a.stats_planes0, a.stats_rows0 = src0.stats_planes, src0.stats_rows
             if src1 is not None:
                 a.c1, a.stats1, a.stats_unit1 = src1.C, src1.stats.data_ptr(), src1.stats_unit
+                a.stats_planes1, a.stats_rows1 = src1.stats_planes, src1.stats_rows
             a.batch, a.H, a.W = self.B, src0.H, src0.H
             gamma, beta = self.f32(lambda: pv(gn.weight)), self.f32(lambda: pv(gn.bias))
             a.gamma, a.beta, a.eps = gamma.data_ptr(), beta.data_ptr(), float(gn.eps)
@@ -411,8 +424,10 @@ class Plan:
         a.apply_silu = 1 if silu else 0
         if src0.has_stats and (src1 is None or src1.has_stats):
             a.stats0, a.stats_unit0 = src0.stats.data_ptr(), src0.stats_unit
+            a.stats_planes0, a.stats_rows0 = src0.stats_planes, src0.stats_rows
             if src1 is not None:
                 a.stats1, a.stats_unit1 = src1.stats.data_ptr(), src1.stats_unit
+                a.stats_planes1, a.stats_rows1 = src1.stats_planes, src1.stats_rows
         if dropout and self.training and self.dropout_p > 0:
             self._drop_layers += 1
             a.dropout_p, a.dropout_seed, a.dropout_layer = self.dropout_p, self.dropout_seed.data_ptr(), self._drop_layers
@@ -519,6 +534,20 @@ class Plan:
         return out
 
     def upsample(self, src: Act, conv: nn.Conv2d) -> Act:
+        """UpSample (modules.py:89-92): nearest x2 + 3x3 conv.  Inference plans fold the upsampling into the conv
+        (idf_conv_desc.up2: the GEMM runs on the input grid, four taps per output parity, pre-summed weights, the
+        epilogue scatters the parities: 4/9 of the FLOPs and no upsampled tensor); training plans materialise it."""
+        cout = conv.out_channels
+        if UPSAMPLE_FOLD and not self.training and cout in (64, 128) and src.C % 64 == 0:
+            H = src.H
+            out = self.ws.alloc(2 * H, cout)
+            wp = self.weight(lambda: pack_conv3x3_up2(pv(conv.weight)))
+            bias = self.f32(lambda: pv(conv.bias).repeat(4))
+            # FLOP accounting stays ALGORITHMIC (SURVEY section 8d: the reference's 9 taps on each of the 4 output pixels
+            # of an input pixel); the kernel executes 4/9 of these MACs
+            self.conv([src], taps_up2(src.C, H, H), wp, bias, H, cout, cout, out=out, up2=True,
+                      real_macs_per_row=4 * 9 * src.C * cout)
+            return out
         up = self.ws.alloc(src.H * 2, src.C)
         self._emit("upsample2x", self.lib.idf_upsample2x, (src.t.data_ptr(), up.t.data_ptr(), self.B, src.H, src.H, src.C))
         if self.training:

@@ -53,6 +53,39 @@ def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
     return w.detach().permute(0, 2, 3, 1).reshape(co, 9 * ci)
 
 
+def taps_up2(cin: int, H: int, W: int, src: int = 0) -> List[KBlock]:
+    """K-blocks of a nearest-x2-upsample + 3x3 conv folded onto the INPUT grid (idf_conv_desc.up2): the four taps of
+    output parity (0, 0) -- input rows {y-1, y} x columns {x-1, x} -- tap-major, then 64-channel slices; parity
+    (py, px) uses the same taps shifted by py rows and px pixels (done by the kernel per column tile)."""
+    kb: List[KBlock] = []
+    for dy in (-1, 0):
+        for dx in (-1, 0):
+            kb += [(src, c0, dy * (W + 1) + dx) for c0 in range(0, cin, 64)]
+    return kb
+
+
+def pack_conv3x3_up2(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> [4*Cout, 4*Cin]: row block p = 2*py + px holds the weights of output parity (py, px), k =
+    (ty*2 + tx)*Cin + c for the 2x2 input neighbourhood (ty, tx); the 3x3 taps that read the same input pixel after
+    nearest upsampling are summed (ky -> ty: parity 0: {0} | {1, 2}; parity 1: {0, 1} | {2})."""
+    grp = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    co, ci = w.shape[0], w.shape[1]
+    w = w.detach()
+    blocks = []
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = []
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    acc = None
+                    for ky in grp[py][ty]:
+                        for kx in grp[px][tx]:
+                            acc = w[:, :, ky, kx] if acc is None else acc + w[:, :, ky, kx]
+                    taps.append(acc)                                # [Cout, Cin]
+            blocks.append(torch.stack(taps, dim=1).reshape(co, 4 * ci))
+    return torch.cat(blocks, dim=0)
+
+
 def tap_offsets3x3(H: int, W: int) -> List[int]:
     """Row offset of each of the 9 taps (tap = ky*3 + kx) in the pad-flat layout."""
     return [(t // 3 - 1) * (W + 1) + (t % 3 - 1) for t in range(9)]

@@ -341,6 +341,74 @@ def test_upsample2x(lib):
     assert pad_is_zero(out, B, 2 * H, 2 * H)
 
 
+@pytest.mark.parametrize("cin,cout,H,B", [(128, 128, 8, 3), (128, 128, 16, 5), (64, 64, 16, 2), (128, 128, 32, 2), (192, 128, 8, 7)])
+def test_upsample_folded_into_conv(lib, cin, cout, H, B):
+    """idf_conv_desc.up2: conv3x3(nearest_x2(x)) computed on the input grid with four pre-summed taps per output
+    parity (UpSample, modules.py:89-92) -- output, zero pads, and the GroupNorm statistics (4 parity planes over the
+    input grid) consumed by the AdaGN kernel, against F.interpolate + F.conv2d."""
+    from infodiffusion_b200 import layout
+    from infodiffusion_b200._lib import AdaGNArgs, ConvDesc
+    g = torch.Generator(device=DEV).manual_seed(900 + cin + H)
+    x = rbf(torch.randn(B, cin, H, H, device=DEV, generator=g))
+    w = torch.randn(cout, cin, 3, 3, device=DEV, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, device=DEV, generator=g)
+    wp = layout.pack_conv3x3_up2(w).to(BF).contiguous()
+    # reference with the SAME (pre-summed, bf16-rounded) weights: undo the packing per parity
+    up = F.interpolate(x, scale_factor=2.0, mode="nearest")
+    ref_exact = F.conv2d(up.double(), w.double(), b.double(), padding=1)
+    rows_in, rows_up = B * (H + 1) * (H + 1), B * (2 * H + 1) * (2 * H + 1)
+    out = torch.zeros(rows_up, cout, device=DEV, dtype=BF)
+    tiles_in = (rows_in + 127) // 128
+    stats = torch.zeros(2 * tiles_in * 4 * 4 * cout * 2, device=DEV)
+    xs = pf(x)
+    d = ConvDesc()
+    d.n_src = 1
+    d.src[0], d.src_rows[0], d.src_ld[0] = xs.data_ptr(), xs.shape[0], cin
+    kb = layout.taps_up2(cin, H, H)
+    d.num_kb = len(kb)
+    for k, (si, c0, off) in enumerate(kb):
+        d.kb_src[k], d.kb_c0[k], d.kb_rowoff[k] = si, c0, off
+    bias4 = b.repeat(4).contiguous()
+    d.weight, d.cout_pad, d.block_n, d.cout, d.bias = wp.data_ptr(), 4 * cout, cout, cout, bias4.data_ptr()
+    d.batch, d.H, d.W, d.epilogue, d.up2 = B, H, H, 0, 1
+    d.out, d.out_ld, d.stats_out = out.data_ptr(), cout, stats.data_ptr()
+    h = C.c_void_p()
+    check(lib.idf_conv_plan_create(C.byref(d), C.byref(h)))
+    check(lib.idf_conv_run(h, stream()))
+    torch.cuda.synchronize()
+    unit = int(lib.idf_conv_plan_stats_unit(h))
+    lib.idf_conv_plan_destroy(h)
+    assert pad_is_zero(out, B, 2 * H, 2 * H)
+    # bf16 rounding of the pre-summed weights differs from rounding each 3x3 tap: compare against both
+    assert_close(unpf(out, B, 2 * H, 2 * H), ref_exact, rel_l2=6e-3, max_rel=3e-2, what=f"up2 conv {cin}->{cout}@{H}")
+    wq = wp.float().reshape(4, cout, 4, cin)
+    refq = torch.zeros_like(ref_exact)
+    xp = F.pad(x.double(), (1, 1, 1, 1))
+    for py in (0, 1):
+        for px in (0, 1):
+            acc = b.double()[None, :, None, None].expand(B, cout, H, H).clone()
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    patch = xp[:, :, py + ty:py + ty + H, px + tx:px + tx + H]
+                    acc += torch.einsum("oc,bchw->bohw", wq[py * 2 + px, :, ty * 2 + tx, :].double(), patch)
+            refq[:, :, py::2, px::2] = acc
+    assert_close(unpf(out, B, 2 * H, 2 * H), refq, what=f"up2 conv (same packed weights) {cin}->{cout}@{H}")
+    # the statistics feed an AdaGN of the upsampled map
+    a = AdaGNArgs()
+    gamma, beta = torch.rand(cout, device=DEV, generator=g) + 0.5, torch.randn(cout, device=DEV, generator=g)
+    o1, o2 = torch.zeros_like(out), torch.zeros_like(out)
+    a.src0, a.c0, a.batch, a.H, a.W = out.data_ptr(), cout, B, 2 * H, 2 * H
+    a.gamma, a.beta, a.eps, a.apply_silu = gamma.data_ptr(), beta.data_ptr(), 1e-5, 1
+    a.out = o1.data_ptr()
+    st_ref = tile_partials(out, B, 2 * H, 2 * H)
+    a.stats0 = st_ref.data_ptr()
+    check(lib.idf_adagn_silu_fwd(C.byref(a), stream()))
+    a.out, a.stats0, a.stats_unit0, a.stats_planes0, a.stats_rows0 = o2.data_ptr(), stats.data_ptr(), unit, 4, (H + 1) * (H + 1)
+    check(lib.idf_adagn_silu_fwd(C.byref(a), stream()))
+    torch.cuda.synchronize()
+    assert_close(o2.float(), o1.float(), rel_l2=1e-3, max_rel=2e-2, what="AdaGN from up2 statistics vs window statistics")
+
+
 def test_im2col_head_and_gemm(lib):
     from infodiffusion_b200 import layout
     g = torch.Generator(device=DEV).manual_seed(9)
