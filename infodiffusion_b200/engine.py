@@ -19,6 +19,9 @@ Fusions relative to the reference's one-op-per-kernel execution (modules.py / mo
   * tail conv + DDPM/DDIM/reverse-DDIM update of x                   -> GEMM epilogue (sampler mode)
   * every temb_proj / aemb_proj Linear of all 22 blocks              -> two batched GEMMs, hoisted out
     of the step loop (the timestep side becomes a [T, 4992] table, the z side is step-invariant)
+  * nearest x2 upsampling + conv (inference)                         -> one 4-tap GEMM per output parity on the input grid
+  * AdaGN + SiLU of the 64x64 maps (inference, batch >= 128)         -> applied to the consumer conv's A operand in
+    shared memory (transform warps); the normalised activation never exists in HBM
 """
 from __future__ import annotations
 
