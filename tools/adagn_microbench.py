@@ -33,7 +33,8 @@ for knob in ("adagn_ring", "adagn_ctas"):
     if os.environ.get(knob.upper()):
         _lib.check(lib.idf_set_option(knob.encode(), int(os.environ[knob.upper()])))
         print(knob, "=", os.environ[knob.upper()])
-for (B, H, Cc) in [(256, 64, 64), (256, 32, 128), (256, 16, 128)]:
+SHAPES = [(256, 64, 64), (256, 32, 128), (256, 16, 128), (256, 8, 128), (256, 16, 256), (256, 8, 256), (32, 64, 64), (32, 32, 128)]
+for (B, H, Cc) in SHAPES:
     rows = B * (H + 1) * (H + 1)
     x = torch.randn(rows, Cc, device=dev).to(BF)
     out = torch.zeros_like(x)

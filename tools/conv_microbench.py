@@ -21,7 +21,7 @@ PAIR_DEFAULT = int(os.environ.get("IDF_CONV_PAIR", "1"))
 _lib.check(lib.idf_set_option(b"conv_pair", PAIR_DEFAULT))
 
 
-def make(cin, cout, H, residual, stats, skip, xf=False):
+def make(cin, cout, H, residual, stats, skip, xf=False, bn=None):
     rows = B * (H + 1) * (H + 1)
     x = torch.randn(rows, cin, device=dev).to(BF)
     w = (torch.randn(cout, 9 * cin, device=dev) * 0.02).to(BF)
@@ -36,7 +36,7 @@ def make(cin, cout, H, residual, stats, skip, xf=False):
     d.num_kb = len(kb)
     for k, (si, c0, off) in enumerate(kb):
         d.kb_src[k], d.kb_c0[k], d.kb_rowoff[k] = si, c0, off
-    bn = 128 if cout % 128 == 0 else 64
+    bn = bn or (128 if cout % 128 == 0 else 64)
     d.weight, d.cout_pad, d.block_n, d.cout, d.bias = w.data_ptr(), cout, bn, cout, b.data_ptr()
     d.batch, d.H, d.W, d.epilogue = B, H, H, 0
     d.out, d.out_ld = out.data_ptr(), cout
