@@ -119,11 +119,14 @@ __device__ __forceinline__ void residual_fetch(const ConvKernelParams& p, int64_
 __device__ __forceinline__ void epilogue_drain_chunk(const ConvKernelParams& p, const uint32_t (&v)[32],
                                                      int64_t warp_row0, bool valid, int col0, int lane, uint32_t stage,
                                                      uint32_t bias_sa, const uint4 (&res)[4], uint64_t* staged,
-                                                     uint64_t* sdone, uint32_t use, int64_t up_row = -1, int up_col0 = 0) {
+                                                     uint64_t* sdone, uint32_t use, int64_t up_row = -1, int up_col0 = 0,
+                                                     int trow = -1) {
   const int sub_row = lane >> 2, sub_chunk = lane & 3;     // coalesced distribution: row = 8 i + sub_row
   if (lane == 0) {
     bulk_wait_read<1>();                     // all but the newest store (which reads the OTHER tile) are done reading
+    if (trow >= 0) IDF_TRACE(2, trow);
     mbar_wait(sdone, (use & 1u) ^ 1u);       // the statistics of this tile's previous contents have been taken
+    if (trow >= 0) IDF_TRACE(3, trow);
   }
   __syncwarp();
   if (p.residual != nullptr) {
@@ -171,6 +174,7 @@ __device__ __forceinline__ void epilogue_drain_chunk(const ConvKernelParams& p, 
     if (warp_row0 < p.rows && p.up2 == 0) tma_store_2d(&p.tmOut, stage, col0, static_cast<int32_t>(warp_row0));
     bulk_commit();
     mbar_arrive(staged);
+    if (trow >= 0) IDF_TRACE(4, trow);
   }
 }
 
@@ -762,6 +766,9 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
 #pragma unroll 1
           for (int c = half; c < CHUNKS; c += 2) {   // items (m, c) alternate between the halves (CHUNKS is even)
             uint32_t v[32];
+            // trace builds: the first drain warp's chunks of the first items go to trace rows 32 + 4 * item + tile
+            const int trow = (e == 0 && iter < 8 && m < 4) ? 32 + 4 * iter + m : -1;
+            if (lane == 0 && trow >= 0) IDF_TRACE(0, trow);
             tmem_ld_32x32(t0 + static_cast<uint32_t>(m * BN + c * 32), v);
             uint4 res_cur[4];
 #pragma unroll
@@ -776,13 +783,14 @@ __global__ void __launch_bounds__(conv_threads(XF), 1) conv_halo_kernel(const __
               residual_fetch(p, (static_cast<int64_t>(nms) * MT + nm) * kBM + q * 32, nnt * BN + nc * 32, lane, res_next);
             }
             tmem_ld_wait();
+            if (lane == 0 && trow >= 0) IDF_TRACE(1, trow);
             if (m == MT - 1 && c + 2 >= CHUNKS) release_acc(as);   // last TMEM read of this warp: release the accumulators early
             const uint32_t sl = 2u * e + (k & 1u);
             int64_t up_row = -1;
             if (p.up2 != 0)        // (n, y, x) of the input grid -> parity (nt >> 1, nt & 1) of the (2H) x (2W) output map
               up_row = (static_cast<int64_t>(img) * (2 * p.H + 1) + 2 * y + (nt >> 1)) * (2 * p.W + 1) + 2 * x + (nt & 1);
             epilogue_drain_chunk(p, v, wr0, valid, nt * BN + c * 32, lane, stage_sa + sl * kStageTile, bias_sa, res_cur,
-                                 staged + sl, sdone + sl, k >> 1, up_row, nt * BN);
+                                 staged + sl, sdone + sl, k >> 1, up_row, nt * BN, trow);
             ++k;
           }
         } else {

@@ -33,3 +33,12 @@ for i in range(16):
     if t[i, 0] == 0:
         break
     print(f"{i:4d}  " + "  ".join(f"{(t[i, k] - t0) / 1e3:12.2f}" if t[i, k] else f"{'':>12s}" for k in range(6)))
+# first drain warp's chunks (trace rows 32 + 4*item + tile): TMEM load issued / data in registers / previous TMA store
+# has read the tile / statistics warp done with the tile / tile written + TMA store issued
+print("\nfirst drain warp, per (item, tile):  tmem_ld  ld_done  store_read  stats_done  staged   (us since the first TMA issue)")
+for i in range(6):
+    for m in range(4):
+        r = 32 + 4 * i + m
+        if t[r, 0] == 0:
+            continue
+        print(f"  item {i} tile {m}: " + "  ".join(f"{(t[r, k] - t0) / 1e3:9.2f}" for k in range(5)))
